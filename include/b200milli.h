@@ -1,0 +1,169 @@
+/* b200milli — B200-native (sm_100a) implementation of milli's query-time scoring path.
+ *
+ * C ABI of the drop-in boundary.  The reference has no FFI for this path; its
+ * seams are Rust-internal.  Each entry point names the reference interface a Rust shim would
+ * replace with a call to it (paths relative to the meilisearch checkout, v1.50.0 @ 5cb2f2e).
+ * Conventions: caller allocates every output; the library never frees caller memory; handles are
+ * opaque; every function returns 0 on success or a negative B200_ERR_* code, with a message
+ * available from b200_last_error(); no exceptions/panics cross the boundary; one handle may be
+ * used from many threads (calls are serialised per handle; each call runs on the handle's stream).
+ * There is NO CPU fallback: without a CUDA device b200_open fails with B200_ERR_NO_DEVICE.
+ */
+#ifndef B200MILLI_H
+#define B200MILLI_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_ERR_NO_DEVICE (-1)   /* no CUDA device / driver (the product never falls back to the CPU) */
+#define B200_ERR_CUDA (-2)        /* a CUDA call failed; see b200_last_error */
+#define B200_ERR_INVALID (-3)     /* bad argument */
+#define B200_ERR_UNSUPPORTED (-4) /* query feature outside the implemented scope (phrases, negative words, synonyms, ...) */
+#define B200_ERR_CAPACITY (-5)    /* a device work queue / arena overflowed */
+#define B200_ERR_STATE (-6)       /* call order (e.g. search before b200_stage_finish) */
+
+typedef struct b200_index b200_index;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+/* Replaces: opening the LMDB env for search (crates/milli/src/index.rs:129-…) — here a device-resident copy. */
+int b200_open(int device_ordinal, b200_index **out);
+void b200_close(b200_index *);
+const char *b200_last_error(const b200_index *); /* valid until the next call on the handle */
+/* message of the last failure of b200_open itself */
+const char *b200_open_error(void);
+
+/* ---- staging: done once, copies everything (LMDB pages are only borrowed for a RoTxn) --- */
+/* database ids, in the key/value formats of crates/milli/src/index.rs:97-124 and
+ * heed_codec/{str_beu32_codec.rs (StrBEU16Codec), str_str_u8_codec.rs (U8StrStrCodec)};
+ * values are CboRoaringBitmapCodec bytes (heed_codec/roaring_bitmap/cbo_roaring_bitmap_codec.rs:15-85). */
+enum b200_db {
+    B200_DB_WORD_DOCIDS = 0,               /* key: word */
+    B200_DB_EXACT_WORD_DOCIDS = 1,         /* key: word */
+    B200_DB_WORD_PREFIX_DOCIDS = 2,        /* key: prefix */
+    B200_DB_EXACT_WORD_PREFIX_DOCIDS = 3,  /* key: prefix */
+    B200_DB_WORD_PAIR_PROXIMITY_DOCIDS = 4,/* key: u8 prox | w1 | 0x00 | w2 */
+    B200_DB_WORD_POSITION_DOCIDS = 5,      /* key: word | 0x00 | u16 BE bucketed position */
+    B200_DB_WORD_FID_DOCIDS = 6,           /* key: word | 0x00 | u16 BE field id */
+    B200_DB_WORD_PREFIX_POSITION_DOCIDS = 7,
+    B200_DB_WORD_PREFIX_FID_DOCIDS = 8,
+    B200_DB_FIELD_ID_WORD_COUNT_DOCIDS = 9,/* key: u16 BE fid | u8 count */
+    B200_DB_COUNT = 10
+};
+/* Replaces Index::words_fst (index.rs:1238): the FST enumerated once on the host into its sorted word list. */
+int b200_stage_dictionary(b200_index *, const uint8_t *word_bytes, const uint64_t *word_offsets, uint64_t n_words);
+/* Replaces the typed `Database<..., CboRoaringBitmapCodec>` handles read by search/new/db_cache.rs:183-719.
+ * Keys must be in LMDB (bytewise) order. */
+int b200_stage_db(b200_index *, int db, uint64_t n_keys, const uint8_t *key_bytes, const uint64_t *key_offsets,
+                  const uint8_t *val_bytes, const uint64_t *val_offsets);
+/* Replaces Index::documents_ids (index.rs, main["documents-ids"]); CBO bytes. */
+int b200_stage_documents_ids(b200_index *, const uint8_t *cbo, uint64_t len);
+
+/* criteria (crates/milli/src/criterion.rs:121-131) */
+enum b200_criterion { B200_C_WORDS = 0, B200_C_TYPO = 1, B200_C_PROXIMITY = 2, B200_C_ATTRIBUTE = 3, B200_C_ATTRIBUTE_RANK = 4,
+                      B200_C_WORD_POSITION = 5, B200_C_SORT = 6, B200_C_EXACTNESS = 7 };
+typedef struct {
+    uint32_t n_fields;              /* searchable fields; fid = 0..n_fields-1 */
+    const uint16_t *weights;        /* fieldids_weights_map: fid -> weight */
+    const int32_t *criteria;        /* index `criteria` setting */
+    uint32_t n_criteria;
+    int32_t authorize_typos;        /* index.rs authorize-typos */
+    uint32_t min_word_len_one_typo; /* index.rs:46 (5) */
+    uint32_t min_word_len_two_typos;/* index.rs:47 (9) */
+    int32_t prefix_search;          /* PrefixSearch::IndexingTime (1) / Disabled (0) */
+    const char *exact_words;        /* '\n'-joined exact_words set (may be NULL) */
+} b200_settings;
+int b200_stage_settings(b200_index *, const b200_settings *);
+/* Uploads everything to HBM and builds the device directories.  Must follow the stage_* calls. */
+int b200_stage_finish(b200_index *);
+/* Replaces the arroy/hannoy item nodes read by VectorStore (crates/milli/src/vector/store.rs:1427-1434):
+ * one f32[d] vector per row + its docid.  Stored on device as fp16 rows + f32 inverse norms. */
+int b200_stage_embeddings(b200_index *, const float *vectors, uint64_t n, uint32_t d, const uint32_t *docids);
+/* Embedder `distribution` (crates/milli/src/vector/distribution.rs): enabled=0 disables the shift. */
+int b200_stage_distribution(b200_index *, int enabled, float mean, float sigma);
+
+/* ---- S3: term derivation --------------------------------------------------------------- */
+/* Replaces Interned<QueryTerm>::compute_fully_if_needed -> find_one_typo_derivations /
+ * find_one_two_typo_derivations (crates/milli/src/search/new/query_term/compute_derivations.rs:21-168),
+ * i.e. `fst.search_with_state(Intersection/Union(StartsWith, LevenshteinDFA))`.
+ * For word i (bytes words[word_off[i]..word_off[i+1]]), max_typo[i] in {1,2}, is_prefix[i] in {0,1}:
+ * one_out[i*150..] gets up to 150 dictionary ranks at distance 1, two_out[i*50..] up to 50 at distance 2
+ * (ascending rank order, caps and first-letter rule exactly as the reference). */
+#define B200_MAX_ONE_TYPO 150
+#define B200_MAX_TWO_TYPOS 50
+int b200_derive_batch(b200_index *, uint32_t n_words, const char *words, const uint32_t *word_off, const uint8_t *max_typo,
+                      const uint8_t *is_prefix, uint32_t *one_out, uint32_t *n_one, uint32_t *two_out, uint32_t *n_two);
+
+/* ---- S4: vector store ------------------------------------------------------------------ */
+/* Replaces VectorStore::nns_by_vector (crates/milli/src/vector/store.rs:638-675) for a batch of queries:
+ * exact scan, ascending distance (1 - cos)/2, ties by ascending docid.
+ * queries: n_q x d f32 (host).  cand_bitmap: optional dense little-endian u64 words over docids (filter),
+ * shared by the batch (NULL = all).  ids_out/dist_out: n_q x limit; n_out: n_q. */
+int b200_nns_batch(b200_index *, const float *queries, uint32_t n_q, uint32_t d, uint32_t limit, const uint64_t *cand_bitmap,
+                   uint64_t n_cand_words, uint32_t *ids_out, float *dist_out, uint32_t *n_out);
+
+/* ---- S0: whole search ------------------------------------------------------------------ */
+/* Replaces milli::Search::execute / execute_hybrid (crates/milli/src/search/mod.rs:280-415,
+ * search/hybrid.rs:264-366) for a batch of queries against one index, as called from
+ * search_from_kind (crates/meilisearch/src/search/mod.rs:2126-2148) / SearchByIndex::execute
+ * (crates/meilisearch/src/search/federated/perform.rs:1544).
+ * Queries arrive tokenised (charabia stays on the host): tokens of query i are
+ * [token_begin[i], token_begin[i+1]); kind: 0 Word, 1 StopWord, 2 Separator(Soft), 3 Separator(Hard). */
+enum b200_tms { B200_TMS_LAST = 0, B200_TMS_ALL = 1, B200_TMS_FREQUENCY = 2 };
+typedef struct {
+    uint32_t n_queries;
+    const uint32_t *token_begin;  /* n_queries + 1 */
+    const uint8_t *token_kind;
+    const uint32_t *lemma_off;    /* n_tokens + 1 */
+    const char *lemma_bytes;
+    int32_t terms_matching_strategy; /* b200_tms */
+    int32_t scoring_strategy;        /* 0 Skip, 1 Detailed (score_details.rs:431-438) */
+    uint32_t offset, limit;          /* Search::offset / limit */
+    uint32_t words_limit;            /* Search::words_limit (default 10) */
+    const float *vectors;            /* n_queries x d, or NULL: the `semantic` vector per query */
+    int32_t mode;                    /* 0 keyword (execute), 1 semantic (execute with vector), 2 hybrid (execute_hybrid) */
+    float semantic_ratio;            /* hybrid only */
+} b200_query_batch;
+#define B200_MAX_SCORES 12
+/* score kinds: ScoreDetails variants (score_details.rs:9-32) */
+enum b200_score_kind { B200_S_WORDS = 0, B200_S_TYPO = 1, B200_S_PROXIMITY = 2, B200_S_FID = 3, B200_S_POSITION = 4,
+                       B200_S_EXACT_ATTRIBUTE = 5, B200_S_EXACT_WORDS = 6, B200_S_VECTOR = 7, B200_S_SKIPPED = 8 };
+typedef struct {                  /* SearchResult (search/mod.rs:526-535), flattened; all caller-allocated */
+    uint32_t *docids;             /* n_queries x limit      documents_ids */
+    uint32_t *n_hits;             /* n_queries */
+    uint8_t *n_scores;            /* n_queries x limit      len of document_scores[i] (Detailed only) */
+    uint8_t *score_kind;          /* n_queries x limit x B200_MAX_SCORES */
+    uint32_t *score_rank;         /* idem: Rank.rank  (score_details.rs:512-522) */
+    uint32_t *score_max;          /* idem: Rank.max_rank */
+    float *score_sim;             /* idem: Vector.similarity, -1 when None */
+    uint64_t *n_candidates;       /* n_queries: candidates.len() */
+    uint32_t *semantic_hits;      /* n_queries: execute_hybrid's semantic_hit_count (may be NULL) */
+    int32_t *status;              /* n_queries: 0 or a B200_ERR_* for that query (e.g. UNSUPPORTED) */
+} b200_results;
+int b200_search_batch(b200_index *, const b200_query_batch *, b200_results *);
+
+/* ---- introspection for measurement ----------------------------------------------------- */
+/* kernel classes for the per-kernel accounting below */
+enum b200_kernel { B200_K_LEV = 0, B200_K_COMPACT = 1, B200_K_PAIR_PROBE = 2, B200_K_SCATTER = 3, B200_K_EVAL_PATHS = 4, B200_K_EMIT = 5,
+                   B200_K_VEC_DIST = 6, B200_K_TOPK = 7, B200_K_COUNT = 8 };
+typedef struct {
+    uint64_t kernel_launches;     /* kernels launched by the library since the last reset */
+    uint64_t device_steps;        /* host<->device round trips since the last reset */
+    uint64_t posting_bytes;       /* algorithmic bytes: stored bytes of posting lists read */
+    uint64_t matrix_bytes;        /* algorithmic bytes: condition/bucket matrix words read+written */
+    uint64_t dictionary_bytes;    /* algorithmic bytes of the term-derivation sweeps */
+    uint64_t vector_bytes;        /* algorithmic bytes of the distance scans */
+    double kernel_ms[8];          /* CUDA-event time accumulated per kernel class (events on the library's stream) */
+    uint64_t kernel_count[8];     /* launches per kernel class */
+    uint64_t kernel_bytes[8];     /* algorithmic bytes attributed to each kernel class */
+    double device_ms;             /* CUDA-event time from the first to the last kernel of every step */
+    uint64_t hbm_bytes_staged;
+} b200_stats;
+int b200_get_stats(b200_index *, b200_stats *out);
+int b200_reset_stats(b200_index *);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,356 @@
+// C ABI (include/b200milli.h) over the engine; hybrid merge (search/hybrid.rs) lives here because it is pure host logic
+// over two result lists.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "engine.h"
+
+using namespace b200;
+
+struct b200_index {
+    Engine e;
+};
+
+static thread_local std::string g_open_error;
+
+extern "C" {
+
+const char *b200_open_error(void) { return g_open_error.c_str(); }
+
+int b200_open(int device_ordinal, b200_index **out) {
+    *out = nullptr;
+    int n = 0;
+    cudaError_t err = cudaGetDeviceCount(&n);
+    if (err != cudaSuccess || n == 0) {
+        g_open_error = std::string("no CUDA device: ") + (err != cudaSuccess ? cudaGetErrorString(err) : "device count is 0") +
+                       " (b200milli has no CPU fallback)";
+        return B200_ERR_NO_DEVICE;
+    }
+    if (device_ordinal < 0 || device_ordinal >= n) {
+        g_open_error = "device ordinal out of range";
+        return B200_ERR_INVALID;
+    }
+    b200_index *h = new (std::nothrow) b200_index();
+    if (!h) return B200_ERR_INVALID;
+    h->e.device = device_ordinal;
+    if ((err = cudaSetDevice(device_ordinal)) != cudaSuccess || (err = cudaStreamCreateWithFlags(&h->e.stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (err = cudaEventCreate(&h->e.ev0)) != cudaSuccess || (err = cudaEventCreate(&h->e.ev1)) != cudaSuccess) {
+        g_open_error = std::string("CUDA init failed: ") + cudaGetErrorString(err);
+        delete h;
+        return B200_ERR_CUDA;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device_ordinal) == cudaSuccess) h->e.sm_count = prop.multiProcessorCount;
+    *out = h;
+    return B200_OK;
+}
+void b200_close(b200_index *h) { delete h; }
+const char *b200_last_error(const b200_index *h) { return h ? h->e.last_error.c_str() : "null handle"; }
+
+int b200_stage_dictionary(b200_index *h, const uint8_t *bytes, const uint64_t *offsets, uint64_t n) {
+    std::lock_guard<std::mutex> g(h->e.mu);
+    h->e.raw_dict_off.assign(offsets, offsets + n + 1);
+    h->e.raw_dict_bytes.assign(bytes, bytes + offsets[n]);
+    return B200_OK;
+}
+int b200_stage_db(b200_index *h, int db, uint64_t n, const uint8_t *kb, const uint64_t *ko, const uint8_t *vb, const uint64_t *vo) {
+    std::lock_guard<std::mutex> g(h->e.mu);
+    if (db < 0 || db >= B200_DB_COUNT) return h->e.fail(B200_ERR_INVALID, "unknown database id");
+    RawDb &d = h->e.raw_dbs[db];
+    d.n = n;
+    d.koff.assign(ko, ko + n + 1);
+    d.voff.assign(vo, vo + n + 1);
+    d.keys.assign(kb, kb + ko[n]);
+    d.vals.assign(vb, vb + vo[n]);
+    return B200_OK;
+}
+int b200_stage_documents_ids(b200_index *h, const uint8_t *cbo, uint64_t len) {
+    std::lock_guard<std::mutex> g(h->e.mu);
+    h->e.raw_docids.assign(cbo, cbo + len);
+    return B200_OK;
+}
+int b200_stage_settings(b200_index *h, const b200_settings *s) {
+    std::lock_guard<std::mutex> g(h->e.mu);
+    Settings &t = h->e.hix.settings;
+    if (s->n_fields == 0 || s->n_fields > 1024) return h->e.fail(B200_ERR_INVALID, "n_fields out of range");
+    t.n_fields = s->n_fields;
+    t.weights.assign(s->weights, s->weights + s->n_fields);
+    t.criteria.assign(s->criteria, s->criteria + s->n_criteria);
+    t.authorize_typos = s->authorize_typos != 0;
+    t.one_typo = s->min_word_len_one_typo;
+    t.two_typos = s->min_word_len_two_typos;
+    t.prefix_search = s->prefix_search != 0;
+    t.exact_words.clear();
+    if (s->exact_words) {
+        std::string cur;
+        for (const char *p = s->exact_words;; p++) {
+            if (*p == '\n' || *p == 0) {
+                if (!cur.empty()) t.exact_words[cur] = 1;
+                cur.clear();
+                if (!*p) break;
+            } else
+                cur.push_back(*p);
+        }
+    }
+    return B200_OK;
+}
+int b200_stage_finish(b200_index *h) {
+    std::lock_guard<std::mutex> g(h->e.mu);
+    Settings keep = h->e.hix.settings;
+    int rc = h->e.stage_finish();
+    h->e.hix.settings = keep;
+    return rc;
+}
+int b200_stage_embeddings(b200_index *h, const float *v, uint64_t n, uint32_t d, const uint32_t *docids) {
+    std::lock_guard<std::mutex> g(h->e.mu);
+    return h->e.stage_embeddings(v, n, d, docids);
+}
+int b200_stage_distribution(b200_index *h, int enabled, float mean, float sigma) {
+    std::lock_guard<std::mutex> g(h->e.mu);
+    h->e.has_distribution = enabled != 0 && sigma > 0.f;
+    h->e.dist_mean = mean;
+    h->e.dist_sigma = sigma;
+    return B200_OK;
+}
+int b200_derive_batch(b200_index *h, uint32_t n, const char *words, const uint32_t *off, const uint8_t *mt, const uint8_t *ip, uint32_t *one,
+                      uint32_t *n_one, uint32_t *two, uint32_t *n_two) {
+    std::lock_guard<std::mutex> g(h->e.mu);
+    return h->e.derive_batch(n, words, off, mt, ip, one, n_one, two, n_two);
+}
+int b200_nns_batch(b200_index *h, const float *q, uint32_t n_q, uint32_t d, uint32_t limit, const uint64_t *cand, uint64_t ncw, uint32_t *ids,
+                   float *dist, uint32_t *n_out) {
+    std::lock_guard<std::mutex> g(h->e.mu);
+    return h->e.nns_batch(q, n_q, d, limit, cand, ncw, ids, dist, n_out);
+}
+int b200_search_batch(b200_index *h, const b200_query_batch *b, b200_results *r) {
+    std::lock_guard<std::mutex> g(h->e.mu);
+    if (!h->e.staged) return h->e.fail(B200_ERR_STATE, "search before b200_stage_finish");
+    return h->e.search_batch(b, r);
+}
+int b200_get_stats(b200_index *h, b200_stats *out) {
+    std::lock_guard<std::mutex> g(h->e.mu);
+    *out = h->e.stats;
+    return B200_OK;
+}
+int b200_reset_stats(b200_index *h) {
+    std::lock_guard<std::mutex> g(h->e.mu);
+    uint64_t staged = h->e.stats.hbm_bytes_staged;
+    h->e.stats = b200_stats{};
+    h->e.stats.hbm_bytes_staged = staged;
+    return B200_OK;
+}
+}
+
+// ================================================================================= semantic + hybrid
+namespace b200 {
+
+static float distribution_shift(float mean, float sigma, float score) {  // vector/distribution.rs:103-130
+    float factor = 0.4f / sigma, offset = 0.5f - factor * mean;
+    float s = factor * score + offset;
+    if (s <= 0.f) s = 1.1920929e-7f;
+    if (s > 1.f) s = 1.f;
+    return s;
+}
+
+// execute_vector_search (search/new/mod.rs:744-808): one VectorSort rule over documents_ids; buckets = runs of equal
+// distance in ascending docid order (vector_sort.rs:80-95), which the (distance, docid) ordering of nns_batch reproduces.
+int Engine::semantic_batch(const b200_query_batch *b, b200_results *r, uint32_t offset, uint32_t limit) {
+    if (!b->vectors) return fail(B200_ERR_INVALID, "semantic search without vectors");
+    uint32_t k = offset + limit;
+    if (k == 0) k = 1;
+    std::vector<uint32_t> ids((size_t)b->n_queries * k), n(b->n_queries);
+    std::vector<float> dist((size_t)b->n_queries * k);
+    int rc = nns_batch(b->vectors, b->n_queries, dix.emb_d, k, nullptr, 0, ids.data(), dist.data(), n.data());
+    if (rc != B200_OK) return rc;
+    for (uint32_t q = 0; q < b->n_queries; q++) {
+        uint32_t hits = n[q] > offset ? std::min(limit, n[q] - offset) : 0;
+        r->n_hits[q] = hits;
+        if (r->status) r->status[q] = 0;
+        if (r->n_candidates) r->n_candidates[q] = hix.n_documents;
+        for (uint32_t i = 0; i < hits; i++) {
+            size_t src = (size_t)q * k + offset + i, at = (size_t)q * limit + i;
+            r->docids[at] = ids[src];
+            float sim = 1.0f - dist[src];
+            if (has_distribution) sim = distribution_shift(dist_mean, dist_sigma, sim);
+            if (r->n_scores) {
+                r->n_scores[at] = 1;
+                r->score_kind[at * B200_MAX_SCORES] = B200_S_VECTOR;
+                r->score_rank[at * B200_MAX_SCORES] = 0;
+                r->score_max[at * B200_MAX_SCORES] = 1;
+                r->score_sim[at * B200_MAX_SCORES] = sim;
+            }
+        }
+    }
+    return B200_OK;
+}
+
+namespace {
+struct Hit {
+    uint32_t doc;
+    std::vector<double> values;  // ScoreDetails::score_values (score_details.rs:156-175)
+    uint8_t n_scores;
+    uint8_t kind[B200_MAX_SCORES];
+    uint32_t rank[B200_MAX_SCORES], maxr[B200_MAX_SCORES];
+    float sim[B200_MAX_SCORES];
+};
+void rank_merge(uint64_t &orank, uint64_t &omax, uint64_t irank, uint64_t imax) {
+    orank = orank > 0 ? orank - 1 : 0;
+    orank *= imax;
+    omax *= imax;
+    orank += irank;
+}
+void fill_values(Hit &h) {
+    bool in_rank = false;
+    uint64_t rk = 0, mx = 1;
+    for (int s = 0; s < h.n_scores; s++) {
+        if (h.kind[s] == B200_S_VECTOR) {
+            if (in_rank) {
+                h.values.push_back((double)rk / (double)mx);
+                in_rank = false;
+            }
+            h.values.push_back(h.sim[s] < 0 ? 0.0 : (double)h.sim[s]);
+        } else if (!in_rank) {
+            rk = h.rank[s];
+            mx = h.maxr[s];
+            in_rank = true;
+        } else
+            rank_merge(rk, mx, h.rank[s], h.maxr[s]);
+    }
+    if (in_rank) h.values.push_back((double)rk / (double)mx);
+}
+double global_score(const Hit &h) {
+    uint64_t rk = 1, mx = 1;
+    bool sem = false;
+    double sv = 0;
+    for (int s = 0; s < h.n_scores; s++) {
+        if (h.kind[s] == B200_S_VECTOR) {
+            sem = true;
+            sv = h.sim[s] < 0 ? 0.0 : (double)h.sim[s];
+        } else
+            rank_merge(rk, mx, h.rank[s], h.maxr[s]);
+    }
+    return sem ? sv : (double)rk / (double)mx;
+}
+int compare_scores(const Hit &l, float lr, const Hit &r, float rr) {  // hybrid.rs:32-80
+    for (size_t i = 0;; i++) {
+        bool hl = i < l.values.size(), hr = i < r.values.size();
+        if (!hl && !hr) return 0;
+        if (!hl) return -1;
+        if (!hr) return 1;
+        double a = l.values[i] * (double)lr, b = r.values[i] * (double)rr;
+        if (std::fabs(a - b) <= 2.220446049250313e-16) continue;
+        return a < b ? -1 : 1;
+    }
+}
+}  // namespace
+
+// Search::execute_hybrid (search/hybrid.rs:264-366)
+int Engine::search_batch(const b200_query_batch *b, b200_results *r) {
+    if (b->mode == 0) return keyword_batch(b, r, b->offset, b->limit, b->scoring_strategy);
+    if (b->mode == 1) return semantic_batch(b, r, b->offset, b->limit);
+    if (b->mode != 2) return fail(B200_ERR_INVALID, "unknown search mode");
+    const uint32_t NQ = b->n_queries, L = b->limit + b->offset, lim = std::max(1u, L);
+    struct Side {
+        std::vector<uint32_t> docids, n_hits, rank, maxr;
+        std::vector<uint8_t> n_scores, kind;
+        std::vector<float> sim;
+        std::vector<uint64_t> n_cand;
+        std::vector<int32_t> status;
+        b200_results view;
+        Side(uint32_t nq, uint32_t l)
+            : docids((size_t)nq * l), n_hits(nq), rank((size_t)nq * l * B200_MAX_SCORES), maxr((size_t)nq * l * B200_MAX_SCORES),
+              n_scores((size_t)nq * l), kind((size_t)nq * l * B200_MAX_SCORES), sim((size_t)nq * l * B200_MAX_SCORES), n_cand(nq), status(nq) {
+            view = b200_results{docids.data(), n_hits.data(), n_scores.data(), kind.data(), rank.data(), maxr.data(), sim.data(), n_cand.data(), nullptr, status.data()};
+        }
+    };
+    Side kw(NQ, lim), vec(NQ, lim);
+    int rc = keyword_batch(b, &kw.view, 0, lim, 1);
+    if (rc != B200_OK) return rc;
+    bool have_vec = b->vectors != nullptr;
+    if (have_vec) {
+        rc = semantic_batch(b, &vec.view, 0, lim);
+        if (rc != B200_OK) return rc;
+    }
+    float kr = 1.0f - b->semantic_ratio, vr = b->semantic_ratio;
+    auto load = [&](const Side &s, uint32_t q, uint32_t i) {
+        Hit h;
+        size_t at = (size_t)q * lim + i;
+        h.doc = s.docids[at];
+        h.n_scores = s.n_scores[at];
+        for (int k = 0; k < h.n_scores; k++) {
+            h.kind[k] = s.kind[at * B200_MAX_SCORES + k];
+            h.rank[k] = s.rank[at * B200_MAX_SCORES + k];
+            h.maxr[k] = s.maxr[at * B200_MAX_SCORES + k];
+            h.sim[k] = s.sim[at * B200_MAX_SCORES + k];
+        }
+        fill_values(h);
+        return h;
+    };
+    for (uint32_t q = 0; q < NQ; q++) {
+        if (r->status) r->status[q] = kw.status[q];
+        if (kw.status[q] != 0) {
+            r->n_hits[q] = 0;
+            continue;
+        }
+        std::vector<Hit> K, V;
+        for (uint32_t i = 0; i < kw.n_hits[q]; i++) K.push_back(load(kw, q, i));
+        // results_good_enough (:368-386)
+        bool good = K.size() >= L;
+        if (good)
+            for (auto &h : K)
+                if (global_score(h) * (double)kr < 0.45) {
+                    good = false;
+                    break;
+                }
+        std::vector<const Hit *> merged;
+        uint32_t sem = 0;
+        bool semantic_used = false;
+        if (good || !have_vec) {
+            for (auto &h : K) merged.push_back(&h);
+            if (merged.size() > b->offset)
+                merged.erase(merged.begin(), merged.begin() + b->offset);
+            else
+                merged.clear();
+            if (merged.size() > b->limit) merged.resize(b->limit);
+        } else {
+            semantic_used = true;
+            for (uint32_t i = 0; i < vec.n_hits[q]; i++) V.push_back(load(vec, q, i));
+            size_t vi = 0, ki = 0, skipped = 0;
+            std::vector<uint32_t> seen;
+            while ((vi < V.size() || ki < K.size()) && merged.size() < b->limit) {
+                bool take_vec = vi >= V.size() ? false : (ki >= K.size() ? true : compare_scores(V[vi], vr, K[ki], kr) >= 0);
+                const Hit *h = take_vec ? &V[vi++] : &K[ki++];
+                if (std::find(seen.begin(), seen.end(), h->doc) != seen.end()) continue;
+                seen.push_back(h->doc);
+                if (skipped < b->offset) {
+                    skipped++;
+                    continue;
+                }
+                if (take_vec) sem++;
+                merged.push_back(h);
+            }
+        }
+        r->n_hits[q] = (uint32_t)merged.size();
+        if (r->semantic_hits) r->semantic_hits[q] = semantic_used ? sem : 0;
+        if (r->n_candidates) r->n_candidates[q] = semantic_used ? std::max<uint64_t>(kw.n_cand[q], vec.n_cand[q]) : kw.n_cand[q];
+        for (size_t i = 0; i < merged.size(); i++) {
+            size_t at = (size_t)q * b->limit + i;
+            const Hit &h = *merged[i];
+            r->docids[at] = h.doc;
+            if (r->n_scores) {
+                r->n_scores[at] = h.n_scores;
+                for (int k = 0; k < h.n_scores; k++) {
+                    r->score_kind[at * B200_MAX_SCORES + k] = h.kind[k];
+                    r->score_rank[at * B200_MAX_SCORES + k] = h.rank[k];
+                    r->score_max[at * B200_MAX_SCORES + k] = h.maxr[k];
+                    r->score_sim[at * B200_MAX_SCORES + k] = h.sim[k];
+                }
+            }
+        }
+    }
+    return B200_OK;
+}
+
+}  // namespace b200

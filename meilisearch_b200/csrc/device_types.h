@@ -1,0 +1,90 @@
+// POD structures shared by the host engine and the CUDA kernels.
+#pragma once
+#include <cstdint>
+
+namespace b200 {
+
+struct DListRef {  // mirrors host ListRef
+    unsigned long long off;
+    uint32_t card;
+    uint32_t dense;
+};
+
+// ---- term derivation (lev kernel) ----
+constexpr int LEV_MAX_Q = 64;        // longest query word handled on device (bytes)
+constexpr int LEV_TERMS_PER_CTA = 32;
+constexpr int LEV_REC_CAP = 2048;    // match records (32 words each) per term
+struct LevTerm {
+    uint8_t q[LEV_MAX_Q];
+    uint8_t len;
+    int8_t k_same;    // budget when first chars are equal
+    int8_t k_diff;    // budget when they differ (-1: excluded)
+    uint8_t prefix;   // prefix automaton
+};
+struct LevRec {
+    uint32_t base;              // first word id of the 32-word group
+    uint32_t pad;
+    unsigned long long codes;   // 2 bits per lane: 0 none, 1 same-first d=1, 2 same-first d=2, 3 different-first (d=1)
+};
+
+// ---- rule activations ----
+constexpr uint32_t MAX_COSTS = 128;
+constexpr uint32_t MAX_PATH_LEN = 32;
+constexpr uint32_t JOB_CHUNK = 2048;  // elements (sparse) or rows (dense) per scatter job
+
+struct ActDesc {
+    // parent universe: rows (p_uw,p_ub); child = rows where OR(p_out[col_lo..col_hi)) != 0. p_out==0: take p_ub as is.
+    const uint32_t *p_uw;            // nullptr => identity (row j is word j)
+    const unsigned long long *p_ub;
+    const unsigned long long *p_out; // column-major, leading dimension p_ld
+    uint32_t p_rows, p_ld, p_col_lo, p_col_hi;
+    // this activation
+    uint32_t *uw;
+    unsigned long long *ub;
+    unsigned long long *C;    // column-major [n_cols][ld], scratch for this step
+    unsigned long long *out;  // column-major [n_costs+1][ld]; last column = matched by no path
+    uint32_t ld, n_cols, n_costs, n_paths;
+    uint32_t colprog_off, colprog_len;
+    uint32_t path_off;        // into PathRec[]
+    uint32_t res_off;         // into results u32[]: [0] rows, [1..n_costs+1] counts, then survived[n_paths]
+};
+
+struct ColOp {  // executed per row before the paths
+    uint16_t op;  // 0 AND dst=a&b, 1 OR dst=a|b, 2 ANDNOT dst=a&~b, 3 COPY dst=a
+    uint16_t dst, a, b;
+};
+
+struct PathRec {
+    uint32_t cond_off;  // into u16 cond pool
+    uint16_t cost_idx;
+    uint8_t len;
+    uint8_t lcp;        // conditions shared with the previous path
+};
+
+struct Job {  // scatter one chunk of one posting list into column `col` of activation `act`
+    uint32_t act, col, list, chunk;
+};
+
+struct PairSet {  // expanded on device into Jobs: all (l, r) pairs of two word sets
+    uint32_t act, col;
+    uint32_t left_off, n_left, right_off, n_right;  // into the step's u32 word pool
+    uint8_t fwd_prox, bwd_prox;  // 0 = no lookup in that direction
+    uint8_t right_is_range;      // right entries are [lo,hi) dictionary ranges (prefix db): n_right pairs of u32
+    uint8_t pad;
+    uint32_t probe_base;         // first global probe index of this set
+};
+
+struct EmitDesc {  // append the first docids of OR(out[col_lo..col_hi)) to a result buffer
+    const uint32_t *uw;
+    const unsigned long long *ub;
+    const unsigned long long *out;  // nullptr: emit ub itself
+    uint32_t rows, ld, col_lo, col_hi;
+    uint32_t skip, take;
+    uint32_t *dst;
+};
+
+struct TileDesc {
+    uint32_t act, row_begin;
+};
+
+}  // namespace b200

@@ -1,0 +1,124 @@
+// The engine behind the C ABI: staged index in HBM + batched search.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200milli.h"
+#include "device_types.h"
+#include "host_index.h"
+#include "query_model.h"
+
+namespace b200 {
+
+struct DeviceIndex {
+    uint8_t *dict_bytes = nullptr;
+    uint32_t *dict_off = nullptr;
+    uint32_t *pool = nullptr;
+    DListRef *lists = nullptr;
+    unsigned long long *pair_keys = nullptr;
+    unsigned long long *base_ub = nullptr;
+    // embeddings
+    void *emb = nullptr;  // __half[n][d]
+    float *emb_inv_norm = nullptr;
+    uint32_t *emb_docids = nullptr;
+    uint64_t emb_n = 0;
+    uint32_t emb_d = 0;
+};
+
+template <class T>
+struct DevBuf {  // grow-only device buffer
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 4 + 64;
+        cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct Engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    std::string last_error;
+    // staging inputs
+    std::vector<uint8_t> raw_dict_bytes;
+    std::vector<uint64_t> raw_dict_off;
+    RawDb raw_dbs[10];
+    std::vector<uint8_t> raw_docids;
+    bool staged = false;
+    HostIndex hix;
+    DeviceIndex dix;
+    bool has_distribution = false;
+    float dist_mean = 0, dist_sigma = 0;
+    b200_stats stats{};
+    int sm_count = 148;
+    // pools
+    uint8_t *arena = nullptr;
+    size_t arena_bytes = 0;
+    uint8_t *scratch = nullptr;
+    size_t scratch_bytes = 0;
+    DevBuf<uint8_t> d_step;     // per-step input blob
+    DevBuf<uint32_t> d_results; // per-step results
+    DevBuf<Job> d_queue;
+    DevBuf<uint32_t> d_qcount;
+    DevBuf<uint32_t> d_docids_out;  // n_queries x limit
+    uint8_t *h_step = nullptr;      // pinned
+    size_t h_step_cap = 0;
+    uint32_t *h_results = nullptr;  // pinned
+    size_t h_results_cap = 0;
+    // lev buffers
+    DevBuf<LevTerm> d_lev_terms;
+    DevBuf<LevRec> d_lev_recs;
+    DevBuf<uint32_t> d_lev_u32;  // rec_count | one_out | n_one | two_out | n_two | status
+    // vector buffers
+    DevBuf<float> d_vq, d_vdist, d_vsel_dist;
+    DevBuf<uint32_t> d_vsel_ids, d_vsel_n;
+    DevBuf<unsigned long long> d_cand;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> ev_pool;  // pairs recorded around kernels, resolved after the step's sync
+    struct Timed { int cls; size_t a, b; };
+    std::vector<Timed> timed;
+    size_t ev_used = 0;
+    // record an event (from the pool) on the stream; returns its index
+    size_t mark();
+    void time_kernel(int cls, size_t a, size_t b, uint64_t bytes) {
+        timed.push_back(Timed{cls, a, b});
+        stats.kernel_count[cls]++;
+        stats.kernel_bytes[cls] += bytes;
+        stats.kernel_launches++;
+    }
+    void resolve_timers();  // after a stream sync
+
+    int fail(int code, const std::string &msg) {
+        last_error = msg;
+        return code;
+    }
+    int cuda_fail(cudaError_t e, const char *what) { return fail(B200_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e)); }
+
+    int stage_finish();
+    int stage_embeddings(const float *vectors, uint64_t n, uint32_t d, const uint32_t *docids);
+    int derive_batch(uint32_t n, const char *words, const uint32_t *off, const uint8_t *max_typo, const uint8_t *is_prefix, uint32_t *one_out,
+                     uint32_t *n_one, uint32_t *two_out, uint32_t *n_two);
+    int nns_batch(const float *queries, uint32_t n_q, uint32_t d, uint32_t limit, const uint64_t *cand, uint64_t n_cand_words, uint32_t *ids_out,
+                  float *dist_out, uint32_t *n_out);
+    int search_batch(const b200_query_batch *b, b200_results *r);
+    int keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t offset, uint32_t limit, int scoring);
+    int semantic_batch(const b200_query_batch *b, b200_results *r, uint32_t offset, uint32_t limit);
+    ~Engine();
+};
+
+}  // namespace b200

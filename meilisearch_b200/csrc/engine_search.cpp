@@ -1,0 +1,1691 @@
+// Batched keyword search: Search::execute for a batch of queries against the HBM-resident index.
+//
+// Control stays on the host (query graphs have tens of nodes), data stays on the device.  One host<->device round
+// trip ("step") per ranking-rule *activation*: the step resolves every edge condition of the rule for the
+// activation's universe into a bit-matrix and evaluates the whole cost-ordered path table with first-match
+// semantics, which yields all buckets of that activation at once.  The reference interleaves the
+// same work lazily (graph_based_ranking_rule.rs:220-368); the buckets are identical because a rule's universe only
+// ever shrinks by the buckets it has already returned (bucket_sort.rs:298).
+//
+// Restated from: search/mod.rs:280-467, search/new/mod.rs:273-320,510-649,812-916, bucket_sort.rs:23-460,
+// graph_based_ranking_rule.rs:136-368, ranking_rule_graph/{build.rs,cheapest_paths.rs,words,typo,proximity,fid,position,
+// exactness}, exact_attribute.rs:96-301, query_graph.rs:96-187,254-301,346-406,453-543, query_term/parse_query.rs:28-300,
+// query_term/compute_derivations.rs:170-253,363-383, resolve_query_graph.rs:33-130.
+#include <atomic>
+#include <cstring>
+#include <functional>
+#include <set>
+#include <thread>
+
+#include "engine.h"
+#include "kernels.h"
+
+namespace b200 {
+
+#define CU(call, what)                                     \
+    do {                                                   \
+        cudaError_t e_ = (call);                           \
+        if (e_ != cudaSuccess) return cuda_fail(e_, what); \
+    } while (0)
+
+namespace {
+
+enum RuleKind { RK_WORDS = 0, RK_TYPO, RK_PROXIMITY, RK_FID, RK_POSITION, RK_EXACTNESS, RK_EXACT_ATTRIBUTE, RK_RESOLVE };
+
+struct UnsupportedQuery {
+    std::string why;
+};
+struct TooComplex {
+    std::string why;
+};
+
+// ------------------------------------------------------------------------------------------------ terms
+struct WordRef {
+    uint32_t rank;
+    bool derived;
+};
+
+struct QCtx {
+    const HostIndex &ix;
+    std::vector<ETerm> terms;
+    explicit QCtx(const HostIndex &i) : ix(i) {}
+};
+
+uint8_t number_of_typos_allowed(const HostIndex &ix, const std::string &w) {  // parse_query.rs:204-225 (ASCII)
+    const Settings &s = ix.settings;
+    if (!s.authorize_typos || w.size() < s.one_typo || s.exact_words.count(w)) return 0;
+    return w.size() < s.two_typos ? 1 : 2;
+}
+
+// compute_derivations.rs:170-253 (zero-typo part; no synonyms)
+ETerm term_from_word(const HostIndex &ix, const std::string &word, uint8_t max_typo, bool is_prefix, bool is_ngram) {
+    ETerm t;
+    t.original = word;
+    if (word.size() > 250) {
+        t.empty_term = true;
+        return t;
+    }
+    int32_t pid = ix.find_prefix(word);
+    bool use_pdb = is_prefix && pid >= 0 && (ix.pd_list[pid] != NO_LIST || (!is_ngram && ix.epd_list[pid] != NO_LIST));
+    if (use_pdb) t.prefix_db = pid;
+    t.exact = (int32_t)ix.find_word(word);
+    if (is_prefix && !use_pdb) {
+        uint64_t lo, hi;
+        ix.prefix_range(word, lo, hi);
+        for (uint64_t i = lo; i < hi; i++) {
+            if ((int64_t)i == t.exact) continue;
+            t.prefix_of.push_back((uint32_t)i);
+            if (t.prefix_of.size() >= 1000) break;
+        }
+    }
+    t.max_lev = max_typo;
+    t.is_prefix = is_prefix;
+    t.is_ngram = is_ngram;
+    return t;
+}
+
+// compute_derivations.rs:363-383
+void find_split_words(const HostIndex &ix, ETerm &t) {
+    const std::string &o = t.original;
+    uint32_t best = 0;
+    t.has_split = false;
+    for (size_t i = 1; i < o.size(); i++) {
+        int64_t l = ix.find_word((const uint8_t *)o.data(), i), r = ix.find_word((const uint8_t *)o.data() + i, o.size() - i);
+        if (l < 0 || r < 0) continue;
+        uint32_t list = ix.find_pair(1, (uint32_t)l, (uint32_t)r);
+        if (list == NO_LIST) continue;
+        uint32_t freq = ix.lists[list].card;
+        if (!t.has_split || freq > best) {
+            t.has_split = true;
+            best = freq;
+            t.split_l = (uint32_t)l;
+            t.split_r = (uint32_t)r;
+            t.split_list = list;
+        }
+    }
+    if (t.has_split && t.is_ngram && t.max_lev <= 1) {
+        // only for the <=1 typo initialisation (compute_derivations.rs:297-311): drop the split equal to the ngram's own words
+        if (t.ngram_words.size() == 2 && ix.word(t.split_l) == t.ngram_words[0] && ix.word(t.split_r) == t.ngram_words[1]) t.has_split = false;
+    }
+}
+
+bool exact_term(const QCtx &c, const ETermSubset &s, uint32_t &w) {  // query_term/mod.rs:131-143 (words only)
+    const ETerm &t = c.terms[s.term];
+    if (t.is_ngram || t.exact < 0) return false;
+    if (!s.zero.contains_word((uint32_t)t.exact)) return false;
+    w = (uint32_t)t.exact;
+    return true;
+}
+bool use_prefix_db(const QCtx &c, const ETermSubset &s, uint32_t &pid, bool &derived) {  // :177-198
+    const ETerm &t = c.terms[s.term];
+    if (t.prefix_db < 0) return false;
+    bool ok = s.zero.kind == N_ALL || (s.zero.kind == N_SUBSET && t.exact >= 0 && s.zero.contains_word((uint32_t)t.exact));
+    if (!ok) return false;
+    pid = (uint32_t)t.prefix_db;
+    derived = t.is_ngram;
+    return true;
+}
+std::vector<WordRef> all_single_words(const QCtx &c, const ETermSubset &s) {  // :199-292
+    const ETerm &t = c.terms[s.term];
+    std::vector<WordRef> r;
+    if (s.zero.kind != N_NOTHING) {
+        if (t.exact >= 0 && s.zero.contains_word((uint32_t)t.exact)) r.push_back({(uint32_t)t.exact, t.is_ngram});
+        for (auto w : t.prefix_of)
+            if (s.zero.contains_word(w)) r.push_back({w, t.is_ngram});
+    }
+    if (s.one.kind != N_NOTHING)
+        for (auto w : t.one_typo)
+            if (s.one.contains_word(w)) r.push_back({w, true});
+    if (s.two.kind != N_NOTHING)
+        for (auto w : t.two_typo)
+            if (s.two.contains_word(w)) r.push_back({w, true});
+    return r;
+}
+bool has_split_phrase(const QCtx &c, const ETermSubset &s) {  // all_phrases :293-329 restricted to split words
+    const ETerm &t = c.terms[s.term];
+    if (!t.has_split) return false;
+    return s.one.kind == N_ALL || (s.one.kind == N_SUBSET && s.one.split);
+}
+uint8_t max_typo_cost(const QCtx &c, const ETermSubset &s) {  // :340-370
+    const ETerm &t = c.terms[s.term];
+    switch (t.max_lev) {
+        case 0: return 1;  // allows_split_words (no phrases here)
+        case 1: return s.one.is_empty() ? 0 : 1;
+        default: return s.two.is_empty() ? (s.one.is_empty() ? 0 : 1) : 2;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ graph
+void build_initial_edges(EGraph &g) {  // query_graph.rs:254-301
+    for (auto &n : g.nodes) {
+        n.pred.clear();
+        n.succ.clear();
+    }
+    uint16_t n = (uint16_t)g.nodes.size();
+    for (uint16_t id = 0; id < n; id++) {
+        int end_prev;
+        if (g.nodes[id].kind == ND_TERM)
+            end_prev = g.nodes[id].term.t1;
+        else if (g.nodes[id].kind == ND_START)
+            end_prev = -1;
+        else
+            continue;
+        int mn = 32767;
+        std::vector<uint16_t> succ;
+        for (uint16_t j = 0; j < n; j++) {
+            int start_next;
+            if (g.nodes[j].kind == ND_TERM)
+                start_next = g.nodes[j].term.t0;
+            else if (g.nodes[j].kind == ND_END)
+                start_next = 32767;
+            else
+                continue;
+            if (start_next <= end_prev) continue;
+            if (start_next < mn) {
+                mn = start_next;
+                succ.clear();
+                succ.push_back(j);
+            } else if (start_next == mn)
+                succ.push_back(j);
+        }
+        g.nodes[id].succ = succ;
+        for (auto s : succ) sorted_insert(g.nodes[s].pred, id);
+    }
+}
+
+void remove_nodes_keep_edges(EGraph &g, const std::vector<uint16_t> &nodes) {  // :190-210
+    for (auto id : nodes) {
+        auto pred = g.nodes[id].pred, succ = g.nodes[id].succ;
+        for (auto p : pred) {
+            sorted_remove(g.nodes[p].succ, id);
+            for (auto s : succ) sorted_insert(g.nodes[p].succ, s);
+        }
+        for (auto s : succ) {
+            sorted_remove(g.nodes[s].pred, id);
+            for (auto p : pred) sorted_insert(g.nodes[s].pred, p);
+        }
+        g.nodes[id].kind = ND_DELETED;
+        g.nodes[id].pred.clear();
+        g.nodes[id].succ.clear();
+    }
+}
+
+// removal_order_for_terms_matching_strategy_last (:346-406): groups of nodes, cheapest removal first
+std::vector<std::vector<uint16_t>> removal_order_last(const EGraph &g) {
+    int first = 255, last = 0;
+    for (auto &n : g.nodes)
+        if (n.kind == ND_TERM) {
+            last = std::max<int>(last, n.term.t1);
+            first = std::min<int>(first, n.term.t0);
+        }
+    if (first >= last) return {};
+    std::map<uint16_t, std::vector<uint16_t>> groups;
+    bool mandatory = false;
+    for (uint16_t id = 0; id < g.nodes.size(); id++) {
+        const ENode &n = g.nodes[id];
+        if (n.kind != ND_TERM) continue;
+        if (n.term.ts.mandatory) {
+            mandatory = true;
+            continue;
+        }
+        uint16_t cost = 0;
+        for (int t = n.term.t0; t <= n.term.t1; t++) cost = std::max<uint16_t>(cost, (uint16_t)(1 + last - t));
+        groups[cost].push_back(id);
+    }
+    std::vector<std::vector<uint16_t>> res;
+    for (auto &kv : groups) res.push_back(kv.second);
+    if (!mandatory && !res.empty()) res.pop_back();
+    return res;
+}
+
+// ------------------------------------------------------------------------------------------------ activations
+struct ECond {
+    int rule = 0;
+    ELocated term;
+    uint8_t nbr_typos = 0;
+    bool prox_uninit = false;
+    ELocated left;
+    uint8_t cost = 0;
+    bool has_fid = false;
+    uint16_t fid = 0;
+    std::vector<uint16_t> positions;
+    bool exact_in_attribute = false;
+    // what a surviving path hands to the next rule (ComputedCondition::{start,end}_term_subset)
+    bool has_start = false;
+    ELocated start_subset, end_subset;
+    uint16_t col = 0;
+    std::string key() const {
+        std::string s = std::to_string(rule) + ":" + term.key() + ":" + std::to_string(nbr_typos) + (prox_uninit ? "U" : "T");
+        if (prox_uninit) s += left.key() + "c" + std::to_string(cost);
+        s += has_fid ? "f" + std::to_string(fid) : "f-";
+        for (auto p : positions) s += "," + std::to_string(p);
+        s += exact_in_attribute ? "E" : "A";
+        return s;
+    }
+};
+
+struct EEdge {
+    uint16_t src, dst;
+    uint32_t cost;
+    int32_t cond;
+    std::vector<uint8_t> skip;  // nodes_to_skip
+};
+
+struct EPath {
+    uint32_t cost;
+    std::vector<uint16_t> conds;  // condition ids
+};
+
+struct StepOut {  // per-activation device work, appended to the step blob by the driver
+    std::vector<Job> jobs;            // act filled in by the driver
+    std::vector<PairSet> pairsets;    // left_off/right_off relative to `words`
+    std::vector<uint32_t> words;
+    std::vector<ColOp> colprog;
+    std::vector<PathRec> paths;       // cond_off relative to `condpool`
+    std::vector<uint16_t> condpool;
+    uint32_t n_cols = 0, n_costs = 0;
+    uint64_t posting_bytes = 0;
+};
+
+struct Level {
+    int rule_idx = -1;  // index in the query's rule list; -1 = universe resolution
+    int kind = RK_RESOLVE;
+    EGraph graph;
+    std::vector<ECond> conds;
+    std::vector<EPath> paths;  // sorted by (cost, DFS order)
+    std::vector<uint32_t> cost_vals;
+    std::vector<uint16_t> path_cost_idx;
+    uint64_t next_max_cost = 1;
+    // device buffers (arena)
+    uint32_t *uw = nullptr;
+    unsigned long long *ub = nullptr, *out = nullptr;
+    uint32_t ld = 0, rows = 0, res_off = 0;
+    std::vector<uint32_t> counts;  // per cost idx, last = unmatched
+    std::vector<uint8_t> survived;
+    size_t cursor = 0;
+    uint64_t universe_count = 0;
+};
+
+struct EmitReq {
+    EmitDesc d;
+};
+
+struct QState {
+    QCtx ctx;
+    int status = 0;
+    std::string error;
+    bool done = false, placeholder = false;
+    EGraph graph;
+    std::vector<int> rules;  // RuleKind per rule
+    std::vector<Level> levels;
+    std::vector<EScore> rr_scores;
+    uint32_t n_results = 0;
+    uint64_t cur_offset = 0;
+    uint64_t n_candidates = 0;
+    std::vector<std::vector<EScore>> scores;  // per hit
+    // pending device work for the next step
+    bool want_activation = false;
+    StepOut pend;
+    std::vector<EmitReq> emits;
+    // parent of the pending activation
+    const uint32_t *p_uw = nullptr;
+    const unsigned long long *p_ub = nullptr, *p_out = nullptr;
+    uint32_t p_rows = 0, p_ld = 0, p_col = 0, p_cap = 0;
+    explicit QState(const HostIndex &ix) : ctx(ix) {}
+};
+
+struct ActBuilder {
+    const QCtx &c;
+    StepOut &o;
+    uint16_t next_col = 0;
+    std::map<uint32_t, uint16_t> phrase_cols;  // split-phrase pair list -> column
+    ActBuilder(const QCtx &ctx, StepOut &out) : c(ctx), o(out) {}
+    uint16_t new_col() { return next_col++; }
+    void add_list(uint16_t col, uint32_t list) {
+        if (list == NO_LIST) return;
+        const ListRef &lr = c.ix.lists[list];
+        if (lr.card == 0) return;
+        uint32_t units = lr.dense ? c.ix.n_words64 : lr.card;
+        uint32_t nch = (units + JOB_CHUNK - 1) / JOB_CHUNK;
+        for (uint32_t k = 0; k < nch; k++) o.jobs.push_back(Job{0, col, list, k});
+        o.posting_bytes += lr.dense ? (uint64_t)c.ix.n_words64 * 8 : (uint64_t)lr.card * 4;
+    }
+    void op(uint16_t code, uint16_t dst, uint16_t a, uint16_t b) { o.colprog.push_back(ColOp{code, dst, a, b}); }
+    // Word::Original -> exact_word_docids | word_docids ; Word::Derived -> word_docids   (db_cache.rs:183-205)
+    void add_word_docids(uint16_t col, const WordRef &w) {
+        add_list(col, c.ix.wd_list[w.rank]);
+        if (!w.derived) add_list(col, c.ix.ewd_list[w.rank]);
+    }
+    uint16_t phrase_col(uint32_t pair_list) {  // docids of the 2-word split phrase == its proximity-1 pair list
+        auto it = phrase_cols.find(pair_list);
+        if (it != phrase_cols.end()) return it->second;
+        uint16_t col = new_col();
+        add_list(col, pair_list);
+        phrase_cols.emplace(pair_list, col);
+        return col;
+    }
+    // compute_query_term_subset_docids (resolve_query_graph.rs:33-59) into `col`
+    void term_docids(uint16_t col, const ETermSubset &s) {
+        for (auto &w : all_single_words(c, s)) add_word_docids(col, w);
+        if (has_split_phrase(c, s)) add_list(col, c.terms[s.term].split_list);
+        uint32_t pid;
+        bool derived;
+        if (use_prefix_db(c, s, pid, derived)) {
+            add_list(col, c.ix.pd_list[pid]);
+            if (!derived) add_list(col, c.ix.epd_list[pid]);
+        }
+    }
+    uint32_t push_words(const std::vector<uint32_t> &w) {
+        uint32_t off = (uint32_t)o.words.size();
+        o.words.insert(o.words.end(), w.begin(), w.end());
+        return off;
+    }
+    void add_pairset(uint16_t col, const std::vector<uint32_t> &left, const std::vector<uint32_t> &right, uint8_t fwd, uint8_t bwd, bool range) {
+        uint32_t nr = range ? (uint32_t)right.size() / 2 : (uint32_t)right.size();
+        if (left.empty() || nr == 0 || (fwd == 0 && bwd == 0)) return;
+        PairSet ps{};
+        ps.col = col;
+        ps.left_off = push_words(left);
+        ps.n_left = (uint32_t)left.size();
+        ps.right_off = push_words(right);
+        ps.n_right = nr;
+        ps.fwd_prox = fwd;
+        ps.bwd_prox = bwd;
+        ps.right_is_range = range ? 1 : 0;
+        o.pairsets.push_back(ps);
+    }
+};
+
+// proximity/compute_docids.rs:15-108 as device work
+void build_proximity_cond(ActBuilder &b, const ECond &cond) {
+    const QCtx &c = b.c;
+    if (!cond.prox_uninit) {
+        b.term_docids(cond.col, cond.term.ts);
+        return;
+    }
+    uint8_t right_len = (uint8_t)cond.term.n_term_ids();
+    uint8_t fwd = (uint8_t)(1 + cond.cost - right_len), bwd = (uint8_t)(cond.cost - right_len);
+    if (fwd > 3) fwd = 0;  // keys only exist for proximities 1..3
+    if (bwd > 3) bwd = 0;
+    // left derivations: plain words, and the last word of the split phrase
+    std::vector<uint32_t> left_words;
+    for (auto &w : all_single_words(c, cond.left.ts)) left_words.push_back(w.rank);
+    std::sort(left_words.begin(), left_words.end());
+    left_words.erase(std::unique(left_words.begin(), left_words.end()), left_words.end());
+    const ETerm &lt = c.terms[cond.left.ts.term];
+    bool left_phrase = has_split_phrase(c, cond.left.ts);
+    std::vector<uint32_t> right_words;
+    for (auto &w : all_single_words(c, cond.term.ts)) right_words.push_back(w.rank);
+    std::sort(right_words.begin(), right_words.end());
+    right_words.erase(std::unique(right_words.begin(), right_words.end()), right_words.end());
+    const ETerm &rt = c.terms[cond.term.ts.term];
+    bool right_phrase = has_split_phrase(c, cond.term.ts);
+    // prefix-db part (compute_prefix_edges :110-170)
+    uint32_t pid;
+    bool pderived;
+    if (use_prefix_db(c, cond.term.ts, pid, pderived)) {
+        uint64_t lo, hi;
+        b.c.ix.prefix_range(b.c.ix.prefixes[pid], lo, hi);
+        std::vector<uint32_t> range{(uint32_t)lo, (uint32_t)hi};
+        b.add_pairset(cond.col, left_words, range, fwd, 0, true);
+        int64_t prefix_as_word = c.ix.find_word(c.ix.prefixes[pid]);
+        if (prefix_as_word >= 0 && bwd) b.add_pairset(cond.col, left_words, {(uint32_t)prefix_as_word}, 0, bwd, false);
+        if (left_phrase) {
+            uint16_t t = b.new_col();
+            b.add_pairset(t, {lt.split_r}, range, fwd, 0, true);
+            b.op(0, t, t, b.phrase_col(lt.split_list));
+            b.op(1, cond.col, cond.col, t);
+        }
+    }
+    // non-prefix part (compute_non_prefix_edges :172-211)
+    b.add_pairset(cond.col, left_words, right_words, fwd, bwd, false);
+    if (left_phrase) {  // (left phrase, right word): forward only, inside the phrase docids
+        uint16_t t = b.new_col();
+        b.add_pairset(t, {lt.split_r}, right_words, fwd, 0, false);
+        b.op(0, t, t, b.phrase_col(lt.split_list));
+        b.op(1, cond.col, cond.col, t);
+    }
+    if (right_phrase) {  // (left word, right phrase)
+        uint16_t t = b.new_col();
+        b.add_pairset(t, left_words, {rt.split_l}, fwd, 0, false);
+        b.op(0, t, t, b.phrase_col(rt.split_list));
+        b.op(1, cond.col, cond.col, t);
+    }
+    if (left_phrase && right_phrase) {
+        uint16_t t = b.new_col();
+        b.add_pairset(t, {lt.split_r}, {rt.split_l}, fwd, 0, false);
+        b.op(0, t, t, b.phrase_col(lt.split_list));
+        b.op(0, t, t, b.phrase_col(rt.split_list));
+        b.op(1, cond.col, cond.col, t);
+    }
+}
+
+void build_cond(ActBuilder &b, const ECond &cond) {
+    const QCtx &c = b.c;
+    switch (cond.rule) {
+        case RK_WORDS:
+        case RK_TYPO:
+        case RK_RESOLVE: b.term_docids(cond.col, cond.term.ts); break;
+        case RK_PROXIMITY: build_proximity_cond(b, cond); break;
+        case RK_FID: {  // resolve_query_graph.rs:61-93
+            if (!cond.has_fid) break;
+            for (auto &w : all_single_words(c, cond.term.ts)) b.add_list(cond.col, c.ix.word_fid_list(w.rank, cond.fid));
+            if (has_split_phrase(c, cond.term.ts)) {
+                const ETerm &t = c.terms[cond.term.ts.term];
+                uint32_t l = c.ix.word_fid_list(t.split_l, cond.fid);
+                if (l != NO_LIST) {
+                    uint16_t tf = b.new_col();
+                    b.add_list(tf, l);
+                    b.op(0, tf, tf, b.phrase_col(t.split_list));
+                    b.op(1, cond.col, cond.col, tf);
+                }
+            }
+            uint32_t pid;
+            bool derived;
+            if (use_prefix_db(c, cond.term.ts, pid, derived)) b.add_list(cond.col, c.ix.prefix_fid_list(pid, cond.fid));
+            break;
+        }
+        case RK_POSITION: {  // position/mod.rs:24-47 + resolve_query_graph.rs:95-130
+            auto words = all_single_words(c, cond.term.ts);
+            bool ph = has_split_phrase(c, cond.term.ts);
+            uint16_t tf = 0;
+            bool have_tf = false;
+            uint32_t pid;
+            bool derived;
+            bool pdb = use_prefix_db(c, cond.term.ts, pid, derived);
+            for (auto p : cond.positions) {
+                for (auto &w : words) b.add_list(cond.col, c.ix.word_pos_list(w.rank, p));
+                if (ph) {
+                    uint32_t l = c.ix.word_pos_list(c.terms[cond.term.ts.term].split_l, p);
+                    if (l != NO_LIST) {
+                        if (!have_tf) {
+                            tf = b.new_col();
+                            have_tf = true;
+                        }
+                        b.add_list(tf, l);
+                    }
+                }
+                if (pdb) b.add_list(cond.col, c.ix.prefix_pos_list(pid, p));
+            }
+            if (have_tf) {
+                b.op(0, tf, tf, b.phrase_col(c.terms[cond.term.ts.term].split_list));
+                b.op(1, cond.col, cond.col, tf);
+            }
+            break;
+        }
+        case RK_EXACTNESS: {  // exactness/mod.rs:19-73
+            if (cond.exact_in_attribute) {
+                uint32_t w;
+                if (exact_term(c, cond.term.ts, w)) b.add_word_docids(cond.col, WordRef{w, false});
+            } else
+                b.term_docids(cond.col, cond.term.ts);
+            break;
+        }
+    }
+}
+
+uint32_t position_cost_from_distance(uint32_t d) {  // position/mod.rs:129-143
+    if (d == 0) return 0;
+    if (d == 1) return 1;
+    if (d <= 4) return 2;
+    if (d <= 7) return 3;
+    if (d <= 11) return 4;
+    if (d <= 16) return 5;
+    if (d <= 24) return 6;
+    if (d <= 64) return 7;
+    if (d <= 256) return 8;
+    if (d <= 1024) return 9;
+    return 10;
+}
+uint16_t bucketed_position(uint16_t rel) {  // lib.rs:248-260
+    if (rel < 16) return rel;
+    if (rel < 24) return 24;
+    uint32_t p = 1;
+    while (p < rel) p <<= 1;
+    return (uint16_t)p;
+}
+
+struct CondTable {
+    std::vector<ECond> items;
+    std::map<std::string, uint32_t> ids;
+    uint32_t insert(ECond c) {
+        std::string k = c.key();
+        auto it = ids.find(k);
+        if (it != ids.end()) return it->second;
+        items.push_back(std::move(c));
+        ids.emplace(k, (uint32_t)items.size() - 1);
+        return (uint32_t)items.size() - 1;
+    }
+};
+
+// G::build_edges for the six graph rules
+std::vector<std::pair<uint32_t, uint32_t>> build_edges(const QCtx &c, int rule, CondTable &ct, const ELocated *from, const ELocated &to) {
+    std::vector<std::pair<uint32_t, uint32_t>> edges;
+    auto base = [&]() {
+        ECond x;
+        x.rule = rule;
+        x.term = to;
+        x.end_subset = to;
+        return x;
+    };
+    switch (rule) {
+        case RK_WORDS: edges.push_back({0, ct.insert(base())}); break;
+        case RK_TYPO: {  // typo/mod.rs:42-77
+            uint32_t bc = to.n_term_ids() == 1 ? 0 : to.n_term_ids();
+            uint8_t mx = max_typo_cost(c, to.ts);
+            for (uint8_t n = 0; n <= mx; n++) {
+                ECond x = base();
+                x.nbr_typos = n;
+                if (n != 0) x.term.ts.zero = ESubset{};
+                if (n != 1) x.term.ts.one = ESubset{};
+                if (n != 2) x.term.ts.two = ESubset{};
+                x.end_subset = x.term;
+                edges.push_back({n + bc, ct.insert(x)});
+            }
+            break;
+        }
+        case RK_PROXIMITY: {  // proximity/build.rs:10-56
+            uint32_t rmax = to.n_term_ids() - 1;
+            if (!from || (uint16_t)(from->pe + 1) != to.ps) {
+                edges.push_back({rmax, ct.insert(base())});
+                break;
+            }
+            for (uint32_t cost = rmax; cost < 3 + rmax; cost++) {
+                ECond x = base();
+                x.prox_uninit = true;
+                x.left = *from;
+                x.cost = (uint8_t)(cost + 1);
+                x.has_start = true;
+                x.start_subset = *from;
+                edges.push_back({cost, ct.insert(x)});
+            }
+            edges.push_back({3 + rmax, ct.insert(base())});
+            break;
+        }
+        case RK_FID: {  // fid/mod.rs:49-121; edge order: ascending fid (the reference iterates an FxHashSet)
+            std::set<uint16_t> fields;
+            for (auto &w : all_single_words(c, to.ts))
+                for (uint32_t i = c.ix.wf_off[w.rank]; i < c.ix.wf_off[w.rank + 1]; i++) fields.insert(c.ix.wf_fid[i]);
+            if (has_split_phrase(c, to.ts)) {
+                const ETerm &t = c.terms[to.ts.term];
+                for (uint32_t w : {t.split_l, t.split_r})
+                    for (uint32_t i = c.ix.wf_off[w]; i < c.ix.wf_off[w + 1]; i++) fields.insert(c.ix.wf_fid[i]);
+            }
+            uint32_t pid;
+            bool derived;
+            if (use_prefix_db(c, to.ts, pid, derived))
+                for (uint32_t i = c.ix.pf_off[pid]; i < c.ix.pf_off[pid + 1]; i++) fields.insert(c.ix.pf_fid[i]);
+            uint16_t cur_max = 0;
+            for (auto fid : fields) {
+                if (fid >= c.ix.settings.weights.size()) continue;
+                uint16_t weight = c.ix.settings.weights[fid];
+                cur_max = std::max(cur_max, weight);
+                ECond x = base();
+                x.has_fid = true;
+                x.fid = fid;
+                edges.push_back({(uint32_t)weight * to.n_term_ids(), ct.insert(x)});
+            }
+            uint16_t mw = c.ix.settings.max_weight();
+            if (cur_max < mw) edges.push_back({(uint32_t)mw * to.n_term_ids(), ct.insert(base())});
+            break;
+        }
+        case RK_POSITION: {  // position/mod.rs:50-126; edge order: ascending cost (FxHashMap in the reference)
+            std::set<uint16_t> all_pos;
+            for (auto &w : all_single_words(c, to.ts))
+                for (uint32_t i = c.ix.wp_off[w.rank]; i < c.ix.wp_off[w.rank + 1]; i++) all_pos.insert(c.ix.wp_pos[i]);
+            if (has_split_phrase(c, to.ts)) {
+                uint32_t w = c.terms[to.ts.term].split_l;
+                for (uint32_t i = c.ix.wp_off[w]; i < c.ix.wp_off[w + 1]; i++) all_pos.insert(c.ix.wp_pos[i]);
+            }
+            uint32_t pid;
+            bool derived;
+            if (use_prefix_db(c, to.ts, pid, derived))
+                for (uint32_t i = c.ix.pp_off[pid]; i < c.ix.pp_off[pid + 1]; i++) all_pos.insert(c.ix.pp_pos[i]);
+            std::map<uint32_t, std::vector<uint16_t>> by_cost;
+            for (auto p : all_pos) {
+                uint32_t dist = p > to.ps ? p - to.ps : to.ps - p, cost = 0;
+                for (uint32_t i = 0; i < to.n_term_ids(); i++) cost += position_cost_from_distance(dist + i);
+                by_cost[cost].push_back(p);
+            }
+            uint32_t max_cost = to.n_term_ids() * 10;
+            for (auto &kv : by_cost) {
+                ECond x = base();
+                x.positions = kv.second;
+                edges.push_back({kv.first, ct.insert(x)});
+            }
+            if (!by_cost.count(max_cost)) edges.push_back({max_cost, ct.insert(base())});
+            break;
+        }
+        case RK_EXACTNESS: {  // exactness/mod.rs:45-91
+            ECond e = base();
+            e.exact_in_attribute = true;
+            {  // end_term_subset: keep_only_exact_term + mandatory
+                uint32_t w;
+                if (exact_term(c, to.ts, w)) {
+                    e.end_subset.ts.zero = ESubset{N_SUBSET, {w}, false};
+                    e.end_subset.ts.one = ESubset{};
+                    e.end_subset.ts.two = ESubset{};
+                }
+                e.end_subset.ts.mandatory = true;
+            }
+            uint32_t ei = ct.insert(e), ai = ct.insert(base());
+            edges.push_back({0, ei});
+            edges.push_back({to.n_term_ids(), ai});
+            break;
+        }
+    }
+    return edges;
+}
+
+constexpr size_t MAX_PATHS = 60000;
+
+// Build graph + enumerate all START->END paths (cheapest_paths.rs semantics without the dead-end cache: every
+// path is handed to the device, which finds the empty ones itself).
+void prepare_graph_rule(const QCtx &c, int rule, bool has_tms, int tms, Level &L) {
+    const EGraph &qg = L.graph;
+    uint16_t n = (uint16_t)qg.nodes.size();
+    // cost of ignoring a node (graph_based_ranking_rule.rs:149-193)
+    std::vector<int> ignore_cost(n, -1);
+    std::vector<std::vector<uint8_t>> ignore_skip(n);
+    if (has_tms && tms == B200_TMS_LAST) {
+        std::vector<uint8_t> forbidden(n, 0);
+        for (auto &grp : removal_order_last(qg)) {
+            for (auto nd : grp) {
+                ignore_cost[nd] = 1;
+                ignore_skip[nd] = forbidden;
+            }
+            for (auto nd : grp) forbidden[nd] = 1;
+        }
+    }
+    CondTable ct;
+    std::vector<EEdge> edges;
+    std::vector<std::vector<uint32_t>> eon(n);
+    auto insert_edge = [&](EEdge e) {
+        for (uint32_t i = 0; i < edges.size(); i++)
+            if (edges[i].src == e.src && edges[i].dst == e.dst && edges[i].cost == e.cost && edges[i].cond == e.cond) return i;
+        edges.push_back(std::move(e));
+        return (uint32_t)edges.size() - 1;
+    };
+    std::vector<uint8_t> none(n, 0);
+    for (uint16_t src = 0; src < n; src++) {
+        const ENode &sn = qg.nodes[src];
+        if (sn.kind != ND_TERM && sn.kind != ND_START) continue;
+        for (auto dst : sn.succ) {
+            const ENode &dn = qg.nodes[dst];
+            if (dn.kind == ND_END) {
+                eon[src].push_back(insert_edge(EEdge{src, dst, 0, -1, none}));
+                continue;
+            }
+            if (ignore_cost[dst] >= 0)
+                eon[src].push_back(insert_edge(EEdge{src, dst, (uint32_t)ignore_cost[dst] * dn.term.n_term_ids(), -1, ignore_skip[dst]}));
+            for (auto &e : build_edges(c, rule, ct, sn.kind == ND_TERM ? &sn.term : nullptr, dn.term))
+                eon[src].push_back(insert_edge(EEdge{src, dst, e.first, (int32_t)e.second, none}));
+        }
+    }
+    for (auto &v : eon) {
+        std::sort(v.begin(), v.end());
+        v.erase(std::unique(v.begin(), v.end()), v.end());
+    }
+    L.conds = ct.items;
+    // max cost over the graph ignoring skip constraints (find_all_costs_to_end :285-310)
+    std::vector<std::set<uint64_t>> costs(n);
+    std::vector<int> state(n, 0);
+    std::function<void(uint16_t)> visit = [&](uint16_t nd) {
+        if (state[nd]) return;
+        state[nd] = 1;
+        if (nd == qg.end) {
+            costs[nd] = {0};
+            return;
+        }
+        for (auto ei : eon[nd]) {
+            visit(edges[ei].dst);
+            for (auto x : costs[edges[ei].dst]) costs[nd].insert(edges[ei].cost + x);
+        }
+    };
+    visit(qg.root);
+    uint64_t mx = costs[qg.root].empty() ? 0 : *costs[qg.root].rbegin();
+    L.next_max_cost = 1 + mx;
+    // enumerate
+    struct Found {
+        uint32_t cost;
+        std::vector<uint16_t> conds;
+    };
+    std::vector<Found> found;
+    std::vector<uint16_t> path;
+    std::vector<uint8_t> visited(n, 0), to_skip(n, 0);
+    std::function<void(uint16_t, uint32_t)> dfs = [&](uint16_t node, uint32_t cost) {
+        for (auto ei : eon[node]) {
+            const EEdge &e = edges[ei];
+            if (e.cond >= 0) {
+                if (to_skip[e.dst]) continue;
+                bool clash = false;
+                for (uint16_t k = 0; k < n && !clash; k++) clash = e.skip[k] && visited[k];
+                if (clash) continue;
+                if (costs[e.dst].empty()) continue;
+                path.push_back((uint16_t)e.cond);
+                visited[e.dst] = 1;
+                std::vector<uint8_t> old = to_skip;
+                for (uint16_t k = 0; k < n; k++) to_skip[k] |= e.skip[k];
+                dfs(e.dst, cost + e.cost);
+                to_skip = old;
+                visited[e.dst] = 0;
+                path.pop_back();
+            } else {
+                if (e.dst == qg.end) {
+                    found.push_back({cost + e.cost, path});
+                    if (found.size() > MAX_PATHS) throw TooComplex{"ranking-rule graph has more than 60000 paths"};
+                } else {
+                    if (costs[e.dst].empty()) continue;
+                    std::vector<uint8_t> old = to_skip;
+                    for (uint16_t k = 0; k < n; k++) to_skip[k] |= e.skip[k];
+                    dfs(e.dst, cost + e.cost);
+                    to_skip = old;
+                }
+            }
+        }
+    };
+    dfs(qg.root, 0);
+    std::stable_sort(found.begin(), found.end(), [](const Found &a, const Found &b) { return a.cost < b.cost; });
+    L.paths.clear();
+    L.cost_vals.clear();
+    L.path_cost_idx.clear();
+    for (auto &f : found) {
+        if (L.cost_vals.empty() || L.cost_vals.back() != f.cost) L.cost_vals.push_back(f.cost);
+        L.path_cost_idx.push_back((uint16_t)(L.cost_vals.size() - 1));
+        L.paths.push_back(EPath{f.cost, std::move(f.conds)});
+    }
+    if (L.cost_vals.size() > MAX_COSTS) throw TooComplex{"more than 128 distinct costs in one ranking rule"};
+}
+
+// universe resolution (resolve_query_graph.rs:133-185 == union over START->END routes of the AND of the term docids)
+void prepare_resolve(const QCtx &c, Level &L) {
+    const EGraph &g = L.graph;
+    L.conds.clear();
+    std::vector<int> cond_of(g.nodes.size(), -1);
+    for (uint16_t i = 0; i < g.nodes.size(); i++)
+        if (g.nodes[i].kind == ND_TERM) {
+            ECond x;
+            x.rule = RK_RESOLVE;
+            x.term = g.nodes[i].term;
+            x.end_subset = x.term;
+            cond_of[i] = (int)L.conds.size();
+            L.conds.push_back(x);
+        }
+    L.paths.clear();
+    std::vector<uint16_t> path;
+    std::function<void(uint16_t)> dfs = [&](uint16_t node) {
+        for (auto s : g.nodes[node].succ) {
+            if (s == g.end) {
+                L.paths.push_back(EPath{0, path});
+                if (L.paths.size() > MAX_PATHS) throw TooComplex{"query graph has too many routes"};
+            } else {
+                path.push_back((uint16_t)cond_of[s]);
+                dfs(s);
+                path.pop_back();
+            }
+        }
+    };
+    dfs(g.root);
+    L.cost_vals = {0};
+    L.path_cost_idx.assign(L.paths.size(), 0);
+    L.next_max_cost = 1;
+    (void)c;
+}
+
+// exact_attribute.rs:96-240 as three first-match paths: [A]=ExactMatch, [B]=MatchesStart, []=NoExactMatch
+void prepare_exact_attribute(const QCtx &c, Level &L, StepOut &o) {
+    const EGraph &g = L.graph;
+    ActBuilder b(c, o);
+    uint16_t colA = b.new_col(), colB = b.new_col();
+    L.conds.clear();
+    for (int k = 0; k < 2; k++) {
+        ECond x;
+        x.rule = RK_EXACT_ATTRIBUTE;
+        x.col = k == 0 ? colA : colB;
+        L.conds.push_back(x);
+    }
+    L.paths = {EPath{0, {0}}, EPath{1, {1}}, EPath{2, {}}};
+    L.cost_vals = {0, 1, 2};
+    L.path_cost_idx = {0, 1, 2};
+    L.next_max_cost = 3;
+    struct Info {
+        uint32_t word;
+        uint16_t start_position;
+        uint8_t start_term_id;
+        size_t position_count;
+    };
+    std::vector<Info> ets;
+    for (auto &n : g.nodes) {
+        if (n.kind != ND_TERM) continue;
+        uint32_t w;
+        if (!exact_term(c, n.term.ts, w)) continue;
+        ets.push_back({w, n.term.ps, n.term.t0, (size_t)n.term.pe - n.term.ps + 1});
+    }
+    std::stable_sort(ets.begin(), ets.end(), [](const Info &a, const Info &b2) { return a.start_term_id < b2.start_term_id; });
+    {
+        std::vector<Info> dd;
+        for (auto &e : ets)
+            if (dd.empty() || dd.back().start_term_id != e.start_term_id) dd.push_back(e);
+        ets.swap(dd);
+    }
+    size_t count_all = 0;
+    for (auto &e : ets) count_all += e.position_count;
+    bool empty_state = ets.empty() || ets[0].start_term_id != 0;
+    uint8_t prev = 0;
+    for (auto &e : ets) {
+        if (e.start_term_id < prev || e.start_term_id - prev > 1) empty_state = true;
+        prev = e.start_term_id;
+    }
+    if (!empty_state) {
+        // candidates = AND_i word_position[w_i, bucketed(pos_i)]
+        uint16_t cand = b.new_col();
+        bool first = true;
+        for (auto &e : ets) {
+            uint16_t t = first ? cand : b.new_col();
+            b.add_list(t, c.ix.word_pos_list(e.word, bucketed_position(e.start_position)));
+            if (!first) b.op(0, cand, cand, t);
+            first = false;
+        }
+        for (uint16_t fid = 0; fid < c.ix.settings.n_fields; fid++) {
+            uint16_t swe = b.new_col();
+            b.op(3, swe, cand, 0);
+            for (auto &e : ets) {
+                uint16_t t = b.new_col();
+                b.add_list(t, c.ix.word_fid_list(e.word, fid));
+                b.op(0, swe, swe, t);
+            }
+            uint16_t cnt = b.new_col();
+            if (count_all < 255) {
+                auto it = c.ix.fwc_list.find(((uint32_t)fid << 8) | (uint32_t)count_all);
+                if (it != c.ix.fwc_list.end()) b.add_list(cnt, it->second);
+            }
+            uint16_t t1 = b.new_col();
+            b.op(0, t1, swe, cnt);
+            b.op(1, colA, colA, t1);
+            uint16_t t2 = b.new_col();
+            b.op(2, t2, swe, cnt);
+            b.op(1, colB, colB, t2);
+        }
+    }
+    o.n_cols = b.next_col;
+}
+
+// query_graph.rs:453-543
+EGraph build_from_paths(const std::vector<std::vector<const ECond *>> &paths) {
+    std::vector<std::vector<ELocated>> single;
+    for (auto &path : paths) {
+        std::vector<ELocated> processed;
+        bool have_prev = false;
+        ELocated prev;
+        for (auto *cd : path) {
+            if (have_prev) {
+                if (cd->has_start) {
+                    ELocated start = cd->start_subset;
+                    if (start.t0 == prev.t0 && start.t1 == prev.t1) {
+                        start.ts.intersect(prev.ts);
+                        processed.push_back(start);
+                    } else {
+                        processed.push_back(prev);
+                        processed.push_back(start);
+                    }
+                } else
+                    processed.push_back(prev);
+            } else if (cd->has_start)
+                processed.push_back(cd->start_subset);
+            prev = cd->end_subset;
+            have_prev = true;
+        }
+        if (have_prev) processed.push_back(prev);
+        single.push_back(std::move(processed));
+    }
+    EGraph g;
+    g.nodes.resize(2);
+    g.nodes[0].kind = ND_START;
+    g.nodes[1].kind = ND_END;
+    std::map<std::string, uint16_t> ids;
+    std::vector<std::vector<uint16_t>> pid;
+    for (auto &path : single) {
+        std::vector<std::string> suffix(path.size());
+        std::string acc;
+        for (size_t i = path.size(); i-- > 0;) {
+            acc = path[i].key() + "|" + acc;
+            suffix[i] = acc;
+        }
+        std::vector<uint16_t> p;
+        for (size_t i = 0; i < path.size(); i++) {
+            auto it = ids.find(suffix[i]);
+            if (it == ids.end()) {
+                ENode nd;
+                nd.kind = ND_TERM;
+                nd.term = path[i];
+                g.nodes.push_back(nd);
+                it = ids.emplace(suffix[i], (uint16_t)(g.nodes.size() - 1)).first;
+            }
+            p.push_back(it->second);
+        }
+        pid.push_back(std::move(p));
+    }
+    for (auto &p : pid) {
+        uint16_t prev = g.root;
+        for (auto id : p) {
+            sorted_insert(g.nodes[prev].succ, id);
+            sorted_insert(g.nodes[id].pred, prev);
+            prev = id;
+        }
+        sorted_insert(g.nodes[prev].succ, g.end);
+        sorted_insert(g.nodes[g.end].pred, prev);
+    }
+    return g;
+}
+
+// conditions -> columns, scatter jobs, column program, path table
+void emit_activation_work(const QCtx &c, Level &L, StepOut &o) {
+    if (L.kind != RK_EXACT_ATTRIBUTE) {
+        ActBuilder b(c, o);
+        for (auto &cd : L.conds) cd.col = b.new_col();
+        for (auto &cd : L.conds) build_cond(b, cd);
+        o.n_cols = b.next_col;
+    }
+    o.n_costs = (uint32_t)L.cost_vals.size();
+    const std::vector<uint16_t> *prevp = nullptr;
+    std::vector<uint16_t> prev_cols, cur_cols;
+    for (size_t p = 0; p < L.paths.size(); p++) {
+        cur_cols.clear();
+        for (auto ci : L.paths[p].conds) cur_cols.push_back(L.conds[ci].col);
+        if (cur_cols.size() > MAX_PATH_LEN) throw TooComplex{"path longer than 32 conditions"};
+        uint32_t lcp = 0;
+        if (prevp)
+            while (lcp < prev_cols.size() && lcp < cur_cols.size() && prev_cols[lcp] == cur_cols[lcp]) lcp++;
+        PathRec pr;
+        pr.cond_off = (uint32_t)o.condpool.size();
+        pr.cost_idx = L.path_cost_idx[p];
+        pr.len = (uint8_t)cur_cols.size();
+        pr.lcp = (uint8_t)lcp;
+        o.paths.push_back(pr);
+        o.condpool.insert(o.condpool.end(), cur_cols.begin(), cur_cols.end());
+        prev_cols = cur_cols;
+        prevp = &prev_cols;
+    }
+}
+
+// located_query_terms_from_tokens (parse_query.rs:28-202) without phrases / negative words
+void parse_query(QState &q, const b200_query_batch *b, uint32_t qi) {
+    const HostIndex &ix = q.ctx.ix;
+    struct Tok {
+        int kind;
+        std::string lemma;
+    };
+    std::vector<Tok> toks;
+    for (uint32_t t = b->token_begin[qi]; t < b->token_begin[qi + 1]; t++)
+        toks.push_back({b->token_kind[t], std::string(b->lemma_bytes + b->lemma_off[t], b->lemma_off[t + 1] - b->lemma_off[t])});
+    if (toks.size() > 1000) toks.resize(1000);
+    std::vector<std::pair<uint32_t, uint16_t>> located;  // (term id, position)
+    uint16_t position = 0xffff;
+    bool encountered_whitespace = true;
+    size_t words_limit = b->words_limit ? b->words_limit : 10;
+    for (size_t ti = 0; ti < toks.size(); ti++) {
+        const Tok &tk = toks[ti];
+        if (tk.lemma.empty()) continue;
+        if (located.size() >= words_limit) break;
+        bool has_next = ti + 1 < toks.size();
+        if (tk.kind == 0 || tk.kind == 1) {
+            position = (uint16_t)(position + 1);
+            if (has_next) {
+                if (tk.kind == 0) {
+                    q.ctx.terms.push_back(term_from_word(ix, tk.lemma, number_of_typos_allowed(ix, tk.lemma), false, false));
+                    located.push_back({(uint32_t)q.ctx.terms.size() - 1, position});
+                }
+            } else {
+                q.ctx.terms.push_back(term_from_word(ix, tk.lemma, number_of_typos_allowed(ix, tk.lemma), ix.settings.prefix_search, false));
+                located.push_back({(uint32_t)q.ctx.terms.size() - 1, position});
+            }
+        } else {
+            if (tk.kind == 3) position = (uint16_t)(position + 7);
+            if (tk.lemma.find('"') != std::string::npos) throw UnsupportedQuery{"phrase queries (\"...\") are not implemented on the device path"};
+            if (tk.lemma == "-" && encountered_whitespace && has_next) throw UnsupportedQuery{"the negative operator is not implemented on the device path"};
+        }
+        char last = tk.lemma.back();
+        encountered_whitespace = (last == ' ' || last == '\t' || last == '\n');
+    }
+    // QueryGraph::from_query (query_graph.rs:96-187) + make_ngram (parse_query.rs:227-300)
+    EGraph &g = q.graph;
+    g.nodes.clear();
+    g.nodes.resize(2);
+    g.nodes[0].kind = ND_START;
+    g.nodes[1].kind = ND_END;
+    auto add_term_node = [&](uint32_t term, uint16_t ps, uint16_t pe, uint8_t t0, uint8_t t1) {
+        ENode n;
+        n.kind = ND_TERM;
+        n.term.ts = ETermSubset::full(term);
+        n.term.ps = ps;
+        n.term.pe = pe;
+        n.term.t0 = t0;
+        n.term.t1 = t1;
+        g.nodes.push_back(n);
+    };
+    auto make_ngram = [&](size_t from, size_t to) -> bool {
+        for (size_t i = from; i < to; i++)
+            if (located[i].second != (uint16_t)(located[i + 1].second - 1)) return false;
+        std::string s;
+        std::vector<std::string> ws;
+        for (size_t i = from; i <= to; i++) {
+            ws.push_back(q.ctx.terms[located[i].first].original);
+            s += ws.back();
+        }
+        if (s.size() > 250) return false;
+        bool is_prefix = q.ctx.terms[located[to].first].is_prefix;
+        uint8_t n = number_of_typos_allowed(ix, s), dec = (uint8_t)(to - from);
+        ETerm t = term_from_word(ix, s, n > dec ? (uint8_t)(n - dec) : 0, is_prefix, true);
+        t.ngram_words = ws;
+        t.is_ngram = true;
+        q.ctx.terms.push_back(std::move(t));
+        add_term_node((uint32_t)q.ctx.terms.size() - 1, located[from].second, located[to].second, (uint8_t)from, (uint8_t)to);
+        return true;
+    };
+    for (size_t i = 0; i < located.size(); i++) {
+        add_term_node(located[i].first, located[i].second, located[i].second, (uint8_t)i, (uint8_t)i);
+        if (i >= 1) make_ngram(i - 1, i);
+        if (i >= 2) make_ngram(i - 2, i);
+    }
+    build_initial_edges(g);
+    q.placeholder = located.empty();
+}
+
+// get_ranking_rules_for_query_graph_search (search/new/mod.rs:510-649)
+std::vector<int> rule_list(const Settings &s, int tms) {
+    std::vector<int> rules;
+    bool words = tms == B200_TMS_ALL, typo = false, prox = false, attr = false, attr_rank = false, wpos = false, exact = false;
+    for (int rr : s.criteria) {
+        if ((rr == B200_C_TYPO || rr == B200_C_ATTRIBUTE || rr == B200_C_ATTRIBUTE_RANK || rr == B200_C_WORD_POSITION || rr == B200_C_PROXIMITY ||
+             rr == B200_C_EXACTNESS) &&
+            !words) {
+            rules.push_back(RK_WORDS);
+            words = true;
+        }
+        switch (rr) {
+            case B200_C_WORDS:
+                if (!words) {
+                    rules.push_back(RK_WORDS);
+                    words = true;
+                }
+                break;
+            case B200_C_TYPO:
+                if (!typo) {
+                    typo = true;
+                    rules.push_back(RK_TYPO);
+                }
+                break;
+            case B200_C_PROXIMITY:
+                if (!prox) {
+                    prox = true;
+                    rules.push_back(RK_PROXIMITY);
+                }
+                break;
+            case B200_C_ATTRIBUTE:
+                if (!(attr || attr_rank || wpos)) {
+                    attr = true;
+                    rules.push_back(RK_FID);
+                    rules.push_back(RK_POSITION);
+                }
+                break;
+            case B200_C_ATTRIBUTE_RANK:
+                if (!(attr || attr_rank)) {
+                    attr_rank = true;
+                    rules.push_back(RK_FID);
+                }
+                break;
+            case B200_C_WORD_POSITION:
+                if (!(attr || wpos)) {
+                    wpos = true;
+                    rules.push_back(RK_POSITION);
+                }
+                break;
+            case B200_C_EXACTNESS:
+                if (!exact) {
+                    exact = true;
+                    rules.push_back(RK_EXACT_ATTRIBUTE);
+                    rules.push_back(RK_EXACTNESS);
+                }
+                break;
+            default: break;  // sort: no sort criteria on this path
+        }
+    }
+    return rules;
+}
+
+uint8_t score_kind_of(int rk) {
+    switch (rk) {
+        case RK_WORDS: return B200_S_WORDS;
+        case RK_TYPO: return B200_S_TYPO;
+        case RK_PROXIMITY: return B200_S_PROXIMITY;
+        case RK_FID: return B200_S_FID;
+        case RK_POSITION: return B200_S_POSITION;
+        case RK_EXACT_ATTRIBUTE: return B200_S_EXACT_ATTRIBUTE;
+        default: return B200_S_EXACT_WORDS;
+    }
+}
+
+struct Blob {  // step input blob with aligned sections
+    std::vector<uint8_t> bytes;
+    template <class T>
+    size_t add(const std::vector<T> &v) {
+        size_t off = (bytes.size() + 15) & ~(size_t)15;
+        bytes.resize(off + v.size() * sizeof(T));
+        if (!v.empty()) memcpy(bytes.data() + off, v.data(), v.size() * sizeof(T));
+        return off;
+    }
+};
+
+template <class F>
+void parallel_for(size_t n, unsigned nt, F f) {
+    if (n == 0) return;
+    nt = (unsigned)std::min<size_t>(nt, n);
+    if (nt <= 1) {
+        for (size_t i = 0; i < n; i++) f(i);
+        return;
+    }
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++)
+        th.emplace_back([&]() {
+            for (;;) {
+                size_t i = next.fetch_add(1);
+                if (i >= n) break;
+                f(i);
+            }
+        });
+    for (auto &x : th) x.join();
+}
+
+}  // namespace
+
+// ================================================================================================ driver
+int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t offset, uint32_t limit, int scoring) {
+    CU(cudaSetDevice(device), "cudaSetDevice");
+    const uint32_t NQ = b->n_queries;
+    const unsigned NT = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    const bool skip_scoring = scoring == 0;
+    const uint32_t length = limit, from = offset;
+    const int tms = b->terms_matching_strategy;
+    if (tms == B200_TMS_FREQUENCY) return fail(B200_ERR_UNSUPPORTED, "TermsMatchingStrategy::Frequency is not implemented on the device path");
+    std::vector<std::unique_ptr<QState>> qs(NQ);
+    for (uint32_t i = 0; i < NQ; i++) qs[i].reset(new QState(hix));
+
+    // ---- phase 1: tokens -> terms -> query graph
+    parallel_for(NQ, NT, [&](size_t i) {
+        QState &q = *qs[i];
+        try {
+            parse_query(q, b, (uint32_t)i);
+        } catch (const UnsupportedQuery &u) {
+            q.status = B200_ERR_UNSUPPORTED;
+            q.error = u.why;
+            q.done = true;
+        }
+    });
+    // ---- phase 2: typo derivations for every term of the batch in one device sweep
+    {
+        std::vector<char> wbytes;
+        std::vector<uint32_t> woff{0};
+        std::vector<uint8_t> mt, ip;
+        for (auto &qp : qs) {
+            if (qp->done) continue;
+            for (auto &t : qp->ctx.terms) {
+                if (t.empty_term || t.max_lev == 0) continue;
+                if (t.original.size() > LEV_MAX_Q) {
+                    qp->status = B200_ERR_UNSUPPORTED;
+                    qp->error = "typo-tolerant word longer than 64 bytes";
+                    qp->done = true;
+                    break;
+                }
+                t.lev_slot = (int32_t)mt.size();
+                wbytes.insert(wbytes.end(), t.original.begin(), t.original.end());
+                woff.push_back((uint32_t)wbytes.size());
+                mt.push_back(t.max_lev);
+                ip.push_back(t.is_prefix ? 1 : 0);
+            }
+        }
+        uint32_t n = (uint32_t)mt.size();
+        std::vector<uint32_t> one((size_t)n * 150), n_one(n), two((size_t)n * 50), n_two(n);
+        if (n) {
+            int rc = derive_batch(n, wbytes.data(), woff.data(), mt.data(), ip.data(), one.data(), n_one.data(), two.data(), n_two.data());
+            if (rc != B200_OK) return rc;
+        }
+        parallel_for(NQ, NT, [&](size_t i) {
+            QState &q = *qs[i];
+            if (q.done) return;
+            for (auto &t : q.ctx.terms) {
+                if (t.empty_term) continue;
+                if (t.lev_slot >= 0) {
+                    size_t s = (size_t)t.lev_slot;
+                    t.one_typo.assign(one.begin() + s * 150, one.begin() + s * 150 + n_one[s]);
+                    t.two_typo.assign(two.begin() + s * 50, two.begin() + s * 50 + n_two[s]);
+                }
+                find_split_words(hix, t);
+            }
+        });
+    }
+    // ---- result buffers
+    CU(d_docids_out.reserve((size_t)NQ * std::max(1u, length)), "alloc results");
+    size_t arena_used = 0, scratch_used = 0;
+    auto arena_alloc = [&](size_t bytes) -> uint8_t * {
+        size_t off = (arena_used + 255) & ~(size_t)255;
+        if (off + bytes > arena_bytes) return nullptr;
+        arena_used = off + bytes;
+        return arena + off;
+    };
+
+    // ---- phase 3: initial requests (universe resolution) or placeholder emission
+    std::vector<int> rules = rule_list(hix.settings, tms);
+    auto request_activation = [&](QState &q, Level &&L, const uint32_t *p_uw, const unsigned long long *p_ub, const unsigned long long *p_out,
+                                  uint32_t p_rows, uint32_t p_ld, uint32_t p_col, uint32_t cap) {
+        q.pend = StepOut{};
+        if (L.kind == RK_EXACT_ATTRIBUTE) prepare_exact_attribute(q.ctx, L, q.pend);
+        emit_activation_work(q.ctx, L, q.pend);
+        q.levels.push_back(std::move(L));
+        q.want_activation = true;
+        q.p_uw = p_uw;
+        q.p_ub = p_ub;
+        q.p_out = p_out;
+        q.p_rows = p_rows;
+        q.p_ld = p_ld;
+        q.p_col = p_col;
+        q.p_cap = cap;
+    };
+    auto start_query = [&](QState &q) {
+        q.rules = rules;
+        if (q.placeholder) {
+            // placeholder search: no text rules (search/new/mod.rs:353-416) -> universe in docid order (bucket_sort.rs:104-116)
+            q.n_candidates = hix.n_documents;
+            EmitReq e{};
+            e.d.uw = nullptr;
+            e.d.ub = dix.base_ub;
+            e.d.out = nullptr;
+            e.d.rows = hix.n_words64;
+            e.d.ld = hix.n_words64;
+            e.d.skip = from;
+            uint64_t avail = hix.n_documents > from ? hix.n_documents - from : 0;
+            e.d.take = (uint32_t)std::min<uint64_t>(avail, length);
+            q.n_results = e.d.take;
+            q.scores.assign(q.n_results, {});
+            if (e.d.take) q.emits.push_back(e);
+            q.done = true;
+            return;
+        }
+        // resolve_maximally_reduced_query_graph (search/new/mod.rs:273-301)
+        Level L;
+        L.kind = RK_RESOLVE;
+        L.graph = q.graph;
+        if (tms == B200_TMS_LAST) {
+            std::vector<uint16_t> rm;
+            for (auto &grp : removal_order_last(q.graph))
+                for (auto nd : grp) rm.push_back(nd);
+            remove_nodes_keep_edges(L.graph, rm);
+        }
+        prepare_resolve(q.ctx, L);
+        request_activation(q, std::move(L), nullptr, dix.base_ub, nullptr, hix.n_words64, hix.n_words64, 0, hix.n_words64);
+    };
+    std::vector<std::string> errs(NQ);
+    parallel_for(NQ, NT, [&](size_t i) {
+        QState &q = *qs[i];
+        if (q.done) return;
+        try {
+            start_query(q);
+        } catch (const TooComplex &t) {
+            q.status = B200_ERR_CAPACITY;
+            q.error = t.why;
+            q.done = true;
+        }
+    });
+
+    // advance one query's bucket sort until it needs the device again (bucket_sort.rs:193-330)
+    auto emit_bucket = [&](QState &q, Level &L, uint32_t col_lo, uint32_t col_hi, uint64_t count) {
+        if (count == 0) return;
+        uint64_t skip = 0;
+        uint64_t take = 0;
+        if (q.cur_offset < from) {
+            if (q.cur_offset + count >= from) {
+                skip = from - q.cur_offset;
+                take = std::min<uint64_t>(count - skip, length - q.n_results);
+            }
+        } else
+            take = std::min<uint64_t>(count, length - q.n_results);
+        if (take) {
+            EmitReq e{};
+            e.d.uw = L.uw;
+            e.d.ub = L.ub;
+            e.d.out = L.out;
+            e.d.rows = L.rows;
+            e.d.ld = L.ld;
+            e.d.col_lo = col_lo;
+            e.d.col_hi = col_hi;
+            e.d.skip = (uint32_t)skip;
+            e.d.take = (uint32_t)take;
+            // dst carries the offset inside the query's result row; the driver turns it into a device pointer
+            e.d.dst = reinterpret_cast<uint32_t *>((uintptr_t)q.n_results);
+            q.emits.push_back(e);
+            for (uint64_t k = 0; k < take; k++) q.scores.push_back(skip_scoring ? std::vector<EScore>{} : q.rr_scores);
+            q.n_results += (uint32_t)take;
+        }
+        q.cur_offset += count;
+    };
+    auto advance = [&](QState &q) {
+        const size_t n_rules = q.rules.size();
+        for (;;) {
+            if (q.n_results >= length) break;
+            if (q.levels.empty()) break;
+            size_t cur = q.levels.size() - 1;  // level index; rule index = cur - 1 (level 0 = resolve)
+            Level &L = q.levels[cur];
+            auto back = [&]() {
+                q.levels.pop_back();
+                if (!q.levels.empty() && q.levels.size() - 1 >= 1) {
+                    size_t rule_cur = q.levels.size() - 2;
+                    if (q.rr_scores.size() > rule_cur) q.rr_scores.pop_back();
+                } else if (q.levels.size() == 1)
+                    q.rr_scores.clear();
+            };
+            if (L.kind == RK_RESOLVE) {
+                // the resolve level is not a ranking rule: after it, start rule 0 on its bucket 0
+                if (L.cursor > 0) {
+                    q.levels.clear();
+                    break;
+                }
+                L.cursor = 1;
+                q.n_candidates = L.counts[0];
+                uint64_t cnt = L.counts[0];
+                if (cnt < from) {  // bucket_sort.rs:52-64
+                    q.levels.clear();
+                    break;
+                }
+                if (n_rules == 0) {
+                    emit_bucket(q, L, 0, 1, cnt);
+                    q.levels.clear();
+                    break;
+                }
+                Level C;
+                C.rule_idx = 0;
+                C.kind = q.rules[0];
+                C.graph = q.graph;
+                if (C.kind != RK_EXACT_ATTRIBUTE) prepare_graph_rule(q.ctx, C.kind, C.kind == RK_WORDS, tms, C);
+                uint32_t cap = (uint32_t)std::min<uint64_t>(cnt, L.rows);
+                request_activation(q, std::move(C), L.uw, L.ub, L.out, L.rows, L.ld, 0, cap);
+                return;
+            }
+            size_t rule_cur = (size_t)L.rule_idx;
+            if (L.universe_count == 0 || (skip_scoring && L.universe_count == 1)) {
+                if (L.universe_count == 1) emit_bucket(q, L, (uint32_t)L.cursor, (uint32_t)L.cost_vals.size() + 1, 1);
+                back();
+                continue;
+            }
+            size_t ci = L.cursor;
+            while (ci < L.cost_vals.size() && L.counts[ci] == 0) ci++;
+            if (ci >= L.cost_vals.size()) {
+                back();
+                continue;
+            }
+            L.cursor = ci + 1;
+            uint64_t cnt = L.counts[ci];
+            EScore sc{score_kind_of(L.kind), (uint32_t)(L.next_max_cost - L.cost_vals[ci]), (uint32_t)L.next_max_cost, -1.f};
+            q.rr_scores.push_back(sc);
+            L.universe_count -= cnt;
+            if (rule_cur == n_rules - 1 || (skip_scoring && cnt <= 1) || q.cur_offset + cnt < from) {
+                emit_bucket(q, L, (uint32_t)ci, (uint32_t)ci + 1, cnt);
+                q.rr_scores.pop_back();
+                continue;
+            }
+            // descend: the next rule iterates on this bucket with the query graph of the paths that produced it
+            Level C;
+            C.rule_idx = (int)rule_cur + 1;
+            C.kind = q.rules[rule_cur + 1];
+            if (L.kind == RK_EXACT_ATTRIBUTE)
+                C.graph = L.graph;
+            else {
+                std::vector<std::vector<const ECond *>> good;
+                for (size_t p = 0; p < L.paths.size(); p++) {
+                    if (L.path_cost_idx[p] != ci || !L.survived[p]) continue;
+                    std::vector<const ECond *> pc;
+                    for (auto c : L.paths[p].conds) pc.push_back(&L.conds[c]);
+                    good.push_back(std::move(pc));
+                }
+                C.graph = build_from_paths(good);
+            }
+            if (C.kind != RK_EXACT_ATTRIBUTE) prepare_graph_rule(q.ctx, C.kind, false, tms, C);
+            uint32_t cap = (uint32_t)std::min<uint64_t>(cnt, L.rows);
+            request_activation(q, std::move(C), L.uw, L.ub, L.out, L.rows, L.ld, (uint32_t)ci, cap);
+            return;
+        }
+        q.done = true;
+    };
+
+    // ---- phase 4: step loop
+    float ms_fill = 0, ms_eval = 0, ms_emit = 0;
+    cudaEvent_t e0 = ev0, e1 = ev1;
+    for (;;) {
+        // gather
+        std::vector<uint32_t> act_q;
+        std::vector<uint32_t> emit_q;
+        for (uint32_t i = 0; i < NQ; i++) {
+            if (qs[i]->want_activation) act_q.push_back(i);
+            if (!qs[i]->emits.empty()) emit_q.push_back(i);
+        }
+        if (act_q.empty() && emit_q.empty()) break;
+        stats.device_steps++;
+        std::vector<ActDesc> acts(act_q.size());
+        std::vector<Job> jobs;
+        std::vector<PairSet> sets;
+        std::vector<uint32_t> words;
+        std::vector<ColOp> colprog;
+        std::vector<PathRec> paths;
+        std::vector<uint16_t> condpool;
+        std::vector<TileDesc> tiles;
+        std::vector<EmitDesc> emits;
+        uint32_t res_words = 0, n_probes = 0;
+        scratch_used = 0;
+        for (size_t a = 0; a < act_q.size(); a++) {
+            QState &q = *qs[act_q[a]];
+            Level &L = q.levels.back();
+            StepOut &o = q.pend;
+            ActDesc &d = acts[a];
+            memset(&d, 0, sizeof d);
+            d.p_uw = q.p_uw;
+            d.p_ub = q.p_ub;
+            d.p_out = q.p_out;
+            d.p_rows = q.p_rows;
+            d.p_ld = q.p_ld;
+            d.p_col_lo = q.p_col;
+            d.p_col_hi = q.p_col + 1;
+            uint32_t ld = std::max(1u, q.p_cap);
+            d.ld = ld;
+            d.n_cols = std::max(1u, o.n_cols);
+            d.n_costs = o.n_costs;
+            d.n_paths = (uint32_t)o.paths.size();
+            size_t persist = (size_t)ld * 4 + 256 + (size_t)ld * 8 + 256 + (size_t)ld * 8 * (o.n_costs + 1);
+            uint8_t *pb = arena_alloc(persist);
+            size_t cbytes = (size_t)ld * 8 * d.n_cols;
+            size_t coff = (scratch_used + 255) & ~(size_t)255;
+            if (!pb || coff + cbytes > scratch_bytes)
+                return fail(B200_ERR_CAPACITY, "device arena exhausted: lower the batch size or raise B200_ARENA_MB / B200_SCRATCH_MB");
+            scratch_used = coff + cbytes;
+            d.uw = reinterpret_cast<uint32_t *>(pb);
+            d.ub = reinterpret_cast<unsigned long long *>(pb + (((size_t)ld * 4 + 255) & ~(size_t)255));
+            d.out = d.ub + (((size_t)ld + 31) & ~(size_t)31);
+            d.C = reinterpret_cast<unsigned long long *>(scratch + coff);
+            L.uw = d.uw;
+            L.ub = d.ub;
+            L.out = d.out;
+            L.ld = ld;
+            d.colprog_off = (uint32_t)colprog.size();
+            d.colprog_len = (uint32_t)o.colprog.size();
+            colprog.insert(colprog.end(), o.colprog.begin(), o.colprog.end());
+            d.path_off = (uint32_t)paths.size();
+            uint32_t cbase = (uint32_t)condpool.size();
+            for (auto pr : o.paths) {
+                pr.cond_off += cbase;
+                paths.push_back(pr);
+            }
+            condpool.insert(condpool.end(), o.condpool.begin(), o.condpool.end());
+            d.res_off = res_words;
+            L.res_off = res_words;
+            res_words += 2 + o.n_costs + d.n_paths;
+            for (auto j : o.jobs) {
+                j.act = (uint32_t)a;
+                jobs.push_back(j);
+            }
+            uint32_t wbase = (uint32_t)words.size();
+            words.insert(words.end(), o.words.begin(), o.words.end());
+            for (auto ps : o.pairsets) {
+                ps.act = (uint32_t)a;
+                ps.left_off += wbase;
+                ps.right_off += wbase;
+                ps.probe_base = n_probes;
+                n_probes += ps.n_left * ps.n_right;
+                sets.push_back(ps);
+            }
+            for (uint32_t r0 = 0; r0 < ld; r0 += 128) tiles.push_back(TileDesc{(uint32_t)a, r0});
+            stats.posting_bytes += o.posting_bytes;
+            stats.matrix_bytes += (uint64_t)ld * 8 * (d.n_cols + o.n_costs + 2);
+            q.want_activation = false;
+        }
+        for (auto qi : emit_q) {
+            QState &q = *qs[qi];
+            for (auto &e : q.emits) {
+                EmitDesc d = e.d;
+                d.dst = d_docids_out.p + (size_t)qi * std::max(1u, length) + (uint32_t)(uintptr_t)e.d.dst;
+                emits.push_back(d);
+            }
+            q.emits.clear();
+        }
+        // pack + upload
+        Blob blob;
+        size_t o_acts = blob.add(acts), o_sets = blob.add(sets), o_words = blob.add(words), o_colprog = blob.add(colprog),
+               o_paths = blob.add(paths), o_cond = blob.add(condpool), o_tiles = blob.add(tiles), o_emits = blob.add(emits);
+        size_t nbytes = blob.bytes.size() + 16;
+        if (nbytes > h_step_cap) {
+            if (h_step) cudaFreeHost(h_step);
+            h_step_cap = nbytes * 2;
+            CU(cudaMallocHost((void **)&h_step, h_step_cap), "pinned step buffer");
+        }
+        memcpy(h_step, blob.bytes.data(), blob.bytes.size());
+        CU(d_step.reserve(nbytes), "step buffer");
+        CU(cudaMemcpyAsync(d_step.p, h_step, nbytes, cudaMemcpyHostToDevice, stream), "H2D step");
+        const size_t qcap_needed = jobs.size() + ((size_t)1 << 20);
+        size_t qcap = std::max<size_t>(qcap_needed, (size_t)4 << 20);
+        CU(d_queue.reserve(qcap), "job queue");
+        qcap = d_queue.cap;
+        CU(d_qcount.reserve(4), "job counter");
+        CU(d_results.reserve(res_words + 4), "results");
+        if (res_words + 4 > h_results_cap) {
+            if (h_results) cudaFreeHost(h_results);
+            h_results_cap = (size_t)(res_words + 4) * 2;
+            CU(cudaMallocHost((void **)&h_results, h_results_cap * 4), "pinned results");
+        }
+        uint32_t n_static = (uint32_t)jobs.size();
+        if (!jobs.empty()) CU(cudaMemcpyAsync(d_queue.p, jobs.data(), jobs.size() * sizeof(Job), cudaMemcpyHostToDevice, stream), "H2D jobs");
+        CU(cudaMemcpyAsync(d_qcount.p, &n_static, 4, cudaMemcpyHostToDevice, stream), "H2D job count");
+        const ActDesc *dacts = reinterpret_cast<const ActDesc *>(d_step.p + o_acts);
+        // 1. emissions queued before this step's activations (they may read buffers the activations reuse)
+        CU(cudaEventRecord(e0, stream), "event");
+        if (!emits.empty()) {
+            size_t a = mark();
+            CU(launch_emit(stream, reinterpret_cast<const EmitDesc *>(d_step.p + o_emits), (uint32_t)emits.size()), "emit");
+            time_kernel(B200_K_EMIT, a, mark(), (uint64_t)emits.size() * 64);
+        }
+        if (!acts.empty()) {
+            CU(cudaMemsetAsync(d_results.p, 0, (size_t)(res_words + 4) * 4, stream), "zero results");
+            CU(cudaMemsetAsync(scratch, 0, scratch_used, stream), "zero condition matrix");
+            uint64_t compact_bytes = 0, eval_bytes = 0, fill_bytes = 0;
+            for (size_t a = 0; a < acts.size(); a++) {
+                compact_bytes += (uint64_t)acts[a].p_rows * 8 + (uint64_t)acts[a].ld * 12;
+                eval_bytes += (uint64_t)acts[a].ld * 8 * (acts[a].n_cols + acts[a].n_costs + 2);
+                fill_bytes += qs[act_q[a]]->pend.posting_bytes;
+            }
+            size_t t0 = mark();
+            CU(launch_compact(stream, dacts, (uint32_t)acts.size(), d_results.p), "compact");
+            size_t t1 = mark();
+            time_kernel(B200_K_COMPACT, t0, t1, compact_bytes);
+            CU(launch_pair_probe(stream, reinterpret_cast<const PairSet *>(d_step.p + o_sets), (uint32_t)sets.size(), n_probes,
+                                 reinterpret_cast<const uint32_t *>(d_step.p + o_words), dix.pair_keys, hix.pair_keys.size(), hix.pair_list_base,
+                                 dix.lists, dacts, d_results.p, d_queue.p, d_qcount.p, (uint32_t)qcap),
+               "pair probe");
+            size_t t2 = mark();
+            if (n_probes) time_kernel(B200_K_PAIR_PROBE, t1, t2, (uint64_t)n_probes * 8 * 23);
+            CU(launch_scatter(stream, (uint32_t)sm_count * 8, d_queue.p, d_qcount.p, (uint32_t)qcap, dacts, d_results.p, dix.lists, dix.pool), "scatter");
+            size_t t3 = mark();
+            time_kernel(B200_K_SCATTER, t2, t3, fill_bytes);
+            CU(launch_eval(stream, reinterpret_cast<const TileDesc *>(d_step.p + o_tiles), (uint32_t)tiles.size(), dacts, d_results.p,
+                           reinterpret_cast<const ColOp *>(d_step.p + o_colprog), reinterpret_cast<const PathRec *>(d_step.p + o_paths),
+                           reinterpret_cast<const uint16_t *>(d_step.p + o_cond)),
+               "eval paths");
+            time_kernel(B200_K_EVAL_PATHS, t3, mark(), eval_bytes);
+            CU(cudaMemcpyAsync(h_results, d_results.p, (size_t)res_words * 4, cudaMemcpyDeviceToHost, stream), "D2H results");
+            CU(cudaMemcpyAsync(h_results + res_words, d_qcount.p, 4, cudaMemcpyDeviceToHost, stream), "D2H job count");
+        }
+        CU(cudaEventRecord(e1, stream), "event");
+        CU(cudaStreamSynchronize(stream), "step sync");
+        {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            stats.device_ms += ms;
+            resolve_timers();
+        }
+        if (!acts.empty() && h_results[res_words] > qcap) return fail(B200_ERR_CAPACITY, "scatter job queue overflow");
+        // scatter results back, advance every query that got its activation
+        parallel_for(act_q.size(), NT, [&](size_t a) {
+            QState &q = *qs[act_q[a]];
+            Level &L = q.levels.back();
+            const uint32_t *res = h_results + L.res_off;
+            L.rows = res[0];
+            size_t nc = L.cost_vals.size();
+            L.counts.assign(res + 1, res + 1 + nc + 1);
+            L.survived.assign(L.paths.size(), 0);
+            for (size_t p = 0; p < L.paths.size(); p++) L.survived[p] = res[2 + nc + p] ? 1 : 0;
+            L.universe_count = 0;
+            for (auto c : L.counts) L.universe_count += c;
+            L.cursor = 0;
+            try {
+                advance(q);
+            } catch (const TooComplex &t) {
+                q.status = B200_ERR_CAPACITY;
+                q.error = t.why;
+                q.done = true;
+                q.want_activation = false;
+            }
+        });
+    }
+    (void)ms_fill;
+    (void)ms_eval;
+    (void)ms_emit;
+    // ---- outputs
+    std::vector<uint32_t> out_ids((size_t)NQ * std::max(1u, length));
+    CU(cudaMemcpyAsync(out_ids.data(), d_docids_out.p, out_ids.size() * 4, cudaMemcpyDeviceToHost, stream), "D2H docids");
+    CU(cudaStreamSynchronize(stream), "sync");
+    for (uint32_t i = 0; i < NQ; i++) {
+        QState &q = *qs[i];
+        if (r->status) r->status[i] = q.status;
+        if (q.status != 0) {
+            r->n_hits[i] = 0;
+            if (r->n_candidates) r->n_candidates[i] = 0;
+            last_error = q.error;
+            continue;
+        }
+        r->n_hits[i] = q.n_results;
+        if (r->n_candidates) r->n_candidates[i] = q.n_candidates;
+        for (uint32_t k = 0; k < q.n_results; k++) {
+            r->docids[(size_t)i * limit + k] = out_ids[(size_t)i * std::max(1u, length) + k];
+            if (r->n_scores) {
+                const auto &sc = q.scores[k];
+                size_t ns = std::min<size_t>(sc.size(), B200_MAX_SCORES);
+                r->n_scores[(size_t)i * limit + k] = (uint8_t)ns;
+                for (size_t s = 0; s < ns; s++) {
+                    size_t at = ((size_t)i * limit + k) * B200_MAX_SCORES + s;
+                    r->score_kind[at] = sc[s].kind;
+                    r->score_rank[at] = sc[s].rank;
+                    r->score_max[at] = sc[s].max_rank;
+                    r->score_sim[at] = sc[s].sim;
+                }
+            }
+        }
+    }
+    return B200_OK;
+}
+
+}  // namespace b200

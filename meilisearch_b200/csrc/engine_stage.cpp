@@ -1,0 +1,282 @@
+// Staging to HBM, term derivation (S3) and the vector store (S4).
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+
+#include "engine.h"
+#include "kernels.h"
+
+namespace b200 {
+
+#define CU(call, what)                         \
+    do {                                       \
+        cudaError_t e_ = (call);               \
+        if (e_ != cudaSuccess) return cuda_fail(e_, what); \
+    } while (0)
+
+template <class T>
+static cudaError_t upload(T **dst, const T *src, size_t n) {
+    *dst = nullptr;
+    if (n == 0) n = 1;
+    cudaError_t e = cudaMalloc((void **)dst, n * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (src) return cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice);
+    return cudaMemset(*dst, 0, n * sizeof(T));
+}
+
+Engine::~Engine() {
+    cudaSetDevice(device);
+    for (void *p : {(void *)dix.dict_bytes, (void *)dix.dict_off, (void *)dix.pool, (void *)dix.lists, (void *)dix.pair_keys, (void *)dix.base_ub,
+                    (void *)dix.emb, (void *)dix.emb_inv_norm, (void *)dix.emb_docids, (void *)arena, (void *)scratch})
+        if (p) cudaFree(p);
+    d_step.release();
+    d_results.release();
+    d_queue.release();
+    d_qcount.release();
+    d_docids_out.release();
+    d_lev_terms.release();
+    d_lev_recs.release();
+    d_lev_u32.release();
+    d_vq.release();
+    d_vdist.release();
+    d_vsel_dist.release();
+    d_vsel_ids.release();
+    d_vsel_n.release();
+    d_cand.release();
+    if (h_step) cudaFreeHost(h_step);
+    if (h_results) cudaFreeHost(h_results);
+    for (auto e : ev_pool) cudaEventDestroy(e);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+size_t Engine::mark() {
+    if (ev_used == ev_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        ev_pool.push_back(e);
+    }
+    cudaEventRecord(ev_pool[ev_used], stream);
+    return ev_used++;
+}
+void Engine::resolve_timers() {
+    for (auto &t : timed) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ev_pool[t.a], ev_pool[t.b]) == cudaSuccess) stats.kernel_ms[t.cls] += ms;
+    }
+    timed.clear();
+    ev_used = 0;
+}
+
+int Engine::stage_finish() {
+    CU(cudaSetDevice(device), "cudaSetDevice");
+    try {
+        build_host_index(raw_dict_bytes, raw_dict_off, raw_dbs, raw_docids, hix);
+    } catch (const std::exception &e) {
+        return fail(B200_ERR_INVALID, e.what());
+    }
+    Settings keep = hix.settings;
+    (void)keep;
+    // dictionary
+    std::vector<uint32_t> off32(hix.dict_off.size());
+    for (size_t i = 0; i < off32.size(); i++) off32[i] = (uint32_t)hix.dict_off[i];
+    if (off32.empty()) off32.push_back(0);
+    CU(upload(&dix.dict_bytes, hix.dict_bytes.data(), hix.dict_bytes.size()), "upload dictionary");
+    CU(upload(&dix.dict_off, off32.data(), off32.size()), "upload dictionary offsets");
+    // posting store
+    CU(upload(&dix.pool, hix.pool.data(), hix.pool.size()), "upload posting pool");
+    static_assert(sizeof(ListRef) == sizeof(DListRef), "ListRef layout");
+    CU(upload(&dix.lists, reinterpret_cast<const DListRef *>(hix.lists.data()), hix.lists.size()), "upload list table");
+    CU(upload(&dix.pair_keys, reinterpret_cast<const unsigned long long *>(hix.pair_keys.data()), hix.pair_keys.size()), "upload pair keys");
+    CU(upload(&dix.base_ub, reinterpret_cast<const unsigned long long *>(hix.base_ub.data()), hix.base_ub.size()), "upload universe");
+    stats.hbm_bytes_staged = hix.dict_bytes.size() + off32.size() * 4 + hix.pool.size() * 4 + hix.lists.size() * sizeof(ListRef) +
+                             hix.pair_keys.size() * 8 + hix.base_ub.size() * 8;
+    std::vector<uint32_t>().swap(hix.pool);
+    // release the raw staging copies
+    for (auto &db : raw_dbs) {
+        std::vector<uint8_t>().swap(db.keys);
+        std::vector<uint8_t>().swap(db.vals);
+        std::vector<uint64_t>().swap(db.koff);
+        std::vector<uint64_t>().swap(db.voff);
+    }
+    // work pools
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b), "cudaMemGetInfo");
+    auto env_mb = [](const char *name, size_t dflt) {
+        const char *v = getenv(name);
+        return v ? (size_t)atoll(v) << 20 : dflt;
+    };
+    arena_bytes = env_mb("B200_ARENA_MB", std::min<size_t>(free_b / 4, (size_t)24 << 30));
+    scratch_bytes = env_mb("B200_SCRATCH_MB", std::min<size_t>(free_b / 8, (size_t)12 << 30));
+    CU(cudaMalloc((void **)&arena, arena_bytes), "alloc arena");
+    CU(cudaMalloc((void **)&scratch, scratch_bytes), "alloc scratch");
+    staged = true;
+    return B200_OK;
+}
+
+int Engine::stage_embeddings(const float *vectors, uint64_t n, uint32_t d, const uint32_t *docids) {
+    CU(cudaSetDevice(device), "cudaSetDevice");
+    if (d == 0 || d % 8 != 0) return fail(B200_ERR_INVALID, "embedding dimension must be a positive multiple of 8");
+    for (void *p : {(void *)dix.emb, (void *)dix.emb_inv_norm, (void *)dix.emb_docids})
+        if (p) cudaFree(p);
+    dix.emb = nullptr;
+    dix.emb_inv_norm = nullptr;
+    dix.emb_docids = nullptr;
+    // fp16 rows + inverse norms computed from the fp32 input (the norm arroy stores in the item header)
+    std::vector<__half> h((size_t)n * d);
+    std::vector<float> inv(n);
+    for (uint64_t r = 0; r < n; r++) {
+        double s = 0;
+        const float *v = vectors + r * d;
+        for (uint32_t i = 0; i < d; i++) {
+            s += (double)v[i] * v[i];
+            h[r * d + i] = __float2half_rn(v[i]);
+        }
+        float nrm = (float)std::sqrt(s);
+        inv[r] = nrm > 0.f ? 1.0f / nrm : 0.f;
+    }
+    __half *dm = nullptr;
+    CU(upload(&dm, h.data(), h.size()), "upload embeddings");
+    dix.emb = dm;
+    CU(upload(&dix.emb_inv_norm, inv.data(), inv.size()), "upload norms");
+    std::vector<uint32_t> ids(n);
+    for (uint64_t r = 0; r < n; r++) ids[r] = docids ? docids[r] : (uint32_t)r;
+    CU(upload(&dix.emb_docids, ids.data(), ids.size()), "upload embedding docids");
+    dix.emb_n = n;
+    dix.emb_d = d;
+    stats.hbm_bytes_staged += h.size() * 2 + inv.size() * 4 + ids.size() * 4;
+    return B200_OK;
+}
+
+int Engine::derive_batch(uint32_t n, const char *words, const uint32_t *off, const uint8_t *max_typo, const uint8_t *is_prefix,
+                         uint32_t *one_out, uint32_t *n_one, uint32_t *two_out, uint32_t *n_two) {
+    if (!staged) return fail(B200_ERR_STATE, "derive before b200_stage_finish");
+    CU(cudaSetDevice(device), "cudaSetDevice");
+    if (n == 0) return B200_OK;
+    std::vector<LevTerm> terms(n);
+    for (uint32_t i = 0; i < n; i++) {
+        uint32_t len = off[i + 1] - off[i];
+        if (len == 0 || len > LEV_MAX_Q) return fail(B200_ERR_UNSUPPORTED, "derive: word longer than 64 bytes (or empty)");
+        LevTerm &t = terms[i];
+        memset(&t, 0, sizeof t);
+        memcpy(t.q, words + off[i], len);
+        t.len = (uint8_t)len;
+        t.k_same = max_typo[i] >= 2 ? 2 : 1;
+        t.k_diff = max_typo[i] >= 2 ? 1 : -1;
+        t.prefix = is_prefix[i] ? 1 : 0;
+        if (max_typo[i] == 0) t.k_same = -1;
+    }
+    CU(d_lev_terms.reserve(n), "alloc lev terms");
+    CU(d_lev_recs.reserve((size_t)n * LEV_REC_CAP), "alloc lev records");
+    size_t per = 1 + 150 + 1 + 50 + 1 + 1;
+    CU(d_lev_u32.reserve((size_t)n * per), "alloc lev outputs");
+    uint32_t *rec_count = d_lev_u32.p, *d_one = rec_count + n, *d_n_one = d_one + (size_t)n * 150, *d_two = d_n_one + n,
+             *d_n_two = d_two + (size_t)n * 50;
+    int32_t *d_status = reinterpret_cast<int32_t *>(d_n_two + n);
+    CU(cudaMemcpyAsync(d_lev_terms.p, terms.data(), n * sizeof(LevTerm), cudaMemcpyHostToDevice, stream), "H2D lev terms");
+    size_t m0 = mark();
+    CU(launch_lev(stream, dix.dict_bytes, dix.dict_off, (uint32_t)hix.n_words, d_lev_terms.p, n, d_lev_recs.p, rec_count, d_one, d_n_one, d_two,
+                  d_n_two, d_status),
+       "lev kernels");
+    size_t m1 = mark();
+    uint64_t lev_bytes = (uint64_t)((n + LEV_TERMS_PER_CTA - 1) / LEV_TERMS_PER_CTA) * (hix.dict_bytes.size() + 4 * hix.n_words);
+    time_kernel(B200_K_LEV, m0, m1, lev_bytes);
+    stats.kernel_launches += 1;
+    stats.dictionary_bytes += lev_bytes;
+    std::vector<int32_t> status(n);
+    CU(cudaMemcpyAsync(one_out, d_one, (size_t)n * 150 * 4, cudaMemcpyDeviceToHost, stream), "D2H");
+    CU(cudaMemcpyAsync(n_one, d_n_one, (size_t)n * 4, cudaMemcpyDeviceToHost, stream), "D2H");
+    CU(cudaMemcpyAsync(two_out, d_two, (size_t)n * 50 * 4, cudaMemcpyDeviceToHost, stream), "D2H");
+    CU(cudaMemcpyAsync(n_two, d_n_two, (size_t)n * 4, cudaMemcpyDeviceToHost, stream), "D2H");
+    CU(cudaMemcpyAsync(status.data(), d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, stream), "D2H");
+    CU(cudaStreamSynchronize(stream), "sync");
+    resolve_timers();
+    for (uint32_t i = 0; i < n; i++)
+        if (status[i] != 0) return fail(B200_ERR_CAPACITY, "derive: match-record capacity exceeded for a term");
+    return B200_OK;
+}
+
+int Engine::nns_batch(const float *queries, uint32_t n_q, uint32_t d, uint32_t limit, const uint64_t *cand, uint64_t n_cand_words,
+                      uint32_t *ids_out, float *dist_out, uint32_t *n_out) {
+    CU(cudaSetDevice(device), "cudaSetDevice");
+    if (!dix.emb) return fail(B200_ERR_STATE, "nns before b200_stage_embeddings");
+    if (d != dix.emb_d) return fail(B200_ERR_INVALID, "nns: query dimension differs from the staged embeddings");
+    if (n_q == 0) return B200_OK;
+    const uint64_t N = dix.emb_n;
+    const uint32_t tie_cap = 1024;
+    const uint32_t QT = 8;  // queries per scan pass
+    uint32_t chunk = std::min<uint32_t>(n_q, 64);  // queries whose distance rows are resident at once
+    CU(d_vq.reserve((size_t)chunk * d + chunk), "alloc queries");
+    CU(d_vdist.reserve((size_t)chunk * N), "alloc distances");
+    CU(d_vsel_dist.reserve((size_t)chunk * (limit + tie_cap)), "alloc selection");
+    CU(d_vsel_ids.reserve((size_t)chunk * (limit + tie_cap)), "alloc selection");
+    CU(d_vsel_n.reserve((size_t)chunk * 2), "alloc selection");
+    const unsigned long long *d_c = nullptr;
+    if (cand) {
+        CU(d_cand.reserve(n_cand_words), "alloc candidates");
+        CU(cudaMemcpyAsync(d_cand.p, cand, n_cand_words * 8, cudaMemcpyHostToDevice, stream), "H2D candidates");
+        d_c = d_cand.p;
+    }
+    std::vector<float> qinv(chunk);
+    std::vector<float> sel_d((size_t)chunk * (limit + tie_cap));
+    std::vector<uint32_t> sel_i((size_t)chunk * (limit + tie_cap)), sel_n((size_t)chunk * 2);
+    float total_ms = 0;
+    for (uint32_t q0 = 0; q0 < n_q; q0 += chunk) {
+        uint32_t nq = std::min(chunk, n_q - q0);
+        for (uint32_t q = 0; q < nq; q++) {
+            double s = 0;
+            const float *v = queries + (size_t)(q0 + q) * d;
+            for (uint32_t i = 0; i < d; i++) s += (double)v[i] * v[i];
+            float nrm = (float)std::sqrt(s);
+            qinv[q] = nrm > 0.f ? 1.0f / nrm : 0.f;
+        }
+        float *d_qinv = d_vq.p + (size_t)chunk * d;
+        CU(cudaMemcpyAsync(d_vq.p, queries + (size_t)q0 * d, (size_t)nq * d * 4, cudaMemcpyHostToDevice, stream), "H2D queries");
+        CU(cudaMemcpyAsync(d_qinv, qinv.data(), nq * 4, cudaMemcpyHostToDevice, stream), "H2D query norms");
+        for (uint32_t t = 0; t < nq;) {
+            uint32_t left = nq - t;
+            int qt = left >= 8 ? 8 : (left >= 4 ? 4 : (left >= 2 ? 2 : 1));
+            (void)QT;
+            size_t m0 = mark();
+            CU(launch_vec_dist(stream, sm_count * 6, qt, dix.emb, dix.emb_inv_norm, dix.emb_docids, N, d, d_vq.p + (size_t)t * d, d_qinv + t, d_c,
+                               n_cand_words, d_vdist.p + (size_t)t * N),
+               "vec_dist");
+            size_t m1 = mark();
+            uint64_t vb = N * d * 2 + N * 4 + (d_c ? N / 8 : 0) + (uint64_t)qt * d * 4 + (uint64_t)qt * N * 4;
+            time_kernel(B200_K_VEC_DIST, m0, m1, vb);
+            stats.vector_bytes += vb;
+            t += qt;
+        }
+        size_t k0 = mark();
+        CU(launch_topk(stream, nq, d_vdist.p, dix.emb_docids, N, limit, tie_cap, d_vsel_dist.p, d_vsel_ids.p, d_vsel_n.p), "topk");
+        size_t k1 = mark();
+        time_kernel(B200_K_TOPK, k0, k1, (uint64_t)nq * N * 4 * 4);
+        CU(cudaMemcpyAsync(sel_d.data(), d_vsel_dist.p, (size_t)nq * (limit + tie_cap) * 4, cudaMemcpyDeviceToHost, stream), "D2H");
+        CU(cudaMemcpyAsync(sel_i.data(), d_vsel_ids.p, (size_t)nq * (limit + tie_cap) * 4, cudaMemcpyDeviceToHost, stream), "D2H");
+        CU(cudaMemcpyAsync(sel_n.data(), d_vsel_n.p, (size_t)nq * 2 * 4, cudaMemcpyDeviceToHost, stream), "D2H");
+        CU(cudaStreamSynchronize(stream), "sync");
+        resolve_timers();
+        for (uint32_t q = 0; q < nq; q++) {
+            std::vector<std::pair<float, uint32_t>> c;
+            const float *sd = sel_d.data() + (size_t)q * (limit + tie_cap);
+            const uint32_t *si = sel_i.data() + (size_t)q * (limit + tie_cap);
+            for (uint32_t i = 0; i < sel_n[2 * q]; i++) c.push_back({sd[i], si[i]});
+            for (uint32_t i = 0; i < sel_n[2 * q + 1]; i++) c.push_back({sd[limit + i], si[limit + i]});
+            std::sort(c.begin(), c.end());
+            uint32_t n = (uint32_t)std::min<size_t>(c.size(), limit);
+            n_out[q0 + q] = n;
+            for (uint32_t i = 0; i < n; i++) {
+                ids_out[(size_t)(q0 + q) * limit + i] = c[i].second;
+                dist_out[(size_t)(q0 + q) * limit + i] = c[i].first;
+            }
+        }
+    }
+    (void)total_ms;
+    return B200_OK;
+}
+
+}  // namespace b200

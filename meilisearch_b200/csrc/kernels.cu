@@ -1,0 +1,740 @@
+// CUDA kernels for sm_100a.  HBM/L2-bound integer work: 128-bit coalesced loads where rows are streamed,
+// warp shuffles/ballots for reductions and ordered compaction, no tensor cores.
+//
+//   lev_match_kernel / lev_finalize_kernel   term derivation: Levenshtein(<=2, transposition) x dictionary
+//   act_compact_kernel                       child universe = non-zero words of a parent bucket
+//   pair_probe_kernel                        (prox,w1,w2) directory probes -> scatter jobs
+//   scatter_kernel                           posting lists -> condition bit-matrix columns
+//   eval_paths_kernel                        column program + first-match path evaluation -> buckets
+//   emit_kernel                              bucket -> first-k docids, ascending
+//   vec_dist_kernel / topk_*                 cosine distance scan + exact top-k
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "device_types.h"
+#include "kernels.h"
+
+namespace b200 {
+
+// ======================================================================================== lev
+// Banded restricted Damerau-Levenshtein: returns min(distance, k+1).  prefix: min over prefixes of w.
+__device__ __forceinline__ int banded_osa(const uint8_t *q, int m, const uint8_t *w, int n, int k, bool prefix) {
+    const int INF = k + 1;
+    // column j holds D[i][j] for i = j + b - k, b in [0, 2k]
+    int c2[5], c1[5], c0[5];
+#pragma unroll
+    for (int b = 0; b < 5; b++) {
+        int i = b - k;
+        c1[b] = (b <= 2 * k && i >= 0 && i <= m) ? (i < INF ? i : INF) : INF;
+        c2[b] = INF;
+    }
+    int best = INF;
+    if (prefix && m <= k) best = m;  // empty prefix (never happens for words long enough to have typos)
+    int jmax = n;
+    if (jmax > m + k) jmax = m + k;
+    if (!prefix && (n > m + k || n < m - k)) return INF;
+    if (prefix && n < m - k) return INF;
+    for (int j = 1; j <= jmax; j++) {
+        uint8_t wc = w[j - 1];
+        uint8_t wp = j > 1 ? w[j - 2] : 0;
+        int rowmin = INF;
+#pragma unroll
+        for (int b = 0; b < 5; b++) {
+            int v = INF;
+            if (b <= 2 * k) {
+                int i = j + b - k;
+                if (i >= 0 && i <= m) {
+                    if (i == 0)
+                        v = j;
+                    else {
+                        int del = (b > 0) ? c0[b - 1] + 1 : INF;              // D[i-1][j] + 1
+                        int ins = (b < 2 * k) ? c1[b + 1] + 1 : INF;          // D[i][j-1] + 1
+                        int sub = c1[b] + (q[i - 1] != wc ? 1 : 0);           // D[i-1][j-1] + cost
+                        v = min(del, min(ins, sub));
+                        if (i > 1 && j > 1 && q[i - 1] == wp && q[i - 2] == wc) v = min(v, c2[b] + 1);  // D[i-2][j-2] + 1
+                    }
+                    if (v > INF) v = INF;
+                }
+            }
+            c0[b] = v;
+            rowmin = min(rowmin, v);
+        }
+        if (prefix) {
+            int b = m - j + k;
+            if (b >= 0 && b <= 2 * k) best = min(best, c0[b]);
+        }
+#pragma unroll
+        for (int b = 0; b < 5; b++) {
+            c2[b] = c1[b];
+            c1[b] = c0[b];
+        }
+        if (rowmin >= INF && !prefix) {
+            // both this and (via c2) an earlier column may still matter for a transposition; stop only when two columns are dead
+            int m2 = INF;
+#pragma unroll
+            for (int b = 0; b < 5; b++) m2 = min(m2, c2[b]);
+            if (m2 >= INF) return INF;
+        }
+    }
+    if (prefix) return best;
+    int b = m - n + k;
+    return (b >= 0 && b <= 2 * k) ? c1[b] : INF;
+}
+
+// grid.x: 256-word tiles of the dictionary; grid.y: chunks of LEV_TERMS_PER_CTA terms.
+__global__ void __launch_bounds__(256) lev_match_kernel(const uint8_t *__restrict__ dict_bytes, const uint32_t *__restrict__ dict_off,
+                                                        uint32_t n_words, const LevTerm *__restrict__ terms, uint32_t n_terms,
+                                                        LevRec *__restrict__ recs, uint32_t *__restrict__ rec_count) {
+    __shared__ LevTerm sterms[LEV_TERMS_PER_CTA];
+    __shared__ uint8_t sbytes[8192];
+    uint32_t t0 = blockIdx.y * LEV_TERMS_PER_CTA;
+    uint32_t nt = min((uint32_t)LEV_TERMS_PER_CTA, n_terms - t0);
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(terms + t0);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(sterms);
+        for (uint32_t i = threadIdx.x; i < nt * sizeof(LevTerm) / 4; i += blockDim.x) dst[i] = src[i];
+    }
+    uint32_t w0 = blockIdx.x * 256;
+    uint32_t wn = min(256u, n_words - w0);
+    uint32_t byte0 = dict_off[w0], byte1 = dict_off[w0 + wn];
+    bool in_smem = (byte1 - byte0) <= sizeof(sbytes);
+    if (in_smem)
+        for (uint32_t i = threadIdx.x; i < byte1 - byte0; i += blockDim.x) sbytes[i] = dict_bytes[byte0 + i];
+    __syncthreads();
+    uint32_t wid = w0 + threadIdx.x;
+    bool valid = threadIdx.x < wn;
+    uint32_t off = valid ? dict_off[wid] : byte0;
+    int n = valid ? (int)(dict_off[wid + 1] - off) : 0;
+    const uint8_t *w = in_smem ? (sbytes + (off - byte0)) : (dict_bytes + off);
+    uint8_t w0c = n > 0 ? w[0] : 0, w1c = n > 1 ? w[1] : 0;
+    uint32_t lane = threadIdx.x & 31;
+    for (uint32_t t = 0; t < nt; t++) {
+        const LevTerm &T = sterms[t];
+        int code = 0;
+        if (valid && n > 0) {
+            int m = T.len;
+            bool sf = (T.q[0] == w0c);
+            int k = sf ? T.k_same : T.k_diff;
+            if (k >= 0) {
+                bool len_ok = T.prefix ? (n >= m - k) : (n >= m - k && n <= m + k);
+                // different first char at distance <= 1: the single edit sits on the first position
+                if (len_ok && !sf && m >= 2) len_ok = (w1c == T.q[1]) || (w1c == T.q[0]) || (w0c == T.q[1]);
+                if (len_ok) {
+                    int d = banded_osa(T.q, m, w, n, k, T.prefix != 0);
+                    if (d <= k && d > 0) code = sf ? d : 3;
+                }
+            }
+        }
+        unsigned hit = __ballot_sync(0xffffffffu, code != 0);
+        if (hit) {
+            // assemble the 2-bit codes of the 32 lanes
+            unsigned long long mine = (unsigned long long)code << (2 * lane);
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) mine |= __shfl_xor_sync(0xffffffffu, mine, s);
+            if (lane == 0) {
+                uint32_t slot = atomicAdd(&rec_count[t0 + t], 1u);
+                if (slot < LEV_REC_CAP) {
+                    LevRec r;
+                    r.base = w0 + (threadIdx.x & ~31u);
+                    r.pad = 0;
+                    r.codes = mine;
+                    recs[(size_t)(t0 + t) * LEV_REC_CAP + slot] = r;
+                }
+            }
+        }
+    }
+}
+
+// One thread per term: order the records by word id and replay the reference's capped, order-dependent
+// classification (compute_derivations.rs:89-105, 128-166).
+__global__ void lev_finalize_kernel(LevRec *__restrict__ recs, const uint32_t *__restrict__ rec_count, const LevTerm *__restrict__ terms,
+                                    uint32_t n_terms, uint32_t *__restrict__ one_out, uint32_t *__restrict__ n_one,
+                                    uint32_t *__restrict__ two_out, uint32_t *__restrict__ n_two, int32_t *__restrict__ status) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_terms) return;
+    uint32_t cnt = rec_count[t];
+    if (cnt > LEV_REC_CAP) {
+        status[t] = -5;
+        cnt = LEV_REC_CAP;
+    } else
+        status[t] = 0;
+    LevRec *r = recs + (size_t)t * LEV_REC_CAP;
+    for (uint32_t i = 1; i < cnt; i++) {  // insertion sort by base
+        LevRec x = r[i];
+        uint32_t j = i;
+        while (j > 0 && r[j - 1].base > x.base) {
+            r[j] = r[j - 1];
+            j--;
+        }
+        r[j] = x;
+    }
+    bool two_budget = terms[t].k_same >= 2;
+    uint32_t c1 = 0, c2 = 0;
+    uint32_t *o1 = one_out + (size_t)t * 150, *o2 = two_out + (size_t)t * 50;
+    for (uint32_t i = 0; i < cnt; i++) {
+        unsigned long long codes = r[i].codes;
+        for (int l = 0; l < 32 && codes; l++, codes >>= 2) {
+            int code = (int)(codes & 3);
+            if (!code) continue;
+            uint32_t wid = r[i].base + l;
+            if (!two_budget) {  // find_one_typo_derivations: same first char, d == 1, cap 150
+                if (code == 1 && c1 < 150) o1[c1++] = wid;
+                continue;
+            }
+            bool fin1 = c1 >= 150, fin2 = c2 >= 50;
+            if (fin1 && fin2) break;
+            if (code == 3 && !fin2) {
+                o2[c2++] = wid;
+                continue;
+            }
+            int d = (code == 2) ? 2 : 1;  // second_dfa.distance: 1 for a different first char
+            if (d == 1) {
+                if (!fin1) o1[c1++] = wid;
+            } else if (!fin2)
+                o2[c2++] = wid;
+        }
+        if (c1 >= 150 && (c2 >= 50 || !two_budget)) break;
+    }
+    n_one[t] = c1;
+    n_two[t] = c2;
+}
+
+// ======================================================================================== activations
+__device__ __forceinline__ int find_row(const uint32_t *uw, uint32_t rows, uint32_t w) {
+    uint32_t lo = 0, hi = rows;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (uw[mid] < w)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return (lo < rows && uw[lo] == w) ? (int)lo : -1;
+}
+
+// one CTA per activation: ordered compaction of the parent's non-zero bucket words
+__global__ void __launch_bounds__(256) act_compact_kernel(const ActDesc *__restrict__ acts, uint32_t *__restrict__ results) {
+    const ActDesc a = acts[blockIdx.x];
+    __shared__ uint32_t warp_sums[8];
+    __shared__ uint32_t base;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    uint32_t lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    for (uint32_t j0 = 0; j0 < a.p_rows; j0 += 256) {
+        uint32_t j = j0 + threadIdx.x;
+        unsigned long long v = 0;
+        if (j < a.p_rows) {
+            if (a.p_out) {
+                for (uint32_t c = a.p_col_lo; c < a.p_col_hi; c++) v |= a.p_out[(size_t)c * a.p_ld + j];
+            } else
+                v = a.p_ub[j];
+        }
+        unsigned m = __ballot_sync(0xffffffffu, v != 0);
+        uint32_t wcount = __popc(m), wpre = __popc(m & ((1u << lane) - 1));
+        if (lane == 0) warp_sums[wrp] = wcount;
+        __syncthreads();
+        uint32_t before = base;
+        for (uint32_t k = 0; k < wrp; k++) before += warp_sums[k];
+        if (v != 0) {
+            uint32_t at = before + wpre;
+            if (at < a.ld) {
+                a.uw[at] = a.p_uw ? a.p_uw[j] : j;
+                a.ub[at] = v;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tot = 0;
+            for (int k = 0; k < 8; k++) tot += warp_sums[k];
+            base += tot;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) results[a.res_off] = min(base, a.ld);
+}
+
+__device__ __forceinline__ int64_t pair_lower_bound(const unsigned long long *keys, uint64_t n, unsigned long long k) {
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (keys[mid] < k)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return (int64_t)lo;
+}
+
+__device__ __forceinline__ void push_list_jobs(Job *queue, uint32_t *qcount, uint32_t qcap, uint32_t act, uint32_t col, uint32_t list,
+                                               const DListRef &lr, uint32_t rows_hint) {
+    uint32_t units = lr.dense ? rows_hint : lr.card;
+    uint32_t nchunks = (units + JOB_CHUNK - 1) / JOB_CHUNK;
+    if (nchunks == 0) return;
+    uint32_t at = atomicAdd(qcount, nchunks);
+    for (uint32_t c = 0; c < nchunks; c++)
+        if (at + c < qcap) queue[at + c] = Job{act, col, list, c};
+}
+
+// one thread per probe: (pairset, l, r); each probe may look up the forward and the backward key
+__global__ void __launch_bounds__(256) pair_probe_kernel(const PairSet *__restrict__ sets, uint32_t n_sets, uint32_t n_probes,
+                                                         const uint32_t *__restrict__ wordpool, const unsigned long long *__restrict__ pair_keys,
+                                                         uint64_t n_pairs, uint32_t pair_list_base, const DListRef *__restrict__ lists,
+                                                         const ActDesc *__restrict__ acts, const uint32_t *__restrict__ results,
+                                                         Job *__restrict__ queue, uint32_t *__restrict__ qcount, uint32_t qcap) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_probes) return;
+    // find the set: last s with probe_base <= p
+    uint32_t lo = 0, hi = n_sets;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (sets[mid].probe_base <= p)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    const PairSet s = sets[lo];
+    uint32_t idx = p - s.probe_base;
+    uint32_t rows = results[acts[s.act].res_off];
+    if (rows == 0) return;
+    uint32_t li = idx / s.n_right, ri = idx % s.n_right;
+    uint32_t w1 = wordpool[s.left_off + li];
+    if (s.right_is_range) {
+        uint32_t rlo = wordpool[s.right_off + 2 * ri], rhi = wordpool[s.right_off + 2 * ri + 1];
+        if (s.fwd_prox) {
+            unsigned long long k0 = ((unsigned long long)s.fwd_prox << 42) | ((unsigned long long)w1 << 21) | rlo;
+            unsigned long long k1 = ((unsigned long long)s.fwd_prox << 42) | ((unsigned long long)w1 << 21) | rhi;
+            int64_t a = pair_lower_bound(pair_keys, n_pairs, k0), b = pair_lower_bound(pair_keys, n_pairs, k1);
+            for (int64_t i = a; i < b; i++) {
+                uint32_t list = pair_list_base + (uint32_t)i;
+                push_list_jobs(queue, qcount, qcap, s.act, s.col, list, lists[list], rows);
+            }
+        }
+        return;
+    }
+    uint32_t w2 = wordpool[s.right_off + ri];
+    if (s.fwd_prox) {
+        unsigned long long k = ((unsigned long long)s.fwd_prox << 42) | ((unsigned long long)w1 << 21) | w2;
+        int64_t i = pair_lower_bound(pair_keys, n_pairs, k);
+        if ((uint64_t)i < n_pairs && pair_keys[i] == k) {
+            uint32_t list = pair_list_base + (uint32_t)i;
+            push_list_jobs(queue, qcount, qcap, s.act, s.col, list, lists[list], rows);
+        }
+    }
+    if (s.bwd_prox) {
+        unsigned long long k = ((unsigned long long)s.bwd_prox << 42) | ((unsigned long long)w2 << 21) | w1;
+        int64_t i = pair_lower_bound(pair_keys, n_pairs, k);
+        if ((uint64_t)i < n_pairs && pair_keys[i] == k) {
+            uint32_t list = pair_list_base + (uint32_t)i;
+            push_list_jobs(queue, qcount, qcap, s.act, s.col, list, lists[list], rows);
+        }
+    }
+}
+
+// one warp per job
+__global__ void __launch_bounds__(256) scatter_kernel(const Job *__restrict__ queue, const uint32_t *__restrict__ qcount, uint32_t qcap,
+                                                      const ActDesc *__restrict__ acts, const uint32_t *__restrict__ results,
+                                                      const DListRef *__restrict__ lists, const uint32_t *__restrict__ pool) {
+    uint32_t n_jobs = min(*qcount, qcap);
+    uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
+    uint32_t lane = threadIdx.x & 31;
+    for (uint32_t jb = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; jb < n_jobs; jb += warps_total) {
+        const Job job = queue[jb];
+        const ActDesc &a = acts[job.act];
+        uint32_t rows = results[a.res_off];
+        if (rows == 0) continue;
+        const DListRef lr = lists[job.list];
+        unsigned long long *col = a.C + (size_t)job.col * a.ld;
+        if (lr.dense) {
+            const unsigned long long *words = reinterpret_cast<const unsigned long long *>(pool + lr.off);
+            uint32_t r0 = job.chunk * JOB_CHUNK, r1 = min(rows, r0 + JOB_CHUNK);
+            for (uint32_t j = r0 + lane; j < r1; j += 32) {
+                unsigned long long v = words[a.uw[j]] & a.ub[j];
+                if (v) atomicOr(&col[j], v);
+            }
+            continue;
+        }
+        const uint32_t *ids = pool + lr.off;
+        if ((unsigned long long)rows * 16ull < lr.card) {
+            // universe much smaller than the list: walk the rows and binary-search the list (chunk 0 does it all)
+            if (job.chunk != 0) continue;
+            for (uint32_t j = lane; j < rows; j += 32) {
+                uint32_t w = a.uw[j];
+                uint32_t lo = 0, hi = lr.card, key = w << 6;
+                while (lo < hi) {
+                    uint32_t mid = (lo + hi) >> 1;
+                    if (ids[mid] < key)
+                        lo = mid + 1;
+                    else
+                        hi = mid;
+                }
+                unsigned long long v = 0;
+                while (lo < lr.card && (ids[lo] >> 6) == w) {
+                    v |= 1ull << (ids[lo] & 63);
+                    lo++;
+                }
+                v &= a.ub[j];
+                if (v) atomicOr(&col[j], v);
+            }
+            continue;
+        }
+        uint32_t e0 = job.chunk * JOB_CHUNK, e1 = min(lr.card, e0 + JOB_CHUNK);
+        for (uint32_t e = e0 + lane; e < e1; e += 32) {
+            uint32_t d = ids[e];
+            int j = find_row(a.uw, rows, d >> 6);
+            if (j >= 0) {
+                unsigned long long bit = 1ull << (d & 63);
+                if (a.ub[j] & bit) atomicOr(&col[j], bit);
+            }
+        }
+    }
+}
+
+// thread per row: column program, then first-match evaluation of the cost-ordered path table
+__global__ void __launch_bounds__(128) eval_paths_kernel(const TileDesc *__restrict__ tiles, const ActDesc *__restrict__ acts,
+                                                         uint32_t *__restrict__ results, const ColOp *__restrict__ colprog,
+                                                         const PathRec *__restrict__ paths, const uint16_t *__restrict__ condpool) {
+    const TileDesc tile = tiles[blockIdx.x];
+    const ActDesc &a = acts[tile.act];
+    __shared__ uint32_t counts[MAX_COSTS + 1];
+    uint32_t rows = results[a.res_off];
+    if (tile.row_begin >= rows) return;
+    for (uint32_t i = threadIdx.x; i <= a.n_costs; i += blockDim.x) counts[i] = 0;
+    __syncthreads();
+    uint32_t j = tile.row_begin + threadIdx.x;
+    if (j < rows) {
+        const size_t ld = a.ld;
+        unsigned long long *C = a.C;
+        for (uint32_t i = 0; i < a.colprog_len; i++) {
+            const ColOp op = colprog[a.colprog_off + i];
+            unsigned long long x = C[(size_t)op.a * ld + j], r;
+            if (op.op == 3)
+                r = x;
+            else {
+                unsigned long long y = C[(size_t)op.b * ld + j];
+                r = op.op == 0 ? (x & y) : (op.op == 1 ? (x | y) : (x & ~y));
+            }
+            C[(size_t)op.dst * ld + j] = r;
+        }
+        unsigned long long u = a.ub[j];
+        unsigned long long taken = 0;
+        for (uint32_t c = 0; c <= a.n_costs; c++) a.out[(size_t)c * ld + j] = 0;
+        unsigned long long stack[MAX_PATH_LEN];
+        uint32_t dead = 0xffffffffu;  // paths sharing >= dead conditions with the failed prefix are skipped
+        for (uint32_t p = 0; p < a.n_paths; p++) {
+            const PathRec pr = paths[a.path_off + p];
+            uint32_t l = pr.lcp;
+            if (l >= dead) continue;
+            dead = 0xffffffffu;
+            unsigned long long m = l == 0 ? u : stack[l - 1];
+            for (uint32_t d = l; d < pr.len; d++) {
+                m &= C[(size_t)condpool[pr.cond_off + d] * ld + j];
+                stack[d] = m;
+                if (m == 0) {
+                    dead = d + 1;
+                    break;
+                }
+            }
+            if (m == 0) {
+                if (pr.len == 0) dead = 0xffffffffu;
+                continue;
+            }
+            unsigned long long matched = m & ~taken;
+            if (matched) {
+                taken |= matched;
+                a.out[(size_t)pr.cost_idx * ld + j] |= matched;
+                atomicAdd(&counts[pr.cost_idx], (uint32_t)__popcll(matched));
+                results[a.res_off + 2 + a.n_costs + p] = 1;  // benign race: all writers store 1
+            }
+            if (taken == u) break;
+        }
+        unsigned long long rest = u & ~taken;
+        if (rest) {
+            a.out[(size_t)a.n_costs * ld + j] = rest;
+            atomicAdd(&counts[a.n_costs], (uint32_t)__popcll(rest));
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i <= a.n_costs; i += blockDim.x)
+        if (counts[i]) atomicAdd(&results[a.res_off + 1 + i], counts[i]);
+}
+
+// one warp per emission: ascending docids of OR(out[col_lo..col_hi)), skipping `skip`, taking `take`
+__global__ void __launch_bounds__(128) emit_kernel(const EmitDesc *__restrict__ emits, uint32_t n_emits) {
+    uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (e >= n_emits) return;
+    const EmitDesc d = emits[e];
+    uint32_t lane = threadIdx.x & 31;
+    uint32_t seen = 0, written = 0;
+    for (uint32_t j0 = 0; j0 < d.rows && written < d.take; j0 += 32) {
+        uint32_t j = j0 + lane;
+        unsigned long long v = 0;
+        if (j < d.rows) {
+            if (d.out) {
+                for (uint32_t c = d.col_lo; c < d.col_hi; c++) v |= d.out[(size_t)c * d.ld + j];
+            } else
+                v = d.ub[j];
+        }
+        uint32_t pc = (uint32_t)__popcll(v);
+        uint32_t pre = pc;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, pre, s);
+            if (lane >= (uint32_t)s) pre += t;
+        }
+        uint32_t total = __shfl_sync(0xffffffffu, pre, 31);
+        uint32_t first = seen + pre - pc;  // rank of this lane's first doc within the bucket
+        if (v) {
+            uint32_t base = d.uw ? d.uw[j] : j;
+            uint32_t rk = first;
+            while (v) {
+                uint32_t bit = (uint32_t)__ffsll((long long)v) - 1;
+                v &= v - 1;
+                if (rk >= d.skip) {
+                    uint32_t o = rk - d.skip;
+                    if (o < d.take) d.dst[o] = base * 64 + bit;
+                }
+                rk++;
+            }
+        }
+        seen += total;
+        written = seen > d.skip ? seen - d.skip : 0;
+    }
+}
+
+// ======================================================================================== vector stage
+// distance = (1 - cos)/2, cos = q.v / (|q||v|): arroy/hannoy `Cosine`.  One warp per row,
+// 3 x 128-bit loads per lane per 768-d fp16 row; QT query vectors are held in shared memory as fp32.
+template <int QT>
+__global__ void __launch_bounds__(256) vec_dist_kernel(const __half *__restrict__ mat, const float *__restrict__ inv_norm,
+                                                       const uint32_t *__restrict__ docids, uint64_t n_rows, uint32_t d,
+                                                       const float *__restrict__ queries /* QT x d */, const float *__restrict__ q_inv_norm,
+                                                       const unsigned long long *__restrict__ cand, uint64_t n_cand_words,
+                                                       float *__restrict__ dist /* QT x n_rows */) {
+    extern __shared__ float sq[];  // QT * d
+    const uint32_t vpr = d / 8;  // 128-bit vectors per row
+    for (uint32_t i = threadIdx.x; i < QT * d; i += blockDim.x) {
+        uint32_t q = i / d, e = i % d;
+        sq[q * d + (e & 7) * vpr + (e >> 3)] = queries[i];  // [q][k][v]: lanes read consecutive banks
+    }
+    __syncthreads();
+    uint32_t lane = threadIdx.x & 31;
+    uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    uint32_t vec_per_row = d / 8;  // uint4 = 8 halfs
+    for (uint64_t r = warp; r < n_rows; r += n_warps) {
+        bool ok = true;
+        if (cand) {
+            uint32_t doc = docids[r];
+            ok = (doc >> 6) < n_cand_words && ((cand[doc >> 6] >> (doc & 63)) & 1);
+        }
+        if (!ok) {
+            if (lane < QT) dist[(uint64_t)lane * n_rows + r] = 3.0f;  // > any distance: never selected
+            continue;
+        }
+        const uint4 *row = reinterpret_cast<const uint4 *>(mat + r * d);
+        float acc[QT];
+#pragma unroll
+        for (int q = 0; q < QT; q++) acc[q] = 0.f;
+#pragma unroll 3
+        for (uint32_t v = lane; v < vec_per_row; v += 32) {
+            uint4 x = __ldg(row + v);
+            const __half2 *h = reinterpret_cast<const __half2 *>(&x);
+            float f[8];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                float2 t = __half22float2(h[k]);
+                f[2 * k] = t.x;
+                f[2 * k + 1] = t.y;
+            }
+#pragma unroll
+            for (int q = 0; q < QT; q++) {
+                const float *qq = sq + q * d + v;
+#pragma unroll
+                for (int k = 0; k < 8; k++) acc[q] = fmaf(f[k], qq[k * vpr], acc[q]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < QT; q++) {
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], s);
+        }
+        if (lane == 0) {
+            float vn = inv_norm[r];
+#pragma unroll
+            for (int q = 0; q < QT; q++) {
+                float dd = 0.f;
+                float pn = vn * q_inv_norm[q];
+                if (pn > 0.f && isfinite(pn)) {
+                    float cs = acc[q] * pn;
+                    cs = fminf(1.f, fmaxf(-1.f, cs));
+                    dd = (1.f - cs) * 0.5f;
+                }
+                dist[(uint64_t)q * n_rows + r] = dd;
+            }
+        }
+    }
+}
+
+// exact top-k by two-level radix select on the (non-negative) float bit patterns; one CTA per query
+__global__ void __launch_bounds__(1024) topk_select_kernel(const float *__restrict__ dist, const uint32_t *__restrict__ docids,
+                                                           uint64_t n_rows, uint32_t k, uint32_t tie_cap, float *__restrict__ out_dist,
+                                                           uint32_t *__restrict__ out_ids, uint32_t *__restrict__ out_n /* per query */) {
+    __shared__ uint32_t hist[4096];
+    __shared__ uint32_t s_prefix, s_remaining, s_count_lt, s_count_eq;
+    const float *dq = dist + (uint64_t)blockIdx.x * n_rows;
+    float *od = out_dist + (uint64_t)blockIdx.x * (k + tie_cap);
+    uint32_t *oi = out_ids + (uint64_t)blockIdx.x * (k + tie_cap);
+    // number of selectable rows (distance <= 1.0)
+    uint32_t prefix = 0, remaining = k;
+    // three passes of 12 + 12 + 8 bits, most significant first
+    const int shifts[3] = {20, 8, 0};
+    const int bits[3] = {12, 12, 8};
+    uint32_t mask_hi = 0;
+    for (int pass = 0; pass < 3; pass++) {
+        for (uint32_t i = threadIdx.x; i < 4096; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        for (uint64_t r = threadIdx.x; r < n_rows; r += blockDim.x) {
+            float v = dq[r];
+            if (v > 1.5f) continue;
+            uint32_t b = __float_as_uint(v);
+            if ((b & mask_hi) == prefix) atomicAdd(&hist[(b >> shifts[pass]) & ((1u << bits[pass]) - 1)], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t acc = 0, nb = 1u << bits[pass], sel = nb - 1;
+            bool found = false;
+            for (uint32_t i = 0; i < nb; i++) {
+                if (acc + hist[i] >= remaining) {
+                    sel = i;
+                    found = true;
+                    break;
+                }
+                acc += hist[i];
+            }
+            if (!found) {  // fewer than k selectable rows: everything qualifies
+                s_prefix = 0xffffffffu;
+                s_remaining = 0;
+            } else {
+                s_prefix = prefix | (sel << shifts[pass]);
+                s_remaining = remaining - acc;
+            }
+        }
+        __syncthreads();
+        if (s_prefix == 0xffffffffu) {
+            prefix = 0xffffffffu;
+            break;
+        }
+        prefix = s_prefix;
+        remaining = s_remaining;
+        mask_hi |= ((1u << bits[pass]) - 1) << shifts[pass];
+        __syncthreads();
+    }
+    // prefix == bit pattern of the k-th smallest distance (or 0xffffffff: take all)
+    if (threadIdx.x == 0) {
+        s_count_lt = 0;
+        s_count_eq = 0;
+    }
+    __syncthreads();
+    for (uint64_t r = threadIdx.x; r < n_rows; r += blockDim.x) {
+        float v = dq[r];
+        if (v > 1.5f) continue;
+        uint32_t b = __float_as_uint(v);
+        if (prefix == 0xffffffffu || b < prefix) {
+            uint32_t at = atomicAdd(&s_count_lt, 1u);
+            if (at < k) {
+                od[at] = v;
+                oi[at] = docids[r];
+            }
+        } else if (b == prefix) {
+            uint32_t at = atomicAdd(&s_count_eq, 1u);
+            if (at < tie_cap) {
+                od[k + at] = v;
+                oi[k + at] = docids[r];
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        out_n[2 * blockIdx.x] = min(s_count_lt, k);
+        out_n[2 * blockIdx.x + 1] = min(s_count_eq, tie_cap);
+    }
+}
+
+// ======================================================================================== launch wrappers
+#define CK(x)                          \
+    do {                               \
+        cudaError_t e_ = (x);          \
+        if (e_ != cudaSuccess) return e_; \
+    } while (0)
+
+cudaError_t launch_lev(cudaStream_t s, const uint8_t *dict_bytes, const uint32_t *dict_off, uint32_t n_words, const LevTerm *terms,
+                       uint32_t n_terms, LevRec *recs, uint32_t *rec_count, uint32_t *one_out, uint32_t *n_one, uint32_t *two_out,
+                       uint32_t *n_two, int32_t *status) {
+    if (n_terms == 0 || n_words == 0) return cudaSuccess;
+    CK(cudaMemsetAsync(rec_count, 0, sizeof(uint32_t) * n_terms, s));
+    dim3 grid((n_words + 255) / 256, (n_terms + LEV_TERMS_PER_CTA - 1) / LEV_TERMS_PER_CTA);
+    lev_match_kernel<<<grid, 256, 0, s>>>(dict_bytes, dict_off, n_words, terms, n_terms, recs, rec_count);
+    lev_finalize_kernel<<<(n_terms + 63) / 64, 64, 0, s>>>(recs, rec_count, terms, n_terms, one_out, n_one, two_out, n_two, status);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_compact(cudaStream_t s, const ActDesc *acts, uint32_t n_acts, uint32_t *results) {
+    if (!n_acts) return cudaSuccess;
+    act_compact_kernel<<<n_acts, 256, 0, s>>>(acts, results);
+    return cudaGetLastError();
+}
+cudaError_t launch_pair_probe(cudaStream_t s, const PairSet *sets, uint32_t n_sets, uint32_t n_probes, const uint32_t *wordpool,
+                              const unsigned long long *pair_keys, uint64_t n_pairs, uint32_t pair_list_base, const DListRef *lists,
+                              const ActDesc *acts, const uint32_t *results, Job *queue, uint32_t *qcount, uint32_t qcap) {
+    if (!n_probes) return cudaSuccess;
+    pair_probe_kernel<<<(n_probes + 255) / 256, 256, 0, s>>>(sets, n_sets, n_probes, wordpool, pair_keys, n_pairs, pair_list_base, lists, acts,
+                                                             results, queue, qcount, qcap);
+    return cudaGetLastError();
+}
+cudaError_t launch_scatter(cudaStream_t s, uint32_t n_ctas, const Job *queue, const uint32_t *qcount, uint32_t qcap, const ActDesc *acts,
+                           const uint32_t *results, const DListRef *lists, const uint32_t *pool) {
+    scatter_kernel<<<n_ctas, 256, 0, s>>>(queue, qcount, qcap, acts, results, lists, pool);
+    return cudaGetLastError();
+}
+cudaError_t launch_eval(cudaStream_t s, const TileDesc *tiles, uint32_t n_tiles, const ActDesc *acts, uint32_t *results, const ColOp *colprog,
+                        const PathRec *paths, const uint16_t *condpool) {
+    if (!n_tiles) return cudaSuccess;
+    eval_paths_kernel<<<n_tiles, 128, 0, s>>>(tiles, acts, results, colprog, paths, condpool);
+    return cudaGetLastError();
+}
+cudaError_t launch_emit(cudaStream_t s, const EmitDesc *emits, uint32_t n_emits) {
+    if (!n_emits) return cudaSuccess;
+    emit_kernel<<<(n_emits * 32 + 127) / 128, 128, 0, s>>>(emits, n_emits);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_vec_dist(cudaStream_t s, int n_ctas, int qt, const void *mat, const float *inv_norm, const uint32_t *docids, uint64_t n_rows,
+                            uint32_t d, const float *queries, const float *q_inv_norm, const unsigned long long *cand, uint64_t n_cand_words,
+                            float *dist) {
+    size_t smem = (size_t)qt * d * sizeof(float);
+    const __half *m = reinterpret_cast<const __half *>(mat);
+#define VD(QT)                                                                                                           \
+    case QT:                                                                                                             \
+        CK(cudaFuncSetAttribute(vec_dist_kernel<QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+        vec_dist_kernel<QT><<<n_ctas, 256, smem, s>>>(m, inv_norm, docids, n_rows, d, queries, q_inv_norm, cand, n_cand_words, dist); \
+        break;
+    switch (qt) {
+        VD(1)
+        VD(2)
+        VD(4)
+        VD(8)
+        default: return cudaErrorInvalidValue;
+    }
+#undef VD
+    return cudaGetLastError();
+}
+cudaError_t launch_topk(cudaStream_t s, uint32_t n_q, const float *dist, const uint32_t *docids, uint64_t n_rows, uint32_t k, uint32_t tie_cap,
+                        float *out_dist, uint32_t *out_ids, uint32_t *out_n) {
+    if (!n_q) return cudaSuccess;
+    topk_select_kernel<<<n_q, 1024, 0, s>>>(dist, docids, n_rows, k, tie_cap, out_dist, out_ids, out_n);
+    return cudaGetLastError();
+}
+
+}  // namespace b200

@@ -1,0 +1,25 @@
+// Launch wrappers of kernels.cu (host-callable; keep CUDA types out of the engine's headers).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "device_types.h"
+
+namespace b200 {
+cudaError_t launch_lev(cudaStream_t s, const uint8_t *dict_bytes, const uint32_t *dict_off, uint32_t n_words, const LevTerm *terms,
+                       uint32_t n_terms, LevRec *recs, uint32_t *rec_count, uint32_t *one_out, uint32_t *n_one, uint32_t *two_out,
+                       uint32_t *n_two, int32_t *status);
+cudaError_t launch_compact(cudaStream_t s, const ActDesc *acts, uint32_t n_acts, uint32_t *results);
+cudaError_t launch_pair_probe(cudaStream_t s, const PairSet *sets, uint32_t n_sets, uint32_t n_probes, const uint32_t *wordpool,
+                              const unsigned long long *pair_keys, uint64_t n_pairs, uint32_t pair_list_base, const DListRef *lists,
+                              const ActDesc *acts, const uint32_t *results, Job *queue, uint32_t *qcount, uint32_t qcap);
+cudaError_t launch_scatter(cudaStream_t s, uint32_t n_ctas, const Job *queue, const uint32_t *qcount, uint32_t qcap, const ActDesc *acts,
+                           const uint32_t *results, const DListRef *lists, const uint32_t *pool);
+cudaError_t launch_eval(cudaStream_t s, const TileDesc *tiles, uint32_t n_tiles, const ActDesc *acts, uint32_t *results, const ColOp *colprog,
+                        const PathRec *paths, const uint16_t *condpool);
+cudaError_t launch_emit(cudaStream_t s, const EmitDesc *emits, uint32_t n_emits);
+cudaError_t launch_vec_dist(cudaStream_t s, int n_ctas, int qt, const void *mat_fp16, const float *inv_norm, const uint32_t *docids,
+                            uint64_t n_rows, uint32_t d, const float *queries, const float *q_inv_norm, const unsigned long long *cand,
+                            uint64_t n_cand_words, float *dist);
+cudaError_t launch_topk(cudaStream_t s, uint32_t n_q, const float *dist, const uint32_t *docids, uint64_t n_rows, uint32_t k, uint32_t tie_cap,
+                        float *out_dist, uint32_t *out_ids, uint32_t *out_n);
+}  // namespace b200

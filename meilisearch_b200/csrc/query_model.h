@@ -1,0 +1,127 @@
+// Host-side query model of the engine: terms, term subsets, query graph, ranking-rule graph.
+// B200-native restatement (word ids are dictionary ranks, derivations arrive from the device):
+//   crates/milli/src/search/new/query_term/{mod.rs,ntypo_subset.rs,parse_query.rs,compute_derivations.rs:170-253}
+//   crates/milli/src/search/new/query_graph.rs
+//   crates/milli/src/search/new/ranking_rule_graph/{build.rs,mod.rs} and the six rule directories
+// Scope: words, soft/hard separators, prefix, typos, n-grams, split words.  User phrases, the negative
+// operator and synonyms are reported as B200_ERR_UNSUPPORTED.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "host_index.h"
+
+namespace b200 {
+
+enum { N_ALL = 0, N_SUBSET = 1, N_NOTHING = 2 };
+
+struct ETerm {  // QueryTerm (query_term/mod.rs:43-54)
+    std::string original;
+    bool is_ngram = false;
+    std::vector<std::string> ngram_words;
+    uint8_t max_lev = 0;
+    bool is_prefix = false;
+    bool empty_term = false;  // longer than MAX_WORD_LENGTH
+    int32_t exact = -1;       // dictionary rank of `original`, or -1
+    std::vector<uint32_t> prefix_of;
+    int32_t prefix_db = -1;   // prefix id
+    std::vector<uint32_t> one_typo, two_typo;
+    bool has_split = false;
+    uint32_t split_l = 0, split_r = 0, split_list = NO_LIST;
+    int32_t lev_slot = -1;    // index into the device derivation batch
+};
+
+struct ESubset {  // NTypoTermSubset; `split` stands for the only phrase a subset can hold here (split words)
+    uint8_t kind = N_NOTHING;
+    std::vector<uint32_t> words;
+    bool split = false;
+    bool contains_word(uint32_t w) const { return kind == N_ALL || (kind == N_SUBSET && std::binary_search(words.begin(), words.end(), w)); }
+    bool is_empty() const { return kind == N_NOTHING || (kind == N_SUBSET && words.empty() && !split); }
+    void intersect(const ESubset &o) {
+        if (kind == N_ALL)
+            *this = o;
+        else if (kind == N_SUBSET) {
+            if (o.kind == N_SUBSET) {
+                std::vector<uint32_t> r;
+                std::set_intersection(words.begin(), words.end(), o.words.begin(), o.words.end(), std::back_inserter(r));
+                words.swap(r);
+                split = split && o.split;
+            } else if (o.kind == N_NOTHING)
+                *this = ESubset{};
+        }
+    }
+    bool operator==(const ESubset &o) const { return kind == o.kind && words == o.words && split == o.split; }
+    void key(std::string &s) const {
+        s.push_back((char)('A' + kind));
+        for (auto w : words) {
+            s.push_back('w');
+            s += std::to_string(w);
+        }
+        if (split) s.push_back('s');
+        s.push_back(';');
+    }
+};
+
+struct ETermSubset {
+    uint32_t term = 0;
+    ESubset zero, one, two;
+    bool mandatory = false;
+    static ETermSubset full(uint32_t t) {
+        ETermSubset s;
+        s.term = t;
+        s.zero.kind = s.one.kind = s.two.kind = N_ALL;
+        return s;
+    }
+    void intersect(const ETermSubset &o) {
+        zero.intersect(o.zero);
+        one.intersect(o.one);
+        two.intersect(o.two);
+    }
+};
+
+struct ELocated {  // LocatedQueryTermSubset
+    ETermSubset ts;
+    uint16_t ps = 0, pe = 0;
+    uint8_t t0 = 0, t1 = 0;
+    uint32_t n_term_ids() const { return (uint32_t)t1 - t0 + 1; }
+    std::string key() const {
+        std::string s = "T" + std::to_string(ts.term) + (ts.mandatory ? "!" : ".");
+        ts.zero.key(s);
+        ts.one.key(s);
+        ts.two.key(s);
+        s += "@" + std::to_string(ps) + "-" + std::to_string(pe) + "#" + std::to_string(t0) + "-" + std::to_string(t1);
+        return s;
+    }
+};
+
+enum { ND_TERM = 0, ND_DELETED = 1, ND_START = 2, ND_END = 3 };
+struct ENode {
+    int kind = ND_DELETED;
+    ELocated term;
+    std::vector<uint16_t> pred, succ;  // ascending
+};
+struct EGraph {
+    uint16_t root = 0, end = 1;
+    std::vector<ENode> nodes;
+};
+
+inline void sorted_insert(std::vector<uint16_t> &v, uint16_t x) {
+    auto it = std::lower_bound(v.begin(), v.end(), x);
+    if (it == v.end() || *it != x) v.insert(it, x);
+}
+inline void sorted_remove(std::vector<uint16_t> &v, uint16_t x) {
+    auto it = std::lower_bound(v.begin(), v.end(), x);
+    if (it != v.end() && *it == x) v.erase(it);
+}
+
+// score kinds = b200_score_kind
+struct EScore {
+    uint8_t kind;
+    uint32_t rank, max_rank;
+    float sim;
+};
+
+}  // namespace b200
