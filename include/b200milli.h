@@ -158,6 +158,7 @@ typedef struct {
     uint64_t kernel_count[8];     /* launches per kernel class */
     uint64_t kernel_bytes[8];     /* algorithmic bytes attributed to each kernel class */
     double device_ms;             /* CUDA-event time from the first to the last kernel of every step */
+    uint64_t h2d_bytes, d2h_bytes; /* bytes copied across PCIe/NVLink-C2C by search/derive/nns calls */
     uint64_t hbm_bytes_staged;
 } b200_stats;
 int b200_get_stats(b200_index *, b200_stats *out);

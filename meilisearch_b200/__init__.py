@@ -53,7 +53,8 @@ class _Results(C.Structure):
 class _Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("device_steps", C.c_uint64), ("posting_bytes", C.c_uint64), ("matrix_bytes", C.c_uint64),
                 ("dictionary_bytes", C.c_uint64), ("vector_bytes", C.c_uint64), ("kernel_ms", C.c_double * 8),
-                ("kernel_count", C.c_uint64 * 8), ("kernel_bytes", C.c_uint64 * 8), ("device_ms", C.c_double), ("hbm_bytes_staged", C.c_uint64)]
+                ("kernel_count", C.c_uint64 * 8), ("kernel_bytes", C.c_uint64 * 8), ("device_ms", C.c_double), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("hbm_bytes_staged", C.c_uint64)]
 
 
 KERNELS = ["lev_match", "act_compact", "pair_probe", "scatter", "eval_paths", "emit", "vec_dist", "topk_select"]

@@ -29,8 +29,33 @@ struct LevRec {
 
 // ---- rule activations ----
 constexpr uint32_t MAX_COSTS = 128;
-constexpr uint32_t MAX_PATH_LEN = 32;
 constexpr uint32_t JOB_CHUNK = 2048;  // elements (sparse) or rows (dense) per scatter job
+
+// An activation evaluates a small DAG ("state graph") over the activation's universe, 64 documents per thread:
+//   S[state][r] = documents that can go from `state` to END spending exactly r        (backward min-plus DP, bit-sliced)
+//   bucket[ci]  = S[ROOT][cost_vals[ci]] minus the cheaper buckets                    (= the rule's buckets, all at once)
+//   walk        = per document the first START->END path in edge order among its cheapest ones; distinct paths are
+//                 reported to the host, which rebuilds the next query graph from them (graph_based_ranking_rule.rs:340-353)
+struct DpState {
+    uint32_t edge_begin;  // into DpEdge[], edges in visiting (DFS) order
+    uint32_t pair_off;    // first S column of this state
+    uint16_t n_edges;
+    uint16_t rmin, rcount;  // S columns cover costs [rmin, rmin + rcount)
+    uint16_t pad;
+};
+struct DpEdge {
+    uint16_t dst;   // state index (always greater than the source: states are in topological order)
+    uint16_t cost;
+    uint16_t col;   // condition column, 0xffff = unconditional
+    uint16_t pad;
+};
+constexpr uint32_t MAX_WALK = 14;  // edges on a START->END path (10 words + END, with slack)
+struct PathOut {     // one distinct first-match path
+    uint32_t act;
+    uint16_t cost_idx;
+    uint16_t len;
+    uint16_t edges[MAX_WALK];  // activation-local DpEdge indices
+};
 
 struct ActDesc {
     // parent universe: rows (p_uw,p_ub); child = rows where OR(p_out[col_lo..col_hi)) != 0. p_out==0: take p_ub as is.
@@ -42,23 +67,20 @@ struct ActDesc {
     uint32_t *uw;
     unsigned long long *ub;
     unsigned long long *C;    // column-major [n_cols][ld], scratch for this step
+    unsigned long long *S;    // column-major [n_pairs][ld], scratch
     unsigned long long *out;  // column-major [n_costs+1][ld]; last column = matched by no path
-    uint32_t ld, n_cols, n_costs, n_paths;
+    unsigned long long *tab;  // path dedup table (tab_size slots, zeroed), scratch
+    uint32_t ld, n_cols, n_costs, n_states;
+    uint32_t state_off, edge_off, cost_off;  // into DpState[], DpEdge[], u16 cost_vals[]
     uint32_t colprog_off, colprog_len;
-    uint32_t path_off;        // into PathRec[]
-    uint32_t res_off;         // into results u32[]: [0] rows, [1..n_costs+1] counts, then survived[n_paths]
+    uint32_t tab_size, want_paths;
+    uint32_t res_off;         // into results u32[]: [0] rows, [1..n_costs+1] counts
+    uint32_t pad;
 };
 
 struct ColOp {  // executed per row before the paths
     uint16_t op;  // 0 AND dst=a&b, 1 OR dst=a|b, 2 ANDNOT dst=a&~b, 3 COPY dst=a
     uint16_t dst, a, b;
-};
-
-struct PathRec {
-    uint32_t cond_off;  // into u16 cond pool
-    uint16_t cost_idx;
-    uint8_t len;
-    uint8_t lcp;        // conditions shared with the previous path
 };
 
 struct Job {  // scatter one chunk of one posting list into column `col` of activation `act`

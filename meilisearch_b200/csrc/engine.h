@@ -74,7 +74,8 @@ struct Engine {
     DevBuf<uint8_t> d_step;     // per-step input blob
     DevBuf<uint32_t> d_results; // per-step results
     DevBuf<Job> d_queue;
-    DevBuf<uint32_t> d_qcount;
+    DevBuf<uint32_t> d_qcount;   // [0] scatter jobs, [1] surviving paths
+    DevBuf<PathOut> d_pathbuf;
     DevBuf<uint32_t> d_docids_out;  // n_queries x limit
     uint8_t *h_step = nullptr;      // pinned
     size_t h_step_cap = 0;

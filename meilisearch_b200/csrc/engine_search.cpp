@@ -271,9 +271,14 @@ struct EEdge {
     std::vector<uint8_t> skip;  // nodes_to_skip
 };
 
-struct EPath {
+struct SEdge {  // edge of the state graph handed to the device
+    uint16_t src, dst;  // state ids (topological)
     uint32_t cost;
-    std::vector<uint16_t> conds;  // condition ids
+    int32_t cond;       // condition id or -1
+};
+struct SurvPath {
+    uint16_t cost_idx;
+    std::vector<uint16_t> edges;  // state-graph edge ids, START..END
 };
 
 struct StepOut {  // per-activation device work, appended to the step blob by the driver
@@ -281,9 +286,10 @@ struct StepOut {  // per-activation device work, appended to the step blob by th
     std::vector<PairSet> pairsets;    // left_off/right_off relative to `words`
     std::vector<uint32_t> words;
     std::vector<ColOp> colprog;
-    std::vector<PathRec> paths;       // cond_off relative to `condpool`
-    std::vector<uint16_t> condpool;
-    uint32_t n_cols = 0, n_costs = 0;
+    std::vector<DpState> dp_states;   // edge_begin relative to dp_edges
+    std::vector<DpEdge> dp_edges;
+    std::vector<uint16_t> cost_vals;
+    uint32_t n_cols = 0, n_costs = 0, n_pairs = 0, want_paths = 0;
     uint64_t posting_bytes = 0;
 };
 
@@ -292,16 +298,20 @@ struct Level {
     int kind = RK_RESOLVE;
     EGraph graph;
     std::vector<ECond> conds;
-    std::vector<EPath> paths;  // sorted by (cost, DFS order)
+    // state graph: states in topological order (0 = START, last = END); edges grouped by source in visiting order
+    uint16_t n_states = 0;
+    std::vector<SEdge> sedges;
+    std::vector<uint32_t> state_edge_begin;            // n_states + 1
+    std::vector<std::pair<uint16_t, uint16_t>> state_cost_range;  // (rmin, rcount) per state
     std::vector<uint32_t> cost_vals;
-    std::vector<uint16_t> path_cost_idx;
+    bool want_paths = false;
+    std::vector<SurvPath> surv;
     uint64_t next_max_cost = 1;
     // device buffers (arena)
     uint32_t *uw = nullptr;
     unsigned long long *ub = nullptr, *out = nullptr;
     uint32_t ld = 0, rows = 0, res_off = 0;
     std::vector<uint32_t> counts;  // per cost idx, last = unmatched
-    std::vector<uint8_t> survived;
     size_t cursor = 0;
     uint64_t universe_count = 0;
 };
@@ -677,6 +687,64 @@ std::vector<std::pair<uint32_t, uint32_t>> build_edges(const QCtx &c, int rule, 
     return edges;
 }
 
+// Topologically order the states reachable from START that reach END, compute per-state feasible cost ranges, root costs.
+template <class AE>
+void finish_state_graph(Level &L, const std::vector<AE> &aedges, uint32_t root, uint32_t end, bool want_paths) {
+    // collect states
+    std::map<uint32_t, std::vector<size_t>> out_edges;
+    for (size_t i = 0; i < aedges.size(); i++) out_edges[aedges[i].src].push_back(i);
+    // feasible costs to END (memoised DFS)
+    std::map<uint32_t, std::set<uint32_t>> costs;
+    std::map<uint32_t, int> st;
+    std::vector<uint32_t> topo_rev;  // post-order
+    std::function<void(uint32_t)> visit = [&](uint32_t s) {
+        if (st[s]) return;
+        st[s] = 1;
+        if (s == end)
+            costs[s].insert(0);
+        else
+            for (auto ei : out_edges[s]) {
+                visit(aedges[ei].dst);
+                for (auto c : costs[aedges[ei].dst]) costs[s].insert(aedges[ei].cost + c);
+            }
+        topo_rev.push_back(s);
+    };
+    visit(root);
+    // keep states that reach END; order = reverse post-order, END forced last
+    std::vector<uint32_t> order;
+    for (auto it = topo_rev.rbegin(); it != topo_rev.rend(); ++it)
+        if (*it != end && !costs[*it].empty()) order.push_back(*it);
+    if (order.empty() || order[0] != root) order.insert(order.begin(), root);  // START with no way to END: no buckets
+    order.push_back(end);
+    std::map<uint32_t, uint16_t> idx;
+    for (size_t i = 0; i < order.size(); i++) idx[order[i]] = (uint16_t)i;
+    L.n_states = (uint16_t)order.size();
+    L.sedges.clear();
+    L.state_edge_begin.assign(L.n_states + 1, 0);
+    L.state_cost_range.assign(L.n_states, {0, 0});
+    for (size_t i = 0; i < order.size(); i++) {
+        L.state_edge_begin[i] = (uint32_t)L.sedges.size();
+        uint32_t s = order[i];
+        if (!costs[s].empty()) {
+            uint32_t lo = *costs[s].begin(), hi = *costs[s].rbegin();
+            if (hi >= 65535) throw TooComplex{"ranking-rule cost above 65534"};
+            L.state_cost_range[i] = {(uint16_t)lo, (uint16_t)(hi - lo + 1)};
+        }
+        if (s == end) continue;
+        for (auto ei : out_edges[s]) {
+            const AE &e = aedges[ei];
+            if (e.dst != end && costs[e.dst].empty()) continue;
+            if (!idx.count(e.dst)) continue;
+            L.sedges.push_back(SEdge{(uint16_t)i, idx[e.dst], e.cost, e.cond});
+        }
+    }
+    L.state_edge_begin[L.n_states] = (uint32_t)L.sedges.size();
+    L.cost_vals.assign(costs[root].begin(), costs[root].end());
+    if (L.cost_vals.size() > MAX_COSTS) throw TooComplex{"more than 128 distinct costs in one ranking rule"};
+    if (L.sedges.size() > 60000) throw TooComplex{"ranking-rule graph too large"};
+    L.want_paths = want_paths;
+}
+
 constexpr size_t MAX_PATHS = 60000;
 
 // Build graph + enumerate all START->END paths (cheapest_paths.rs semantics without the dead-end cache: every
@@ -745,56 +813,31 @@ void prepare_graph_rule(const QCtx &c, int rule, bool has_tms, int tms, Level &L
     visit(qg.root);
     uint64_t mx = costs[qg.root].empty() ? 0 : *costs[qg.root].rbegin();
     L.next_max_cost = 1 + mx;
-    // enumerate
-    struct Found {
-        uint32_t cost;
-        std::vector<uint16_t> conds;
+    // state graph for the device.  Without a matching strategy a state is a query-graph node.  With `Last`, once a term has
+    // been skipped every later term must be skipped too (cheapest_paths.rs:189-281 with the removal order of
+    // query_graph.rs:346-406), so a node splits into a "matching" and a "skipping" state.
+    struct AEdge {
+        uint32_t src, dst, cost;
+        int32_t cond;
     };
-    std::vector<Found> found;
-    std::vector<uint16_t> path;
-    std::vector<uint8_t> visited(n, 0), to_skip(n, 0);
-    std::function<void(uint16_t, uint32_t)> dfs = [&](uint16_t node, uint32_t cost) {
-        for (auto ei : eon[node]) {
-            const EEdge &e = edges[ei];
-            if (e.cond >= 0) {
-                if (to_skip[e.dst]) continue;
-                bool clash = false;
-                for (uint16_t k = 0; k < n && !clash; k++) clash = e.skip[k] && visited[k];
-                if (clash) continue;
-                if (costs[e.dst].empty()) continue;
-                path.push_back((uint16_t)e.cond);
-                visited[e.dst] = 1;
-                std::vector<uint8_t> old = to_skip;
-                for (uint16_t k = 0; k < n; k++) to_skip[k] |= e.skip[k];
-                dfs(e.dst, cost + e.cost);
-                to_skip = old;
-                visited[e.dst] = 0;
-                path.pop_back();
-            } else {
+    std::vector<AEdge> aedges;
+    auto sid = [&](uint16_t node, int skipping) { return (uint32_t)node * 2 + (uint32_t)skipping; };
+    for (uint16_t nd = 0; nd < n; nd++) {
+        for (int sk = 0; sk < 2; sk++) {
+            if (sk == 1 && (nd == qg.root || nd == qg.end)) continue;
+            for (auto ei : eon[nd]) {
+                const EEdge &e = edges[ei];
                 if (e.dst == qg.end) {
-                    found.push_back({cost + e.cost, path});
-                    if (found.size() > MAX_PATHS) throw TooComplex{"ranking-rule graph has more than 60000 paths"};
+                    aedges.push_back({sid(nd, sk), sid(qg.end, 0), e.cost, -1});
+                } else if (e.cond >= 0) {
+                    if (sk == 0) aedges.push_back({sid(nd, 0), sid(e.dst, 0), e.cost, e.cond});
                 } else {
-                    if (costs[e.dst].empty()) continue;
-                    std::vector<uint8_t> old = to_skip;
-                    for (uint16_t k = 0; k < n; k++) to_skip[k] |= e.skip[k];
-                    dfs(e.dst, cost + e.cost);
-                    to_skip = old;
+                    aedges.push_back({sid(nd, sk), sid(e.dst, 1), e.cost, -1});  // skip edge
                 }
             }
         }
-    };
-    dfs(qg.root, 0);
-    std::stable_sort(found.begin(), found.end(), [](const Found &a, const Found &b) { return a.cost < b.cost; });
-    L.paths.clear();
-    L.cost_vals.clear();
-    L.path_cost_idx.clear();
-    for (auto &f : found) {
-        if (L.cost_vals.empty() || L.cost_vals.back() != f.cost) L.cost_vals.push_back(f.cost);
-        L.path_cost_idx.push_back((uint16_t)(L.cost_vals.size() - 1));
-        L.paths.push_back(EPath{f.cost, std::move(f.conds)});
     }
-    if (L.cost_vals.size() > MAX_COSTS) throw TooComplex{"more than 128 distinct costs in one ranking rule"};
+    finish_state_graph(L, aedges, sid(qg.root, 0), sid(qg.end, 0), true);
 }
 
 // universe resolution (resolve_query_graph.rs:133-185 == union over START->END routes of the AND of the term docids)
@@ -811,23 +854,16 @@ void prepare_resolve(const QCtx &c, Level &L) {
             cond_of[i] = (int)L.conds.size();
             L.conds.push_back(x);
         }
-    L.paths.clear();
-    std::vector<uint16_t> path;
-    std::function<void(uint16_t)> dfs = [&](uint16_t node) {
-        for (auto s : g.nodes[node].succ) {
-            if (s == g.end) {
-                L.paths.push_back(EPath{0, path});
-                if (L.paths.size() > MAX_PATHS) throw TooComplex{"query graph has too many routes"};
-            } else {
-                path.push_back((uint16_t)cond_of[s]);
-                dfs(s);
-                path.pop_back();
-            }
-        }
+    struct AEdge {
+        uint32_t src, dst, cost;
+        int32_t cond;
     };
-    dfs(g.root);
-    L.cost_vals = {0};
-    L.path_cost_idx.assign(L.paths.size(), 0);
+    std::vector<AEdge> ae;
+    for (uint16_t u = 0; u < g.nodes.size(); u++) {
+        if (g.nodes[u].kind != ND_TERM && g.nodes[u].kind != ND_START) continue;
+        for (auto v : g.nodes[u].succ) ae.push_back({u, v, 0, v == g.end ? -1 : cond_of[v]});
+    }
+    finish_state_graph(L, ae, g.root, g.end, false);
     L.next_max_cost = 1;
     (void)c;
 }
@@ -844,9 +880,14 @@ void prepare_exact_attribute(const QCtx &c, Level &L, StepOut &o) {
         x.col = k == 0 ? colA : colB;
         L.conds.push_back(x);
     }
-    L.paths = {EPath{0, {0}}, EPath{1, {1}}, EPath{2, {}}};
-    L.cost_vals = {0, 1, 2};
-    L.path_cost_idx = {0, 1, 2};
+    {
+        struct AEdge {
+            uint32_t src, dst, cost;
+            int32_t cond;
+        };
+        std::vector<AEdge> ae{{0, 1, 0, 0}, {0, 1, 1, 1}, {0, 1, 2, -1}, {1, 2, 0, -1}};
+        finish_state_graph(L, ae, 0, 2, false);
+    }
     L.next_max_cost = 3;
     struct Info {
         uint32_t word;
@@ -978,7 +1019,7 @@ EGraph build_from_paths(const std::vector<std::vector<const ECond *>> &paths) {
     return g;
 }
 
-// conditions -> columns, scatter jobs, column program, path table
+// conditions -> columns, scatter jobs, column program; state graph -> device form
 void emit_activation_work(const QCtx &c, Level &L, StepOut &o) {
     if (L.kind != RK_EXACT_ATTRIBUTE) {
         ActBuilder b(c, o);
@@ -987,25 +1028,28 @@ void emit_activation_work(const QCtx &c, Level &L, StepOut &o) {
         o.n_cols = b.next_col;
     }
     o.n_costs = (uint32_t)L.cost_vals.size();
-    const std::vector<uint16_t> *prevp = nullptr;
-    std::vector<uint16_t> prev_cols, cur_cols;
-    for (size_t p = 0; p < L.paths.size(); p++) {
-        cur_cols.clear();
-        for (auto ci : L.paths[p].conds) cur_cols.push_back(L.conds[ci].col);
-        if (cur_cols.size() > MAX_PATH_LEN) throw TooComplex{"path longer than 32 conditions"};
-        uint32_t lcp = 0;
-        if (prevp)
-            while (lcp < prev_cols.size() && lcp < cur_cols.size() && prev_cols[lcp] == cur_cols[lcp]) lcp++;
-        PathRec pr;
-        pr.cond_off = (uint32_t)o.condpool.size();
-        pr.cost_idx = L.path_cost_idx[p];
-        pr.len = (uint8_t)cur_cols.size();
-        pr.lcp = (uint8_t)lcp;
-        o.paths.push_back(pr);
-        o.condpool.insert(o.condpool.end(), cur_cols.begin(), cur_cols.end());
-        prev_cols = cur_cols;
-        prevp = &prev_cols;
+    o.want_paths = L.want_paths ? 1 : 0;
+    uint32_t pair = 0;
+    for (uint16_t st = 0; st < L.n_states; st++) {
+        DpState ds{};
+        ds.edge_begin = L.state_edge_begin[st];
+        ds.n_edges = (uint16_t)(L.state_edge_begin[st + 1] - L.state_edge_begin[st]);
+        ds.rmin = L.state_cost_range[st].first;
+        ds.rcount = L.state_cost_range[st].second;
+        if (st + 1 == L.n_states) {  // END: the single pair (cost 0)
+            ds.rmin = 0;
+            ds.rcount = 1;
+        }
+        ds.pair_off = pair;
+        pair += ds.rcount;
+        o.dp_states.push_back(ds);
     }
+    o.n_pairs = std::max(1u, pair);
+    for (auto &e : L.sedges) {
+        if (e.cost > 65534) throw TooComplex{"edge cost too large"};
+        o.dp_edges.push_back(DpEdge{e.dst, (uint16_t)e.cost, e.cond >= 0 ? L.conds[e.cond].col : (uint16_t)0xffff, 0});
+    }
+    for (auto cv : L.cost_vals) o.cost_vals.push_back((uint16_t)cv);
 }
 
 // located_query_terms_from_tokens (parse_query.rs:28-202) without phrases / negative words
@@ -1088,6 +1132,7 @@ void parse_query(QState &q, const b200_query_batch *b, uint32_t qi) {
         if (i >= 2) make_ngram(i - 2, i);
     }
     build_initial_edges(g);
+    if (located.size() > 12) throw UnsupportedQuery{"more than 12 query words"};
     q.placeholder = located.empty();
 }
 
@@ -1439,11 +1484,16 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             if (L.kind == RK_EXACT_ATTRIBUTE)
                 C.graph = L.graph;
             else {
+                // the paths that took at least one document, in visiting order (= lexicographic in edge ids)
+                std::vector<const SurvPath *> sp;
+                for (auto &p : L.surv)
+                    if (p.cost_idx == ci) sp.push_back(&p);
+                std::sort(sp.begin(), sp.end(), [](const SurvPath *x, const SurvPath *y) { return x->edges < y->edges; });
                 std::vector<std::vector<const ECond *>> good;
-                for (size_t p = 0; p < L.paths.size(); p++) {
-                    if (L.path_cost_idx[p] != ci || !L.survived[p]) continue;
+                for (auto *p : sp) {
                     std::vector<const ECond *> pc;
-                    for (auto c : L.paths[p].conds) pc.push_back(&L.conds[c]);
+                    for (auto e : p->edges)
+                        if (L.sedges[e].cond >= 0) pc.push_back(&L.conds[L.sedges[e].cond]);
                     good.push_back(std::move(pc));
                 }
                 C.graph = build_from_paths(good);
@@ -1474,12 +1524,14 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         std::vector<PairSet> sets;
         std::vector<uint32_t> words;
         std::vector<ColOp> colprog;
-        std::vector<PathRec> paths;
-        std::vector<uint16_t> condpool;
+        std::vector<DpState> dstates;
+        std::vector<DpEdge> dedges;
+        std::vector<uint16_t> costpool;
         std::vector<TileDesc> tiles;
         std::vector<EmitDesc> emits;
         uint32_t res_words = 0, n_probes = 0;
         scratch_used = 0;
+        size_t s_used = 0;
         for (size_t a = 0; a < act_q.size(); a++) {
             QState &q = *qs[act_q[a]];
             Level &L = q.levels.back();
@@ -1497,14 +1549,22 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             d.ld = ld;
             d.n_cols = std::max(1u, o.n_cols);
             d.n_costs = o.n_costs;
-            d.n_paths = (uint32_t)o.paths.size();
+            d.n_states = (uint32_t)o.dp_states.size();
+            d.want_paths = o.want_paths;
+            d.tab_size = o.want_paths ? 4096 : 1;
             size_t persist = (size_t)ld * 4 + 256 + (size_t)ld * 8 + 256 + (size_t)ld * 8 * (o.n_costs + 1);
             uint8_t *pb = arena_alloc(persist);
-            size_t cbytes = (size_t)ld * 8 * d.n_cols;
+            size_t cbytes = (size_t)ld * 8 * d.n_cols, sbytes = (size_t)ld * 8 * o.n_pairs, tbytes = (size_t)d.tab_size * 8;
+            // zeroed zone (condition matrix + path table) grows from the front of the scratch pool, the DP table from the back
             size_t coff = (scratch_used + 255) & ~(size_t)255;
-            if (!pb || coff + cbytes > scratch_bytes)
+            size_t toff = (coff + cbytes + 255) & ~(size_t)255;
+            size_t s_need = (sbytes + 255) & ~(size_t)255;
+            if (!pb || toff + tbytes + s_need + s_used > scratch_bytes)
                 return fail(B200_ERR_CAPACITY, "device arena exhausted: lower the batch size or raise B200_ARENA_MB / B200_SCRATCH_MB");
-            scratch_used = coff + cbytes;
+            scratch_used = toff + tbytes;
+            s_used += s_need;
+            d.S = reinterpret_cast<unsigned long long *>(scratch + scratch_bytes - s_used);
+            d.tab = reinterpret_cast<unsigned long long *>(scratch + toff);
             d.uw = reinterpret_cast<uint32_t *>(pb);
             d.ub = reinterpret_cast<unsigned long long *>(pb + (((size_t)ld * 4 + 255) & ~(size_t)255));
             d.out = d.ub + (((size_t)ld + 31) & ~(size_t)31);
@@ -1516,16 +1576,15 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             d.colprog_off = (uint32_t)colprog.size();
             d.colprog_len = (uint32_t)o.colprog.size();
             colprog.insert(colprog.end(), o.colprog.begin(), o.colprog.end());
-            d.path_off = (uint32_t)paths.size();
-            uint32_t cbase = (uint32_t)condpool.size();
-            for (auto pr : o.paths) {
-                pr.cond_off += cbase;
-                paths.push_back(pr);
-            }
-            condpool.insert(condpool.end(), o.condpool.begin(), o.condpool.end());
+            d.state_off = (uint32_t)dstates.size();
+            d.edge_off = (uint32_t)dedges.size();
+            d.cost_off = (uint32_t)costpool.size();
+            dstates.insert(dstates.end(), o.dp_states.begin(), o.dp_states.end());
+            dedges.insert(dedges.end(), o.dp_edges.begin(), o.dp_edges.end());
+            costpool.insert(costpool.end(), o.cost_vals.begin(), o.cost_vals.end());
             d.res_off = res_words;
             L.res_off = res_words;
-            res_words += 2 + o.n_costs + d.n_paths;
+            res_words += 2 + o.n_costs;
             for (auto j : o.jobs) {
                 j.act = (uint32_t)a;
                 jobs.push_back(j);
@@ -1542,7 +1601,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             }
             for (uint32_t r0 = 0; r0 < ld; r0 += 128) tiles.push_back(TileDesc{(uint32_t)a, r0});
             stats.posting_bytes += o.posting_bytes;
-            stats.matrix_bytes += (uint64_t)ld * 8 * (d.n_cols + o.n_costs + 2);
+            stats.matrix_bytes += (uint64_t)ld * 8 * (d.n_cols + o.n_pairs + o.n_costs + 2);
             q.want_activation = false;
         }
         for (auto qi : emit_q) {
@@ -1557,7 +1616,8 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         // pack + upload
         Blob blob;
         size_t o_acts = blob.add(acts), o_sets = blob.add(sets), o_words = blob.add(words), o_colprog = blob.add(colprog),
-               o_paths = blob.add(paths), o_cond = blob.add(condpool), o_tiles = blob.add(tiles), o_emits = blob.add(emits);
+               o_states = blob.add(dstates), o_edges = blob.add(dedges), o_costs = blob.add(costpool), o_tiles = blob.add(tiles),
+               o_emits = blob.add(emits);
         size_t nbytes = blob.bytes.size() + 16;
         if (nbytes > h_step_cap) {
             if (h_step) cudaFreeHost(h_step);
@@ -1567,11 +1627,14 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         memcpy(h_step, blob.bytes.data(), blob.bytes.size());
         CU(d_step.reserve(nbytes), "step buffer");
         CU(cudaMemcpyAsync(d_step.p, h_step, nbytes, cudaMemcpyHostToDevice, stream), "H2D step");
+        stats.h2d_bytes += nbytes + jobs.size() * sizeof(Job) + 4;
+        stats.d2h_bytes += (size_t)res_words * 4 + 4;
         const size_t qcap_needed = jobs.size() + ((size_t)1 << 20);
         size_t qcap = std::max<size_t>(qcap_needed, (size_t)4 << 20);
         CU(d_queue.reserve(qcap), "job queue");
         qcap = d_queue.cap;
         CU(d_qcount.reserve(4), "job counter");
+        const size_t PATH_CAP = (size_t)1 << 20;
         CU(d_results.reserve(res_words + 4), "results");
         if (res_words + 4 > h_results_cap) {
             if (h_results) cudaFreeHost(h_results);
@@ -1592,10 +1655,13 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         if (!acts.empty()) {
             CU(cudaMemsetAsync(d_results.p, 0, (size_t)(res_words + 4) * 4, stream), "zero results");
             CU(cudaMemsetAsync(scratch, 0, scratch_used, stream), "zero condition matrix");
+            CU(d_pathbuf.reserve(PATH_CAP), "path buffer");
+            CU(d_qcount.reserve(4), "counters");
+            CU(cudaMemsetAsync(d_qcount.p + 1, 0, 4, stream), "zero path count");
             uint64_t compact_bytes = 0, eval_bytes = 0, fill_bytes = 0;
             for (size_t a = 0; a < acts.size(); a++) {
                 compact_bytes += (uint64_t)acts[a].p_rows * 8 + (uint64_t)acts[a].ld * 12;
-                eval_bytes += (uint64_t)acts[a].ld * 8 * (acts[a].n_cols + acts[a].n_costs + 2);
+                eval_bytes += (uint64_t)acts[a].ld * 8 * (acts[a].n_cols + qs[act_q[a]]->pend.n_pairs + acts[a].n_costs + 2);
                 fill_bytes += qs[act_q[a]]->pend.posting_bytes;
             }
             size_t t0 = mark();
@@ -1612,12 +1678,13 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             size_t t3 = mark();
             time_kernel(B200_K_SCATTER, t2, t3, fill_bytes);
             CU(launch_eval(stream, reinterpret_cast<const TileDesc *>(d_step.p + o_tiles), (uint32_t)tiles.size(), dacts, d_results.p,
-                           reinterpret_cast<const ColOp *>(d_step.p + o_colprog), reinterpret_cast<const PathRec *>(d_step.p + o_paths),
-                           reinterpret_cast<const uint16_t *>(d_step.p + o_cond)),
+                           reinterpret_cast<const ColOp *>(d_step.p + o_colprog), reinterpret_cast<const DpState *>(d_step.p + o_states),
+                           reinterpret_cast<const DpEdge *>(d_step.p + o_edges), reinterpret_cast<const uint16_t *>(d_step.p + o_costs), d_pathbuf.p,
+                           d_qcount.p + 1, (uint32_t)PATH_CAP),
                "eval paths");
             time_kernel(B200_K_EVAL_PATHS, t3, mark(), eval_bytes);
             CU(cudaMemcpyAsync(h_results, d_results.p, (size_t)res_words * 4, cudaMemcpyDeviceToHost, stream), "D2H results");
-            CU(cudaMemcpyAsync(h_results + res_words, d_qcount.p, 4, cudaMemcpyDeviceToHost, stream), "D2H job count");
+            CU(cudaMemcpyAsync(h_results + res_words, d_qcount.p, 8, cudaMemcpyDeviceToHost, stream), "D2H counters");
         }
         CU(cudaEventRecord(e1, stream), "event");
         CU(cudaStreamSynchronize(stream), "step sync");
@@ -1628,6 +1695,25 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             resolve_timers();
         }
         if (!acts.empty() && h_results[res_words] > qcap) return fail(B200_ERR_CAPACITY, "scatter job queue overflow");
+        std::vector<PathOut> pouts;
+        if (!acts.empty()) {
+            uint32_t np = h_results[res_words + 1];
+            if (np > PATH_CAP) return fail(B200_ERR_CAPACITY, "surviving-path buffer overflow");
+            pouts.resize(np);
+            if (np) {
+                CU(cudaMemcpyAsync(pouts.data(), d_pathbuf.p, (size_t)np * sizeof(PathOut), cudaMemcpyDeviceToHost, stream), "D2H paths");
+                CU(cudaStreamSynchronize(stream), "sync paths");
+                stats.d2h_bytes += (size_t)np * sizeof(PathOut);
+            }
+            for (size_t a = 0; a < act_q.size(); a++) qs[act_q[a]]->levels.back().surv.clear();
+            for (auto &po : pouts) {
+                Level &L = qs[act_q[po.act]]->levels.back();
+                SurvPath sp;
+                sp.cost_idx = po.cost_idx;
+                sp.edges.assign(po.edges, po.edges + std::min<uint32_t>(po.len, MAX_WALK));
+                L.surv.push_back(std::move(sp));
+            }
+        }
         // scatter results back, advance every query that got its activation
         parallel_for(act_q.size(), NT, [&](size_t a) {
             QState &q = *qs[act_q[a]];
@@ -1636,8 +1722,6 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             L.rows = res[0];
             size_t nc = L.cost_vals.size();
             L.counts.assign(res + 1, res + 1 + nc + 1);
-            L.survived.assign(L.paths.size(), 0);
-            for (size_t p = 0; p < L.paths.size(); p++) L.survived[p] = res[2 + nc + p] ? 1 : 0;
             L.universe_count = 0;
             for (auto c : L.counts) L.universe_count += c;
             L.cursor = 0;
@@ -1657,6 +1741,8 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
     // ---- outputs
     std::vector<uint32_t> out_ids((size_t)NQ * std::max(1u, length));
     CU(cudaMemcpyAsync(out_ids.data(), d_docids_out.p, out_ids.size() * 4, cudaMemcpyDeviceToHost, stream), "D2H docids");
+    stats.d2h_bytes += out_ids.size() * 4;
+    stats.h2d_bytes += (size_t)b->lemma_off[b->token_begin[NQ]] + (size_t)b->token_begin[NQ] * 5 + (size_t)NQ * 4;
     CU(cudaStreamSynchronize(stream), "sync");
     for (uint32_t i = 0; i < NQ; i++) {
         QState &q = *qs[i];

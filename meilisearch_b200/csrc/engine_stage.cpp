@@ -36,6 +36,7 @@ Engine::~Engine() {
     d_results.release();
     d_queue.release();
     d_qcount.release();
+    d_pathbuf.release();
     d_docids_out.release();
     d_lev_terms.release();
     d_lev_recs.release();
@@ -178,6 +179,8 @@ int Engine::derive_batch(uint32_t n, const char *words, const uint32_t *off, con
              *d_n_two = d_two + (size_t)n * 50;
     int32_t *d_status = reinterpret_cast<int32_t *>(d_n_two + n);
     CU(cudaMemcpyAsync(d_lev_terms.p, terms.data(), n * sizeof(LevTerm), cudaMemcpyHostToDevice, stream), "H2D lev terms");
+    stats.h2d_bytes += n * sizeof(LevTerm);
+    stats.d2h_bytes += (size_t)n * (150 + 50 + 3) * 4;
     size_t m0 = mark();
     CU(launch_lev(stream, dix.dict_bytes, dix.dict_off, (uint32_t)hix.n_words, d_lev_terms.p, n, d_lev_recs.p, rec_count, d_one, d_n_one, d_two,
                   d_n_two, d_status),
@@ -236,6 +239,8 @@ int Engine::nns_batch(const float *queries, uint32_t n_q, uint32_t d, uint32_t l
         }
         float *d_qinv = d_vq.p + (size_t)chunk * d;
         CU(cudaMemcpyAsync(d_vq.p, queries + (size_t)q0 * d, (size_t)nq * d * 4, cudaMemcpyHostToDevice, stream), "H2D queries");
+        stats.h2d_bytes += (size_t)nq * d * 4 + nq * 4;
+        stats.d2h_bytes += (size_t)nq * (limit + tie_cap) * 8 + nq * 8;
         CU(cudaMemcpyAsync(d_qinv, qinv.data(), nq * 4, cudaMemcpyHostToDevice, stream), "H2D query norms");
         for (uint32_t t = 0; t < nq;) {
             uint32_t left = nq - t;

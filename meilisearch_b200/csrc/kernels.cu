@@ -5,7 +5,7 @@
 //   act_compact_kernel                       child universe = non-zero words of a parent bucket
 //   pair_probe_kernel                        (prox,w1,w2) directory probes -> scatter jobs
 //   scatter_kernel                           posting lists -> condition bit-matrix columns
-//   eval_paths_kernel                        column program + first-match path evaluation -> buckets
+//   eval_dp_kernel                           column program + bit-sliced DP over the rule graph -> buckets + surviving paths
 //   emit_kernel                              bucket -> first-k docids, ascending
 //   vec_dist_kernel / topk_*                 cosine distance scan + exact top-k
 #include <cuda_fp16.h>
@@ -391,10 +391,21 @@ __global__ void __launch_bounds__(256) scatter_kernel(const Job *__restrict__ qu
     }
 }
 
-// thread per row: column program, then first-match evaluation of the cost-ordered path table
-__global__ void __launch_bounds__(128) eval_paths_kernel(const TileDesc *__restrict__ tiles, const ActDesc *__restrict__ acts,
-                                                         uint32_t *__restrict__ results, const ColOp *__restrict__ colprog,
-                                                         const PathRec *__restrict__ paths, const uint16_t *__restrict__ condpool) {
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdull;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ull;
+    x ^= x >> 33;
+    return x;
+}
+
+// thread per row (64 documents): column program, backward DP over the state graph, buckets, first-match walk
+__global__ void __launch_bounds__(128) eval_dp_kernel(const TileDesc *__restrict__ tiles, const ActDesc *__restrict__ acts,
+                                                      uint32_t *__restrict__ results, const ColOp *__restrict__ colprog,
+                                                      const DpState *__restrict__ states, const DpEdge *__restrict__ edges,
+                                                      const uint16_t *__restrict__ costpool, PathOut *__restrict__ pathbuf,
+                                                      uint32_t *__restrict__ path_count, uint32_t path_cap) {
     const TileDesc tile = tiles[blockIdx.x];
     const ActDesc &a = acts[tile.act];
     __shared__ uint32_t counts[MAX_COSTS + 1];
@@ -417,43 +428,116 @@ __global__ void __launch_bounds__(128) eval_paths_kernel(const TileDesc *__restr
             }
             C[(size_t)op.dst * ld + j] = r;
         }
-        unsigned long long u = a.ub[j];
+        const unsigned long long u = a.ub[j];
+        unsigned long long *S = a.S;
+        const DpState *st = states + a.state_off;
+        const DpEdge *ed = edges + a.edge_off;
+        const uint32_t END = a.n_states - 1;
+        // backward DP; END has the single pair (cost 0)
+        S[(size_t)st[END].pair_off * ld + j] = u;
+        for (int s = (int)END - 1; s >= 0; s--) {
+            const DpState ss = st[s];
+            for (uint32_t k = 0; k < ss.rcount; k++) {
+                uint32_t r = ss.rmin + k;
+                unsigned long long acc = 0;
+                for (uint32_t e = 0; e < ss.n_edges; e++) {
+                    const DpEdge ee = ed[ss.edge_begin + e];
+                    if (ee.cost > r) continue;
+                    const DpState ds = st[ee.dst];
+                    uint32_t rr = r - ee.cost;
+                    if (rr < ds.rmin || rr >= (uint32_t)ds.rmin + ds.rcount) continue;
+                    unsigned long long v = S[(size_t)(ds.pair_off + rr - ds.rmin) * ld + j];
+                    if (v && ee.col != 0xffff) v &= C[(size_t)ee.col * ld + j];
+                    acc |= v;
+                }
+                S[(size_t)(ss.pair_off + k) * ld + j] = acc;
+            }
+        }
+        // buckets: cheapest cost first
+        const DpState root = st[0];
+        const uint16_t *cost_vals = costpool + a.cost_off;
         unsigned long long taken = 0;
-        for (uint32_t c = 0; c <= a.n_costs; c++) a.out[(size_t)c * ld + j] = 0;
-        unsigned long long stack[MAX_PATH_LEN];
-        uint32_t dead = 0xffffffffu;  // paths sharing >= dead conditions with the failed prefix are skipped
-        for (uint32_t p = 0; p < a.n_paths; p++) {
-            const PathRec pr = paths[a.path_off + p];
-            uint32_t l = pr.lcp;
-            if (l >= dead) continue;
-            dead = 0xffffffffu;
-            unsigned long long m = l == 0 ? u : stack[l - 1];
-            for (uint32_t d = l; d < pr.len; d++) {
-                m &= C[(size_t)condpool[pr.cond_off + d] * ld + j];
-                stack[d] = m;
-                if (m == 0) {
-                    dead = d + 1;
-                    break;
+        for (uint32_t ci = 0; ci < a.n_costs; ci++) {
+            uint32_t r = cost_vals[ci];
+            unsigned long long b = 0;
+            if (r >= root.rmin && r < (uint32_t)root.rmin + root.rcount) b = S[(size_t)(root.pair_off + r - root.rmin) * ld + j] & ~taken;
+            a.out[(size_t)ci * ld + j] = b;
+            if (b) {
+                taken |= b;
+                atomicAdd(&counts[ci], (uint32_t)__popcll(b));
+                if (a.want_paths) {
+                    // walk: every document follows the first edge (in order) it satisfies and can still finish from
+                    struct Frame {
+                        unsigned long long mask;
+                        uint16_t state, e, r;
+                    } stack[MAX_WALK];
+                    uint16_t pedges[MAX_WALK];
+                    int d = 0;
+                    stack[0].mask = b;
+                    stack[0].state = 0;
+                    stack[0].e = 0;
+                    stack[0].r = (uint16_t)r;
+                    while (d >= 0) {
+                        Frame &f = stack[d];
+                        const DpState fs = st[f.state];
+                        if (f.mask == 0 || f.e >= fs.n_edges) {
+                            d--;
+                            continue;
+                        }
+                        uint32_t eidx = fs.edge_begin + f.e;
+                        const DpEdge ee = ed[eidx];
+                        f.e++;
+                        if (ee.cost > f.r) continue;
+                        uint32_t rr = f.r - ee.cost;
+                        const DpState ds = st[ee.dst];
+                        if (rr < ds.rmin || rr >= (uint32_t)ds.rmin + ds.rcount) continue;
+                        unsigned long long take = f.mask & S[(size_t)(ds.pair_off + rr - ds.rmin) * ld + j];
+                        if (take && ee.col != 0xffff) take &= C[(size_t)ee.col * ld + j];
+                        if (!take) continue;
+                        f.mask &= ~take;
+                        pedges[d] = (uint16_t)eidx;
+                        if (ee.dst == END) {
+                            // a complete path: report it once per activation
+                            unsigned long long h = 0x9e3779b97f4a7c15ull + ci;
+                            for (int k = 0; k <= d; k++) h = mix64(h ^ pedges[k]) + 0x632be59bd9b4e019ull;
+                            h |= 1ull;
+                            uint32_t slot = (uint32_t)(h % a.tab_size);
+                            bool fresh = false;
+                            for (uint32_t probe = 0; probe < a.tab_size; probe++) {
+                                unsigned long long prev = atomicCAS(&a.tab[slot], 0ull, h);
+                                if (prev == 0ull) {
+                                    fresh = true;
+                                    break;
+                                }
+                                if (prev == h) break;
+                                slot = slot + 1 == a.tab_size ? 0 : slot + 1;
+                            }
+                            if (fresh) {
+                                uint32_t at = atomicAdd(path_count, 1u);
+                                if (at < path_cap) {
+                                    PathOut po;
+                                    po.act = tile.act;
+                                    po.cost_idx = (uint16_t)ci;
+                                    po.len = (uint16_t)(d + 1);
+                                    for (int k = 0; k < (int)MAX_WALK; k++) po.edges[k] = k <= d ? pedges[k] : 0;
+                                    pathbuf[at] = po;
+                                }
+                            }
+                            continue;
+                        }
+                        if (d + 1 >= (int)MAX_WALK) continue;  // host guarantees path length <= MAX_WALK
+                        d++;
+                        stack[d].mask = take;
+                        stack[d].state = ee.dst;
+                        stack[d].e = 0;
+                        stack[d].r = (uint16_t)rr;
+                    }
                 }
             }
-            if (m == 0) {
-                if (pr.len == 0) dead = 0xffffffffu;
-                continue;
-            }
-            unsigned long long matched = m & ~taken;
-            if (matched) {
-                taken |= matched;
-                a.out[(size_t)pr.cost_idx * ld + j] |= matched;
-                atomicAdd(&counts[pr.cost_idx], (uint32_t)__popcll(matched));
-                results[a.res_off + 2 + a.n_costs + p] = 1;  // benign race: all writers store 1
-            }
-            if (taken == u) break;
         }
         unsigned long long rest = u & ~taken;
-        if (rest) {
-            a.out[(size_t)a.n_costs * ld + j] = rest;
-            atomicAdd(&counts[a.n_costs], (uint32_t)__popcll(rest));
-        }
+        a.out[(size_t)a.n_costs * ld + j] = rest;
+        if (rest) atomicAdd(&counts[a.n_costs], (uint32_t)__popcll(rest));
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i <= a.n_costs; i += blockDim.x)
@@ -699,9 +783,10 @@ cudaError_t launch_scatter(cudaStream_t s, uint32_t n_ctas, const Job *queue, co
     return cudaGetLastError();
 }
 cudaError_t launch_eval(cudaStream_t s, const TileDesc *tiles, uint32_t n_tiles, const ActDesc *acts, uint32_t *results, const ColOp *colprog,
-                        const PathRec *paths, const uint16_t *condpool) {
+                        const DpState *states, const DpEdge *edges, const uint16_t *costpool, PathOut *pathbuf, uint32_t *path_count,
+                        uint32_t path_cap) {
     if (!n_tiles) return cudaSuccess;
-    eval_paths_kernel<<<n_tiles, 128, 0, s>>>(tiles, acts, results, colprog, paths, condpool);
+    eval_dp_kernel<<<n_tiles, 128, 0, s>>>(tiles, acts, results, colprog, states, edges, costpool, pathbuf, path_count, path_cap);
     return cudaGetLastError();
 }
 cudaError_t launch_emit(cudaStream_t s, const EmitDesc *emits, uint32_t n_emits) {

@@ -15,7 +15,8 @@ cudaError_t launch_pair_probe(cudaStream_t s, const PairSet *sets, uint32_t n_se
 cudaError_t launch_scatter(cudaStream_t s, uint32_t n_ctas, const Job *queue, const uint32_t *qcount, uint32_t qcap, const ActDesc *acts,
                            const uint32_t *results, const DListRef *lists, const uint32_t *pool);
 cudaError_t launch_eval(cudaStream_t s, const TileDesc *tiles, uint32_t n_tiles, const ActDesc *acts, uint32_t *results, const ColOp *colprog,
-                        const PathRec *paths, const uint16_t *condpool);
+                        const DpState *states, const DpEdge *edges, const uint16_t *costpool, PathOut *pathbuf, uint32_t *path_count,
+                        uint32_t path_cap);
 cudaError_t launch_emit(cudaStream_t s, const EmitDesc *emits, uint32_t n_emits);
 cudaError_t launch_vec_dist(cudaStream_t s, int n_ctas, int qt, const void *mat_fp16, const float *inv_norm, const uint32_t *docids,
                             uint64_t n_rows, uint32_t d, const float *queries, const float *q_inv_norm, const unsigned long long *cand,
