@@ -1408,7 +1408,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             // dst carries the offset inside the query's result row; the driver turns it into a device pointer
             e.d.dst = reinterpret_cast<uint32_t *>((uintptr_t)q.n_results);
             q.emits.push_back(e);
-            for (uint64_t k = 0; k < take; k++) q.scores.push_back(skip_scoring ? std::vector<EScore>{} : q.rr_scores);
+            for (uint64_t k = 0; k < take; k++) q.scores.push_back(q.rr_scores);  // bucket_sort.rs:447-455 records them under either strategy
             q.n_results += (uint32_t)take;
         }
         q.cur_offset += count;
@@ -1725,6 +1725,20 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             L.universe_count = 0;
             for (auto c : L.counts) L.universe_count += c;
             L.cursor = 0;
+            if (getenv("B200_DEBUG")) {
+                std::string msg = "[b200 debug] q" + std::to_string(act_q[a]) + " level " + std::to_string(q.levels.size() - 1) + " kind " +
+                                  std::to_string(L.kind) + " rows " + std::to_string(L.rows) + "/" + std::to_string(L.ld) + " states " +
+                                  std::to_string(L.n_states) + " edges " + std::to_string(L.sedges.size()) + " conds " + std::to_string(L.conds.size()) +
+                                  " cols " + std::to_string(q.pend.n_cols) + " jobs " + std::to_string(q.pend.jobs.size()) + " costs:";
+                for (size_t k = 0; k < L.cost_vals.size(); k++) msg += " " + std::to_string(L.cost_vals[k]) + "=" + std::to_string(L.counts[k]);
+                msg += " rest=" + std::to_string(L.counts.back()) + " surv " + std::to_string(L.surv.size());
+                for (auto &cd : L.conds) {
+                    msg += "\n      cond col" + std::to_string(cd.col) + " " + cd.key().substr(0, 90);
+                }
+                for (auto &e : L.sedges)
+                    msg += "\n      edge " + std::to_string(e.src) + "->" + std::to_string(e.dst) + " cost " + std::to_string(e.cost) + " cond " + std::to_string(e.cond);
+                fprintf(stderr, "%s\n", msg.c_str());
+            }
             try {
                 advance(q);
             } catch (const TooComplex &t) {

@@ -498,8 +498,8 @@ __global__ void __launch_bounds__(128) eval_dp_kernel(const TileDesc *__restrict
                         pedges[d] = (uint16_t)eidx;
                         if (ee.dst == END) {
                             // a complete path: report it once per activation
-                            unsigned long long h = 0x9e3779b97f4a7c15ull + ci;
-                            for (int k = 0; k <= d; k++) h = mix64(h ^ pedges[k]) + 0x632be59bd9b4e019ull;
+                            unsigned long long h = mix64(0x9e3779b97f4a7c15ull * (ci + 1));
+                            for (int k = 0; k <= d; k++) h = mix64(h + 0xd6e8feb86659fd93ull * (unsigned long long)(pedges[k] + 1));
                             h |= 1ull;
                             uint32_t slot = (uint32_t)(h % a.tab_size);
                             bool fresh = false;
