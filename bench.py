@@ -101,11 +101,11 @@ def run_reference(args, rank, world):
 
     img, batches = build_workload(args, 0)
     ix = OracleIndex(img)
-    threads = os.cpu_count() or 1
     sample = min(args.batch, args.cpu_sample)
     from meilisearch_b200.tokenizer import TokenBatch
 
     qs = [TokenBatch(img.synthetic_queries(sample, seed=i)) for i in range(args.distinct_batches)]
+    threads = best_cpu_run(ix, qs[0], sample)["cores"]
     for w in range(args.warmup):
         ix.search_batch(qs[w % len(qs)], n_threads=threads)
     t0 = time.perf_counter()
@@ -125,6 +125,22 @@ def run_reference(args, rank, world):
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out), flush=True)
+
+
+def best_cpu_run(oracle, tokens, sample):
+    """One query per thread (the reference's own concurrency model); the thread count that gives the best QPS is reported."""
+    cores = os.cpu_count() or 1
+    best = None
+    for threads in sorted({cores, max(1, cores // 2), max(1, cores // 4)}, reverse=True):
+        tc = time.perf_counter()
+        r = oracle.search_batch(tokens, n_threads=threads)
+        dt = time.perf_counter() - tc
+        cand = {"value": sample / dt, "unit": "queries/s", "cores": threads, "kind": "port",
+                "sample": f"{sample} queries of the timed workload, {threads} of {cores} host threads (best of {cores}, {cores // 2}, {cores // 4}), "
+                          f"p50 {1e3 * float(np.median(r.seconds)):.2f} ms/query; CPU restatement of milli, not milli itself"}
+        if best is None or cand["value"] > best["value"]:
+            best = cand
+    return best
 
 
 def workload_config(args, img):
@@ -241,15 +257,10 @@ def main():
     from meilisearch_b200.tokenizer import TokenBatch
     from oracle.pyoracle import OracleIndex
 
-    threads = os.cpu_count() or 1
     sample = min(args.batch, args.cpu_sample)
     sq = TokenBatch(img.synthetic_queries(args.batch, seed=1000 * rank + (args.warmup % len(batches)))[:sample])
     o = OracleIndex(img)
-    tc = time.perf_counter()
-    orr = o.search_batch(sq, n_threads=threads)
-    cpu_dt = time.perf_counter() - tc
-    cpu = {"value": sample / cpu_dt, "unit": "queries/s", "cores": threads, "kind": "port",
-           "sample": f"{sample} queries of the timed workload, {threads} threads, p50 {1e3 * float(np.median(orr.seconds)):.2f} ms/query (CPU restatement of milli, not milli itself)"}
+    cpu = best_cpu_run(o, sq, sample)
 
     out = {
         "metric": "queries/sec (batch=1024, typo-tolerant multi-term keyword search, top-20)", "value": total_q / dev_s, "unit": "queries/s",
@@ -265,6 +276,7 @@ def main():
         "cpu_baseline": cpu,
         "parity": parity,
         "queries_ok": n_ok,
+        "host_ms_per_step": {k: v / args.steps for k, v in st["host_ms"].items()},
         "algorithmic_bytes_per_step": {"posting": int(st["posting_bytes"] / args.steps), "matrix": int(st["matrix_bytes"] / args.steps),
                                        "dictionary": int(st["dictionary_bytes"] / args.steps)},
     }

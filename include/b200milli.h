@@ -159,6 +159,8 @@ typedef struct {
     uint64_t kernel_bytes[8];     /* algorithmic bytes attributed to each kernel class */
     double device_ms;             /* CUDA-event time from the first to the last kernel of every step */
     uint64_t h2d_bytes, d2h_bytes; /* bytes copied across PCIe/NVLink-C2C by search/derive/nns calls */
+    double host_ms[8];            /* wall time of the host phases of b200_search_batch: 0 parse, 1 derive (incl. device), 2 term finalisation,
+                                     3 step packing, 4 step device wait, 5 bucket-sort advance, 6 result copy, 7 total */
     uint64_t hbm_bytes_staged;
 } b200_stats;
 int b200_get_stats(b200_index *, b200_stats *out);

@@ -2,7 +2,12 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <condition_variable>
+#include <functional>
 #include <mutex>
+#include <thread>
+#include <atomic>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -49,7 +54,62 @@ struct DevBuf {  // grow-only device buffer
     }
 };
 
+// Persistent worker pool: the per-step host work (one bucket-sort advance per query) is a parallel-for.
+struct WorkerPool {
+    std::vector<std::thread> threads;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::function<void(size_t)> fn;
+    std::atomic<size_t> next{0};
+    size_t n = 0, generation = 0, busy = 0;
+    bool stop = false;
+    explicit WorkerPool(unsigned nt) {
+        for (unsigned t = 0; t < nt; t++)
+            threads.emplace_back([this]() {
+                size_t seen = 0;
+                for (;;) {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv_work.wait(lk, [&] { return stop || generation != seen; });
+                    if (stop) return;
+                    seen = generation;
+                    lk.unlock();
+                    for (;;) {
+                        size_t i = next.fetch_add(1);
+                        if (i >= n) break;
+                        fn(i);
+                    }
+                    lk.lock();
+                    if (--busy == 0) cv_done.notify_all();
+                }
+            });
+    }
+    void run(size_t count, std::function<void(size_t)> f) {
+        if (count == 0) return;
+        if (threads.empty() || count == 1) {
+            for (size_t i = 0; i < count; i++) f(i);
+            return;
+        }
+        std::unique_lock<std::mutex> lk(mu);
+        fn = std::move(f);
+        n = count;
+        next = 0;
+        busy = threads.size();
+        generation++;
+        cv_work.notify_all();
+        cv_done.wait(lk, [&] { return busy == 0; });
+    }
+    ~WorkerPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        cv_work.notify_all();
+        for (auto &t : threads) t.join();
+    }
+};
+
 struct Engine {
+    std::unique_ptr<WorkerPool> pool;
     int device = 0;
     cudaStream_t stream = nullptr;
     std::mutex mu;

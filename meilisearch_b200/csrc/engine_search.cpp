@@ -12,6 +12,7 @@
 // exactness}, exact_attribute.rs:96-301, query_graph.rs:96-187,254-301,346-406,453-543, query_term/parse_query.rs:28-300,
 // query_term/compute_derivations.rs:170-253,363-383, resolve_query_graph.rs:33-130.
 #include <atomic>
+#include <chrono>
 #include <cstring>
 #include <functional>
 #include <set>
@@ -1248,7 +1249,11 @@ void parallel_for(size_t n, unsigned nt, F f) {
 int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t offset, uint32_t limit, int scoring) {
     CU(cudaSetDevice(device), "cudaSetDevice");
     const uint32_t NQ = b->n_queries;
-    const unsigned NT = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    if (!pool) pool.reset(new WorkerPool(std::max(1u, std::min(48u, std::thread::hardware_concurrency()))));
+    auto pfor = [&](size_t n, std::function<void(size_t)> f) { pool->run(n, std::move(f)); };
+    using clk = std::chrono::steady_clock;
+    auto ms_since = [](clk::time_point t) { return std::chrono::duration<double, std::milli>(clk::now() - t).count(); };
+    auto t_total = clk::now();
     const bool skip_scoring = scoring == 0;
     const uint32_t length = limit, from = offset;
     const int tms = b->terms_matching_strategy;
@@ -1257,7 +1262,8 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
     for (uint32_t i = 0; i < NQ; i++) qs[i].reset(new QState(hix));
 
     // ---- phase 1: tokens -> terms -> query graph
-    parallel_for(NQ, NT, [&](size_t i) {
+    auto t_ph = clk::now();
+    pfor(NQ, [&](size_t i) {
         QState &q = *qs[i];
         try {
             parse_query(q, b, (uint32_t)i);
@@ -1267,8 +1273,10 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             q.done = true;
         }
     });
+    stats.host_ms[0] += ms_since(t_ph);
     // ---- phase 2: typo derivations for every term of the batch in one device sweep
     {
+        t_ph = clk::now();
         std::vector<char> wbytes;
         std::vector<uint32_t> woff{0};
         std::vector<uint8_t> mt, ip;
@@ -1295,7 +1303,9 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             int rc = derive_batch(n, wbytes.data(), woff.data(), mt.data(), ip.data(), one.data(), n_one.data(), two.data(), n_two.data());
             if (rc != B200_OK) return rc;
         }
-        parallel_for(NQ, NT, [&](size_t i) {
+        stats.host_ms[1] += ms_since(t_ph);
+        t_ph = clk::now();
+        pfor(NQ, [&](size_t i) {
             QState &q = *qs[i];
             if (q.done) return;
             for (auto &t : q.ctx.terms) {
@@ -1308,6 +1318,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
                 find_split_words(hix, t);
             }
         });
+        stats.host_ms[2] += ms_since(t_ph);
     }
     // ---- result buffers
     CU(d_docids_out.reserve((size_t)NQ * std::max(1u, length)), "alloc results");
@@ -1370,7 +1381,8 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         request_activation(q, std::move(L), nullptr, dix.base_ub, nullptr, hix.n_words64, hix.n_words64, 0, hix.n_words64);
     };
     std::vector<std::string> errs(NQ);
-    parallel_for(NQ, NT, [&](size_t i) {
+    t_ph = clk::now();
+    pfor(NQ, [&](size_t i) {
         QState &q = *qs[i];
         if (q.done) return;
         try {
@@ -1382,6 +1394,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         }
     });
 
+    stats.host_ms[5] += ms_since(t_ph);
     // advance one query's bucket sort until it needs the device again (bucket_sort.rs:193-330)
     auto emit_bucket = [&](QState &q, Level &L, uint32_t col_lo, uint32_t col_hi, uint64_t count) {
         if (count == 0) return;
@@ -1519,6 +1532,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         }
         if (act_q.empty() && emit_q.empty()) break;
         stats.device_steps++;
+        t_ph = clk::now();
         std::vector<ActDesc> acts(act_q.size());
         std::vector<Job> jobs;
         std::vector<PairSet> sets;
@@ -1645,6 +1659,8 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         if (!jobs.empty()) CU(cudaMemcpyAsync(d_queue.p, jobs.data(), jobs.size() * sizeof(Job), cudaMemcpyHostToDevice, stream), "H2D jobs");
         CU(cudaMemcpyAsync(d_qcount.p, &n_static, 4, cudaMemcpyHostToDevice, stream), "H2D job count");
         const ActDesc *dacts = reinterpret_cast<const ActDesc *>(d_step.p + o_acts);
+        stats.host_ms[3] += ms_since(t_ph);
+        t_ph = clk::now();
         // 1. emissions queued before this step's activations (they may read buffers the activations reuse)
         CU(cudaEventRecord(e0, stream), "event");
         if (!emits.empty()) {
@@ -1714,8 +1730,10 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
                 L.surv.push_back(std::move(sp));
             }
         }
+        stats.host_ms[4] += ms_since(t_ph);
+        t_ph = clk::now();
         // scatter results back, advance every query that got its activation
-        parallel_for(act_q.size(), NT, [&](size_t a) {
+        pfor(act_q.size(), [&](size_t a) {
             QState &q = *qs[act_q[a]];
             Level &L = q.levels.back();
             const uint32_t *res = h_results + L.res_off;
@@ -1748,11 +1766,13 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
                 q.want_activation = false;
             }
         });
+        stats.host_ms[5] += ms_since(t_ph);
     }
     (void)ms_fill;
     (void)ms_eval;
     (void)ms_emit;
     // ---- outputs
+    t_ph = clk::now();
     std::vector<uint32_t> out_ids((size_t)NQ * std::max(1u, length));
     CU(cudaMemcpyAsync(out_ids.data(), d_docids_out.p, out_ids.size() * 4, cudaMemcpyDeviceToHost, stream), "D2H docids");
     stats.d2h_bytes += out_ids.size() * 4;
@@ -1785,6 +1805,8 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             }
         }
     }
+    stats.host_ms[6] += ms_since(t_ph);
+    stats.host_ms[7] += ms_since(t_total);
     return B200_OK;
 }
 
