@@ -75,7 +75,7 @@ struct ActDesc {
     uint32_t colprog_off, colprog_len;
     uint32_t tab_size, want_paths;
     uint32_t res_off;         // into results u32[]: [0] rows, [1..n_costs+1] counts
-    uint32_t pad;
+    uint32_t all_conditional; // every START->END path has at least one condition: rows whose columns are all zero match nothing
 };
 
 struct ColOp {  // executed per row before the paths

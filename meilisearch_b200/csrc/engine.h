@@ -108,8 +108,72 @@ struct WorkerPool {
     }
 };
 
+// One software-pipeline lane of the step loop: own stream, step buffers, scratch slice and kernel timers.
+struct Lane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    DevBuf<uint8_t> d_step;
+    DevBuf<uint32_t> d_results, d_qcount;
+    DevBuf<Job> d_queue;
+    DevBuf<PathOut> d_pathbuf;
+    uint8_t *h_step = nullptr;
+    size_t h_step_cap = 0;
+    uint32_t *h_results = nullptr;
+    size_t h_results_cap = 0;
+    uint8_t *scratch = nullptr;
+    size_t scratch_bytes = 0;
+    std::vector<uint32_t> members, act_q;
+    uint32_t res_words = 0;
+    size_t qcap = 0;
+    bool inflight = false;
+    struct Timed {
+        int cls;
+        size_t a, b;
+    };
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<Timed> timed;
+    size_t ev_used = 0;
+    size_t mark() {
+        if (ev_used == ev_pool.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            ev_pool.push_back(e);
+        }
+        cudaEventRecord(ev_pool[ev_used], stream);
+        return ev_used++;
+    }
+    void time_kernel(b200_stats &st, int cls, size_t a, size_t b, uint64_t bytes) {
+        timed.push_back(Timed{cls, a, b});
+        st.kernel_count[cls]++;
+        st.kernel_bytes[cls] += bytes;
+        st.kernel_launches++;
+    }
+    void resolve_timers(b200_stats &st) {
+        for (auto &t : timed) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, ev_pool[t.a], ev_pool[t.b]) == cudaSuccess) st.kernel_ms[t.cls] += ms;
+        }
+        timed.clear();
+        ev_used = 0;
+    }
+    void release() {
+        d_step.release();
+        d_results.release();
+        d_qcount.release();
+        d_queue.release();
+        d_pathbuf.release();
+        if (h_step) cudaFreeHost(h_step);
+        if (h_results) cudaFreeHost(h_results);
+        for (auto e : ev_pool) cudaEventDestroy(e);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
 struct Engine {
     std::unique_ptr<WorkerPool> pool;
+    Lane lanes[2];
     int device = 0;
     cudaStream_t stream = nullptr;
     std::mutex mu;

@@ -290,7 +290,7 @@ struct StepOut {  // per-activation device work, appended to the step blob by th
     std::vector<DpState> dp_states;   // edge_begin relative to dp_edges
     std::vector<DpEdge> dp_edges;
     std::vector<uint16_t> cost_vals;
-    uint32_t n_cols = 0, n_costs = 0, n_pairs = 0, want_paths = 0;
+    uint32_t n_cols = 0, n_costs = 0, n_pairs = 0, want_paths = 0, all_conditional = 0;
     uint64_t posting_bytes = 0;
 };
 
@@ -1030,6 +1030,14 @@ void emit_activation_work(const QCtx &c, Level &L, StepOut &o) {
     }
     o.n_costs = (uint32_t)L.cost_vals.size();
     o.want_paths = L.want_paths ? 1 : 0;
+    // every START->END path carries at least one condition unless START reaches END through unconditional edges only
+    {
+        std::vector<uint8_t> free_reach(L.n_states, 0);
+        if (L.n_states) free_reach[0] = 1;
+        for (auto &e : L.sedges)
+            if (free_reach[e.src] && e.cond < 0) free_reach[e.dst] = 1;  // states are topologically ordered, edges grouped by source
+        o.all_conditional = (L.n_states && free_reach[L.n_states - 1]) ? 0 : 1;
+    }
     uint32_t pair = 0;
     for (uint16_t st = 0; st < L.n_states; st++) {
         DpState ds{};
@@ -1322,7 +1330,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
     }
     // ---- result buffers
     CU(d_docids_out.reserve((size_t)NQ * std::max(1u, length)), "alloc results");
-    size_t arena_used = 0, scratch_used = 0;
+    size_t arena_used = 0;
     auto arena_alloc = [&](size_t bytes) -> uint8_t * {
         size_t off = (arena_used + 255) & ~(size_t)255;
         if (off + bytes > arena_bytes) return nullptr;
@@ -1519,20 +1527,37 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         q.done = true;
     };
 
-    // ---- phase 4: step loop
-    float ms_fill = 0, ms_eval = 0, ms_emit = 0;
-    cudaEvent_t e0 = ev0, e1 = ev1;
-    for (;;) {
-        // gather
-        std::vector<uint32_t> act_q;
+    // ---- phase 4: step loop, software-pipelined over lanes: while one lane's kernels run, the host advances the other lane
+    const unsigned n_lanes = (NQ >= 64 && !getenv("B200_SINGLE_LANE")) ? 2 : 1;
+    for (unsigned l = 0; l < n_lanes; l++) {
+        Lane &ln = lanes[l];
+        if (!ln.stream) {
+            CU(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking), "lane stream");
+            CU(cudaEventCreate(&ln.e0), "lane event");
+            CU(cudaEventCreate(&ln.e1), "lane event");
+        }
+        ln.scratch = scratch + (scratch_bytes / n_lanes) * l;
+        ln.scratch_bytes = scratch_bytes / n_lanes;
+        ln.members.clear();
+        ln.inflight = false;
+    }
+    for (uint32_t i = 0; i < NQ; i++) lanes[i % n_lanes].members.push_back(i);
+    // everything queued on the engine stream so far (derivations) must be visible to the lanes
+    CU(cudaStreamSynchronize(stream), "sync");
+    const size_t PATH_CAP = (size_t)1 << 20;
+
+    // pack the pending work of a lane and enqueue it (no synchronisation). returns <0 on error, 0 idle, 1 launched
+    auto launch = [&](Lane &ln) -> int {
+        auto t_pack = clk::now();
+        ln.act_q.clear();
         std::vector<uint32_t> emit_q;
-        for (uint32_t i = 0; i < NQ; i++) {
-            if (qs[i]->want_activation) act_q.push_back(i);
+        for (auto i : ln.members) {
+            if (qs[i]->want_activation) ln.act_q.push_back(i);
             if (!qs[i]->emits.empty()) emit_q.push_back(i);
         }
-        if (act_q.empty() && emit_q.empty()) break;
+        if (ln.act_q.empty() && emit_q.empty()) return 0;
         stats.device_steps++;
-        t_ph = clk::now();
+        const std::vector<uint32_t> &act_q = ln.act_q;
         std::vector<ActDesc> acts(act_q.size());
         std::vector<Job> jobs;
         std::vector<PairSet> sets;
@@ -1544,8 +1569,8 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         std::vector<TileDesc> tiles;
         std::vector<EmitDesc> emits;
         uint32_t res_words = 0, n_probes = 0;
-        scratch_used = 0;
-        size_t s_used = 0;
+        size_t z_used = 0, s_used = 0;
+        uint64_t compact_bytes = 0, eval_bytes = 0, fill_bytes = 0;
         for (size_t a = 0; a < act_q.size(); a++) {
             QState &q = *qs[act_q[a]];
             Level &L = q.levels.back();
@@ -1566,23 +1591,24 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             d.n_states = (uint32_t)o.dp_states.size();
             d.want_paths = o.want_paths;
             d.tab_size = o.want_paths ? 4096 : 1;
+            d.all_conditional = o.all_conditional;
             size_t persist = (size_t)ld * 4 + 256 + (size_t)ld * 8 + 256 + (size_t)ld * 8 * (o.n_costs + 1);
             uint8_t *pb = arena_alloc(persist);
             size_t cbytes = (size_t)ld * 8 * d.n_cols, sbytes = (size_t)ld * 8 * o.n_pairs, tbytes = (size_t)d.tab_size * 8;
-            // zeroed zone (condition matrix + path table) grows from the front of the scratch pool, the DP table from the back
-            size_t coff = (scratch_used + 255) & ~(size_t)255;
+            // zeroed zone (condition matrix + path table) grows from the front of the lane's scratch, the DP table from the back
+            size_t coff = (z_used + 255) & ~(size_t)255;
             size_t toff = (coff + cbytes + 255) & ~(size_t)255;
             size_t s_need = (sbytes + 255) & ~(size_t)255;
-            if (!pb || toff + tbytes + s_need + s_used > scratch_bytes)
+            if (!pb || toff + tbytes + s_need + s_used > ln.scratch_bytes)
                 return fail(B200_ERR_CAPACITY, "device arena exhausted: lower the batch size or raise B200_ARENA_MB / B200_SCRATCH_MB");
-            scratch_used = toff + tbytes;
+            z_used = toff + tbytes;
             s_used += s_need;
-            d.S = reinterpret_cast<unsigned long long *>(scratch + scratch_bytes - s_used);
-            d.tab = reinterpret_cast<unsigned long long *>(scratch + toff);
+            d.S = reinterpret_cast<unsigned long long *>(ln.scratch + ln.scratch_bytes - s_used);
+            d.tab = reinterpret_cast<unsigned long long *>(ln.scratch + toff);
             d.uw = reinterpret_cast<uint32_t *>(pb);
             d.ub = reinterpret_cast<unsigned long long *>(pb + (((size_t)ld * 4 + 255) & ~(size_t)255));
             d.out = d.ub + (((size_t)ld + 31) & ~(size_t)31);
-            d.C = reinterpret_cast<unsigned long long *>(scratch + coff);
+            d.C = reinterpret_cast<unsigned long long *>(ln.scratch + coff);
             L.uw = d.uw;
             L.ub = d.ub;
             L.out = d.out;
@@ -1615,7 +1641,11 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             }
             for (uint32_t r0 = 0; r0 < ld; r0 += 128) tiles.push_back(TileDesc{(uint32_t)a, r0});
             stats.posting_bytes += o.posting_bytes;
-            stats.matrix_bytes += (uint64_t)ld * 8 * (d.n_cols + o.n_pairs + o.n_costs + 2);
+            uint64_t mb = (uint64_t)ld * 8 * (d.n_cols + o.n_pairs + o.n_costs + 2);
+            stats.matrix_bytes += mb;
+            eval_bytes += mb;
+            compact_bytes += (uint64_t)d.p_rows * 8 + (uint64_t)ld * 12;
+            fill_bytes += o.posting_bytes;
             q.want_activation = false;
         }
         for (auto qi : emit_q) {
@@ -1627,98 +1657,101 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             }
             q.emits.clear();
         }
-        // pack + upload
         Blob blob;
         size_t o_acts = blob.add(acts), o_sets = blob.add(sets), o_words = blob.add(words), o_colprog = blob.add(colprog),
                o_states = blob.add(dstates), o_edges = blob.add(dedges), o_costs = blob.add(costpool), o_tiles = blob.add(tiles),
-               o_emits = blob.add(emits);
+               o_emits = blob.add(emits), o_jobs = blob.add(jobs);
         size_t nbytes = blob.bytes.size() + 16;
-        if (nbytes > h_step_cap) {
-            if (h_step) cudaFreeHost(h_step);
-            h_step_cap = nbytes * 2;
-            CU(cudaMallocHost((void **)&h_step, h_step_cap), "pinned step buffer");
+        if (nbytes > ln.h_step_cap) {
+            if (ln.h_step) cudaFreeHost(ln.h_step);
+            ln.h_step_cap = nbytes * 2;
+            CU(cudaMallocHost((void **)&ln.h_step, ln.h_step_cap), "pinned step buffer");
         }
-        memcpy(h_step, blob.bytes.data(), blob.bytes.size());
-        CU(d_step.reserve(nbytes), "step buffer");
-        CU(cudaMemcpyAsync(d_step.p, h_step, nbytes, cudaMemcpyHostToDevice, stream), "H2D step");
-        stats.h2d_bytes += nbytes + jobs.size() * sizeof(Job) + 4;
-        stats.d2h_bytes += (size_t)res_words * 4 + 4;
-        const size_t qcap_needed = jobs.size() + ((size_t)1 << 20);
-        size_t qcap = std::max<size_t>(qcap_needed, (size_t)4 << 20);
-        CU(d_queue.reserve(qcap), "job queue");
-        qcap = d_queue.cap;
-        CU(d_qcount.reserve(4), "job counter");
-        const size_t PATH_CAP = (size_t)1 << 20;
-        CU(d_results.reserve(res_words + 4), "results");
-        if (res_words + 4 > h_results_cap) {
-            if (h_results) cudaFreeHost(h_results);
-            h_results_cap = (size_t)(res_words + 4) * 2;
-            CU(cudaMallocHost((void **)&h_results, h_results_cap * 4), "pinned results");
-        }
+        memcpy(ln.h_step, blob.bytes.data(), blob.bytes.size());
         uint32_t n_static = (uint32_t)jobs.size();
-        if (!jobs.empty()) CU(cudaMemcpyAsync(d_queue.p, jobs.data(), jobs.size() * sizeof(Job), cudaMemcpyHostToDevice, stream), "H2D jobs");
-        CU(cudaMemcpyAsync(d_qcount.p, &n_static, 4, cudaMemcpyHostToDevice, stream), "H2D job count");
-        const ActDesc *dacts = reinterpret_cast<const ActDesc *>(d_step.p + o_acts);
-        stats.host_ms[3] += ms_since(t_ph);
-        t_ph = clk::now();
-        // 1. emissions queued before this step's activations (they may read buffers the activations reuse)
-        CU(cudaEventRecord(e0, stream), "event");
+        memcpy(ln.h_step + blob.bytes.size(), &n_static, 4);
+        CU(ln.d_step.reserve(nbytes), "step buffer");
+        cudaStream_t st = ln.stream;
+        CU(cudaMemcpyAsync(ln.d_step.p, ln.h_step, nbytes, cudaMemcpyHostToDevice, st), "H2D step");
+        stats.h2d_bytes += nbytes;
+        stats.d2h_bytes += (size_t)res_words * 4 + 8;
+        size_t qcap = std::max<size_t>(jobs.size() + ((size_t)1 << 20), (size_t)4 << 20);
+        CU(ln.d_queue.reserve(qcap), "job queue");
+        qcap = ln.d_queue.cap;
+        CU(ln.d_qcount.reserve(4), "job counter");
+        CU(ln.d_results.reserve(res_words + 4), "results");
+        if (res_words + 4 > ln.h_results_cap) {
+            if (ln.h_results) cudaFreeHost(ln.h_results);
+            ln.h_results_cap = (size_t)(res_words + 4) * 2;
+            CU(cudaMallocHost((void **)&ln.h_results, ln.h_results_cap * 4), "pinned results");
+        }
+        if (!jobs.empty())
+            CU(cudaMemcpyAsync(ln.d_queue.p, ln.d_step.p + o_jobs, jobs.size() * sizeof(Job), cudaMemcpyDeviceToDevice, st), "jobs to queue");
+        CU(cudaMemcpyAsync(ln.d_qcount.p, ln.d_step.p + blob.bytes.size(), 4, cudaMemcpyDeviceToDevice, st), "job count");
+        const ActDesc *dacts = reinterpret_cast<const ActDesc *>(ln.d_step.p + o_acts);
+        // 1. emissions queued before this step's activations
+        CU(cudaEventRecord(ln.e0, st), "event");
         if (!emits.empty()) {
-            size_t a = mark();
-            CU(launch_emit(stream, reinterpret_cast<const EmitDesc *>(d_step.p + o_emits), (uint32_t)emits.size()), "emit");
-            time_kernel(B200_K_EMIT, a, mark(), (uint64_t)emits.size() * 64);
+            size_t m0 = ln.mark();
+            CU(launch_emit(st, reinterpret_cast<const EmitDesc *>(ln.d_step.p + o_emits), (uint32_t)emits.size()), "emit");
+            ln.time_kernel(stats, B200_K_EMIT, m0, ln.mark(), (uint64_t)emits.size() * 64);
         }
         if (!acts.empty()) {
-            CU(cudaMemsetAsync(d_results.p, 0, (size_t)(res_words + 4) * 4, stream), "zero results");
-            CU(cudaMemsetAsync(scratch, 0, scratch_used, stream), "zero condition matrix");
-            CU(d_pathbuf.reserve(PATH_CAP), "path buffer");
-            CU(d_qcount.reserve(4), "counters");
-            CU(cudaMemsetAsync(d_qcount.p + 1, 0, 4, stream), "zero path count");
-            uint64_t compact_bytes = 0, eval_bytes = 0, fill_bytes = 0;
-            for (size_t a = 0; a < acts.size(); a++) {
-                compact_bytes += (uint64_t)acts[a].p_rows * 8 + (uint64_t)acts[a].ld * 12;
-                eval_bytes += (uint64_t)acts[a].ld * 8 * (acts[a].n_cols + qs[act_q[a]]->pend.n_pairs + acts[a].n_costs + 2);
-                fill_bytes += qs[act_q[a]]->pend.posting_bytes;
-            }
-            size_t t0 = mark();
-            CU(launch_compact(stream, dacts, (uint32_t)acts.size(), d_results.p), "compact");
-            size_t t1 = mark();
-            time_kernel(B200_K_COMPACT, t0, t1, compact_bytes);
-            CU(launch_pair_probe(stream, reinterpret_cast<const PairSet *>(d_step.p + o_sets), (uint32_t)sets.size(), n_probes,
-                                 reinterpret_cast<const uint32_t *>(d_step.p + o_words), dix.pair_keys, hix.pair_keys.size(), hix.pair_list_base,
-                                 dix.lists, dacts, d_results.p, d_queue.p, d_qcount.p, (uint32_t)qcap),
+            CU(cudaMemsetAsync(ln.d_results.p, 0, (size_t)(res_words + 4) * 4, st), "zero results");
+            CU(cudaMemsetAsync(ln.scratch, 0, z_used, st), "zero condition matrix");
+            CU(ln.d_pathbuf.reserve(PATH_CAP), "path buffer");
+            CU(cudaMemsetAsync(ln.d_qcount.p + 1, 0, 4, st), "zero path count");
+            size_t t0 = ln.mark();
+            CU(launch_compact(st, dacts, (uint32_t)acts.size(), ln.d_results.p), "compact");
+            size_t t1 = ln.mark();
+            ln.time_kernel(stats, B200_K_COMPACT, t0, t1, compact_bytes);
+            CU(launch_pair_probe(st, reinterpret_cast<const PairSet *>(ln.d_step.p + o_sets), (uint32_t)sets.size(), n_probes,
+                                 reinterpret_cast<const uint32_t *>(ln.d_step.p + o_words), dix.pair_keys, hix.pair_keys.size(), hix.pair_list_base,
+                                 dix.lists, dacts, ln.d_results.p, ln.d_queue.p, ln.d_qcount.p, (uint32_t)qcap),
                "pair probe");
-            size_t t2 = mark();
-            if (n_probes) time_kernel(B200_K_PAIR_PROBE, t1, t2, (uint64_t)n_probes * 8 * 23);
-            CU(launch_scatter(stream, (uint32_t)sm_count * 8, d_queue.p, d_qcount.p, (uint32_t)qcap, dacts, d_results.p, dix.lists, dix.pool), "scatter");
-            size_t t3 = mark();
-            time_kernel(B200_K_SCATTER, t2, t3, fill_bytes);
-            CU(launch_eval(stream, reinterpret_cast<const TileDesc *>(d_step.p + o_tiles), (uint32_t)tiles.size(), dacts, d_results.p,
-                           reinterpret_cast<const ColOp *>(d_step.p + o_colprog), reinterpret_cast<const DpState *>(d_step.p + o_states),
-                           reinterpret_cast<const DpEdge *>(d_step.p + o_edges), reinterpret_cast<const uint16_t *>(d_step.p + o_costs), d_pathbuf.p,
-                           d_qcount.p + 1, (uint32_t)PATH_CAP),
+            size_t t2 = ln.mark();
+            if (n_probes) ln.time_kernel(stats, B200_K_PAIR_PROBE, t1, t2, (uint64_t)n_probes * 8 * 23);
+            CU(launch_scatter(st, (uint32_t)sm_count * 8, ln.d_queue.p, ln.d_qcount.p, (uint32_t)qcap, dacts, ln.d_results.p, dix.lists, dix.pool), "scatter");
+            size_t t3 = ln.mark();
+            ln.time_kernel(stats, B200_K_SCATTER, t2, t3, fill_bytes);
+            CU(launch_eval(st, reinterpret_cast<const TileDesc *>(ln.d_step.p + o_tiles), (uint32_t)tiles.size(), dacts, ln.d_results.p,
+                           reinterpret_cast<const ColOp *>(ln.d_step.p + o_colprog), reinterpret_cast<const DpState *>(ln.d_step.p + o_states),
+                           reinterpret_cast<const DpEdge *>(ln.d_step.p + o_edges), reinterpret_cast<const uint16_t *>(ln.d_step.p + o_costs),
+                           ln.d_pathbuf.p, ln.d_qcount.p + 1, (uint32_t)PATH_CAP),
                "eval paths");
-            time_kernel(B200_K_EVAL_PATHS, t3, mark(), eval_bytes);
-            CU(cudaMemcpyAsync(h_results, d_results.p, (size_t)res_words * 4, cudaMemcpyDeviceToHost, stream), "D2H results");
-            CU(cudaMemcpyAsync(h_results + res_words, d_qcount.p, 8, cudaMemcpyDeviceToHost, stream), "D2H counters");
+            ln.time_kernel(stats, B200_K_EVAL_PATHS, t3, ln.mark(), eval_bytes);
+            CU(cudaMemcpyAsync(ln.h_results, ln.d_results.p, (size_t)res_words * 4, cudaMemcpyDeviceToHost, st), "D2H results");
+            CU(cudaMemcpyAsync(ln.h_results + res_words, ln.d_qcount.p, 8, cudaMemcpyDeviceToHost, st), "D2H counters");
         }
-        CU(cudaEventRecord(e1, stream), "event");
-        CU(cudaStreamSynchronize(stream), "step sync");
+        CU(cudaEventRecord(ln.e1, st), "event");
+        ln.res_words = res_words;
+        ln.qcap = qcap;
+        ln.inflight = true;
+        stats.host_ms[3] += ms_since(t_pack);
+        return 1;
+    };
+
+    // wait for a lane's step, fetch its results and advance its queries
+    auto finish = [&](Lane &ln) -> int {
+        auto t_wait = clk::now();
+        CU(cudaStreamSynchronize(ln.stream), "step sync");
+        ln.inflight = false;
         {
             float ms = 0;
-            cudaEventElapsedTime(&ms, e0, e1);
+            cudaEventElapsedTime(&ms, ln.e0, ln.e1);
             stats.device_ms += ms;
-            resolve_timers();
+            ln.resolve_timers(stats);
         }
-        if (!acts.empty() && h_results[res_words] > qcap) return fail(B200_ERR_CAPACITY, "scatter job queue overflow");
-        std::vector<PathOut> pouts;
-        if (!acts.empty()) {
-            uint32_t np = h_results[res_words + 1];
+        const std::vector<uint32_t> &act_q = ln.act_q;
+        const uint32_t res_words = ln.res_words;
+        if (!act_q.empty()) {
+            if (ln.h_results[res_words] > ln.qcap) return fail(B200_ERR_CAPACITY, "scatter job queue overflow");
+            uint32_t np = ln.h_results[res_words + 1];
             if (np > PATH_CAP) return fail(B200_ERR_CAPACITY, "surviving-path buffer overflow");
-            pouts.resize(np);
+            std::vector<PathOut> pouts(np);
             if (np) {
-                CU(cudaMemcpyAsync(pouts.data(), d_pathbuf.p, (size_t)np * sizeof(PathOut), cudaMemcpyDeviceToHost, stream), "D2H paths");
-                CU(cudaStreamSynchronize(stream), "sync paths");
+                CU(cudaMemcpyAsync(pouts.data(), ln.d_pathbuf.p, (size_t)np * sizeof(PathOut), cudaMemcpyDeviceToHost, ln.stream), "D2H paths");
+                CU(cudaStreamSynchronize(ln.stream), "sync paths");
                 stats.d2h_bytes += (size_t)np * sizeof(PathOut);
             }
             for (size_t a = 0; a < act_q.size(); a++) qs[act_q[a]]->levels.back().surv.clear();
@@ -1730,31 +1763,26 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
                 L.surv.push_back(std::move(sp));
             }
         }
-        stats.host_ms[4] += ms_since(t_ph);
-        t_ph = clk::now();
-        // scatter results back, advance every query that got its activation
+        stats.host_ms[4] += ms_since(t_wait);
+        auto t_adv = clk::now();
+        const bool dbg = getenv("B200_DEBUG") != nullptr;
         pfor(act_q.size(), [&](size_t a) {
             QState &q = *qs[act_q[a]];
             Level &L = q.levels.back();
-            const uint32_t *res = h_results + L.res_off;
+            const uint32_t *res = ln.h_results + L.res_off;
             L.rows = res[0];
             size_t nc = L.cost_vals.size();
             L.counts.assign(res + 1, res + 1 + nc + 1);
             L.universe_count = 0;
             for (auto c : L.counts) L.universe_count += c;
             L.cursor = 0;
-            if (getenv("B200_DEBUG")) {
+            if (dbg) {
                 std::string msg = "[b200 debug] q" + std::to_string(act_q[a]) + " level " + std::to_string(q.levels.size() - 1) + " kind " +
                                   std::to_string(L.kind) + " rows " + std::to_string(L.rows) + "/" + std::to_string(L.ld) + " states " +
                                   std::to_string(L.n_states) + " edges " + std::to_string(L.sedges.size()) + " conds " + std::to_string(L.conds.size()) +
                                   " cols " + std::to_string(q.pend.n_cols) + " jobs " + std::to_string(q.pend.jobs.size()) + " costs:";
                 for (size_t k = 0; k < L.cost_vals.size(); k++) msg += " " + std::to_string(L.cost_vals[k]) + "=" + std::to_string(L.counts[k]);
                 msg += " rest=" + std::to_string(L.counts.back()) + " surv " + std::to_string(L.surv.size());
-                for (auto &cd : L.conds) {
-                    msg += "\n      cond col" + std::to_string(cd.col) + " " + cd.key().substr(0, 90);
-                }
-                for (auto &e : L.sedges)
-                    msg += "\n      edge " + std::to_string(e.src) + "->" + std::to_string(e.dst) + " cost " + std::to_string(e.cost) + " cond " + std::to_string(e.cond);
                 fprintf(stderr, "%s\n", msg.c_str());
             }
             try {
@@ -1766,11 +1794,27 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
                 q.want_activation = false;
             }
         });
-        stats.host_ms[5] += ms_since(t_ph);
+        stats.host_ms[5] += ms_since(t_adv);
+        return 0;
+    };
+
+    for (unsigned l = 0; l < n_lanes; l++) {
+        int rc = launch(lanes[l]);
+        if (rc < 0) return rc;
     }
-    (void)ms_fill;
-    (void)ms_eval;
-    (void)ms_emit;
+    for (;;) {
+        bool any = false;
+        for (unsigned l = 0; l < n_lanes; l++) {
+            Lane &ln = lanes[l];
+            if (!ln.inflight) continue;
+            any = true;
+            int rc = finish(ln);
+            if (rc < 0) return rc;
+            rc = launch(ln);
+            if (rc < 0) return rc;
+        }
+        if (!any) break;
+    }
     // ---- outputs
     t_ph = clk::now();
     std::vector<uint32_t> out_ids((size_t)NQ * std::max(1u, length));
@@ -1805,6 +1849,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             }
         }
     }
+    pfor(NQ, [&](size_t i) { qs[i].reset(); });  // tear the per-query state down in parallel
     stats.host_ms[6] += ms_since(t_ph);
     stats.host_ms[7] += ms_since(t_total);
     return B200_OK;

@@ -32,6 +32,7 @@ Engine::~Engine() {
     for (void *p : {(void *)dix.dict_bytes, (void *)dix.dict_off, (void *)dix.pool, (void *)dix.lists, (void *)dix.pair_keys, (void *)dix.base_ub,
                     (void *)dix.emb, (void *)dix.emb_inv_norm, (void *)dix.emb_docids, (void *)arena, (void *)scratch})
         if (p) cudaFree(p);
+    for (auto &ln : lanes) ln.release();
     d_step.release();
     d_results.release();
     d_queue.release();

@@ -429,6 +429,18 @@ __global__ void __launch_bounds__(128) eval_dp_kernel(const TileDesc *__restrict
             C[(size_t)op.dst * ld + j] = r;
         }
         const unsigned long long u = a.ub[j];
+        if (a.all_conditional) {
+            // a row that satisfies no condition at all cannot be on any path: it only contributes to the "rest" column
+            unsigned long long any = 0;
+            for (uint32_t c = 0; c < a.n_cols; c++) any |= C[(size_t)c * ld + j];
+            if (!any) {
+                for (uint32_t ci = 0; ci < a.n_costs; ci++) a.out[(size_t)ci * ld + j] = 0;
+                a.out[(size_t)a.n_costs * ld + j] = u;
+                if (u) atomicAdd(&counts[a.n_costs], (uint32_t)__popcll(u));
+                goto row_done;
+            }
+        }
+        {
         unsigned long long *S = a.S;
         const DpState *st = states + a.state_off;
         const DpEdge *ed = edges + a.edge_off;
@@ -538,6 +550,8 @@ __global__ void __launch_bounds__(128) eval_dp_kernel(const TileDesc *__restrict
         unsigned long long rest = u & ~taken;
         a.out[(size_t)a.n_costs * ld + j] = rest;
         if (rest) atomicAdd(&counts[a.n_costs], (uint32_t)__popcll(rest));
+        }
+    row_done:;
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i <= a.n_costs; i += blockDim.x)
