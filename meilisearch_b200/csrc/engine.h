@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -54,32 +55,47 @@ struct DevBuf {  // grow-only device buffer
     }
 };
 
-// Persistent worker pool: the per-step host work (one bucket-sort advance per query) is a parallel-for.
+// Persistent worker pool: the per-step host work (one bucket-sort advance per query) is a parallel-for.  Steps arrive every
+// few hundred microseconds, so idle workers spin briefly on the generation counter before they block.
 struct WorkerPool {
     std::vector<std::thread> threads;
     std::mutex mu;
-    std::condition_variable cv_work, cv_done;
+    std::condition_variable cv_work;
     std::function<void(size_t)> fn;
-    std::atomic<size_t> next{0};
-    size_t n = 0, generation = 0, busy = 0;
-    bool stop = false;
+    std::atomic<size_t> next{0}, generation{0}, remaining{0};
+    size_t n = 0;
+    std::atomic<bool> stop{false};
     explicit WorkerPool(unsigned nt) {
         for (unsigned t = 0; t < nt; t++)
             threads.emplace_back([this]() {
                 size_t seen = 0;
                 for (;;) {
-                    std::unique_lock<std::mutex> lk(mu);
-                    cv_work.wait(lk, [&] { return stop || generation != seen; });
-                    if (stop) return;
-                    seen = generation;
-                    lk.unlock();
+                    // spin ~200 us, then sleep
+                    bool got = false;
+                    auto t0 = std::chrono::steady_clock::now();
+                    for (int spin = 0;; spin++) {
+                        if (stop.load(std::memory_order_acquire)) return;
+                        if (generation.load(std::memory_order_acquire) != seen) {
+                            got = true;
+                            break;
+                        }
+                        if ((spin & 63) == 63 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(200)) break;
+#if defined(__x86_64__)
+                        __builtin_ia32_pause();
+#endif
+                    }
+                    if (!got) {
+                        std::unique_lock<std::mutex> lk(mu);
+                        cv_work.wait(lk, [&] { return stop.load() || generation.load() != seen; });
+                        if (stop.load()) return;
+                    }
+                    seen = generation.load(std::memory_order_acquire);
                     for (;;) {
                         size_t i = next.fetch_add(1);
                         if (i >= n) break;
                         fn(i);
+                        remaining.fetch_sub(1, std::memory_order_acq_rel);
                     }
-                    lk.lock();
-                    if (--busy == 0) cv_done.notify_all();
                 }
             });
     }
@@ -89,19 +105,32 @@ struct WorkerPool {
             for (size_t i = 0; i < count; i++) f(i);
             return;
         }
-        std::unique_lock<std::mutex> lk(mu);
-        fn = std::move(f);
-        n = count;
-        next = 0;
-        busy = threads.size();
-        generation++;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            fn = std::move(f);
+            n = count;
+            next.store(0);
+            remaining.store(count);
+            generation.fetch_add(1, std::memory_order_release);
+        }
         cv_work.notify_all();
-        cv_done.wait(lk, [&] { return busy == 0; });
+        // the caller works too
+        for (;;) {
+            size_t i = next.fetch_add(1);
+            if (i >= count) break;
+            fn(i);
+            remaining.fetch_sub(1, std::memory_order_acq_rel);
+        }
+        while (remaining.load(std::memory_order_acquire) != 0) {
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
     }
     ~WorkerPool() {
         {
             std::lock_guard<std::mutex> lk(mu);
-            stop = true;
+            stop.store(true);
         }
         cv_work.notify_all();
         for (auto &t : threads) t.join();

@@ -1558,24 +1558,95 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         if (ln.act_q.empty() && emit_q.empty()) return 0;
         stats.device_steps++;
         const std::vector<uint32_t> &act_q = ln.act_q;
-        std::vector<ActDesc> acts(act_q.size());
-        std::vector<Job> jobs;
-        std::vector<PairSet> sets;
-        std::vector<uint32_t> words;
-        std::vector<ColOp> colprog;
-        std::vector<DpState> dstates;
-        std::vector<DpEdge> dedges;
-        std::vector<uint16_t> costpool;
-        std::vector<TileDesc> tiles;
-        std::vector<EmitDesc> emits;
-        uint32_t res_words = 0, n_probes = 0;
+        const size_t NA = act_q.size();
+        // pass 1 (serial, light): sizes, offsets, device memory
+        struct Plan {
+            uint32_t jobs, sets, words, colprog, states, edges, costs, tiles, probes, res_off;
+            uint32_t ld;
+            uint8_t *pb;
+            size_t coff, toff, soff_from_end;
+            bool identity;
+        };
+        std::vector<Plan> plan(NA);
+        uint32_t n_jobs = 0, n_sets = 0, n_words = 0, n_colprog = 0, n_states = 0, n_edges = 0, n_costs_tot = 0, n_tiles = 0, n_probes = 0, res_words = 0;
         size_t z_used = 0, s_used = 0;
         uint64_t compact_bytes = 0, eval_bytes = 0, fill_bytes = 0;
-        for (size_t a = 0; a < act_q.size(); a++) {
+        for (size_t a = 0; a < NA; a++) {
+            QState &q = *qs[act_q[a]];
+            StepOut &o = q.pend;
+            Plan &pl = plan[a];
+            pl.jobs = n_jobs;
+            pl.sets = n_sets;
+            pl.words = n_words;
+            pl.colprog = n_colprog;
+            pl.states = n_states;
+            pl.edges = n_edges;
+            pl.costs = n_costs_tot;
+            pl.tiles = n_tiles;
+            pl.probes = n_probes;
+            pl.res_off = res_words;
+            uint32_t ld = std::max(1u, q.p_cap);
+            pl.ld = ld;
+            n_jobs += (uint32_t)o.jobs.size();
+            n_sets += (uint32_t)o.pairsets.size();
+            n_words += (uint32_t)o.words.size();
+            n_colprog += (uint32_t)o.colprog.size();
+            n_states += (uint32_t)o.dp_states.size();
+            n_edges += (uint32_t)o.dp_edges.size();
+            n_costs_tot += (uint32_t)o.cost_vals.size();
+            n_tiles += (ld + 127) / 128;
+            for (auto &ps : o.pairsets) n_probes += ps.n_left * ps.n_right;
+            res_words += 2 + o.n_costs;
+            pl.identity = !q.p_uw && !q.p_out;  // first activation of a query: the universe is the dense documents bitmap itself
+            uint32_t n_cols = std::max(1u, o.n_cols);
+            uint32_t tab_size = o.want_paths ? 4096 : 1;
+            size_t persist = pl.identity ? (size_t)ld * 8 * (o.n_costs + 1) : (size_t)ld * 4 + 256 + (size_t)ld * 8 + 256 + (size_t)ld * 8 * (o.n_costs + 1);
+            pl.pb = arena_alloc(persist);
+            size_t cbytes = (size_t)ld * 8 * n_cols, sbytes = (size_t)ld * 8 * o.n_pairs, tbytes = (size_t)tab_size * 8;
+            // zeroed zone (condition matrix + path table) grows from the front of the lane's scratch, the DP table from the back
+            pl.coff = (z_used + 255) & ~(size_t)255;
+            pl.toff = (pl.coff + cbytes + 255) & ~(size_t)255;
+            size_t s_need = (sbytes + 255) & ~(size_t)255;
+            if (!pl.pb || pl.toff + tbytes + s_need + s_used > ln.scratch_bytes)
+                return fail(B200_ERR_CAPACITY, "device arena exhausted: lower the batch size or raise B200_ARENA_MB / B200_SCRATCH_MB");
+            z_used = pl.toff + tbytes;
+            s_used += s_need;
+            pl.soff_from_end = s_used;
+            stats.posting_bytes += o.posting_bytes;
+            uint64_t mb = (uint64_t)ld * 8 * (n_cols + o.n_pairs + o.n_costs + 2);
+            stats.matrix_bytes += mb;
+            eval_bytes += mb;
+            if (!pl.identity) compact_bytes += (uint64_t)q.p_rows * 8 + (uint64_t)ld * 12;
+            fill_bytes += o.posting_bytes;
+        }
+        uint32_t n_emits = 0;
+        for (auto qi : emit_q) n_emits += (uint32_t)qs[qi]->emits.size();
+        // section offsets inside the step blob
+        size_t off = 0;
+        auto section = [&](size_t bytes) {
+            size_t o0 = (off + 15) & ~(size_t)15;
+            off = o0 + bytes;
+            return o0;
+        };
+        size_t o_acts = section(NA * sizeof(ActDesc)), o_sets = section((size_t)n_sets * sizeof(PairSet)), o_words = section((size_t)n_words * 4),
+               o_colprog = section((size_t)n_colprog * sizeof(ColOp)), o_states = section((size_t)n_states * sizeof(DpState)),
+               o_edges = section((size_t)n_edges * sizeof(DpEdge)), o_costs = section((size_t)n_costs_tot * 2),
+               o_tiles = section((size_t)n_tiles * sizeof(TileDesc)), o_emits = section((size_t)n_emits * sizeof(EmitDesc)),
+               o_jobs = section((size_t)n_jobs * sizeof(Job)), o_nstatic = section(16);
+        size_t nbytes = off + 16;
+        if (nbytes > ln.h_step_cap) {
+            if (ln.h_step) cudaFreeHost(ln.h_step);
+            ln.h_step_cap = nbytes * 2;
+            CU(cudaMallocHost((void **)&ln.h_step, ln.h_step_cap), "pinned step buffer");
+        }
+        uint8_t *hb = ln.h_step;
+        // pass 2 (parallel): write every activation's slice of the blob straight into pinned memory
+        pfor(NA, [&](size_t a) {
             QState &q = *qs[act_q[a]];
             Level &L = q.levels.back();
             StepOut &o = q.pend;
-            ActDesc &d = acts[a];
+            const Plan &pl = plan[a];
+            ActDesc d;
             memset(&d, 0, sizeof d);
             d.p_uw = q.p_uw;
             d.p_ub = q.p_ub;
@@ -1584,7 +1655,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             d.p_ld = q.p_ld;
             d.p_col_lo = q.p_col;
             d.p_col_hi = q.p_col + 1;
-            uint32_t ld = std::max(1u, q.p_cap);
+            uint32_t ld = pl.ld;
             d.ld = ld;
             d.n_cols = std::max(1u, o.n_cols);
             d.n_costs = o.n_costs;
@@ -1592,90 +1663,75 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             d.want_paths = o.want_paths;
             d.tab_size = o.want_paths ? 4096 : 1;
             d.all_conditional = o.all_conditional;
-            size_t persist = (size_t)ld * 4 + 256 + (size_t)ld * 8 + 256 + (size_t)ld * 8 * (o.n_costs + 1);
-            uint8_t *pb = arena_alloc(persist);
-            size_t cbytes = (size_t)ld * 8 * d.n_cols, sbytes = (size_t)ld * 8 * o.n_pairs, tbytes = (size_t)d.tab_size * 8;
-            // zeroed zone (condition matrix + path table) grows from the front of the lane's scratch, the DP table from the back
-            size_t coff = (z_used + 255) & ~(size_t)255;
-            size_t toff = (coff + cbytes + 255) & ~(size_t)255;
-            size_t s_need = (sbytes + 255) & ~(size_t)255;
-            if (!pb || toff + tbytes + s_need + s_used > ln.scratch_bytes)
-                return fail(B200_ERR_CAPACITY, "device arena exhausted: lower the batch size or raise B200_ARENA_MB / B200_SCRATCH_MB");
-            z_used = toff + tbytes;
-            s_used += s_need;
-            d.S = reinterpret_cast<unsigned long long *>(ln.scratch + ln.scratch_bytes - s_used);
-            d.tab = reinterpret_cast<unsigned long long *>(ln.scratch + toff);
-            d.uw = reinterpret_cast<uint32_t *>(pb);
-            d.ub = reinterpret_cast<unsigned long long *>(pb + (((size_t)ld * 4 + 255) & ~(size_t)255));
-            d.out = d.ub + (((size_t)ld + 31) & ~(size_t)31);
-            d.C = reinterpret_cast<unsigned long long *>(ln.scratch + coff);
+            d.S = reinterpret_cast<unsigned long long *>(ln.scratch + ln.scratch_bytes - pl.soff_from_end);
+            d.tab = reinterpret_cast<unsigned long long *>(ln.scratch + pl.toff);
+            d.C = reinterpret_cast<unsigned long long *>(ln.scratch + pl.coff);
+            if (pl.identity) {
+                d.uw = nullptr;
+                d.ub = const_cast<unsigned long long *>(q.p_ub);
+                d.out = reinterpret_cast<unsigned long long *>(pl.pb);
+            } else {
+                d.uw = reinterpret_cast<uint32_t *>(pl.pb);
+                d.ub = reinterpret_cast<unsigned long long *>(pl.pb + (((size_t)ld * 4 + 255) & ~(size_t)255));
+                d.out = d.ub + (((size_t)ld + 31) & ~(size_t)31);
+            }
             L.uw = d.uw;
             L.ub = d.ub;
             L.out = d.out;
             L.ld = ld;
-            d.colprog_off = (uint32_t)colprog.size();
+            d.colprog_off = pl.colprog;
             d.colprog_len = (uint32_t)o.colprog.size();
-            colprog.insert(colprog.end(), o.colprog.begin(), o.colprog.end());
-            d.state_off = (uint32_t)dstates.size();
-            d.edge_off = (uint32_t)dedges.size();
-            d.cost_off = (uint32_t)costpool.size();
-            dstates.insert(dstates.end(), o.dp_states.begin(), o.dp_states.end());
-            dedges.insert(dedges.end(), o.dp_edges.begin(), o.dp_edges.end());
-            costpool.insert(costpool.end(), o.cost_vals.begin(), o.cost_vals.end());
-            d.res_off = res_words;
-            L.res_off = res_words;
-            res_words += 2 + o.n_costs;
-            for (auto j : o.jobs) {
-                j.act = (uint32_t)a;
-                jobs.push_back(j);
+            d.state_off = pl.states;
+            d.edge_off = pl.edges;
+            d.cost_off = pl.costs;
+            d.res_off = pl.res_off;
+            L.res_off = pl.res_off;
+            memcpy(hb + o_acts + a * sizeof(ActDesc), &d, sizeof d);
+            if (!o.colprog.empty()) memcpy(hb + o_colprog + (size_t)pl.colprog * sizeof(ColOp), o.colprog.data(), o.colprog.size() * sizeof(ColOp));
+            if (!o.dp_states.empty()) memcpy(hb + o_states + (size_t)pl.states * sizeof(DpState), o.dp_states.data(), o.dp_states.size() * sizeof(DpState));
+            if (!o.dp_edges.empty()) memcpy(hb + o_edges + (size_t)pl.edges * sizeof(DpEdge), o.dp_edges.data(), o.dp_edges.size() * sizeof(DpEdge));
+            if (!o.cost_vals.empty()) memcpy(hb + o_costs + (size_t)pl.costs * 2, o.cost_vals.data(), o.cost_vals.size() * 2);
+            if (!o.words.empty()) memcpy(hb + o_words + (size_t)pl.words * 4, o.words.data(), o.words.size() * 4);
+            Job *jd = reinterpret_cast<Job *>(hb + o_jobs) + pl.jobs;
+            for (size_t k = 0; k < o.jobs.size(); k++) {
+                jd[k] = o.jobs[k];
+                jd[k].act = (uint32_t)a;
             }
-            uint32_t wbase = (uint32_t)words.size();
-            words.insert(words.end(), o.words.begin(), o.words.end());
-            for (auto ps : o.pairsets) {
-                ps.act = (uint32_t)a;
-                ps.left_off += wbase;
-                ps.right_off += wbase;
-                ps.probe_base = n_probes;
-                n_probes += ps.n_left * ps.n_right;
-                sets.push_back(ps);
+            PairSet *sd = reinterpret_cast<PairSet *>(hb + o_sets) + pl.sets;
+            uint32_t pb = pl.probes;
+            for (size_t k = 0; k < o.pairsets.size(); k++) {
+                sd[k] = o.pairsets[k];
+                sd[k].act = (uint32_t)a;
+                sd[k].left_off += pl.words;
+                sd[k].right_off += pl.words;
+                sd[k].probe_base = pb;
+                pb += sd[k].n_left * sd[k].n_right;
             }
-            for (uint32_t r0 = 0; r0 < ld; r0 += 128) tiles.push_back(TileDesc{(uint32_t)a, r0});
-            stats.posting_bytes += o.posting_bytes;
-            uint64_t mb = (uint64_t)ld * 8 * (d.n_cols + o.n_pairs + o.n_costs + 2);
-            stats.matrix_bytes += mb;
-            eval_bytes += mb;
-            compact_bytes += (uint64_t)d.p_rows * 8 + (uint64_t)ld * 12;
-            fill_bytes += o.posting_bytes;
+            TileDesc *td = reinterpret_cast<TileDesc *>(hb + o_tiles) + pl.tiles;
+            for (uint32_t r0 = 0, k = 0; r0 < ld; r0 += 128, k++) td[k] = TileDesc{(uint32_t)a, r0};
             q.want_activation = false;
-        }
-        for (auto qi : emit_q) {
-            QState &q = *qs[qi];
-            for (auto &e : q.emits) {
-                EmitDesc d = e.d;
-                d.dst = d_docids_out.p + (size_t)qi * std::max(1u, length) + (uint32_t)(uintptr_t)e.d.dst;
-                emits.push_back(d);
+        });
+        {
+            EmitDesc *ed = reinterpret_cast<EmitDesc *>(hb + o_emits);
+            size_t k = 0;
+            for (auto qi : emit_q) {
+                QState &q = *qs[qi];
+                for (auto &e : q.emits) {
+                    EmitDesc d = e.d;
+                    d.dst = d_docids_out.p + (size_t)qi * std::max(1u, length) + (uint32_t)(uintptr_t)e.d.dst;
+                    ed[k++] = d;
+                }
+                q.emits.clear();
             }
-            q.emits.clear();
         }
-        Blob blob;
-        size_t o_acts = blob.add(acts), o_sets = blob.add(sets), o_words = blob.add(words), o_colprog = blob.add(colprog),
-               o_states = blob.add(dstates), o_edges = blob.add(dedges), o_costs = blob.add(costpool), o_tiles = blob.add(tiles),
-               o_emits = blob.add(emits), o_jobs = blob.add(jobs);
-        size_t nbytes = blob.bytes.size() + 16;
-        if (nbytes > ln.h_step_cap) {
-            if (ln.h_step) cudaFreeHost(ln.h_step);
-            ln.h_step_cap = nbytes * 2;
-            CU(cudaMallocHost((void **)&ln.h_step, ln.h_step_cap), "pinned step buffer");
-        }
-        memcpy(ln.h_step, blob.bytes.data(), blob.bytes.size());
-        uint32_t n_static = (uint32_t)jobs.size();
-        memcpy(ln.h_step + blob.bytes.size(), &n_static, 4);
+        uint32_t n_static = n_jobs;
+        memcpy(hb + o_nstatic, &n_static, 4);
         CU(ln.d_step.reserve(nbytes), "step buffer");
         cudaStream_t st = ln.stream;
         CU(cudaMemcpyAsync(ln.d_step.p, ln.h_step, nbytes, cudaMemcpyHostToDevice, st), "H2D step");
         stats.h2d_bytes += nbytes;
         stats.d2h_bytes += (size_t)res_words * 4 + 8;
-        size_t qcap = std::max<size_t>(jobs.size() + ((size_t)1 << 20), (size_t)4 << 20);
+        size_t qcap = std::max<size_t>((size_t)n_jobs + ((size_t)1 << 20), (size_t)4 << 20);
         CU(ln.d_queue.reserve(qcap), "job queue");
         qcap = ln.d_queue.cap;
         CU(ln.d_qcount.reserve(4), "job counter");
@@ -1685,27 +1741,26 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             ln.h_results_cap = (size_t)(res_words + 4) * 2;
             CU(cudaMallocHost((void **)&ln.h_results, ln.h_results_cap * 4), "pinned results");
         }
-        if (!jobs.empty())
-            CU(cudaMemcpyAsync(ln.d_queue.p, ln.d_step.p + o_jobs, jobs.size() * sizeof(Job), cudaMemcpyDeviceToDevice, st), "jobs to queue");
-        CU(cudaMemcpyAsync(ln.d_qcount.p, ln.d_step.p + blob.bytes.size(), 4, cudaMemcpyDeviceToDevice, st), "job count");
+        if (n_jobs) CU(cudaMemcpyAsync(ln.d_queue.p, ln.d_step.p + o_jobs, (size_t)n_jobs * sizeof(Job), cudaMemcpyDeviceToDevice, st), "jobs to queue");
+        CU(cudaMemcpyAsync(ln.d_qcount.p, ln.d_step.p + o_nstatic, 4, cudaMemcpyDeviceToDevice, st), "job count");
         const ActDesc *dacts = reinterpret_cast<const ActDesc *>(ln.d_step.p + o_acts);
         // 1. emissions queued before this step's activations
         CU(cudaEventRecord(ln.e0, st), "event");
-        if (!emits.empty()) {
+        if (n_emits) {
             size_t m0 = ln.mark();
-            CU(launch_emit(st, reinterpret_cast<const EmitDesc *>(ln.d_step.p + o_emits), (uint32_t)emits.size()), "emit");
-            ln.time_kernel(stats, B200_K_EMIT, m0, ln.mark(), (uint64_t)emits.size() * 64);
+            CU(launch_emit(st, reinterpret_cast<const EmitDesc *>(ln.d_step.p + o_emits), n_emits), "emit");
+            ln.time_kernel(stats, B200_K_EMIT, m0, ln.mark(), (uint64_t)n_emits * 64);
         }
-        if (!acts.empty()) {
+        if (NA) {
             CU(cudaMemsetAsync(ln.d_results.p, 0, (size_t)(res_words + 4) * 4, st), "zero results");
             CU(cudaMemsetAsync(ln.scratch, 0, z_used, st), "zero condition matrix");
             CU(ln.d_pathbuf.reserve(PATH_CAP), "path buffer");
             CU(cudaMemsetAsync(ln.d_qcount.p + 1, 0, 4, st), "zero path count");
             size_t t0 = ln.mark();
-            CU(launch_compact(st, dacts, (uint32_t)acts.size(), ln.d_results.p), "compact");
+            CU(launch_compact(st, dacts, (uint32_t)NA, ln.d_results.p), "compact");
             size_t t1 = ln.mark();
             ln.time_kernel(stats, B200_K_COMPACT, t0, t1, compact_bytes);
-            CU(launch_pair_probe(st, reinterpret_cast<const PairSet *>(ln.d_step.p + o_sets), (uint32_t)sets.size(), n_probes,
+            CU(launch_pair_probe(st, reinterpret_cast<const PairSet *>(ln.d_step.p + o_sets), n_sets, n_probes,
                                  reinterpret_cast<const uint32_t *>(ln.d_step.p + o_words), dix.pair_keys, hix.pair_keys.size(), hix.pair_list_base,
                                  dix.lists, dacts, ln.d_results.p, ln.d_queue.p, ln.d_qcount.p, (uint32_t)qcap),
                "pair probe");
@@ -1714,7 +1769,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             CU(launch_scatter(st, (uint32_t)sm_count * 8, ln.d_queue.p, ln.d_qcount.p, (uint32_t)qcap, dacts, ln.d_results.p, dix.lists, dix.pool), "scatter");
             size_t t3 = ln.mark();
             ln.time_kernel(stats, B200_K_SCATTER, t2, t3, fill_bytes);
-            CU(launch_eval(st, reinterpret_cast<const TileDesc *>(ln.d_step.p + o_tiles), (uint32_t)tiles.size(), dacts, ln.d_results.p,
+            CU(launch_eval(st, reinterpret_cast<const TileDesc *>(ln.d_step.p + o_tiles), n_tiles, dacts, ln.d_results.p,
                            reinterpret_cast<const ColOp *>(ln.d_step.p + o_colprog), reinterpret_cast<const DpState *>(ln.d_step.p + o_states),
                            reinterpret_cast<const DpEdge *>(ln.d_step.p + o_edges), reinterpret_cast<const uint16_t *>(ln.d_step.p + o_costs),
                            ln.d_pathbuf.p, ln.d_qcount.p + 1, (uint32_t)PATH_CAP),

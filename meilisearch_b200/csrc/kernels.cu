@@ -217,6 +217,10 @@ __device__ __forceinline__ int find_row(const uint32_t *uw, uint32_t rows, uint3
 // one CTA per activation: ordered compaction of the parent's non-zero bucket words
 __global__ void __launch_bounds__(256) act_compact_kernel(const ActDesc *__restrict__ acts, uint32_t *__restrict__ results) {
     const ActDesc a = acts[blockIdx.x];
+    if (!a.uw) {  // the activation works directly on the dense base universe (row j == word j): nothing to compact
+        if (threadIdx.x == 0) results[a.res_off] = a.p_rows;
+        return;
+    }
     __shared__ uint32_t warp_sums[8];
     __shared__ uint32_t base;
     if (threadIdx.x == 0) base = 0;
@@ -332,61 +336,98 @@ __global__ void __launch_bounds__(256) pair_probe_kernel(const PairSet *__restri
     }
 }
 
-// one warp per job
+// Each warp takes 32 jobs at a time: tiny lists (the common case for word-pair lists) are handled one per lane,
+// the others cooperatively by the whole warp, one after the other.
+__device__ __forceinline__ void scatter_job_coop(const Job job, const ActDesc &a, uint32_t rows, const DListRef lr,
+                                                 const uint32_t *__restrict__ pool, uint32_t lane) {
+    unsigned long long *col = a.C + (size_t)job.col * a.ld;
+    if (lr.dense) {
+        const unsigned long long *words = reinterpret_cast<const unsigned long long *>(pool + lr.off);
+        uint32_t r0 = job.chunk * JOB_CHUNK, r1 = min(rows, r0 + JOB_CHUNK);
+        for (uint32_t j = r0 + lane; j < r1; j += 32) {
+            unsigned long long v = words[a.uw ? a.uw[j] : j] & a.ub[j];
+            if (v) atomicOr(&col[j], v);
+        }
+        return;
+    }
+    const uint32_t *ids = pool + lr.off;
+    if (a.uw && (unsigned long long)rows * 16ull < lr.card) {
+        // universe much smaller than the list: walk the rows and binary-search the list (chunk 0 does it all)
+        if (job.chunk != 0) return;
+        for (uint32_t j = lane; j < rows; j += 32) {
+            uint32_t w = a.uw[j];
+            uint32_t lo = 0, hi = lr.card, key = w << 6;
+            while (lo < hi) {
+                uint32_t mid = (lo + hi) >> 1;
+                if (ids[mid] < key)
+                    lo = mid + 1;
+                else
+                    hi = mid;
+            }
+            unsigned long long v = 0;
+            while (lo < lr.card && (ids[lo] >> 6) == w) {
+                v |= 1ull << (ids[lo] & 63);
+                lo++;
+            }
+            v &= a.ub[j];
+            if (v) atomicOr(&col[j], v);
+        }
+        return;
+    }
+    uint32_t e0 = job.chunk * JOB_CHUNK, e1 = min(lr.card, e0 + JOB_CHUNK);
+    for (uint32_t e = e0 + lane; e < e1; e += 32) {
+        uint32_t d = ids[e];
+        int j = a.uw ? find_row(a.uw, rows, d >> 6) : ((d >> 6) < rows ? (int)(d >> 6) : -1);
+        if (j >= 0) {
+            unsigned long long bit = 1ull << (d & 63);
+            if (a.ub[j] & bit) atomicOr(&col[j], bit);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) scatter_kernel(const Job *__restrict__ queue, const uint32_t *__restrict__ qcount, uint32_t qcap,
                                                       const ActDesc *__restrict__ acts, const uint32_t *__restrict__ results,
                                                       const DListRef *__restrict__ lists, const uint32_t *__restrict__ pool) {
     uint32_t n_jobs = min(*qcount, qcap);
     uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
     uint32_t lane = threadIdx.x & 31;
-    for (uint32_t jb = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; jb < n_jobs; jb += warps_total) {
-        const Job job = queue[jb];
-        const ActDesc &a = acts[job.act];
-        uint32_t rows = results[a.res_off];
-        if (rows == 0) continue;
-        const DListRef lr = lists[job.list];
-        unsigned long long *col = a.C + (size_t)job.col * a.ld;
-        if (lr.dense) {
-            const unsigned long long *words = reinterpret_cast<const unsigned long long *>(pool + lr.off);
-            uint32_t r0 = job.chunk * JOB_CHUNK, r1 = min(rows, r0 + JOB_CHUNK);
-            for (uint32_t j = r0 + lane; j < r1; j += 32) {
-                unsigned long long v = words[a.uw[j]] & a.ub[j];
-                if (v) atomicOr(&col[j], v);
-            }
-            continue;
+    for (uint32_t base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; base < n_jobs; base += warps_total * 32) {
+        uint32_t jb = base + lane;
+        bool have = jb < n_jobs;
+        Job job{0, 0, 0, 0};
+        DListRef lr{0, 0, 0};
+        uint32_t rows = 0;
+        if (have) {
+            job = queue[jb];
+            rows = results[acts[job.act].res_off];
+            lr = lists[job.list];
         }
-        const uint32_t *ids = pool + lr.off;
-        if ((unsigned long long)rows * 16ull < lr.card) {
-            // universe much smaller than the list: walk the rows and binary-search the list (chunk 0 does it all)
-            if (job.chunk != 0) continue;
-            for (uint32_t j = lane; j < rows; j += 32) {
-                uint32_t w = a.uw[j];
-                uint32_t lo = 0, hi = lr.card, key = w << 6;
-                while (lo < hi) {
-                    uint32_t mid = (lo + hi) >> 1;
-                    if (ids[mid] < key)
-                        lo = mid + 1;
-                    else
-                        hi = mid;
+        bool live = have && rows > 0 && lr.card > 0;
+        bool small = live && !lr.dense && lr.card <= 16;
+        if (small) {
+            const ActDesc &a = acts[job.act];
+            unsigned long long *col = a.C + (size_t)job.col * a.ld;
+            const uint32_t *ids = pool + lr.off;
+            for (uint32_t e = 0; e < lr.card; e++) {
+                uint32_t d = ids[e];
+                int j = a.uw ? find_row(a.uw, rows, d >> 6) : ((d >> 6) < rows ? (int)(d >> 6) : -1);
+                if (j >= 0) {
+                    unsigned long long bit = 1ull << (d & 63);
+                    if (a.ub[j] & bit) atomicOr(&col[j], bit);
                 }
-                unsigned long long v = 0;
-                while (lo < lr.card && (ids[lo] >> 6) == w) {
-                    v |= 1ull << (ids[lo] & 63);
-                    lo++;
-                }
-                v &= a.ub[j];
-                if (v) atomicOr(&col[j], v);
             }
-            continue;
         }
-        uint32_t e0 = job.chunk * JOB_CHUNK, e1 = min(lr.card, e0 + JOB_CHUNK);
-        for (uint32_t e = e0 + lane; e < e1; e += 32) {
-            uint32_t d = ids[e];
-            int j = find_row(a.uw, rows, d >> 6);
-            if (j >= 0) {
-                unsigned long long bit = 1ull << (d & 63);
-                if (a.ub[j] & bit) atomicOr(&col[j], bit);
-            }
+        unsigned big = __ballot_sync(0xffffffffu, live && !small);
+        while (big) {
+            int src = __ffs(big) - 1;
+            big &= big - 1;
+            Job bj;
+            bj.act = __shfl_sync(0xffffffffu, job.act, src);
+            bj.col = __shfl_sync(0xffffffffu, job.col, src);
+            bj.list = __shfl_sync(0xffffffffu, job.list, src);
+            bj.chunk = __shfl_sync(0xffffffffu, job.chunk, src);
+            uint32_t brows = __shfl_sync(0xffffffffu, rows, src);
+            scatter_job_coop(bj, acts[bj.act], brows, lists[bj.list], pool, lane);
         }
     }
 }
