@@ -256,11 +256,22 @@ struct ECond {
     ELocated start_subset, end_subset;
     uint16_t col = 0;
     std::string key() const {
-        std::string s = std::to_string(rule) + ":" + term.key() + ":" + std::to_string(nbr_typos) + (prox_uninit ? "U" : "T");
-        if (prox_uninit) s += left.key() + "c" + std::to_string(cost);
-        s += has_fid ? "f" + std::to_string(fid) : "f-";
-        for (auto p : positions) s += "," + std::to_string(p);
-        s += exact_in_attribute ? "E" : "A";
+        std::string s;
+        s.reserve(96);
+        s.push_back((char)rule);
+        term.key(s);
+        s.push_back((char)nbr_typos);
+        s.push_back(prox_uninit ? 'U' : 'T');
+        if (prox_uninit) {
+            left.key(s);
+            s.push_back((char)cost);
+        }
+        s.push_back(has_fid ? 'f' : '-');
+        if (has_fid) s.append(reinterpret_cast<const char *>(&fid), 2);
+        uint32_t np = (uint32_t)positions.size();
+        s.append(reinterpret_cast<const char *>(&np), 4);
+        if (np) s.append(reinterpret_cast<const char *>(positions.data()), positions.size() * 2);
+        s.push_back(exact_in_attribute ? 'E' : 'A');
         return s;
     }
 };
@@ -691,52 +702,75 @@ std::vector<std::pair<uint32_t, uint32_t>> build_edges(const QCtx &c, int rule, 
 // Topologically order the states reachable from START that reach END, compute per-state feasible cost ranges, root costs.
 template <class AE>
 void finish_state_graph(Level &L, const std::vector<AE> &aedges, uint32_t root, uint32_t end, bool want_paths) {
-    // collect states
-    std::map<uint32_t, std::vector<size_t>> out_edges;
-    for (size_t i = 0; i < aedges.size(); i++) out_edges[aedges[i].src].push_back(i);
-    // feasible costs to END (memoised DFS)
-    std::map<uint32_t, std::set<uint32_t>> costs;
-    std::map<uint32_t, int> st;
-    std::vector<uint32_t> topo_rev;  // post-order
-    std::function<void(uint32_t)> visit = [&](uint32_t s) {
-        if (st[s]) return;
-        st[s] = 1;
-        if (s == end)
-            costs[s].insert(0);
-        else
-            for (auto ei : out_edges[s]) {
-                visit(aedges[ei].dst);
-                for (auto c : costs[aedges[ei].dst]) costs[s].insert(aedges[ei].cost + c);
+    uint32_t max_id = std::max(root, end);
+    for (auto &e : aedges) max_id = std::max(max_id, std::max(e.src, e.dst));
+    const uint32_t NS = max_id + 1;
+    // adjacency in insertion (= visiting) order
+    std::vector<uint32_t> deg(NS + 1, 0);
+    for (auto &e : aedges) deg[e.src + 1]++;
+    for (uint32_t i = 0; i < NS; i++) deg[i + 1] += deg[i];
+    std::vector<uint32_t> adj(aedges.size());
+    {
+        std::vector<uint32_t> cur(deg.begin(), deg.end() - 1);
+        for (uint32_t i = 0; i < aedges.size(); i++) adj[cur[aedges[i].src]++] = i;
+    }
+    // feasible costs to END (memoised DFS; post-order gives a reverse topological order)
+    std::vector<std::vector<uint32_t>> costs(NS);
+    std::vector<uint8_t> seen(NS, 0);
+    std::vector<uint32_t> post;
+    std::vector<std::pair<uint32_t, uint32_t>> stack;  // (state, next adjacency index)
+    stack.push_back({root, deg[root]});
+    seen[root] = 1;
+    while (!stack.empty()) {
+        uint32_t sst = stack.back().first;
+        uint32_t &k = stack.back().second;
+        if (sst != end && k < deg[sst + 1]) {
+            uint32_t dst = aedges[adj[k++]].dst;
+            if (!seen[dst]) {
+                seen[dst] = 1;
+                stack.push_back({dst, deg[dst]});
             }
-        topo_rev.push_back(s);
-    };
-    visit(root);
-    // keep states that reach END; order = reverse post-order, END forced last
+            continue;
+        }
+        if (sst == end)
+            costs[sst] = {0};
+        else {
+            std::vector<uint32_t> &cs = costs[sst];
+            for (uint32_t kk = deg[sst]; kk < deg[sst + 1]; kk++) {
+                const AE &e = aedges[adj[kk]];
+                for (auto c : costs[e.dst]) cs.push_back(e.cost + c);
+            }
+            std::sort(cs.begin(), cs.end());
+            cs.erase(std::unique(cs.begin(), cs.end()), cs.end());
+        }
+        post.push_back(sst);
+        stack.pop_back();
+    }
     std::vector<uint32_t> order;
-    for (auto it = topo_rev.rbegin(); it != topo_rev.rend(); ++it)
+    for (auto it = post.rbegin(); it != post.rend(); ++it)
         if (*it != end && !costs[*it].empty()) order.push_back(*it);
     if (order.empty() || order[0] != root) order.insert(order.begin(), root);  // START with no way to END: no buckets
     order.push_back(end);
-    std::map<uint32_t, uint16_t> idx;
-    for (size_t i = 0; i < order.size(); i++) idx[order[i]] = (uint16_t)i;
+    std::vector<int32_t> idx(NS, -1);
+    for (size_t i = 0; i < order.size(); i++) idx[order[i]] = (int32_t)i;
     L.n_states = (uint16_t)order.size();
     L.sedges.clear();
     L.state_edge_begin.assign(L.n_states + 1, 0);
     L.state_cost_range.assign(L.n_states, {0, 0});
     for (size_t i = 0; i < order.size(); i++) {
         L.state_edge_begin[i] = (uint32_t)L.sedges.size();
-        uint32_t s = order[i];
-        if (!costs[s].empty()) {
-            uint32_t lo = *costs[s].begin(), hi = *costs[s].rbegin();
+        uint32_t sst = order[i];
+        if (!costs[sst].empty()) {
+            uint32_t lo = costs[sst].front(), hi = costs[sst].back();
             if (hi >= 65535) throw TooComplex{"ranking-rule cost above 65534"};
             L.state_cost_range[i] = {(uint16_t)lo, (uint16_t)(hi - lo + 1)};
         }
-        if (s == end) continue;
-        for (auto ei : out_edges[s]) {
-            const AE &e = aedges[ei];
+        if (sst == end) continue;
+        for (uint32_t kk = deg[sst]; kk < deg[sst + 1]; kk++) {
+            const AE &e = aedges[adj[kk]];
+            if (idx[e.dst] < 0) continue;
             if (e.dst != end && costs[e.dst].empty()) continue;
-            if (!idx.count(e.dst)) continue;
-            L.sedges.push_back(SEdge{(uint16_t)i, idx[e.dst], e.cost, e.cond});
+            L.sedges.push_back(SEdge{(uint16_t)i, (uint16_t)idx[e.dst], e.cost, e.cond});
         }
     }
     L.state_edge_begin[L.n_states] = (uint32_t)L.sedges.size();
@@ -990,7 +1024,11 @@ EGraph build_from_paths(const std::vector<std::vector<const ECond *>> &paths) {
         std::vector<std::string> suffix(path.size());
         std::string acc;
         for (size_t i = path.size(); i-- > 0;) {
-            acc = path[i].key() + "|" + acc;
+            std::string k;
+            k.reserve(64 + acc.size());
+            path[i].key(k);
+            k += acc;
+            acc.swap(k);
             suffix[i] = acc;
         }
         std::vector<uint16_t> p;

@@ -391,9 +391,12 @@ __global__ void __launch_bounds__(256) scatter_kernel(const Job *__restrict__ qu
     uint32_t n_jobs = min(*qcount, qcap);
     uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
     uint32_t lane = threadIdx.x & 31;
-    for (uint32_t base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; base < n_jobs; base += warps_total * 32) {
-        uint32_t jb = base + lane;
-        bool have = jb < n_jobs;
+    // job (k*32 + lane) * warps_total + warp: neighbouring jobs (e.g. the chunks of one long list) go to different warps
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    for (uint32_t k = 0; (unsigned long long)k * 32ull * warps_total + warp < n_jobs; k++) {
+        unsigned long long jb64 = ((unsigned long long)k * 32ull + lane) * warps_total + warp;
+        bool have = jb64 < n_jobs;
+        uint32_t jb = (uint32_t)jb64;
         Job job{0, 0, 0, 0};
         DListRef lr{0, 0, 0};
         uint32_t rows = 0;

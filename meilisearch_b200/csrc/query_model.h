@@ -54,14 +54,12 @@ struct ESubset {  // NTypoTermSubset; `split` stands for the only phrase a subse
         }
     }
     bool operator==(const ESubset &o) const { return kind == o.kind && words == o.words && split == o.split; }
-    void key(std::string &s) const {
+    void key(std::string &s) const {  // binary identity key (cheap: no number formatting)
         s.push_back((char)('A' + kind));
-        for (auto w : words) {
-            s.push_back('w');
-            s += std::to_string(w);
-        }
-        if (split) s.push_back('s');
-        s.push_back(';');
+        uint32_t nw = (uint32_t)words.size();
+        s.append(reinterpret_cast<const char *>(&nw), 4);
+        if (!words.empty()) s.append(reinterpret_cast<const char *>(words.data()), words.size() * 4);
+        s.push_back(split ? 's' : '-');
     }
 };
 
@@ -87,12 +85,22 @@ struct ELocated {  // LocatedQueryTermSubset
     uint16_t ps = 0, pe = 0;
     uint8_t t0 = 0, t1 = 0;
     uint32_t n_term_ids() const { return (uint32_t)t1 - t0 + 1; }
-    std::string key() const {
-        std::string s = "T" + std::to_string(ts.term) + (ts.mandatory ? "!" : ".");
+    void key(std::string &s) const {
+        s.append(reinterpret_cast<const char *>(&ts.term), 4);
+        s.push_back(ts.mandatory ? '!' : '.');
         ts.zero.key(s);
         ts.one.key(s);
         ts.two.key(s);
-        s += "@" + std::to_string(ps) + "-" + std::to_string(pe) + "#" + std::to_string(t0) + "-" + std::to_string(t1);
+        s.append(reinterpret_cast<const char *>(&ps), 2);
+        s.append(reinterpret_cast<const char *>(&pe), 2);
+        s.push_back((char)t0);
+        s.push_back((char)t1);
+        s.push_back('|');
+    }
+    std::string key() const {
+        std::string s;
+        s.reserve(48);
+        key(s);
         return s;
     }
 };
