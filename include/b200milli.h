@@ -20,7 +20,7 @@ extern "C" {
 #define B200_ERR_NO_DEVICE (-1)   /* no CUDA device / driver (the product never falls back to the CPU) */
 #define B200_ERR_CUDA (-2)        /* a CUDA call failed; see b200_last_error */
 #define B200_ERR_INVALID (-3)     /* bad argument */
-#define B200_ERR_UNSUPPORTED (-4) /* query feature outside the implemented scope (phrases, negative words, synonyms, ...) */
+#define B200_ERR_UNSUPPORTED (-4) /* query feature outside the implemented scope (sort, filters, Frequency strategy, ...) */
 #define B200_ERR_CAPACITY (-5)    /* a device work queue / arena overflowed */
 #define B200_ERR_STATE (-6)       /* call order (e.g. search before b200_stage_finish) */
 
@@ -75,6 +75,10 @@ typedef struct {
     const char *exact_words;        /* '\n'-joined exact_words set (may be NULL) */
 } b200_settings;
 int b200_stage_settings(b200_index *, const b200_settings *);
+/* The index `synonyms` database (crates/milli/src/index.rs synonyms; read by compute_derivations.rs:221-239 and
+ * parse_query.rs:277-285): entry i maps the word sequence from_words[i] to the word sequence to_words[i], both already
+ * tokenised and joined by single spaces.  Several entries may share the same `from`.  Replaces any previous set. */
+int b200_stage_synonyms(b200_index *, uint32_t n, const char *const *from_words, const char *const *to_words);
 /* Uploads everything to HBM and builds the device directories.  Must follow the stage_* calls. */
 int b200_stage_finish(b200_index *);
 /* Replaces the arroy/hannoy item nodes read by VectorStore (crates/milli/src/vector/store.rs:1427-1434):

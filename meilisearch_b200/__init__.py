@@ -88,6 +88,7 @@ def load_library():
         l.b200_stage_db.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         l.b200_stage_documents_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         l.b200_stage_settings.argtypes = [C.c_void_p, C.POINTER(_Settings)]
+        l.b200_stage_synonyms.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p)]
         l.b200_stage_finish.argtypes = [C.c_void_p]
         l.b200_stage_embeddings.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
         l.b200_stage_distribution.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float]
@@ -101,7 +102,7 @@ def load_library():
 
 
 SYMBOLS = ["b200_open", "b200_close", "b200_last_error", "b200_open_error", "b200_stage_dictionary", "b200_stage_db",
-           "b200_stage_documents_ids", "b200_stage_settings", "b200_stage_finish", "b200_stage_embeddings", "b200_stage_distribution",
+           "b200_stage_documents_ids", "b200_stage_settings", "b200_stage_synonyms", "b200_stage_finish", "b200_stage_embeddings", "b200_stage_distribution",
            "b200_derive_batch", "b200_nns_batch", "b200_search_batch", "b200_get_stats", "b200_reset_stats"]
 
 
@@ -148,7 +149,7 @@ class Index:
     """The staged index: what milli reads from LMDB at query time, resident in HBM."""
 
     def __init__(self, image=None, *, device=0, criteria=None, authorize_typos=True, one_typo=5, two_typos=9, prefix_search=True,
-                 weights=None, exact_words=()):
+                 weights=None, exact_words=(), synonyms=None):
         self._l = load_library()
         h = C.c_void_p()
         rc = self._l.b200_open(device, C.byref(h))
@@ -158,13 +159,14 @@ class Index:
         self.dim = 0
         if image is not None:
             self.stage(image, criteria=criteria, authorize_typos=authorize_typos, one_typo=one_typo, two_typos=two_typos,
-                       prefix_search=prefix_search, weights=weights, exact_words=exact_words)
+                       prefix_search=prefix_search, weights=weights, exact_words=exact_words, synonyms=synonyms)
 
     def _ck(self, rc):
         if rc != 0:
             raise B200Error(rc, self._l.b200_last_error(self._h).decode())
 
-    def stage(self, image, *, criteria=None, authorize_typos=True, one_typo=5, two_typos=9, prefix_search=True, weights=None, exact_words=()):
+    def stage(self, image, *, criteria=None, authorize_typos=True, one_typo=5, two_typos=9, prefix_search=True, weights=None, exact_words=(),
+              synonyms=None):
         """image: anything with dict_bytes/dict_offsets/n_words, dbs[i].{key_bytes,key_offsets,val_bytes,val_offsets,n_keys},
         documents_ids_cbo, n_fields — i.e. the LMDB databases in their on-disk formats."""
         l = self._l
@@ -177,6 +179,11 @@ class Index:
         s = _Settings(image.n_fields, _p(w), _p(c), len(c), int(authorize_typos), one_typo, two_typos, int(prefix_search),
                       "\n".join(exact_words).encode() if exact_words else None)
         self._ck(l.b200_stage_settings(self._h, C.byref(s)))
+        if synonyms:
+            pairs = [(k, v) for k, vs in synonyms.items() for v in vs]
+            fr = (C.c_char_p * len(pairs))(*[k.encode() for k, _ in pairs])
+            to = (C.c_char_p * len(pairs))(*[v.encode() for _, v in pairs])
+            self._ck(l.b200_stage_synonyms(self._h, len(pairs), fr, to))
         self._ck(l.b200_stage_finish(self._h))
         self.n_fields = image.n_fields
 

@@ -96,6 +96,26 @@ int b200_stage_settings(b200_index *h, const b200_settings *s) {
     }
     return B200_OK;
 }
+static std::vector<std::string> split_ws(const char *s) {
+    std::vector<std::string> out;
+    std::string cur;
+    for (const char *p = s;; p++) {
+        if (*p == ' ' || *p == 0) {
+            if (!cur.empty()) out.push_back(cur);
+            cur.clear();
+            if (!*p) break;
+        } else
+            cur.push_back(*p);
+    }
+    return out;
+}
+int b200_stage_synonyms(b200_index *h, uint32_t n, const char *const *from_words, const char *const *to_words) {
+    std::lock_guard<std::mutex> g(h->e.mu);
+    auto &syn = h->e.hix.settings.synonyms;
+    syn.clear();
+    for (uint32_t i = 0; i < n; i++) syn[split_ws(from_words[i])].push_back(split_ws(to_words[i]));
+    return B200_OK;
+}
 int b200_stage_finish(b200_index *h) {
     std::lock_guard<std::mutex> g(h->e.mu);
     Settings keep = h->e.hix.settings;

@@ -202,6 +202,7 @@ struct Lane {
 
 struct Engine {
     std::unique_ptr<WorkerPool> pool;
+    std::thread reaper;  // frees the previous batch's per-query state in the background
     Lane lanes[2];
     int device = 0;
     cudaStream_t stream = nullptr;

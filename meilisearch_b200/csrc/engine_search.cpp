@@ -49,7 +49,27 @@ struct WordRef {
 struct QCtx {
     const HostIndex &ix;
     std::vector<ETerm> terms;
+    std::vector<EPhrase> phrases;
+    std::map<std::vector<int32_t>, uint32_t> phrase_ids;
+    std::vector<uint32_t> neg_words;    // dictionary ranks of `-word` tokens (absent words exclude nothing)
+    std::vector<uint32_t> neg_phrases;  // phrase ids of `-"..."`
     explicit QCtx(const HostIndex &i) : ix(i) {}
+    uint32_t intern_phrase(const EPhrase &p) {
+        auto it = phrase_ids.find(p.words);
+        if (it != phrase_ids.end()) return it->second;
+        phrases.push_back(p);
+        phrase_ids.emplace(p.words, (uint32_t)phrases.size() - 1);
+        return (uint32_t)phrases.size() - 1;
+    }
+    int32_t word_rank_or_absent(const std::string &w) const {
+        int64_t r = ix.find_word(w);
+        return r >= 0 ? (int32_t)r : -2;
+    }
+    static int32_t first_word(const EPhrase &p) {
+        for (auto w : p.words)
+            if (w != -1) return w;
+        return -1;
+    }
 };
 
 uint8_t number_of_typos_allowed(const HostIndex &ix, const std::string &w) {  // parse_query.rs:204-225 (ASCII)
@@ -58,8 +78,9 @@ uint8_t number_of_typos_allowed(const HostIndex &ix, const std::string &w) {  //
     return w.size() < s.two_typos ? 1 : 2;
 }
 
-// compute_derivations.rs:170-253 (zero-typo part; no synonyms)
-ETerm term_from_word(const HostIndex &ix, const std::string &word, uint8_t max_typo, bool is_prefix, bool is_ngram) {
+// compute_derivations.rs:170-253 (zero-typo part)
+ETerm term_from_word(QCtx &c, const std::string &word, uint8_t max_typo, bool is_prefix, bool is_ngram) {
+    const HostIndex &ix = c.ix;
     ETerm t;
     t.original = word;
     if (word.size() > 250) {
@@ -79,43 +100,71 @@ ETerm term_from_word(const HostIndex &ix, const std::string &word, uint8_t max_t
             if (t.prefix_of.size() >= 1000) break;
         }
     }
+    auto it = ix.settings.synonyms.find(std::vector<std::string>{word});
+    if (it != ix.settings.synonyms.end()) {
+        size_t synonym_word_count = 0, taken = 0;
+        for (auto &syn : it->second) {
+            if (taken++ >= 50) break;                             // MAX_SYNONYM_PHRASE_COUNT
+            if (synonym_word_count + syn.size() > 100) continue;  // MAX_SYNONYM_WORD_COUNT
+            synonym_word_count += syn.size();
+            EPhrase p;
+            for (auto &w : syn) p.words.push_back(c.word_rank_or_absent(w));
+            t.synonyms.push_back(c.intern_phrase(p));
+        }
+        std::sort(t.synonyms.begin(), t.synonyms.end());
+        t.synonyms.erase(std::unique(t.synonyms.begin(), t.synonyms.end()), t.synonyms.end());
+    }
     t.max_lev = max_typo;
     t.is_prefix = is_prefix;
     t.is_ngram = is_ngram;
     return t;
 }
 
-// compute_derivations.rs:363-383
-void find_split_words(const HostIndex &ix, ETerm &t) {
+// compute_derivations.rs:363-383 + 255-317
+void find_split_words(QCtx &c, ETerm &t) {
+    const HostIndex &ix = c.ix;
     const std::string &o = t.original;
-    uint32_t best = 0;
-    t.has_split = false;
+    uint32_t best = 0, bl = 0, br = 0;
+    bool have = false;
+    t.split = -1;
+    if (!t.allows_split_words()) return;
     for (size_t i = 1; i < o.size(); i++) {
         int64_t l = ix.find_word((const uint8_t *)o.data(), i), r = ix.find_word((const uint8_t *)o.data() + i, o.size() - i);
         if (l < 0 || r < 0) continue;
         uint32_t list = ix.find_pair(1, (uint32_t)l, (uint32_t)r);
         if (list == NO_LIST) continue;
         uint32_t freq = ix.lists[list].card;
-        if (!t.has_split || freq > best) {
-            t.has_split = true;
+        if (!have || freq > best) {
+            have = true;
             best = freq;
-            t.split_l = (uint32_t)l;
-            t.split_r = (uint32_t)r;
-            t.split_list = list;
+            bl = (uint32_t)l;
+            br = (uint32_t)r;
         }
     }
-    if (t.has_split && t.is_ngram && t.max_lev <= 1) {
-        // only for the <=1 typo initialisation (compute_derivations.rs:297-311): drop the split equal to the ngram's own words
-        if (t.ngram_words.size() == 2 && ix.word(t.split_l) == t.ngram_words[0] && ix.word(t.split_r) == t.ngram_words[1]) t.has_split = false;
+    if (!have) return;
+    if (t.is_ngram && t.max_lev <= 1) {
+        // only in the <=1 typo initialisation (compute_derivations.rs:297-311): drop the split equal to the ngram's own words
+        if (t.ngram_words.size() == 2 && ix.word(bl) == t.ngram_words[0] && ix.word(br) == t.ngram_words[1]) return;
     }
+    EPhrase p;
+    p.words = {(int32_t)bl, (int32_t)br};
+    t.split = (int32_t)c.intern_phrase(p);
 }
 
-bool exact_term(const QCtx &c, const ETermSubset &s, uint32_t &w) {  // query_term/mod.rs:131-143 (words only)
+struct ExactTermRef {
+    int kind = 0;  // 0 none, 1 word, 2 phrase
+    uint32_t id = 0;
+};
+ExactTermRef exact_term(const QCtx &c, const ETermSubset &s) {  // query_term/mod.rs:131-143
     const ETerm &t = c.terms[s.term];
-    if (t.is_ngram || t.exact < 0) return false;
-    if (!s.zero.contains_word((uint32_t)t.exact)) return false;
-    w = (uint32_t)t.exact;
-    return true;
+    ExactTermRef e;
+    if (t.is_ngram) return e;
+    if (t.phrase >= 0) {
+        if (s.zero.contains_phrase((uint32_t)t.phrase)) e = {2, (uint32_t)t.phrase};
+    } else if (t.exact >= 0) {
+        if (s.zero.contains_word((uint32_t)t.exact)) e = {1, (uint32_t)t.exact};
+    }
+    return e;
 }
 bool use_prefix_db(const QCtx &c, const ETermSubset &s, uint32_t &pid, bool &derived) {  // :177-198
     const ETerm &t = c.terms[s.term];
@@ -142,15 +191,29 @@ std::vector<WordRef> all_single_words(const QCtx &c, const ETermSubset &s) {  //
             if (s.two.contains_word(w)) r.push_back({w, true});
     return r;
 }
-bool has_split_phrase(const QCtx &c, const ETermSubset &s) {  // all_phrases :293-329 restricted to split words
+// all_phrases (:293-329): the zero-typo phrase and the synonyms are returned whatever zero_typo_subset says
+std::vector<uint32_t> all_phrases(const QCtx &c, const ETermSubset &s) {
     const ETerm &t = c.terms[s.term];
-    if (!t.has_split) return false;
-    return s.one.kind == N_ALL || (s.one.kind == N_SUBSET && s.one.split);
+    std::vector<uint32_t> r;
+    if (t.phrase >= 0) r.push_back((uint32_t)t.phrase);
+    for (auto p : t.synonyms) r.push_back(p);
+    if (t.split >= 0 && (s.one.kind == N_ALL || (s.one.kind == N_SUBSET && s.one.contains_phrase((uint32_t)t.split)))) r.push_back((uint32_t)t.split);
+    std::sort(r.begin(), r.end());
+    r.erase(std::unique(r.begin(), r.end()), r.end());
+    return r;
+}
+bool original_phrase(const QCtx &c, const ETermSubset &s, uint32_t &p) {  // :331-339
+    const ETerm &t = c.terms[s.term];
+    if (t.phrase >= 0 && s.zero.contains_phrase((uint32_t)t.phrase)) {
+        p = (uint32_t)t.phrase;
+        return true;
+    }
+    return false;
 }
 uint8_t max_typo_cost(const QCtx &c, const ETermSubset &s) {  // :340-370
     const ETerm &t = c.terms[s.term];
     switch (t.max_lev) {
-        case 0: return 1;  // allows_split_words (no phrases here)
+        case 0: return t.allows_split_words() ? 1 : 0;
         case 1: return s.one.is_empty() ? 0 : 1;
         default: return s.two.is_empty() ? (s.one.is_empty() ? 0 : 1) : 2;
     }
@@ -212,7 +275,7 @@ void remove_nodes_keep_edges(EGraph &g, const std::vector<uint16_t> &nodes) {  /
 }
 
 // removal_order_for_terms_matching_strategy_last (:346-406): groups of nodes, cheapest removal first
-std::vector<std::vector<uint16_t>> removal_order_last(const EGraph &g) {
+std::vector<std::vector<uint16_t>> removal_order_last(const QCtx &c, const EGraph &g) {
     int first = 255, last = 0;
     for (auto &n : g.nodes)
         if (n.kind == ND_TERM) {
@@ -225,7 +288,8 @@ std::vector<std::vector<uint16_t>> removal_order_last(const EGraph &g) {
     for (uint16_t id = 0; id < g.nodes.size(); id++) {
         const ENode &n = g.nodes[id];
         if (n.kind != ND_TERM) continue;
-        if (n.term.ts.mandatory) {
+        uint32_t ph;
+        if (original_phrase(c, n.term.ts, ph) || n.term.ts.mandatory) {
             mandatory = true;
             continue;
         }
@@ -360,7 +424,7 @@ struct ActBuilder {
     const QCtx &c;
     StepOut &o;
     uint16_t next_col = 0;
-    std::map<uint32_t, uint16_t> phrase_cols;  // split-phrase pair list -> column
+    std::map<uint32_t, uint16_t> phrase_cols;  // phrase id -> column
     ActBuilder(const QCtx &ctx, StepOut &out) : c(ctx), o(out) {}
     uint16_t new_col() { return next_col++; }
     void add_list(uint16_t col, uint32_t list) {
@@ -378,18 +442,67 @@ struct ActBuilder {
         add_list(col, c.ix.wd_list[w.rank]);
         if (!w.derived) add_list(col, c.ix.ewd_list[w.rank]);
     }
-    uint16_t phrase_col(uint32_t pair_list) {  // docids of the 2-word split phrase == its proximity-1 pair list
-        auto it = phrase_cols.find(pair_list);
+    // compute_phrase_docids (resolve_query_graph.rs:187-268) as a column: AND of the words' lists, then for every window of
+    // up to three words the AND of the pair-proximity unions.  Universe-restricted like every column; every use of phrase
+    // docids in the reference intersects with the universe anyway.
+    uint16_t phrase_col(uint32_t pid) {
+        auto it = phrase_cols.find(pid);
         if (it != phrase_cols.end()) return it->second;
         uint16_t col = new_col();
-        add_list(col, pair_list);
-        phrase_cols.emplace(pair_list, col);
+        phrase_cols.emplace(pid, col);
+        const std::vector<int32_t> &words = c.phrases[pid].words;
+        std::vector<uint32_t> real;
+        for (auto w : words) {
+            if (w == -2) return col;  // a word that is not in the dictionary: the phrase matches nothing
+            if (w >= 0) real.push_back((uint32_t)w);
+        }
+        if (real.empty()) return col;
+        if (words.size() == 2 && real.size() == 2) {  // docids of a 2-word phrase == its proximity-1 pair list
+            add_list(col, c.ix.find_pair(1, real[0], real[1]));
+            return col;
+        }
+        // plan first: any missing mandatory list makes the phrase empty
+        struct Group {
+            std::vector<uint32_t> lists;
+        };
+        std::vector<Group> groups;
+        for (auto w : real) {
+            Group g;
+            if (c.ix.wd_list[w] != NO_LIST) g.lists.push_back(c.ix.wd_list[w]);
+            if (c.ix.ewd_list[w] != NO_LIST) g.lists.push_back(c.ix.ewd_list[w]);
+            if (g.lists.empty()) return col;
+            groups.push_back(std::move(g));
+        }
+        size_t winsize = std::min<size_t>(words.size(), 3);
+        for (size_t ws = 0; ws + winsize <= words.size(); ws++)
+            for (size_t i = 0; i < winsize; i++) {
+                if (words[ws + i] < 0) continue;
+                for (size_t k = i + 1; k < winsize; k++) {
+                    if (words[ws + k] < 0) continue;
+                    size_t dist = k - i - 1;
+                    Group g;
+                    for (size_t d = 0; d <= dist; d++) {
+                        uint32_t l = c.ix.find_pair((uint32_t)d + 1, (uint32_t)words[ws + i], (uint32_t)words[ws + k]);
+                        if (dist == 0 && l == NO_LIST) return col;
+                        if (l != NO_LIST) g.lists.push_back(l);
+                    }
+                    if (g.lists.empty()) return col;
+                    groups.push_back(std::move(g));
+                }
+            }
+        bool first = true;
+        for (auto &g : groups) {
+            uint16_t t = first ? col : new_col();
+            for (auto l : g.lists) add_list(t, l);
+            if (!first) op(0, col, col, t);
+            first = false;
+        }
         return col;
     }
     // compute_query_term_subset_docids (resolve_query_graph.rs:33-59) into `col`
     void term_docids(uint16_t col, const ETermSubset &s) {
         for (auto &w : all_single_words(c, s)) add_word_docids(col, w);
-        if (has_split_phrase(c, s)) add_list(col, c.terms[s.term].split_list);
+        for (auto p : all_phrases(c, s)) op(1, col, col, phrase_col(p));
         uint32_t pid;
         bool derived;
         if (use_prefix_db(c, s, pid, derived)) {
@@ -429,57 +542,47 @@ void build_proximity_cond(ActBuilder &b, const ECond &cond) {
     uint8_t fwd = (uint8_t)(1 + cond.cost - right_len), bwd = (uint8_t)(cond.cost - right_len);
     if (fwd > 3) fwd = 0;  // keys only exist for proximities 1..3
     if (bwd > 3) bwd = 0;
-    // left derivations: plain words, and the last word of the split phrase
-    std::vector<uint32_t> left_words;
+    // last_words_of_term_derivations (:213-231) / first_word_of_term_iter (:232-251)
+    std::vector<uint32_t> left_words, right_words;
     for (auto &w : all_single_words(c, cond.left.ts)) left_words.push_back(w.rank);
-    std::sort(left_words.begin(), left_words.end());
-    left_words.erase(std::unique(left_words.begin(), left_words.end()), left_words.end());
-    const ETerm &lt = c.terms[cond.left.ts.term];
-    bool left_phrase = has_split_phrase(c, cond.left.ts);
-    std::vector<uint32_t> right_words;
     for (auto &w : all_single_words(c, cond.term.ts)) right_words.push_back(w.rank);
-    std::sort(right_words.begin(), right_words.end());
-    right_words.erase(std::unique(right_words.begin(), right_words.end()), right_words.end());
-    const ETerm &rt = c.terms[cond.term.ts.term];
-    bool right_phrase = has_split_phrase(c, cond.term.ts);
+    for (auto *v : {&left_words, &right_words}) {
+        std::sort(v->begin(), v->end());
+        v->erase(std::unique(v->begin(), v->end()), v->end());
+    }
+    std::vector<std::pair<uint32_t, uint32_t>> left_phr, right_phr;  // (phrase id, boundary word)
+    for (auto p : all_phrases(c, cond.left.ts)) {
+        int32_t last = c.phrases[p].words.empty() ? -1 : c.phrases[p].words.back();
+        if (last >= 0) left_phr.push_back({p, (uint32_t)last});
+    }
+    for (auto p : all_phrases(c, cond.term.ts)) {
+        int32_t first = c.phrases[p].words.empty() ? -1 : c.phrases[p].words.front();
+        if (first >= 0) right_phr.push_back({p, (uint32_t)first});
+    }
+    auto anded = [&](const std::vector<uint32_t> &l, const std::vector<uint32_t> &r, bool range, std::initializer_list<uint32_t> phrases) {
+        uint16_t t = b.new_col();
+        b.add_pairset(t, l, r, fwd, 0, range);  // no swapping when a phrase is involved (:149, :199)
+        for (auto p : phrases) b.op(0, t, t, b.phrase_col(p));
+        b.op(1, cond.col, cond.col, t);
+    };
     // prefix-db part (compute_prefix_edges :110-170)
     uint32_t pid;
     bool pderived;
     if (use_prefix_db(c, cond.term.ts, pid, pderived)) {
         uint64_t lo, hi;
-        b.c.ix.prefix_range(b.c.ix.prefixes[pid], lo, hi);
+        c.ix.prefix_range(c.ix.prefixes[pid], lo, hi);
         std::vector<uint32_t> range{(uint32_t)lo, (uint32_t)hi};
         b.add_pairset(cond.col, left_words, range, fwd, 0, true);
         int64_t prefix_as_word = c.ix.find_word(c.ix.prefixes[pid]);
         if (prefix_as_word >= 0 && bwd) b.add_pairset(cond.col, left_words, {(uint32_t)prefix_as_word}, 0, bwd, false);
-        if (left_phrase) {
-            uint16_t t = b.new_col();
-            b.add_pairset(t, {lt.split_r}, range, fwd, 0, true);
-            b.op(0, t, t, b.phrase_col(lt.split_list));
-            b.op(1, cond.col, cond.col, t);
-        }
+        for (auto &lp : left_phr) anded({lp.second}, range, true, {lp.first});
     }
     // non-prefix part (compute_non_prefix_edges :172-211)
     b.add_pairset(cond.col, left_words, right_words, fwd, bwd, false);
-    if (left_phrase) {  // (left phrase, right word): forward only, inside the phrase docids
-        uint16_t t = b.new_col();
-        b.add_pairset(t, {lt.split_r}, right_words, fwd, 0, false);
-        b.op(0, t, t, b.phrase_col(lt.split_list));
-        b.op(1, cond.col, cond.col, t);
-    }
-    if (right_phrase) {  // (left word, right phrase)
-        uint16_t t = b.new_col();
-        b.add_pairset(t, left_words, {rt.split_l}, fwd, 0, false);
-        b.op(0, t, t, b.phrase_col(rt.split_list));
-        b.op(1, cond.col, cond.col, t);
-    }
-    if (left_phrase && right_phrase) {
-        uint16_t t = b.new_col();
-        b.add_pairset(t, {lt.split_r}, {rt.split_l}, fwd, 0, false);
-        b.op(0, t, t, b.phrase_col(lt.split_list));
-        b.op(0, t, t, b.phrase_col(rt.split_list));
-        b.op(1, cond.col, cond.col, t);
-    }
+    for (auto &lp : left_phr) anded({lp.second}, right_words, false, {lp.first});
+    for (auto &rp : right_phr) anded(left_words, {rp.second}, false, {rp.first});
+    for (auto &lp : left_phr)
+        for (auto &rp : right_phr) anded({lp.second}, {rp.second}, false, {lp.first, rp.first});
 }
 
 void build_cond(ActBuilder &b, const ECond &cond) {
@@ -492,15 +595,15 @@ void build_cond(ActBuilder &b, const ECond &cond) {
         case RK_FID: {  // resolve_query_graph.rs:61-93
             if (!cond.has_fid) break;
             for (auto &w : all_single_words(c, cond.term.ts)) b.add_list(cond.col, c.ix.word_fid_list(w.rank, cond.fid));
-            if (has_split_phrase(c, cond.term.ts)) {
-                const ETerm &t = c.terms[cond.term.ts.term];
-                uint32_t l = c.ix.word_fid_list(t.split_l, cond.fid);
-                if (l != NO_LIST) {
-                    uint16_t tf = b.new_col();
-                    b.add_list(tf, l);
-                    b.op(0, tf, tf, b.phrase_col(t.split_list));
-                    b.op(1, cond.col, cond.col, tf);
-                }
+            for (auto p : all_phrases(c, cond.term.ts)) {
+                int32_t fw = QCtx::first_word(c.phrases[p]);
+                if (fw < 0) continue;
+                uint32_t l = c.ix.word_fid_list((uint32_t)fw, cond.fid);
+                if (l == NO_LIST) continue;
+                uint16_t tf = b.new_col();
+                b.add_list(tf, l);
+                b.op(0, tf, tf, b.phrase_col(p));
+                b.op(1, cond.col, cond.col, tf);
             }
             uint32_t pid;
             bool derived;
@@ -509,36 +612,42 @@ void build_cond(ActBuilder &b, const ECond &cond) {
         }
         case RK_POSITION: {  // position/mod.rs:24-47 + resolve_query_graph.rs:95-130
             auto words = all_single_words(c, cond.term.ts);
-            bool ph = has_split_phrase(c, cond.term.ts);
-            uint16_t tf = 0;
-            bool have_tf = false;
+            auto phrases = all_phrases(c, cond.term.ts);
             uint32_t pid;
             bool derived;
             bool pdb = use_prefix_db(c, cond.term.ts, pid, derived);
             for (auto p : cond.positions) {
                 for (auto &w : words) b.add_list(cond.col, c.ix.word_pos_list(w.rank, p));
-                if (ph) {
-                    uint32_t l = c.ix.word_pos_list(c.terms[cond.term.ts.term].split_l, p);
-                    if (l != NO_LIST) {
-                        if (!have_tf) {
-                            tf = b.new_col();
-                            have_tf = true;
-                        }
-                        b.add_list(tf, l);
-                    }
-                }
                 if (pdb) b.add_list(cond.col, c.ix.prefix_pos_list(pid, p));
             }
-            if (have_tf) {
-                b.op(0, tf, tf, b.phrase_col(c.terms[cond.term.ts.term].split_list));
-                b.op(1, cond.col, cond.col, tf);
+            for (auto ph : phrases) {  // phrase & (first word at any of the positions)
+                int32_t fw = QCtx::first_word(c.phrases[ph]);
+                if (fw < 0) continue;
+                uint16_t tf = 0;
+                bool have = false;
+                for (auto p : cond.positions) {
+                    uint32_t l = c.ix.word_pos_list((uint32_t)fw, p);
+                    if (l == NO_LIST) continue;
+                    if (!have) {
+                        tf = b.new_col();
+                        have = true;
+                    }
+                    b.add_list(tf, l);
+                }
+                if (have) {
+                    b.op(0, tf, tf, b.phrase_col(ph));
+                    b.op(1, cond.col, cond.col, tf);
+                }
             }
             break;
         }
         case RK_EXACTNESS: {  // exactness/mod.rs:19-73
             if (cond.exact_in_attribute) {
-                uint32_t w;
-                if (exact_term(c, cond.term.ts, w)) b.add_word_docids(cond.col, WordRef{w, false});
+                ExactTermRef e = exact_term(c, cond.term.ts);
+                if (e.kind == 1)
+                    b.add_word_docids(cond.col, WordRef{e.id, false});
+                else if (e.kind == 2)
+                    b.op(1, cond.col, cond.col, b.phrase_col(e.id));
             } else
                 b.term_docids(cond.col, cond.term.ts);
             break;
@@ -628,11 +737,10 @@ std::vector<std::pair<uint32_t, uint32_t>> build_edges(const QCtx &c, int rule, 
             std::set<uint16_t> fields;
             for (auto &w : all_single_words(c, to.ts))
                 for (uint32_t i = c.ix.wf_off[w.rank]; i < c.ix.wf_off[w.rank + 1]; i++) fields.insert(c.ix.wf_fid[i]);
-            if (has_split_phrase(c, to.ts)) {
-                const ETerm &t = c.terms[to.ts.term];
-                for (uint32_t w : {t.split_l, t.split_r})
-                    for (uint32_t i = c.ix.wf_off[w]; i < c.ix.wf_off[w + 1]; i++) fields.insert(c.ix.wf_fid[i]);
-            }
+            for (auto p : all_phrases(c, to.ts))
+                for (auto w : c.phrases[p].words)
+                    if (w >= 0)
+                        for (uint32_t i = c.ix.wf_off[w]; i < c.ix.wf_off[w + 1]; i++) fields.insert(c.ix.wf_fid[i]);
             uint32_t pid;
             bool derived;
             if (use_prefix_db(c, to.ts, pid, derived))
@@ -655,9 +763,10 @@ std::vector<std::pair<uint32_t, uint32_t>> build_edges(const QCtx &c, int rule, 
             std::set<uint16_t> all_pos;
             for (auto &w : all_single_words(c, to.ts))
                 for (uint32_t i = c.ix.wp_off[w.rank]; i < c.ix.wp_off[w.rank + 1]; i++) all_pos.insert(c.ix.wp_pos[i]);
-            if (has_split_phrase(c, to.ts)) {
-                uint32_t w = c.terms[to.ts.term].split_l;
-                for (uint32_t i = c.ix.wp_off[w]; i < c.ix.wp_off[w + 1]; i++) all_pos.insert(c.ix.wp_pos[i]);
+            for (auto p : all_phrases(c, to.ts)) {
+                int32_t w = QCtx::first_word(c.phrases[p]);
+                if (w >= 0)
+                    for (uint32_t i = c.ix.wp_off[w]; i < c.ix.wp_off[w + 1]; i++) all_pos.insert(c.ix.wp_pos[i]);
             }
             uint32_t pid;
             bool derived;
@@ -682,9 +791,12 @@ std::vector<std::pair<uint32_t, uint32_t>> build_edges(const QCtx &c, int rule, 
             ECond e = base();
             e.exact_in_attribute = true;
             {  // end_term_subset: keep_only_exact_term + mandatory
-                uint32_t w;
-                if (exact_term(c, to.ts, w)) {
-                    e.end_subset.ts.zero = ESubset{N_SUBSET, {w}, false};
+                ExactTermRef et = exact_term(c, to.ts);
+                if (et.kind) {
+                    ESubset z;
+                    z.kind = N_SUBSET;
+                    (et.kind == 1 ? z.words : z.phrases).push_back(et.id);
+                    e.end_subset.ts.zero = z;
                     e.end_subset.ts.one = ESubset{};
                     e.end_subset.ts.two = ESubset{};
                 }
@@ -792,7 +904,7 @@ void prepare_graph_rule(const QCtx &c, int rule, bool has_tms, int tms, Level &L
     std::vector<std::vector<uint8_t>> ignore_skip(n);
     if (has_tms && tms == B200_TMS_LAST) {
         std::vector<uint8_t> forbidden(n, 0);
-        for (auto &grp : removal_order_last(qg)) {
+        for (auto &grp : removal_order_last(c, qg)) {
             for (auto nd : grp) {
                 ignore_cost[nd] = 1;
                 ignore_skip[nd] = forbidden;
@@ -848,6 +960,16 @@ void prepare_graph_rule(const QCtx &c, int rule, bool has_tms, int tms, Level &L
     visit(qg.root);
     uint64_t mx = costs[qg.root].empty() ? 0 : *costs[qg.root].rbegin();
     L.next_max_cost = 1 + mx;
+    if (has_tms) {  // words matched inside phrases count too (graph_based_ranking_rule.rs:149-157)
+        size_t wip = 0;
+        for (auto &nd : qg.nodes) {
+            uint32_t ph;
+            if (nd.kind == ND_TERM && original_phrase(c, nd.term.ts, ph))
+                for (auto w : c.phrases[ph].words)
+                    if (w != -1) wip++;
+        }
+        L.next_max_cost += wip > 0 ? wip - 1 : 0;
+    }
     // state graph for the device.  Without a matching strategy a state is a query-graph node.  With `Last`, once a term has
     // been skipped every later term must be skipped too (cheapest_paths.rs:189-281 with the removal order of
     // query_graph.rs:346-406), so a node splits into a "matching" and a "skipping" state.
@@ -925,7 +1047,7 @@ void prepare_exact_attribute(const QCtx &c, Level &L, StepOut &o) {
     }
     L.next_max_cost = 3;
     struct Info {
-        uint32_t word;
+        std::vector<int32_t> words;  // the exact term's words (a phrase may hold -1 holes / -2 unknown words)
         uint16_t start_position;
         uint8_t start_term_id;
         size_t position_count;
@@ -933,9 +1055,17 @@ void prepare_exact_attribute(const QCtx &c, Level &L, StepOut &o) {
     std::vector<Info> ets;
     for (auto &n : g.nodes) {
         if (n.kind != ND_TERM) continue;
-        uint32_t w;
-        if (!exact_term(c, n.term.ts, w)) continue;
-        ets.push_back({w, n.term.ps, n.term.t0, (size_t)n.term.pe - n.term.ps + 1});
+        ExactTermRef e = exact_term(c, n.term.ts);
+        if (!e.kind) continue;
+        Info inf;
+        if (e.kind == 1)
+            inf.words = {(int32_t)e.id};
+        else
+            inf.words = c.phrases[e.id].words;
+        inf.start_position = n.term.ps;
+        inf.start_term_id = n.term.t0;
+        inf.position_count = (size_t)n.term.pe - n.term.ps + 1;
+        ets.push_back(std::move(inf));
     }
     std::stable_sort(ets.begin(), ets.end(), [](const Info &a, const Info &b2) { return a.start_term_id < b2.start_term_id; });
     {
@@ -953,23 +1083,28 @@ void prepare_exact_attribute(const QCtx &c, Level &L, StepOut &o) {
         prev = e.start_term_id;
     }
     if (!empty_state) {
-        // candidates = AND_i word_position[w_i, bucketed(pos_i)]
+        // candidates = AND over every word of every exact term of word_position[w, bucketed(pos + offset)]  (:159-186)
         uint16_t cand = b.new_col();
         bool first = true;
-        for (auto &e : ets) {
-            uint16_t t = first ? cand : b.new_col();
-            b.add_list(t, c.ix.word_pos_list(e.word, bucketed_position(e.start_position)));
-            if (!first) b.op(0, cand, cand, t);
-            first = false;
-        }
+        for (auto &e : ets)
+            for (size_t off = 0; off < e.words.size(); off++) {
+                int32_t w = e.words[off];
+                if (w == -1) continue;  // stop-word hole
+                uint16_t t = first ? cand : b.new_col();
+                if (w >= 0) b.add_list(t, c.ix.word_pos_list((uint32_t)w, bucketed_position((uint16_t)(e.start_position + off))));
+                if (!first) b.op(0, cand, cand, t);
+                first = false;
+            }
         for (uint16_t fid = 0; fid < c.ix.settings.n_fields; fid++) {
             uint16_t swe = b.new_col();
             b.op(3, swe, cand, 0);
-            for (auto &e : ets) {
-                uint16_t t = b.new_col();
-                b.add_list(t, c.ix.word_fid_list(e.word, fid));
-                b.op(0, swe, swe, t);
-            }
+            for (auto &e : ets)
+                for (auto w : e.words) {
+                    if (w == -1) continue;
+                    uint16_t t = b.new_col();
+                    if (w >= 0) b.add_list(t, c.ix.word_fid_list((uint32_t)w, fid));
+                    b.op(0, swe, swe, t);
+                }
             uint16_t cnt = b.new_col();
             if (count_all < 255) {
                 auto it = c.ix.fwc_list.find(((uint32_t)fid << 8) | (uint32_t)count_all);
@@ -1064,6 +1199,13 @@ void emit_activation_work(const QCtx &c, Level &L, StepOut &o) {
         ActBuilder b(c, o);
         for (auto &cd : L.conds) cd.col = b.new_col();
         for (auto &cd : L.conds) build_cond(b, cd);
+        if (L.kind == RK_RESOLVE && (!c.neg_words.empty() || !c.neg_phrases.empty())) {
+            // universe -= negative words / phrases (search/mod.rs:436-437,463): every node column loses the ignored documents
+            uint16_t ign = b.new_col();
+            for (auto w : c.neg_words) b.add_word_docids(ign, WordRef{w, false});
+            for (auto ph : c.neg_phrases) b.op(1, ign, ign, b.phrase_col(ph));
+            for (auto &cd : L.conds) b.op(2, cd.col, cd.col, ign);
+        }
         o.n_cols = b.next_col;
     }
     o.n_costs = (uint32_t)L.cost_vals.size();
@@ -1099,9 +1241,10 @@ void emit_activation_work(const QCtx &c, Level &L, StepOut &o) {
     for (auto cv : L.cost_vals) o.cost_vals.push_back((uint16_t)cv);
 }
 
-// located_query_terms_from_tokens (parse_query.rs:28-202) without phrases / negative words
+// located_query_terms_from_tokens (parse_query.rs:28-202)
 void parse_query(QState &q, const b200_query_batch *b, uint32_t qi) {
-    const HostIndex &ix = q.ctx.ix;
+    QCtx &c = q.ctx;
+    const HostIndex &ix = c.ix;
     struct Tok {
         int kind;
         std::string lemma;
@@ -1109,34 +1252,118 @@ void parse_query(QState &q, const b200_query_batch *b, uint32_t qi) {
     std::vector<Tok> toks;
     for (uint32_t t = b->token_begin[qi]; t < b->token_begin[qi + 1]; t++)
         toks.push_back({b->token_kind[t], std::string(b->lemma_bytes + b->lemma_off[t], b->lemma_off[t + 1] - b->lemma_off[t])});
-    if (toks.size() > 1000) toks.resize(1000);
-    std::vector<std::pair<uint32_t, uint16_t>> located;  // (term id, position)
+    if (toks.size() > 1000) toks.resize(1000);  // MAX_TOKEN_COUNT
+    struct Located {
+        uint32_t term;
+        uint16_t ps, pe;
+    };
+    std::vector<Located> located;
+    struct PhraseBuilder {
+        std::vector<int32_t> words;
+        uint16_t start = 0xffff, end = 0xffff;
+        bool is_empty() const {
+            for (auto w : words)
+                if (w != -1) return false;
+            return true;
+        }
+    };
+    auto build_phrase = [&](PhraseBuilder &pb, Located &out) -> bool {
+        if (pb.is_empty()) return false;
+        EPhrase p;
+        p.words = pb.words;
+        ETerm t;
+        t.phrase = (int32_t)c.intern_phrase(p);
+        t.original = "\x01phrase";
+        c.terms.push_back(std::move(t));
+        out = Located{(uint32_t)c.terms.size() - 1, pb.start, pb.end};
+        return true;
+    };
     uint16_t position = 0xffff;
-    bool encountered_whitespace = true;
+    bool encountered_whitespace = true, negative_next_token = false, negative_phrase = false, has_phrase = false;
+    PhraseBuilder phrase;
     size_t words_limit = b->words_limit ? b->words_limit : 10;
+    bool limit_hit = false;
     for (size_t ti = 0; ti < toks.size(); ti++) {
         const Tok &tk = toks[ti];
         if (tk.lemma.empty()) continue;
-        if (located.size() >= words_limit) break;
+        if (located.size() >= words_limit) {
+            limit_hit = true;
+            break;
+        }
         bool has_next = ti + 1 < toks.size();
         if (tk.kind == 0 || tk.kind == 1) {
             position = (uint16_t)(position + 1);
-            if (has_next) {
+            if (has_phrase) {
+                if (phrase.is_empty()) phrase.start = position;
+                phrase.end = position;
+                phrase.words.push_back(tk.kind == 1 ? -1 : c.word_rank_or_absent(tk.lemma));
+            } else if (negative_next_token) {
+                int64_t r = ix.find_word(tk.lemma);
+                if (r >= 0) c.neg_words.push_back((uint32_t)r);
+                negative_next_token = false;
+            } else if (has_next) {
                 if (tk.kind == 0) {
-                    q.ctx.terms.push_back(term_from_word(ix, tk.lemma, number_of_typos_allowed(ix, tk.lemma), false, false));
-                    located.push_back({(uint32_t)q.ctx.terms.size() - 1, position});
+                    c.terms.push_back(term_from_word(c, tk.lemma, number_of_typos_allowed(ix, tk.lemma), false, false));
+                    located.push_back({(uint32_t)c.terms.size() - 1, position, position});
                 }
             } else {
-                q.ctx.terms.push_back(term_from_word(ix, tk.lemma, number_of_typos_allowed(ix, tk.lemma), ix.settings.prefix_search, false));
-                located.push_back({(uint32_t)q.ctx.terms.size() - 1, position});
+                c.terms.push_back(term_from_word(c, tk.lemma, number_of_typos_allowed(ix, tk.lemma), ix.settings.prefix_search, false));
+                located.push_back({(uint32_t)c.terms.size() - 1, position, position});
             }
         } else {
-            if (tk.kind == 3) position = (uint16_t)(position + 7);
-            if (tk.lemma.find('"') != std::string::npos) throw UnsupportedQuery{"phrase queries (\"...\") are not implemented on the device path"};
-            if (tk.lemma == "-" && encountered_whitespace && has_next) throw UnsupportedQuery{"the negative operator is not implemented on the device path"};
+            bool hard = tk.kind == 3;
+            if (hard) position = (uint16_t)(position + 7);
+            bool had = has_phrase;
+            PhraseBuilder cur = phrase;
+            has_phrase = false;
+            phrase = PhraseBuilder();
+            if (hard && had) {  // a hard separator inside a phrase closes it and immediately opens a new one
+                Located lt;
+                if (build_phrase(cur, lt)) {
+                    if (negative_phrase)
+                        c.neg_phrases.push_back((uint32_t)c.terms[lt.term].phrase);
+                    else
+                        located.push_back(lt);
+                }
+                cur = PhraseBuilder();
+            }
+            size_t quotes = 0;
+            for (char ch : tk.lemma)
+                if (ch == '"') quotes++;
+            if (quotes == 0) {
+                has_phrase = had;
+                phrase = cur;
+            } else {
+                if (had) {
+                    quotes -= 1;
+                    Located lt;
+                    if (build_phrase(cur, lt)) {
+                        if (negative_phrase) {
+                            c.neg_phrases.push_back((uint32_t)c.terms[lt.term].phrase);
+                            negative_phrase = false;
+                        } else
+                            located.push_back(lt);
+                    }
+                }
+                if (quotes % 2 == 1) {
+                    negative_phrase = negative_next_token;
+                    has_phrase = true;
+                    phrase = PhraseBuilder();
+                }
+            }
+            negative_next_token = !has_phrase && tk.lemma == "-" && encountered_whitespace;
         }
         char last = tk.lemma.back();
         encountered_whitespace = (last == ' ' || last == '\t' || last == '\n');
+    }
+    if (!limit_hit && has_phrase) {  // a quote that is never closed: the rest of the query is the phrase
+        Located lt;
+        if (build_phrase(phrase, lt)) {
+            if (negative_phrase)
+                c.neg_phrases.push_back((uint32_t)c.terms[lt.term].phrase);
+            else
+                located.push_back(lt);
+        }
     }
     // QueryGraph::from_query (query_graph.rs:96-187) + make_ngram (parse_query.rs:227-300)
     EGraph &g = q.graph;
@@ -1155,32 +1382,46 @@ void parse_query(QState &q, const b200_query_batch *b, uint32_t qi) {
         g.nodes.push_back(n);
     };
     auto make_ngram = [&](size_t from, size_t to) -> bool {
+        for (size_t i = from; i <= to; i++)
+            if (c.terms[located[i].term].phrase >= 0) return false;
         for (size_t i = from; i < to; i++)
-            if (located[i].second != (uint16_t)(located[i + 1].second - 1)) return false;
+            if (located[i].pe != (uint16_t)(located[i + 1].ps - 1)) return false;
         std::string s;
         std::vector<std::string> ws;
         for (size_t i = from; i <= to; i++) {
-            ws.push_back(q.ctx.terms[located[i].first].original);
+            ws.push_back(c.terms[located[i].term].original);
             s += ws.back();
         }
         if (s.size() > 250) return false;
-        bool is_prefix = q.ctx.terms[located[to].first].is_prefix;
+        bool is_prefix = c.terms[located[to].term].is_prefix;
         uint8_t n = number_of_typos_allowed(ix, s), dec = (uint8_t)(to - from);
-        ETerm t = term_from_word(ix, s, n > dec ? (uint8_t)(n - dec) : 0, is_prefix, true);
+        ETerm t = term_from_word(c, s, n > dec ? (uint8_t)(n - dec) : 0, is_prefix, true);
+        auto it = ix.settings.synonyms.find(ws);
+        if (it != ix.settings.synonyms.end()) {
+            for (auto &syn : it->second) {
+                EPhrase p;
+                for (auto &w : syn) p.words.push_back(c.word_rank_or_absent(w));
+                t.synonyms.push_back(c.intern_phrase(p));
+            }
+            std::sort(t.synonyms.begin(), t.synonyms.end());
+            t.synonyms.erase(std::unique(t.synonyms.begin(), t.synonyms.end()), t.synonyms.end());
+        }
         t.ngram_words = ws;
         t.is_ngram = true;
-        q.ctx.terms.push_back(std::move(t));
-        add_term_node((uint32_t)q.ctx.terms.size() - 1, located[from].second, located[to].second, (uint8_t)from, (uint8_t)to);
+        c.terms.push_back(std::move(t));
+        add_term_node((uint32_t)c.terms.size() - 1, located[from].ps, located[to].pe, (uint8_t)from, (uint8_t)to);
         return true;
     };
+    if (located.size() > 12) throw UnsupportedQuery{"more than 12 query terms"};
     for (size_t i = 0; i < located.size(); i++) {
-        add_term_node(located[i].first, located[i].second, located[i].second, (uint8_t)i, (uint8_t)i);
+        add_term_node(located[i].term, located[i].ps, located[i].pe, (uint8_t)i, (uint8_t)i);
         if (i >= 1) make_ngram(i - 1, i);
         if (i >= 2) make_ngram(i - 2, i);
     }
     build_initial_edges(g);
-    if (located.size() > 12) throw UnsupportedQuery{"more than 12 query words"};
     q.placeholder = located.empty();
+    if (q.placeholder && (!c.neg_words.empty() || !c.neg_phrases.empty()))
+        throw UnsupportedQuery{"a query made only of negative terms is not implemented on the device path"};
 }
 
 // get_ranking_rules_for_query_graph_search (search/new/mod.rs:510-649)
@@ -1295,7 +1536,12 @@ void parallel_for(size_t n, unsigned nt, F f) {
 int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t offset, uint32_t limit, int scoring) {
     CU(cudaSetDevice(device), "cudaSetDevice");
     const uint32_t NQ = b->n_queries;
-    if (!pool) pool.reset(new WorkerPool(std::max(1u, std::min(48u, std::thread::hardware_concurrency()))));
+    if (!pool) {
+        unsigned hw = std::thread::hardware_concurrency();
+        const char *env = getenv("B200_HOST_THREADS");
+        unsigned nt = env ? (unsigned)atoi(env) : std::max(4u, std::min(32u, hw / 2));
+        pool.reset(new WorkerPool(std::max(1u, nt) - 1));  // the calling thread works too
+    }
     auto pfor = [&](size_t n, std::function<void(size_t)> f) { pool->run(n, std::move(f)); };
     using clk = std::chrono::steady_clock;
     auto ms_since = [](clk::time_point t) { return std::chrono::duration<double, std::milli>(clk::now() - t).count(); };
@@ -1361,7 +1607,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
                     t.one_typo.assign(one.begin() + s * 150, one.begin() + s * 150 + n_one[s]);
                     t.two_typo.assign(two.begin() + s * 50, two.begin() + s * 50 + n_two[s]);
                 }
-                find_split_words(hix, t);
+                find_split_words(q.ctx, t);
             }
         });
         stats.host_ms[2] += ms_since(t_ph);
@@ -1419,7 +1665,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         L.graph = q.graph;
         if (tms == B200_TMS_LAST) {
             std::vector<uint16_t> rm;
-            for (auto &grp : removal_order_last(q.graph))
+            for (auto &grp : removal_order_last(q.ctx, q.graph))
                 for (auto nd : grp) rm.push_back(nd);
             remove_nodes_keep_edges(L.graph, rm);
         }
@@ -1942,7 +2188,12 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             }
         }
     }
-    pfor(NQ, [&](size_t i) { qs[i].reset(); });  // tear the per-query state down in parallel
+    // tear the per-query state down off the critical path
+    if (reaper.joinable()) reaper.join();
+    {
+        auto *dead = new std::vector<std::unique_ptr<QState>>(std::move(qs));
+        reaper = std::thread([dead]() { delete dead; });
+    }
     stats.host_ms[6] += ms_since(t_ph);
     stats.host_ms[7] += ms_since(t_total);
     return B200_OK;

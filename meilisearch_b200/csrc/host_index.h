@@ -39,6 +39,7 @@ struct Settings {
     uint32_t one_typo = 5, two_typos = 9;
     bool prefix_search = true;
     std::unordered_map<std::string, int> exact_words;
+    std::map<std::vector<std::string>, std::vector<std::vector<std::string>>> synonyms;  // pre-tokenised (index `synonyms` db)
     uint16_t max_weight() const {
         uint16_t m = 0;
         for (auto w : weights) m = m > w ? m : w;

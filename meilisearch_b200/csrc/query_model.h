@@ -29,17 +29,25 @@ struct ETerm {  // QueryTerm (query_term/mod.rs:43-54)
     std::vector<uint32_t> prefix_of;
     int32_t prefix_db = -1;   // prefix id
     std::vector<uint32_t> one_typo, two_typo;
-    bool has_split = false;
-    uint32_t split_l = 0, split_r = 0, split_list = NO_LIST;
-    int32_t lev_slot = -1;    // index into the device derivation batch
+    int32_t phrase = -1;             // zero_typo.phrase: the user phrase this term stands for (phrase id)
+    std::vector<uint32_t> synonyms;  // zero_typo.synonyms (phrase ids)
+    int32_t split = -1;              // one_typo.split_words (phrase id of the 2-word split)
+    int32_t lev_slot = -1;           // index into the device derivation batch
+    bool allows_split_words() const { return phrase < 0; }
 };
 
-struct ESubset {  // NTypoTermSubset; `split` stands for the only phrase a subset can hold here (split words)
+// Phrase (query_term/phrase.rs): dictionary ranks; -1 = stop-word hole; -2 = a word that is not in the dictionary
+struct EPhrase {
+    std::vector<int32_t> words;
+};
+
+struct ESubset {  // NTypoTermSubset
     uint8_t kind = N_NOTHING;
-    std::vector<uint32_t> words;
-    bool split = false;
+    std::vector<uint32_t> words;    // sorted
+    std::vector<uint32_t> phrases;  // sorted phrase ids
     bool contains_word(uint32_t w) const { return kind == N_ALL || (kind == N_SUBSET && std::binary_search(words.begin(), words.end(), w)); }
-    bool is_empty() const { return kind == N_NOTHING || (kind == N_SUBSET && words.empty() && !split); }
+    bool contains_phrase(uint32_t p) const { return kind == N_ALL || (kind == N_SUBSET && std::binary_search(phrases.begin(), phrases.end(), p)); }
+    bool is_empty() const { return kind == N_NOTHING || (kind == N_SUBSET && words.empty() && phrases.empty()); }
     void intersect(const ESubset &o) {
         if (kind == N_ALL)
             *this = o;
@@ -48,18 +56,22 @@ struct ESubset {  // NTypoTermSubset; `split` stands for the only phrase a subse
                 std::vector<uint32_t> r;
                 std::set_intersection(words.begin(), words.end(), o.words.begin(), o.words.end(), std::back_inserter(r));
                 words.swap(r);
-                split = split && o.split;
+                std::vector<uint32_t> rp;
+                std::set_intersection(phrases.begin(), phrases.end(), o.phrases.begin(), o.phrases.end(), std::back_inserter(rp));
+                phrases.swap(rp);
             } else if (o.kind == N_NOTHING)
                 *this = ESubset{};
         }
     }
-    bool operator==(const ESubset &o) const { return kind == o.kind && words == o.words && split == o.split; }
+    bool operator==(const ESubset &o) const { return kind == o.kind && words == o.words && phrases == o.phrases; }
     void key(std::string &s) const {  // binary identity key (cheap: no number formatting)
         s.push_back((char)('A' + kind));
         uint32_t nw = (uint32_t)words.size();
         s.append(reinterpret_cast<const char *>(&nw), 4);
         if (!words.empty()) s.append(reinterpret_cast<const char *>(words.data()), words.size() * 4);
-        s.push_back(split ? 's' : '-');
+        uint32_t np = (uint32_t)phrases.size();
+        s.append(reinterpret_cast<const char *>(&np), 4);
+        if (np) s.append(reinterpret_cast<const char *>(phrases.data()), phrases.size() * 4);
     }
 };
 

@@ -17,6 +17,7 @@ import re
 import sys
 
 REF = "/root/reference/crates/milli/src/search/new/tests"
+SNAPDIR = REF + "/snapshots"
 FILES = ["typo.rs", "proximity.rs", "words_tms.rs", "attribute_fid.rs", "word_position.rs", "exactness.rs",
          "ngram_split_words.rs", "typo_proximity.rs", "proximity_typo.rs", "stop_words.rs"]
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "milli_goldens.json")
@@ -104,6 +105,93 @@ def parse_documents(body):
     return out
 
 
+def find_paren(src, start):
+    """src[start] == '(' -> index just after the matching ')' (aware of strings and raw strings)."""
+    depth, i, n = 0, start, len(src)
+    while i < n:
+        c = src[i]
+        if c == "r" and re.match(r'r#*"', src[i:i + 8]) and not (src[i - 1].isalnum() or src[i - 1] == "_"):
+            hashes = re.match(r'r(#*)"', src[i:i + 8]).group(1)
+            j = src.find('"' + hashes, i + len(hashes) + 2)
+            i = j + len(hashes) + 1
+            continue
+        if c == '"':
+            i += 1
+            while src[i] != '"':
+                if src[i] == "\\":
+                    i += 1
+                i += 1
+        elif c == "(":
+            depth += 1
+        elif c == ")":
+            depth -= 1
+            if depth == 0:
+                return i + 1
+        i += 1
+    raise ValueError("unbalanced parens")
+
+
+SCORE_RE = re.compile(
+    r"Words\(\s*Words\s*\{\s*matching_words:\s*(\d+),\s*max_matching_words:\s*(\d+),?\s*\},?\s*\)|"
+    r"Typo\(\s*Typo\s*\{\s*typo_count:\s*(\d+),\s*max_typo_count:\s*(\d+),?\s*\},?\s*\)|"
+    r"(Proximity|Fid|Position)\(\s*Rank\s*\{\s*rank:\s*(\d+),\s*max_rank:\s*(\d+),?\s*\},?\s*\)|"
+    r"ExactAttribute\(\s*(ExactMatch|MatchesStart|NoExactMatch),?\s*\)|"
+    r"ExactWords\(\s*ExactWords\s*\{\s*matching_words:\s*(\d+),\s*max_matching_words:\s*(\d+),?\s*\},?\s*\)", re.S)
+
+
+def parse_score_list(txt):
+    """one `[ ScoreDetails, ... ]` -> [[kind, rank, max_rank], ...] using ScoreDetails::rank() (score_details.rs:110-125)"""
+    out = []
+    for m in SCORE_RE.finditer(txt):
+        if m.group(1) is not None:
+            out.append(["words", int(m.group(1)), int(m.group(2))])
+        elif m.group(3) is not None:
+            tc, mx = int(m.group(3)), int(m.group(4))
+            out.append(["typo", mx + 1 - tc, mx + 1])
+        elif m.group(5) is not None:
+            out.append([{"Proximity": "proximity", "Fid": "fid", "Position": "position"}[m.group(5)], int(m.group(6)), int(m.group(7))])
+        elif m.group(8) is not None:
+            out.append(["exactAttribute", {"ExactMatch": 3, "MatchesStart": 2, "NoExactMatch": 1}[m.group(8)], 3])
+        else:
+            out.append(["exactWords", int(m.group(9)) + 1, int(m.group(10)) + 1])
+    return out
+
+
+def split_top_level(body):
+    """split the inside of `[ a, b, ... ]` at depth-0 commas"""
+    parts, depth, cur = [], 0, []
+    for ch in body:
+        if ch in "([{":
+            depth += 1
+        elif ch in ")]}":
+            depth -= 1
+        if ch == "," and depth == 0:
+            parts.append("".join(cur))
+            cur = []
+        else:
+            cur.append(ch)
+    if "".join(cur).strip():
+        parts.append("".join(cur))
+    return parts
+
+
+def parse_snapshot_file(path):
+    txt = open(path, encoding="utf-8").read()
+    body = txt.split("---", 2)[2].strip()
+    inner = body[body.index("[") + 1: body.rindex("]")]
+    items = split_top_level(inner)
+    ids, scores = [], []
+    for it in items:
+        it = it.strip()
+        if it.startswith("("):  # (docid, [scores])
+            m = re.match(r"\(\s*(\d+),", it)
+            ids.append(int(m.group(1)))
+            scores.append(parse_score_list(it[m.end():]))
+        else:
+            scores.append(parse_score_list(it))
+    return (ids if ids else None), scores
+
+
 def str_list(arg):
     return [rust_str(x) for x in re.findall(r'"((?:[^"\\]|\\.)*)"', arg)]
 
@@ -118,7 +206,7 @@ SETTING_RE = re.compile(
     r"s\.limit\((?P<limit>\d+)\)|s\.offset\((?P<offset>\d+)\)|"
     r"ScoringStrategy::(?P<scoring>Detailed|Skip)|"
     r"let mut s = (?P<news>index\.search|Search::new)|"
-    r"assert_snapshot!\(format!\(\"\{(?P<var>\w+):\?\}\"\),\s*@\"(?P<ids>\[[^\"]*\])\"\)|"
+    r"(?P<snap>insta::assert_(?:debug_)?snapshot!)\(|"
     r"(?P<create>create_\w*index\w*)\(\)",
     re.S)
 
@@ -176,6 +264,7 @@ def main():
                 continue
             st, docs, bad = None, None, True
             cur = {"tms": "Last", "query": None, "limit": 20, "offset": 0, "scoring": "Skip"}
+            snap_no, last_case, last_query = 0, None, None
             for sm in SETTING_RE.finditer(body):
                 if sm.group("create") is not None:
                     if sm.group("create") not in builders:
@@ -200,21 +289,56 @@ def main():
                     cur["offset"] = int(sm.group("offset"))
                 elif sm.group("scoring") is not None:
                     cur["scoring"] = sm.group("scoring")
-                elif sm.group("ids") is not None:
-                    if not sm.group("var").startswith(("documents_ids", "ids")) or cur["query"] is None:
-                        continue
-                    if bad or not all(ord(ch) < 128 for ch in cur["query"]):
-                        skipped += 1
-                        continue
+                elif sm.group("snap") is not None:
+                    # every insta assertion (inline or not) advances the per-test snapshot counter used in file names
+                    snap_no += 1
+                    close = find_paren(body, sm.end() - 1)
+                    call = body[sm.end():close]
+                    var = re.search(r'format!\("\{(\w+):#?\?\}"\)', call)
+                    inline = re.search(r'@(r#*)?"', call)
                     line = base_line + body.count("\n", 0, sm.start())
-                    cases.append({
-                        "source": f"crates/milli/src/search/new/tests/{fname}:{line}", "test": m.group(1),
-                        "index": {"searchable": st["searchable"], "exact_attributes": st.get("exact_attributes", []),
-                                  "stop_words": st.get("stop_words", []), "docs": docs},
-                        "settings": {k: st[k] for k in ("criteria", "authorize_typos", "exact_words", "synonyms", "one_typo", "two_typos") if k in st},
-                        "tms": cur["tms"].lower(), "scoring": cur["scoring"].lower(), "limit": cur["limit"], "offset": cur["offset"],
-                        "query": cur["query"], "expected_ids": json.loads(sm.group("ids")),
-                    })
+                    if var is None or cur["query"] is None:
+                        continue
+                    vname = var.group(1)
+                    usable = not bad and all(ord(ch) < 128 for ch in cur["query"])
+
+                    def new_case(ids):
+                        return {
+                            "source": f"crates/milli/src/search/new/tests/{fname}:{line}", "test": m.group(1),
+                            "index": {"searchable": st["searchable"], "exact_attributes": st.get("exact_attributes", []),
+                                      "stop_words": st.get("stop_words", []), "docs": docs},
+                            "settings": {k: st[k] for k in ("criteria", "authorize_typos", "exact_words", "synonyms", "one_typo", "two_typos") if k in st},
+                            "tms": cur["tms"].lower(), "scoring": cur["scoring"].lower(), "limit": cur["limit"], "offset": cur["offset"],
+                            "query": cur["query"], "expected_ids": ids,
+                        }
+
+                    if inline and vname.startswith(("documents_ids", "ids")):
+                        lit = re.search(r'@"(\[[^"]*\])"', call)
+                        if lit is None:
+                            continue
+                        if not usable:
+                            skipped += 1
+                            continue
+                        cases.append(new_case(json.loads(lit.group(1))))
+                        last_case = cases[-1]
+                        last_query = cur["query"]
+                    elif not inline and vname in ("document_scores", "document_ids_scores"):
+                        stem = fname[:-3]
+                        tname = m.group(1)[5:] if m.group(1).startswith("test_") else m.group(1)
+                        snap = os.path.join(SNAPDIR, f"milli__search__new__tests__{stem}__{tname}" + (f"-{snap_no}" if snap_no > 1 else "") + ".snap")
+                        if not os.path.exists(snap) or not usable:
+                            skipped += 1
+                            continue
+                        ids, scores = parse_snapshot_file(snap)
+                        rel = "crates/milli/src/search/new/tests/snapshots/" + os.path.basename(snap)
+                        if vname == "document_ids_scores":
+                            c = new_case(ids)
+                            c["expected_scores"] = scores
+                            c["scores_source"] = rel
+                            cases.append(c)
+                        elif last_case is not None and last_query == cur["query"] and len(scores) == len(last_case["expected_ids"]):
+                            last_case["expected_scores"] = scores
+                            last_case["scores_source"] = rel
     # de-duplicate identical corpora into a table to keep the fixture small
     corpora, keyed = [], {}
     for c in cases:

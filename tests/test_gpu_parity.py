@@ -116,26 +116,26 @@ G = load_goldens()
 
 
 def test_reference_goldens_on_gpu(mb):
-    """The reference's own ranking-rule goldens through the CUDA path (cases needing phrases/synonyms are outside the device scope)."""
+    """Every golden extracted from the reference's ranking-rule tests (docids and, where snapshotted, ScoreDetails) through the CUDA path."""
     ran = 0
     images = {}
     for case in G["cases"]:
         s = case["settings"]
-        if s.get("synonyms") or '"' in case["query"] or " -" in case["query"] or case["query"].startswith("-"):
-            continue
         ci = case["index"]
         if ci not in images:
             images[ci] = image_from_corpus(G["corpora"][ci])
         img = images[ci]
         ix = mb.Index(img, criteria=s.get("criteria"), authorize_typos=s.get("authorize_typos", True), one_typo=s.get("one_typo", 5),
-                      two_typos=s.get("two_typos", 9), exact_words=s.get("exact_words", []))
+                      two_typos=s.get("two_typos", 9), exact_words=s.get("exact_words", []), synonyms=s.get("synonyms"))
         res = (ix.search().query(mb.TokenBatch([case["query"]], img.stop_words)).terms_matching_strategy(case["tms"])
                .scoring_strategy(case["scoring"]).limit(max(case["limit"], 1)).offset(case["offset"]).execute())
         assert res.status[0] == 0
         assert res.ids(0) == case["expected_ids"], case["source"]
+        if "expected_scores" in case and case["scoring"] == "detailed":
+            assert [[list(x) for x in row] for row in res.scores(0)] == case["expected_scores"], case["scores_source"]
         ix.close()
         ran += 1
-    assert ran >= 40
+    assert ran == len(G["cases"])
 
 
 @pytest.mark.parametrize("tms,scoring", [("last", "detailed"), ("last", "skip"), ("all", "detailed")])
@@ -202,7 +202,30 @@ def test_hybrid_matches_oracle(mb, synth):
             assert int(got.semantic_hit_count[q]) == int(want.semantic_hits[q])
 
 
+def test_phrases_negatives_match_oracle(mb, synth):
+    from oracle.pyoracle import OracleIndex
+
+    base = synth.synthetic_queries(60, seed=33, with_typos=False)
+    queries = []
+    for i, q in enumerate(base):
+        w = q.split()
+        if i % 3 == 0 and len(w) >= 2:
+            queries.append('"' + " ".join(w[:2]) + '" ' + " ".join(w[2:]))
+        elif i % 3 == 1 and len(w) >= 2:
+            queries.append(" ".join(w[:-1]) + " -" + w[-1])
+        else:
+            queries.append(w[0] + ' "' + " ".join(w[1:]) + '"')
+    tokens = mb.TokenBatch(queries)
+    ix, o = mb.Index(synth), OracleIndex(synth)
+    got = ix.search().query(tokens).scoring_strategy("detailed").execute()
+    want = o.search_batch(tokens, scoring="detailed", n_threads=8)
+    for q in range(len(queries)):
+        assert got.status[q] == 0
+        assert got.ids(q) == want.ids(q), queries[q]
+        assert got.scores(q) == want.scores(q), queries[q]
+
+
 def test_unsupported_is_reported_not_faked(mb, synth):
     ix = mb.Index(synth)
-    res = ix.search().query(['"a phrase" query', "plain"]).execute()
+    res = ix.search().query(["-only -negatives", "plain"]).execute()
     assert res.status[0] == -4 and res.n_hits[0] == 0 and res.status[1] == 0

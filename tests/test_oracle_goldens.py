@@ -28,6 +28,9 @@ def test_reference_golden(case):
     r = ix.search_batch(TokenBatch([case["query"]], img.stop_words), tms=case["tms"], scoring=case["scoring"],
                         limit=max(case["limit"], 1), offset=case["offset"])
     assert r.ids(0) == case["expected_ids"], case["source"]
+    if "expected_scores" in case and case["scoring"] == "detailed":
+        got = [[list(x) for x in row] for row in r.scores(0)]
+        assert got == case["expected_scores"], case["scores_source"]
 
 
 def test_typo_bucketing_scores():
