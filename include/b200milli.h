@@ -150,7 +150,7 @@ int b200_search_batch(b200_index *, const b200_query_batch *, b200_results *);
 /* ---- introspection for measurement ----------------------------------------------------- */
 /* kernel classes for the per-kernel accounting below */
 enum b200_kernel { B200_K_LEV = 0, B200_K_COMPACT = 1, B200_K_PAIR_PROBE = 2, B200_K_SCATTER = 3, B200_K_EVAL_PATHS = 4, B200_K_EMIT = 5,
-                   B200_K_VEC_DIST = 6, B200_K_TOPK = 7, B200_K_COUNT = 8 };
+                   B200_K_VEC_DIST = 6, B200_K_TOPK = 7, B200_K_VEC_GEMM = 8, B200_K_VEC_MERGE = 9, B200_K_COUNT = 10 };
 typedef struct {
     uint64_t kernel_launches;     /* kernels launched by the library since the last reset */
     uint64_t device_steps;        /* host<->device round trips since the last reset */
@@ -158,9 +158,9 @@ typedef struct {
     uint64_t matrix_bytes;        /* algorithmic bytes: condition/bucket matrix words read+written */
     uint64_t dictionary_bytes;    /* algorithmic bytes of the term-derivation sweeps */
     uint64_t vector_bytes;        /* algorithmic bytes of the distance scans */
-    double kernel_ms[8];          /* CUDA-event time accumulated per kernel class (events on the library's stream) */
-    uint64_t kernel_count[8];     /* launches per kernel class */
-    uint64_t kernel_bytes[8];     /* algorithmic bytes attributed to each kernel class */
+    double kernel_ms[10];         /* CUDA-event time accumulated per kernel class (events on the library's stream) */
+    uint64_t kernel_count[10];    /* launches per kernel class */
+    uint64_t kernel_bytes[10];    /* algorithmic bytes attributed to each kernel class */
     double device_ms;             /* CUDA-event time from the first to the last kernel of every step */
     uint64_t h2d_bytes, d2h_bytes; /* bytes copied across PCIe/NVLink-C2C by search/derive/nns calls */
     double host_ms[8];            /* wall time of the host phases of b200_search_batch: 0 parse, 1 derive (incl. device), 2 term finalisation,

@@ -52,12 +52,12 @@ class _Results(C.Structure):
 
 class _Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("device_steps", C.c_uint64), ("posting_bytes", C.c_uint64), ("matrix_bytes", C.c_uint64),
-                ("dictionary_bytes", C.c_uint64), ("vector_bytes", C.c_uint64), ("kernel_ms", C.c_double * 8),
-                ("kernel_count", C.c_uint64 * 8), ("kernel_bytes", C.c_uint64 * 8), ("device_ms", C.c_double), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("host_ms", C.c_double * 8),
+                ("dictionary_bytes", C.c_uint64), ("vector_bytes", C.c_uint64), ("kernel_ms", C.c_double * 10),
+                ("kernel_count", C.c_uint64 * 10), ("kernel_bytes", C.c_uint64 * 10), ("device_ms", C.c_double), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("host_ms", C.c_double * 8),
                 ("hbm_bytes_staged", C.c_uint64)]
 
 
-KERNELS = ["lev_match", "act_compact", "pair_probe", "scatter", "eval_paths", "emit", "vec_dist", "topk_select"]
+KERNELS = ["lev_match", "act_compact", "pair_probe", "scatter", "eval_paths", "emit", "vec_dist", "topk_select", "vec_gemm_topk", "vec_merge"]
 
 
 def build_library(force=False):
@@ -231,7 +231,7 @@ class Index:
         d = {n: getattr(s, n) for n, _ in _Stats._fields_ if not n.startswith("kernel_") and n != "host_ms"}
         d["host_ms"] = dict(zip(["parse", "derive", "terms", "pack", "device_wait", "advance", "results", "total"], list(s.host_ms)))
         d["kernel_launches"] = s.kernel_launches
-        d["kernels"] = {KERNELS[i]: {"ms": s.kernel_ms[i], "count": s.kernel_count[i], "bytes": s.kernel_bytes[i]} for i in range(8)}
+        d["kernels"] = {KERNELS[i]: {"ms": s.kernel_ms[i], "count": s.kernel_count[i], "bytes": s.kernel_bytes[i]} for i in range(len(KERNELS))}
         return d
 
     def reset_stats(self):

@@ -242,7 +242,8 @@ struct Engine {
     // vector buffers
     DevBuf<float> d_vq, d_vdist, d_vsel_dist;
     DevBuf<uint32_t> d_vsel_ids, d_vsel_n;
-    DevBuf<unsigned long long> d_cand;
+    DevBuf<unsigned long long> d_cand, d_vruns, d_vpartial;
+    DevBuf<uint16_t> d_vq16;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> ev_pool;  // pairs recorded around kernels, resolved after the step's sync
     struct Timed { int cls; size_t a, b; };

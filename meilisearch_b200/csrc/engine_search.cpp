@@ -970,31 +970,78 @@ void prepare_graph_rule(const QCtx &c, int rule, bool has_tms, int tms, Level &L
         }
         L.next_max_cost += wip > 0 ? wip - 1 : 0;
     }
-    // state graph for the device.  Without a matching strategy a state is a query-graph node.  With `Last`, once a term has
-    // been skipped every later term must be skipped too (cheapest_paths.rs:189-281 with the removal order of
-    // query_graph.rs:346-406), so a node splits into a "matching" and a "skipping" state.
+    // state graph for the device.  Without a matching strategy a state is a query-graph node.  With `Last`, skipping a node of
+    // removal group k forbids matching any node of a cheaper group afterwards (the skip edge's `nodes_to_skip`,
+    // cheapest_paths.rs:189-281 with the removal order of query_graph.rs:346-406); mandatory nodes (phrases) stay matchable.
+    // The groups are nested, so a state is (node, m) = "nodes of groups < m are forbidden", canonicalised to the groups that
+    // still occur among the node's descendants.
     struct AEdge {
         uint32_t src, dst, cost;
         int32_t cond;
     };
     std::vector<AEdge> aedges;
-    auto sid = [&](uint16_t node, int skipping) { return (uint32_t)node * 2 + (uint32_t)skipping; };
-    for (uint16_t nd = 0; nd < n; nd++) {
-        for (int sk = 0; sk < 2; sk++) {
-            if (sk == 1 && (nd == qg.root || nd == qg.end)) continue;
-            for (auto ei : eon[nd]) {
-                const EEdge &e = edges[ei];
-                if (e.dst == qg.end) {
-                    aedges.push_back({sid(nd, sk), sid(qg.end, 0), e.cost, -1});
-                } else if (e.cond >= 0) {
-                    if (sk == 0) aedges.push_back({sid(nd, 0), sid(e.dst, 0), e.cost, e.cond});
-                } else {
-                    aedges.push_back({sid(nd, sk), sid(e.dst, 1), e.cost, -1});  // skip edge
-                }
+    std::vector<uint16_t> grp(n, 0);  // 1-based removal group, 0 = never removed
+    if (has_tms && tms == B200_TMS_LAST) {
+        uint16_t k = 1;
+        for (auto &g : removal_order_last(c, qg)) {
+            for (auto nd : g) grp[nd] = k;
+            k++;
+        }
+    }
+    // descendants' groups: dgrp[nd] = sorted distinct groups (>0) among strict descendants of nd
+    std::vector<std::vector<uint16_t>> dgrp(n);
+    {
+        std::vector<uint8_t> done(n, 0);
+        std::function<void(uint16_t)> go = [&](uint16_t nd) {
+            if (done[nd]) return;
+            done[nd] = 1;
+            std::vector<uint16_t> &d = dgrp[nd];
+            for (auto s2 : qg.nodes[nd].succ) {
+                go(s2);
+                if (grp[s2]) d.push_back(grp[s2]);
+                d.insert(d.end(), dgrp[s2].begin(), dgrp[s2].end());
+            }
+            std::sort(d.begin(), d.end());
+            d.erase(std::unique(d.begin(), d.end()), d.end());
+        };
+        go(qg.root);
+    }
+    auto canon = [&](uint16_t nd, uint16_t m) -> uint16_t {  // 1 + largest descendant group below m, or 0
+        const std::vector<uint16_t> &d = dgrp[nd];
+        auto it = std::lower_bound(d.begin(), d.end(), m);
+        return it == d.begin() ? 0 : (uint16_t)(*(it - 1) + 1);
+    };
+    std::map<std::pair<uint16_t, uint16_t>, uint32_t> sids;
+    std::vector<std::pair<uint16_t, uint16_t>> work;
+    auto sid = [&](uint16_t node, uint16_t m) {
+        if (node == qg.end) m = 0;
+        auto key = std::make_pair(node, m);
+        auto it = sids.find(key);
+        if (it != sids.end()) return it->second;
+        uint32_t id = (uint32_t)sids.size();
+        sids.emplace(key, id);
+        work.push_back(key);
+        return id;
+    };
+    uint32_t root_sid = sid(qg.root, 0), end_sid = sid(qg.end, 0);
+    for (size_t wi = 0; wi < work.size(); wi++) {
+        auto [nd, m] = work[wi];
+        if (nd == qg.end) continue;
+        uint32_t from = sids[work[wi]];
+        for (auto ei : eon[nd]) {
+            const EEdge &e = edges[ei];
+            if (e.dst == qg.end) {
+                aedges.push_back({from, end_sid, e.cost, -1});
+            } else if (e.cond >= 0) {
+                if (grp[e.dst] && grp[e.dst] < m) continue;  // nodes_to_skip.contains(dest)
+                aedges.push_back({from, sid(e.dst, canon(e.dst, m)), e.cost, e.cond});
+            } else {
+                uint16_t m2 = std::max<uint16_t>(m, grp[e.dst]);
+                aedges.push_back({from, sid(e.dst, canon(e.dst, m2)), e.cost, -1});  // skip edge
             }
         }
     }
-    finish_state_graph(L, aedges, sid(qg.root, 0), sid(qg.end, 0), true);
+    finish_state_graph(L, aedges, root_sid, end_sid, true);
 }
 
 // universe resolution (resolve_query_graph.rs:133-185 == union over START->END routes of the AND of the term docids)

@@ -226,6 +226,59 @@ int Engine::nns_batch(const float *queries, uint32_t n_q, uint32_t d, uint32_t l
         CU(cudaMemcpyAsync(d_cand.p, cand, n_cand_words * 8, cudaMemcpyHostToDevice, stream), "H2D candidates");
         d_c = d_cand.p;
     }
+    // ---- batched path: tcgen05 GEMM with the top-k fused into its epilogue (vec_gemm.cu)
+    {
+        const char *force = getenv("B200_VEC_GEMM");
+        bool want = force ? atoi(force) != 0 : n_q >= 16;
+        if (want && vec_gemm_supported(d, limit)) {
+            const uint32_t tiles_per_pass = (uint32_t)sm_count;  // query tiles resident in one launch
+            std::vector<uint32_t> h_ids, h_n;
+            std::vector<float> h_dist;
+            for (uint32_t q0 = 0; q0 < n_q; q0 += tiles_per_pass * 128) {
+                uint32_t nq = std::min<uint32_t>(n_q - q0, tiles_per_pass * 128);
+                uint32_t n_qtiles = (nq + 127) / 128, n_pad = n_qtiles * 128;
+                uint64_t n_row_tiles = (N + 63) / 64;
+                uint32_t n_groups = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sm_count / n_qtiles, n_row_tiles));
+                CU(d_vq.reserve((size_t)nq * d + n_pad), "alloc queries");
+                CU(d_vq16.reserve((size_t)n_pad * d), "alloc fp16 queries");
+                CU(d_vruns.reserve((size_t)n_qtiles * n_groups * 128 * VEC_GEMM_CAND_CAP), "alloc candidate runs");
+                CU(d_vpartial.reserve((size_t)n_pad * n_groups * VEC_GEMM_KMAX), "alloc partial top-k");
+                CU(d_vsel_dist.reserve((size_t)n_pad * limit), "alloc selection");
+                CU(d_vsel_ids.reserve((size_t)n_pad * limit), "alloc selection");
+                CU(d_vsel_n.reserve(n_pad), "alloc selection");
+                float *d_qinv = d_vq.p + (size_t)nq * d;
+                CU(cudaMemcpyAsync(d_vq.p, queries + (size_t)q0 * d, (size_t)nq * d * 4, cudaMemcpyHostToDevice, stream), "H2D queries");
+                stats.h2d_bytes += (size_t)nq * d * 4;
+                CU(launch_vec_prep_queries(stream, d_vq.p, nq, n_pad, d, d_vq16.p, d_qinv), "vec_prep_queries");
+                stats.kernel_launches++;
+                size_t m0 = mark();
+                CU(launch_vec_gemm_topk(stream, (uint32_t)sm_count, dix.emb, dix.emb_inv_norm, dix.emb_docids, N, d, d_vq16.p, d_qinv, n_qtiles, n_groups,
+                                        d_c, n_cand_words, limit, d_vruns.p, d_vpartial.p, d_vsel_ids.p, d_vsel_dist.p, d_vsel_n.p, nq),
+                   "vec_gemm_topk");
+                size_t m1 = mark();
+                // algorithmic bytes: every query tile streams the matrix once (L2 absorbs the re-reads across tiles of the same rows)
+                time_kernel(B200_K_VEC_GEMM, m0, m1, (uint64_t)N * d * 2 + N * 8 + (uint64_t)n_pad * d * 2);
+                stats.kernel_launches++;  // merge kernel
+                stats.vector_bytes += (uint64_t)N * d * 2;
+                h_ids.resize((size_t)nq * limit);
+                h_dist.resize((size_t)nq * limit);
+                h_n.resize(nq);
+                CU(cudaMemcpyAsync(h_ids.data(), d_vsel_ids.p, (size_t)nq * limit * 4, cudaMemcpyDeviceToHost, stream), "D2H");
+                CU(cudaMemcpyAsync(h_dist.data(), d_vsel_dist.p, (size_t)nq * limit * 4, cudaMemcpyDeviceToHost, stream), "D2H");
+                CU(cudaMemcpyAsync(h_n.data(), d_vsel_n.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, stream), "D2H");
+                stats.d2h_bytes += (size_t)nq * limit * 8 + nq * 4;
+                CU(cudaStreamSynchronize(stream), "sync");
+                resolve_timers();
+                for (uint32_t q = 0; q < nq; q++) {
+                    uint32_t n = std::min(h_n[q], limit);
+                    n_out[q0 + q] = n;
+                    memcpy(ids_out + (size_t)(q0 + q) * limit, h_ids.data() + (size_t)q * limit, (size_t)n * 4);
+                    memcpy(dist_out + (size_t)(q0 + q) * limit, h_dist.data() + (size_t)q * limit, (size_t)n * 4);
+                }
+            }
+            return B200_OK;
+        }
+    }
     std::vector<float> qinv(chunk);
     std::vector<float> sel_d((size_t)chunk * (limit + tie_cap));
     std::vector<uint32_t> sel_i((size_t)chunk * (limit + tie_cap)), sel_n((size_t)chunk * 2);

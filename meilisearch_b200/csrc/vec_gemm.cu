@@ -1,0 +1,439 @@
+// Batched vector stage on the 5th-gen tensor cores: distances of a tile of 128 query vectors against the staged fp16
+// embedding matrix, with the exact top-k selection fused into the epilogue (the distance matrix never exists in HBM).
+//
+// Replaces, for a batch of semantic / hybrid queries, B calls of VectorStore::nns_by_vector
+// (crates/milli/src/vector/store.rs:638-645, reached from VectorSort::fill_buffer, ranking_rules/vector_sort.rs:58-78)
+// with one exhaustive scan: distance = (1 - cos)/2 (arroy/hannoy `Cosine`), ascending, ties by docid.
+//
+// Per CTA (one per SM, 256 threads):
+//   warp 0   TMA producer: the query tile [128 x d] once (A operand, resident: d/64 blocks of 16 KB, 128B-swizzled, K-major),
+//            then matrix row tiles [64 rows x 64 halfs] through a 4-stage ring (B operand)
+//   warp 1   one thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128 queries, N=64 rows, K=16) into one of four TMEM accumulators
+//   warp 2   TMEM allocation (256 columns)
+//   warps 4-7  epilogue: lane = query; tcgen05.ld of 64 fp32 dots, distance, compare with the query's running threshold, append
+//            survivors to the query's candidate run in L2-resident scratch; a warp-cooperative bitonic sort compacts a run to its
+//            k best whenever it fills up, which tightens the threshold.
+// CTA c serves query tile c % n_qtiles and the c / n_qtiles-th slice of the row tiles; vec_merge_kernel merges the slices.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "kernels.h"
+
+namespace b200 {
+
+namespace {
+
+constexpr int GM = 128;        // queries per tile (UMMA M)
+constexpr int GN = 64;         // matrix rows per tile (UMMA N)
+constexpr int GK = 64;         // halfs per k-block = one 128-byte swizzle span
+constexpr int STAGES = 4;      // B ring
+constexpr int ACC_BUFS = 4;    // TMEM accumulators of GN columns each
+constexpr int A_BLOCK = GM * GK * 2;  // 16 KB
+constexpr int B_BLOCK = GN * GK * 2;  // 8 KB
+constexpr int CAND_CAP = VEC_GEMM_CAND_CAP;
+constexpr int KMAX = VEC_GEMM_KMAX;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    uint64_t spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (++spins > (1ull << 26)) __trap();  // a lost arrival must not hang the device
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int32_t c0, int32_t c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// K-major, 128-byte swizzle: 8-row groups are 1024 B apart (SBO); LBO is unused for swizzled K-major operands.
+// Field layout: cute/arch/mma_sm100_desc.hpp (start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout [61,64) = 2).
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3ffff) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::f16 instruction descriptor: D=f32 (bits[4,6)=1), A=B=f16 (0), both K-major, N>>3 at [17,23), M>>4 at [24,29).
+constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(GN >> 3) << 17) | ((uint32_t)(GM >> 4) << 24);
+
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+          "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+
+// ---- warp-cooperative bitonic sort of 256 u64 keys, element e = i*32 + lane held in k[i]
+__device__ __forceinline__ void cswap(unsigned long long &a, unsigned long long &b, bool asc) {
+    unsigned long long lo = a < b ? a : b, hi = a < b ? b : a;
+    a = asc ? lo : hi;
+    b = asc ? hi : lo;
+}
+template <int SIZE, int J>
+__device__ __forceinline__ void sort_step(unsigned long long (&k)[8], uint32_t lane) {
+    if constexpr (J >= 32) {
+        constexpr int RJ = J >> 5;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            if ((i & RJ) == 0) cswap(k[i], k[i | RJ], ((i * 32) & SIZE) == 0);  // lane bits do not reach SIZE >= 64
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t e = (uint32_t)i * 32u + lane;
+            const unsigned long long o = __shfl_xor_sync(0xffffffffu, k[i], J);
+            const bool asc = (e & (uint32_t)SIZE) == 0;
+            const bool lower = (lane & (uint32_t)J) == 0;
+            const unsigned long long lo = k[i] < o ? k[i] : o, hi = k[i] < o ? o : k[i];
+            k[i] = (lower == asc) ? lo : hi;
+        }
+    }
+    if constexpr (J > 1) sort_step<SIZE, J / 2>(k, lane);
+}
+template <int SIZE>
+__device__ __forceinline__ void sort_size(unsigned long long (&k)[8], uint32_t lane) {
+    sort_step<SIZE, SIZE / 2>(k, lane);
+    if constexpr (SIZE < 256) sort_size<SIZE * 2>(k, lane);
+}
+__device__ __forceinline__ void warp_sort256(unsigned long long (&k)[8], uint32_t lane) { sort_size<2>(k, lane); }
+
+// Sort lane `l`'s candidate run and keep its `kk` smallest keys; returns (all lanes) the new count and threshold of that lane.
+__device__ __forceinline__ void compact_run(unsigned long long *run, uint32_t c, uint32_t kk, uint32_t lane, uint32_t &new_cnt,
+                                            unsigned long long &new_thr) {
+    unsigned long long k[8];
+    __syncwarp();  // the owning lane's appends are visible to the whole warp
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint32_t e = (uint32_t)i * 32u + lane;
+        k[i] = e < c ? run[e] : ~0ull;
+    }
+    warp_sort256(k, lane);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint32_t e = (uint32_t)i * 32u + lane;
+        if (e < kk) run[e] = k[i];
+    }
+    // key at rank kk-1
+    const uint32_t ri = (kk - 1) >> 5;  // < KMAX/32 = 4
+    unsigned long long mine = ri == 0 ? k[0] : (ri == 1 ? k[1] : (ri == 2 ? k[2] : k[3]));
+    unsigned long long kth = __shfl_sync(0xffffffffu, mine, (kk - 1) & 31);
+    new_cnt = c < kk ? c : kk;
+    new_thr = c >= kk ? kth : ~0ull;
+    __syncwarp();
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(256, 1)
+    vec_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_m, uint64_t n_rows, uint32_t kblocks,
+                         uint32_t n_qtiles, uint32_t n_groups, const float *__restrict__ inv_norm, const uint32_t *__restrict__ docids,
+                         const float *__restrict__ q_inv_norm, const unsigned long long *__restrict__ cand, uint64_t n_cand_words, uint32_t kk,
+                         unsigned long long *__restrict__ runs /* [cta][128][CAND_CAP] */,
+                         unsigned long long *__restrict__ partial /* [n_qtiles*128][n_groups][KMAX] */) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem;
+    uint8_t *sB = smem + (size_t)kblocks * A_BLOCK;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + STAGES * B_BLOCK);
+    uint64_t *a_full = bars, *b_full = bars + 1, *b_empty = b_full + STAGES, *acc_full = b_empty + STAGES, *acc_empty = acc_full + ACC_BUFS;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + ACC_BUFS);
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t qtile = blockIdx.x % n_qtiles, group = blockIdx.x / n_qtiles;
+    if (group >= n_groups) return;  // whole CTA: before any barrier
+    const uint64_t n_tiles = (n_rows + GN - 1) / GN;
+    const uint64_t tile_lo = n_tiles * group / n_groups, tile_hi = n_tiles * (group + 1) / n_groups;
+
+    if (threadIdx.x == 0) {
+        mbar_init(a_full, 1);
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(b_full + s, 1);
+            mbar_init(b_empty + s, 1);
+        }
+        for (int b = 0; b < ACC_BUFS; b++) {
+            mbar_init(acc_full + b, 1);
+            mbar_init(acc_empty + b, 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(ACC_BUFS * GN))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(a_full, kblocks * A_BLOCK);
+            for (uint32_t kb = 0; kb < kblocks; kb++) tma_load_2d(sA + (size_t)kb * A_BLOCK, &tmap_q, a_full, (int32_t)(kb * GK), (int32_t)(qtile * GM));
+            uint32_t it = 0;
+            for (uint64_t t = tile_lo; t < tile_hi; t++)
+                for (uint32_t kb = 0; kb < kblocks; kb++, it++) {
+                    uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(b_empty + s, ph ^ 1);
+                    mbar_expect_tx(b_full + s, B_BLOCK);
+                    tma_load_2d(sB + (size_t)s * B_BLOCK, &tmap_m, b_full + s, (int32_t)(kb * GK), (int32_t)(t * GN));
+                }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            mbar_wait(a_full, 0);
+            tc_fence_after();
+            uint32_t it = 0, n = 0;
+            for (uint64_t t = tile_lo; t < tile_hi; t++, n++) {
+                uint32_t buf = n % ACC_BUFS, aph = (n / ACC_BUFS) & 1;
+                mbar_wait(acc_empty + buf, aph ^ 1);
+                tc_fence_after();
+                uint32_t tmem_d = tmem_base + buf * GN;
+                for (uint32_t kb = 0; kb < kblocks; kb++, it++) {
+                    uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(b_full + s, ph);
+                    tc_fence_after();
+                    uint64_t ad = make_sdesc(smem_u32(sA + (size_t)kb * A_BLOCK));
+                    uint64_t bd = make_sdesc(smem_u32(sB + (size_t)s * B_BLOCK));
+#pragma unroll
+                    for (uint32_t k = 0; k < GK / 16; k++) umma(tmem_d, ad + 2 * k, bd + 2 * k, (kb | k) != 0);  // +32 B per K=16 step
+                    tc_commit(b_empty + s);
+                }
+                tc_commit(acc_full + buf);
+            }
+        }
+    } else if (warp >= 4) {
+        const uint32_t w = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
+        const uint32_t qrow = qtile * GM + w * 32 + lane;
+        const float qn = q_inv_norm[qrow];
+        unsigned long long *my_run = runs + ((size_t)blockIdx.x * GM + w * 32 + lane) * CAND_CAP;
+        unsigned long long *warp_runs = runs + ((size_t)blockIdx.x * GM + w * 32) * CAND_CAP;
+        uint32_t cnt = 0;
+        unsigned long long thr = ~0ull;
+        uint32_t n = 0;
+        for (uint64_t t = tile_lo; t < tile_hi; t++, n++) {
+            uint32_t buf = n % ACC_BUFS, aph = (n / ACC_BUFS) & 1;
+            mbar_wait(acc_full + buf, aph);
+            tc_fence_after();
+            uint32_t v[GN];
+            uint32_t taddr = tmem_base + ((w * 32u) << 16) + buf * GN;
+            tmem_ld32(taddr, v);
+            tmem_ld32(taddr + 32, v + 32);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + buf);
+            const uint64_t r0 = t * GN;
+            const uint32_t n_valid = (uint32_t)((n_rows - r0) < (uint64_t)GN ? (n_rows - r0) : (uint64_t)GN);
+#pragma unroll
+            for (int j = 0; j < GN; j++) {  // fully unrolled: v[j] stays in registers
+                if ((uint32_t)j < n_valid) {
+                    const uint64_t r = r0 + j;
+                    const uint32_t doc = __ldg(docids + r);
+                    bool ok = true;
+                    if (cand) ok = (doc >> 6) < n_cand_words && ((__ldg(cand + (doc >> 6)) >> (doc & 63)) & 1);
+                    const float pn = __ldg(inv_norm + r) * qn;
+                    float dd = 0.f;
+                    if (pn > 0.f && isfinite(pn)) {
+                        float cs = __uint_as_float(v[j]) * pn;
+                        cs = fminf(1.f, fmaxf(-1.f, cs));
+                        dd = (1.f - cs) * 0.5f;
+                    }
+                    const unsigned long long key = ((unsigned long long)__float_as_uint(dd) << 32) | doc;
+                    if (ok && key < thr) my_run[cnt++] = key;
+                }
+            }
+            uint32_t need = __ballot_sync(0xffffffffu, cnt > (uint32_t)(CAND_CAP - GN));
+            while (need) {
+                uint32_t l = __ffs(need) - 1;
+                need &= need - 1;
+                uint32_t c = __shfl_sync(0xffffffffu, cnt, l), nc;
+                unsigned long long nt;
+                compact_run(warp_runs + (size_t)l * CAND_CAP, c, kk, lane, nc, nt);
+                if (lane == l) {
+                    cnt = nc;
+                    thr = nt;
+                }
+            }
+        }
+        // final: every lane's run sorted, its kk best written to this (query, group) slot
+        __syncwarp();
+        for (uint32_t l = 0; l < 32; l++) {
+            uint32_t c = __shfl_sync(0xffffffffu, cnt, l);
+            unsigned long long *run = warp_runs + (size_t)l * CAND_CAP;
+            unsigned long long k[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                uint32_t e = (uint32_t)i * 32u + lane;
+                k[i] = e < c ? run[e] : ~0ull;
+            }
+            warp_sort256(k, lane);
+            unsigned long long *out = partial + ((size_t)(qtile * GM + w * 32 + l) * n_groups + group) * KMAX;
+#pragma unroll
+            for (int i = 0; i < KMAX / 32; i++) {
+                uint32_t e = (uint32_t)i * 32u + lane;
+                out[e] = e < kk ? k[i] : ~0ull;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(ACC_BUFS * GN)) : "memory");
+    }
+}
+
+// fp32 queries -> fp16 padded tile rows + inverse norms (one warp per query; rows >= n_q are zero)
+__global__ void vec_prep_queries_kernel(const float *__restrict__ q, uint32_t n_q, uint32_t n_pad, uint32_t d, __half *__restrict__ out,
+                                        float *__restrict__ inv) {
+    uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n_pad) return;
+    float s = 0.f;
+    for (uint32_t i = lane; i < d; i += 32) {
+        float x = w < n_q ? q[(size_t)w * d + i] : 0.f;
+        out[(size_t)w * d + i] = __float2half_rn(x);
+        s = fmaf(x, x, s);
+    }
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        float nrm = sqrtf(s);
+        inv[w] = nrm > 0.f ? 1.0f / nrm : 0.f;
+    }
+}
+
+// Merge the per-group sorted runs of one query: keep the KMAX smallest with a bitonic merge of (best ascending, run descending).
+__global__ void __launch_bounds__(KMAX) vec_merge_kernel(const unsigned long long *__restrict__ partial, uint32_t n_groups, uint32_t kk,
+                                                          uint32_t *__restrict__ out_ids, float *__restrict__ out_dist, uint32_t *__restrict__ out_n) {
+    __shared__ unsigned long long s[2 * KMAX];
+    const uint32_t q = blockIdx.x, t = threadIdx.x;
+    const unsigned long long *p = partial + (size_t)q * n_groups * KMAX;
+    s[t] = p[t];
+    for (uint32_t g = 1; g < n_groups; g++) {
+        s[2 * KMAX - 1 - t] = p[(size_t)g * KMAX + t];  // reversed: s[0..2K) is bitonic
+        __syncthreads();
+        {  // first step keeps the lower half only
+            unsigned long long a = s[t], b = s[t + KMAX];
+            s[t] = a < b ? a : b;
+        }
+        __syncthreads();
+        for (uint32_t j = KMAX / 2; j >= 1; j >>= 1) {
+            uint32_t o = t ^ j;
+            unsigned long long a = s[t], b = s[o];
+            __syncthreads();
+            if (o > t) {
+                s[t] = a < b ? a : b;
+                s[o] = a < b ? b : a;
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    unsigned long long key = s[t];
+    if (t < kk) {
+        out_ids[(size_t)q * kk + t] = (uint32_t)key;
+        out_dist[(size_t)q * kk + t] = __uint_as_float((uint32_t)(key >> 32));
+    }
+    uint32_t valid = __syncthreads_count(t < kk && key != ~0ull);
+    if (t == 0) out_n[q] = valid;
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+bool make_map(CUtensorMap *m, const void *base, uint64_t rows, uint32_t d, uint32_t box_rows) {
+    EncodeTiledFn f = encode_tiled();
+    if (!f) return false;
+    cuuint64_t dims[2] = {d, rows};
+    cuuint64_t strides[1] = {(cuuint64_t)d * 2};
+    cuuint32_t box[2] = {(cuuint32_t)GK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return f(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+}  // namespace
+
+size_t vec_gemm_smem_bytes(uint32_t d) { return (size_t)(d / GK) * A_BLOCK + STAGES * B_BLOCK + 256 + 1024; }
+
+bool vec_gemm_supported(uint32_t d, uint32_t limit) { return d % GK == 0 && d >= GK && d <= 768 && limit >= 1 && limit <= KMAX; }
+
+cudaError_t launch_vec_prep_queries(cudaStream_t s, const float *q, uint32_t n_q, uint32_t n_pad, uint32_t d, void *out_fp16, float *inv) {
+    vec_prep_queries_kernel<<<(n_pad * 32 + 255) / 256, 256, 0, s>>>(q, n_q, n_pad, d, reinterpret_cast<__half *>(out_fp16), inv);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_vec_gemm_topk(cudaStream_t s, uint32_t sm_count, const void *mat_fp16, const float *inv_norm, const uint32_t *docids, uint64_t n_rows,
+                                 uint32_t d, const void *q_fp16, const float *q_inv_norm, uint32_t n_qtiles, uint32_t n_groups,
+                                 const unsigned long long *cand, uint64_t n_cand_words, uint32_t k, unsigned long long *runs,
+                                 unsigned long long *partial, uint32_t *out_ids, float *out_dist, uint32_t *out_n, uint32_t n_q) {
+    if (!vec_gemm_supported(d, k) || n_qtiles * n_groups > sm_count || n_groups == 0) return cudaErrorInvalidValue;
+    CUtensorMap mq, mm;
+    if (!make_map(&mq, q_fp16, (uint64_t)n_qtiles * GM, d, GM) || !make_map(&mm, mat_fp16, n_rows, d, GN)) return cudaErrorNotSupported;
+    size_t smem = vec_gemm_smem_bytes(d);
+    cudaError_t e = cudaFuncSetAttribute(vec_gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    vec_gemm_topk_kernel<<<n_qtiles * n_groups, 256, smem, s>>>(mq, mm, n_rows, d / GK, n_qtiles, n_groups, inv_norm, docids, q_inv_norm, cand,
+                                                                n_cand_words, k, runs, partial);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    vec_merge_kernel<<<n_q, KMAX, 0, s>>>(partial, n_groups, k, out_ids, out_dist, out_n);
+    return cudaGetLastError();
+}
+
+}  // namespace b200

@@ -112,6 +112,44 @@ def test_nns_matches_oracle(mb, synth):
                 assert abs(od[k] - dist[i, k]) <= 1e-4 * max(1 - od[k], 1e-3)
 
 
+def test_nns_tensor_core_batch_matches_oracle(mb, synth, monkeypatch):
+    """The batched vector stage (tcgen05 GEMM + fused top-k) against the oracle and against the GEMV scan."""
+    from oracle.pyoracle import OracleIndex
+
+    rng = np.random.default_rng(7)
+    for n, d, nq, k in ((20011, 768, 150, 100), (5000, 128, 40, 7), (300, 64, 17, 128)):
+        emb = rng.standard_normal((n, d)).astype(np.float32)
+        emb[100] = emb[50]
+        docids = rng.permutation(n).astype(np.uint32)
+        ix = mb.Index(synth)
+        ix.set_embeddings(emb, docids)
+        o = OracleIndex(synth)
+        o.set_embeddings(emb.astype(np.float16).astype(np.float32), docids)
+        q = rng.standard_normal((nq, d)).astype(np.float32)
+        q[3] = emb[50]
+        cand = np.zeros((n + 63) // 64, np.uint64)
+        for doc in np.nonzero(rng.random(n) < 0.2)[0]:
+            cand[doc >> 6] |= np.uint64(1) << np.uint64(doc & 63)
+        for cw in (None, cand):
+            monkeypatch.setenv("B200_VEC_GEMM", "1")
+            ix.reset_stats()
+            ids, dist, cnt = ix.nns_by_vector(q, k, cw)
+            assert ix.stats()["kernels"]["vec_gemm_topk"]["count"] >= 1
+            monkeypatch.setenv("B200_VEC_GEMM", "0")
+            ids2, dist2, cnt2 = ix.nns_by_vector(q, k, cw)
+            assert (cnt == cnt2).all()
+            # queries are rounded to fp16 for the tensor cores: 1e-4 relative on the similarity (north_star)
+            for i in range(nq):
+                oid, od = o.nns(q[i], k, cw)
+                assert cnt[i] == len(oid)
+                assert np.allclose(1 - dist[i, : cnt[i]], 1 - od, rtol=1e-4, atol=2e-5), (n, d, i)
+                assert (np.diff(dist[i, : cnt[i]]) >= 0).all()
+                assert len(set(ids[i, : cnt[i]].tolist())) == cnt[i]
+                for j in np.nonzero(ids[i, : cnt[i]] != oid)[0]:
+                    assert abs(od[j] - dist[i, j]) <= 1e-4 * max(1 - od[j], 1e-3) + 2e-5
+            assert np.allclose(dist[:, : cnt.min()], dist2[:, : cnt.min()], rtol=1e-4, atol=2e-5)
+
+
 G = load_goldens()
 
 
@@ -227,5 +265,12 @@ def test_phrases_negatives_match_oracle(mb, synth):
 
 def test_unsupported_is_reported_not_faked(mb, synth):
     ix = mb.Index(synth)
-    res = ix.search().query(["-only -negatives", "plain"]).execute()
-    assert res.status[0] == -4 and res.n_hits[0] == 0 and res.status[1] == 0
+    w = synth.synthetic_queries(1, seed=5, with_typos=False)[0].split()[0]
+    long_query = " ".join(synth.synthetic_queries(8, seed=6, with_typos=False))
+    assert len(long_query.split()) > 12
+    res = ix.search().query(["-" + w, "plain", long_query]).words_limit(20).execute()
+    assert res.status[0] == -4 and res.n_hits[0] == 0
+    assert res.status[1] == 0
+    assert res.status[2] == -4 and res.n_hits[2] == 0
+    # with the default words_limit (10) the same long query is in scope
+    assert ix.search().query([long_query]).execute().status[0] == 0
