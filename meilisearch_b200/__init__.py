@@ -175,7 +175,7 @@ class Index:
             self._ck(l.b200_stage_db(self._h, i, db.n_keys, _p(db.key_bytes), _p(db.key_offsets), _p(db.val_bytes), _p(db.val_offsets)))
         self._ck(l.b200_stage_documents_ids(self._h, _p(image.documents_ids_cbo), len(image.documents_ids_cbo)))
         w = np.asarray(weights if weights is not None else list(range(image.n_fields)), np.uint16)
-        c = np.asarray([CRITERIA[x] for x in (criteria or DEFAULT_CRITERIA)], np.int32)
+        c = np.asarray([CRITERIA[x] for x in (DEFAULT_CRITERIA if criteria is None else criteria)], np.int32)
         s = _Settings(image.n_fields, _p(w), _p(c), len(c), int(authorize_typos), one_typo, two_typos, int(prefix_search),
                       "\n".join(exact_words).encode() if exact_words else None)
         self._ck(l.b200_stage_settings(self._h, C.byref(s)))

@@ -152,6 +152,13 @@ struct Lane {
     uint8_t *scratch = nullptr;
     size_t scratch_bytes = 0;
     std::vector<uint32_t> members, act_q;
+    // a lane is driven by its own host thread with its own slice of the workers, of the arena and of the statistics
+    std::unique_ptr<WorkerPool> pool;
+    uint8_t *arena = nullptr;
+    size_t arena_bytes = 0, arena_used = 0;
+    b200_stats lst{};
+    int rc = 0;
+    std::string error;
     uint32_t res_words = 0;
     size_t qcap = 0;
     bool inflight = false;
@@ -203,7 +210,8 @@ struct Lane {
 struct Engine {
     std::unique_ptr<WorkerPool> pool;
     std::thread reaper;  // frees the previous batch's per-query state in the background
-    Lane lanes[2];
+    static constexpr unsigned MAX_LANES = 4;
+    Lane lanes[MAX_LANES];
     int device = 0;
     cudaStream_t stream = nullptr;
     std::mutex mu;
@@ -259,7 +267,9 @@ struct Engine {
     }
     void resolve_timers();  // after a stream sync
 
+    std::mutex err_mu;  // lanes report errors from their own threads
     int fail(int code, const std::string &msg) {
+        std::lock_guard<std::mutex> g(err_mu);
         last_error = msg;
         return code;
     }

@@ -344,7 +344,6 @@ struct EEdge {
     uint16_t src, dst;
     uint32_t cost;
     int32_t cond;
-    std::vector<uint8_t> skip;  // nodes_to_skip
 };
 
 struct SEdge {  // edge of the state graph handed to the device
@@ -676,22 +675,32 @@ uint16_t bucketed_position(uint16_t rel) {  // lib.rs:248-260
     return (uint16_t)p;
 }
 
+// Conditions of one rule graph.  The reference interns conditions (DedupInterner); here equal conditions can only arise from the
+// same destination node (they are functions of `to`, plus `from` for proximity), so they are built once per destination and
+// shared by id — no structural hashing on the hot path.
 struct CondTable {
     std::vector<ECond> items;
-    std::map<std::string, uint32_t> ids;
+    CondTable() { items.reserve(48); }
     uint32_t insert(ECond c) {
-        std::string k = c.key();
-        auto it = ids.find(k);
-        if (it != ids.end()) return it->second;
         items.push_back(std::move(c));
-        ids.emplace(k, (uint32_t)items.size() - 1);
         return (uint32_t)items.size() - 1;
     }
 };
 
 // G::build_edges for the six graph rules
-std::vector<std::pair<uint32_t, uint32_t>> build_edges(const QCtx &c, int rule, CondTable &ct, const ELocated *from, const ELocated &to) {
+std::vector<std::pair<uint32_t, uint32_t>> build_edges(const QCtx &c, int rule, CondTable &ct, const ELocated *from, const ELocated &to,
+                                                     int32_t *base_cache = nullptr) {
     std::vector<std::pair<uint32_t, uint32_t>> edges;
+    auto base_id = [&]() -> uint32_t {
+        if (base_cache && *base_cache >= 0) return (uint32_t)*base_cache;
+        ECond x;
+        x.rule = rule;
+        x.term = to;
+        x.end_subset = to;
+        uint32_t id = ct.insert(std::move(x));
+        if (base_cache) *base_cache = (int32_t)id;
+        return id;
+    };
     auto base = [&]() {
         ECond x;
         x.rule = rule;
@@ -718,7 +727,7 @@ std::vector<std::pair<uint32_t, uint32_t>> build_edges(const QCtx &c, int rule, 
         case RK_PROXIMITY: {  // proximity/build.rs:10-56
             uint32_t rmax = to.n_term_ids() - 1;
             if (!from || (uint16_t)(from->pe + 1) != to.ps) {
-                edges.push_back({rmax, ct.insert(base())});
+                edges.push_back({rmax, base_id()});
                 break;
             }
             for (uint32_t cost = rmax; cost < 3 + rmax; cost++) {
@@ -730,7 +739,7 @@ std::vector<std::pair<uint32_t, uint32_t>> build_edges(const QCtx &c, int rule, 
                 x.start_subset = *from;
                 edges.push_back({cost, ct.insert(x)});
             }
-            edges.push_back({3 + rmax, ct.insert(base())});
+            edges.push_back({3 + rmax, base_id()});
             break;
         }
         case RK_FID: {  // fid/mod.rs:49-121; edge order: ascending fid (the reference iterates an FxHashSet)
@@ -901,64 +910,79 @@ void prepare_graph_rule(const QCtx &c, int rule, bool has_tms, int tms, Level &L
     uint16_t n = (uint16_t)qg.nodes.size();
     // cost of ignoring a node (graph_based_ranking_rule.rs:149-193)
     std::vector<int> ignore_cost(n, -1);
-    std::vector<std::vector<uint8_t>> ignore_skip(n);
-    if (has_tms && tms == B200_TMS_LAST) {
-        std::vector<uint8_t> forbidden(n, 0);
-        for (auto &grp : removal_order_last(c, qg)) {
-            for (auto nd : grp) {
-                ignore_cost[nd] = 1;
-                ignore_skip[nd] = forbidden;
-            }
-            for (auto nd : grp) forbidden[nd] = 1;
-        }
-    }
+    if (has_tms && tms == B200_TMS_LAST)
+        for (auto &grp : removal_order_last(c, qg))
+            for (auto nd : grp) ignore_cost[nd] = 1;
     CondTable ct;
     std::vector<EEdge> edges;
     std::vector<std::vector<uint32_t>> eon(n);
-    auto insert_edge = [&](EEdge e) {
-        for (uint32_t i = 0; i < edges.size(); i++)
-            if (edges[i].src == e.src && edges[i].dst == e.dst && edges[i].cost == e.cost && edges[i].cond == e.cond) return i;
-        edges.push_back(std::move(e));
-        return (uint32_t)edges.size() - 1;
-    };
-    std::vector<uint8_t> none(n, 0);
+    // every (src, dst) pair is visited once, so edges are distinct by construction; conditions that depend on the destination only
+    // are built once per destination and shared by all its predecessors
+    std::vector<std::vector<std::pair<uint32_t, uint32_t>>> dst_edges(n);
+    std::vector<uint8_t> dst_done(n, 0);
+    std::vector<int32_t> base_cond(n, -1);
     for (uint16_t src = 0; src < n; src++) {
         const ENode &sn = qg.nodes[src];
         if (sn.kind != ND_TERM && sn.kind != ND_START) continue;
         for (auto dst : sn.succ) {
             const ENode &dn = qg.nodes[dst];
             if (dn.kind == ND_END) {
-                eon[src].push_back(insert_edge(EEdge{src, dst, 0, -1, none}));
+                edges.push_back(EEdge{src, dst, 0, -1});
+                eon[src].push_back((uint32_t)edges.size() - 1);
                 continue;
             }
-            if (ignore_cost[dst] >= 0)
-                eon[src].push_back(insert_edge(EEdge{src, dst, (uint32_t)ignore_cost[dst] * dn.term.n_term_ids(), -1, ignore_skip[dst]}));
-            for (auto &e : build_edges(c, rule, ct, sn.kind == ND_TERM ? &sn.term : nullptr, dn.term))
-                eon[src].push_back(insert_edge(EEdge{src, dst, e.first, (int32_t)e.second, none}));
+            if (ignore_cost[dst] >= 0) {
+                edges.push_back(EEdge{src, dst, (uint32_t)ignore_cost[dst] * dn.term.n_term_ids(), -1});
+                eon[src].push_back((uint32_t)edges.size() - 1);
+            }
+            const std::vector<std::pair<uint32_t, uint32_t>> *es;
+            std::vector<std::pair<uint32_t, uint32_t>> pair_edges;
+            if (rule == RK_PROXIMITY) {
+                pair_edges = build_edges(c, rule, ct, sn.kind == ND_TERM ? &sn.term : nullptr, dn.term, &base_cond[dst]);
+                es = &pair_edges;
+            } else {
+                if (!dst_done[dst]) {
+                    dst_edges[dst] = build_edges(c, rule, ct, nullptr, dn.term);
+                    dst_done[dst] = 1;
+                }
+                es = &dst_edges[dst];
+            }
+            for (auto &e : *es) {
+                edges.push_back(EEdge{src, dst, e.first, (int32_t)e.second});
+                eon[src].push_back((uint32_t)edges.size() - 1);
+            }
         }
     }
-    for (auto &v : eon) {
-        std::sort(v.begin(), v.end());
-        v.erase(std::unique(v.begin(), v.end()), v.end());
+    L.conds = std::move(ct.items);
+    // max cost over the graph ignoring skip constraints (the maximum of find_all_costs_to_end :285-310)
+    uint64_t mx = 0;
+    {
+        std::vector<int64_t> best(n, -2);  // -2 unvisited, -1 END unreachable
+        std::vector<std::pair<uint16_t, uint32_t>> stk{{qg.root, 0}};
+        while (!stk.empty()) {
+            uint16_t nd = stk.back().first;
+            uint32_t &k = stk.back().second;
+            if (nd == qg.end) {
+                best[nd] = 0;
+                stk.pop_back();
+                continue;
+            }
+            if (k < eon[nd].size()) {
+                uint16_t d2 = edges[eon[nd][k++]].dst;
+                if (best[d2] == -2) {
+                    best[d2] = -3;  // on the stack (the graph is a DAG)
+                    stk.push_back({d2, 0});
+                }
+                continue;
+            }
+            int64_t m = -1;
+            for (auto ei : eon[nd])
+                if (best[edges[ei].dst] >= 0) m = std::max<int64_t>(m, (int64_t)edges[ei].cost + best[edges[ei].dst]);
+            best[nd] = m;
+            stk.pop_back();
+        }
+        mx = best[qg.root] > 0 ? (uint64_t)best[qg.root] : 0;
     }
-    L.conds = ct.items;
-    // max cost over the graph ignoring skip constraints (find_all_costs_to_end :285-310)
-    std::vector<std::set<uint64_t>> costs(n);
-    std::vector<int> state(n, 0);
-    std::function<void(uint16_t)> visit = [&](uint16_t nd) {
-        if (state[nd]) return;
-        state[nd] = 1;
-        if (nd == qg.end) {
-            costs[nd] = {0};
-            return;
-        }
-        for (auto ei : eon[nd]) {
-            visit(edges[ei].dst);
-            for (auto x : costs[edges[ei].dst]) costs[nd].insert(edges[ei].cost + x);
-        }
-    };
-    visit(qg.root);
-    uint64_t mx = costs[qg.root].empty() ? 0 : *costs[qg.root].rbegin();
     L.next_max_cost = 1 + mx;
     if (has_tms) {  // words matched inside phrases count too (graph_based_ranking_rule.rs:149-157)
         size_t wip = 0;
@@ -1619,6 +1643,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         std::vector<char> wbytes;
         std::vector<uint32_t> woff{0};
         std::vector<uint8_t> mt, ip;
+        std::unordered_map<std::string, int32_t> slot_of;
         for (auto &qp : qs) {
             if (qp->done) continue;
             for (auto &t : qp->ctx.terms) {
@@ -1629,7 +1654,17 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
                     qp->done = true;
                     break;
                 }
+                // identical (word, budget, prefix) terms of different queries share one derivation slot
+                std::string key = t.original;
+                key.push_back((char)('0' + t.max_lev));
+                key.push_back(t.is_prefix ? 'p' : 'w');
+                auto it = slot_of.find(key);
+                if (it != slot_of.end()) {
+                    t.lev_slot = it->second;
+                    continue;
+                }
                 t.lev_slot = (int32_t)mt.size();
+                slot_of.emplace(std::move(key), t.lev_slot);
                 wbytes.insert(wbytes.end(), t.original.begin(), t.original.end());
                 woff.push_back((uint32_t)wbytes.size());
                 mt.push_back(t.max_lev);
@@ -1661,18 +1696,27 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
     }
     // ---- result buffers
     CU(d_docids_out.reserve((size_t)NQ * std::max(1u, length)), "alloc results");
-    size_t arena_used = 0;
-    auto arena_alloc = [&](size_t bytes) -> uint8_t * {
-        size_t off = (arena_used + 255) & ~(size_t)255;
-        if (off + bytes > arena_bytes) return nullptr;
-        arena_used = off + bytes;
-        return arena + off;
+    // optional host profile (B200_PROFILE=1): summed thread time per section, printed per batch
+    static std::atomic<uint64_t> prof_ns[8];
+    const bool prof = getenv("B200_PROFILE") != nullptr;
+    if (prof)
+        for (auto &x : prof_ns) x = 0;
+    struct ProfScope {
+        std::atomic<uint64_t> *slot;
+        clk::time_point t0;
+        ProfScope(std::atomic<uint64_t> *s2) : slot(s2) {
+            if (slot) t0 = clk::now();
+        }
+        ~ProfScope() {
+            if (slot) *slot += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(clk::now() - t0).count();
+        }
     };
-
+#define PROF(i) ProfScope prof_scope_##i(prof ? &prof_ns[i] : nullptr)
     // ---- phase 3: initial requests (universe resolution) or placeholder emission
     std::vector<int> rules = rule_list(hix.settings, tms);
     auto request_activation = [&](QState &q, Level &&L, const uint32_t *p_uw, const unsigned long long *p_ub, const unsigned long long *p_out,
                                   uint32_t p_rows, uint32_t p_ld, uint32_t p_col, uint32_t cap) {
+        PROF(2);
         q.pend = StepOut{};
         if (L.kind == RK_EXACT_ATTRIBUTE) prepare_exact_attribute(q.ctx, L, q.pend);
         emit_activation_work(q.ctx, L, q.pend);
@@ -1802,7 +1846,10 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
                 C.rule_idx = 0;
                 C.kind = q.rules[0];
                 C.graph = q.graph;
-                if (C.kind != RK_EXACT_ATTRIBUTE) prepare_graph_rule(q.ctx, C.kind, C.kind == RK_WORDS, tms, C);
+                if (C.kind != RK_EXACT_ATTRIBUTE) {
+                    PROF(1);
+                    prepare_graph_rule(q.ctx, C.kind, C.kind == RK_WORDS, tms, C);
+                }
                 uint32_t cap = (uint32_t)std::min<uint64_t>(cnt, L.rows);
                 request_activation(q, std::move(C), L.uw, L.ub, L.out, L.rows, L.ld, 0, cap);
                 return;
@@ -1837,6 +1884,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
                 C.graph = L.graph;
             else {
                 // the paths that took at least one document, in visiting order (= lexicographic in edge ids)
+                PROF(0);
                 std::vector<const SurvPath *> sp;
                 for (auto &p : L.surv)
                     if (p.cost_idx == ci) sp.push_back(&p);
@@ -1850,7 +1898,10 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
                 }
                 C.graph = build_from_paths(good);
             }
-            if (C.kind != RK_EXACT_ATTRIBUTE) prepare_graph_rule(q.ctx, C.kind, false, tms, C);
+            if (C.kind != RK_EXACT_ATTRIBUTE) {
+                PROF(1);
+                prepare_graph_rule(q.ctx, C.kind, false, tms, C);
+            }
             uint32_t cap = (uint32_t)std::min<uint64_t>(cnt, L.rows);
             request_activation(q, std::move(C), L.uw, L.ub, L.out, L.rows, L.ld, (uint32_t)ci, cap);
             return;
@@ -1858,8 +1909,22 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         q.done = true;
     };
 
-    // ---- phase 4: step loop, software-pipelined over lanes: while one lane's kernels run, the host advances the other lane
-    const unsigned n_lanes = (NQ >= 64 && !getenv("B200_SINGLE_LANE")) ? 2 : 1;
+    // ---- phase 4: step loop.  The batch is split over lanes; every lane has its own stream, device buffers, arena slice, host
+    // driver thread and worker sub-pool, so the host phases of one lane overlap both the kernels and the host phases of the others.
+    unsigned n_lanes = NQ >= 64 ? 2 : 1;
+    if (const char *env = getenv("B200_LANES")) n_lanes = (unsigned)std::max(1, std::min((int)MAX_LANES, atoi(env)));
+    if (getenv("B200_SINGLE_LANE")) n_lanes = 1;
+    if (NQ < n_lanes) n_lanes = 1;
+    {
+        unsigned hw = std::thread::hardware_concurrency();
+        const char *env = getenv("B200_HOST_THREADS");
+        unsigned nt = env ? (unsigned)atoi(env) : std::max(4u, std::min(64u, hw / 2));
+        unsigned per_lane = std::max(1u, nt / n_lanes);
+        for (unsigned l = 0; l < n_lanes; l++) {
+            Lane &ln = lanes[l];
+            if (!ln.pool || ln.pool->threads.size() + 1 != per_lane) ln.pool.reset(new WorkerPool(per_lane - 1));
+        }
+    }
     for (unsigned l = 0; l < n_lanes; l++) {
         Lane &ln = lanes[l];
         if (!ln.stream) {
@@ -1867,11 +1932,21 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             CU(cudaEventCreate(&ln.e0), "lane event");
             CU(cudaEventCreate(&ln.e1), "lane event");
         }
-        ln.scratch = scratch + (scratch_bytes / n_lanes) * l;
-        ln.scratch_bytes = scratch_bytes / n_lanes;
+        ln.scratch = scratch + (((scratch_bytes / n_lanes) * l) & ~(size_t)255);
+        ln.scratch_bytes = (scratch_bytes / n_lanes) & ~(size_t)255;
+        ln.arena = arena + (((arena_bytes / n_lanes) * l) & ~(size_t)255);
+        ln.arena_bytes = (arena_bytes / n_lanes) & ~(size_t)255;
+        ln.arena_used = 0;
+        ln.lst = b200_stats{};
+        ln.rc = 0;
+        ln.error.clear();
         ln.members.clear();
         ln.inflight = false;
     }
+    auto lane_fail = [&](Lane &ln, int code, const char *msg) {
+        ln.error = msg;
+        return fail(code, msg);
+    };
     for (uint32_t i = 0; i < NQ; i++) lanes[i % n_lanes].members.push_back(i);
     // everything queued on the engine stream so far (derivations) must be visible to the lanes
     CU(cudaStreamSynchronize(stream), "sync");
@@ -1887,7 +1962,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             if (!qs[i]->emits.empty()) emit_q.push_back(i);
         }
         if (ln.act_q.empty() && emit_q.empty()) return 0;
-        stats.device_steps++;
+        ln.lst.device_steps++;
         const std::vector<uint32_t> &act_q = ln.act_q;
         const size_t NA = act_q.size();
         // pass 1 (serial, light): sizes, offsets, device memory
@@ -1932,20 +2007,24 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             uint32_t n_cols = std::max(1u, o.n_cols);
             uint32_t tab_size = o.want_paths ? 4096 : 1;
             size_t persist = pl.identity ? (size_t)ld * 8 * (o.n_costs + 1) : (size_t)ld * 4 + 256 + (size_t)ld * 8 + 256 + (size_t)ld * 8 * (o.n_costs + 1);
-            pl.pb = arena_alloc(persist);
+            {
+                size_t aoff = (ln.arena_used + 255) & ~(size_t)255;
+                pl.pb = aoff + persist <= ln.arena_bytes ? ln.arena + aoff : nullptr;
+                if (pl.pb) ln.arena_used = aoff + persist;
+            }
             size_t cbytes = (size_t)ld * 8 * n_cols, sbytes = (size_t)ld * 8 * o.n_pairs, tbytes = (size_t)tab_size * 8;
             // zeroed zone (condition matrix + path table) grows from the front of the lane's scratch, the DP table from the back
             pl.coff = (z_used + 255) & ~(size_t)255;
             pl.toff = (pl.coff + cbytes + 255) & ~(size_t)255;
             size_t s_need = (sbytes + 255) & ~(size_t)255;
             if (!pl.pb || pl.toff + tbytes + s_need + s_used > ln.scratch_bytes)
-                return fail(B200_ERR_CAPACITY, "device arena exhausted: lower the batch size or raise B200_ARENA_MB / B200_SCRATCH_MB");
+                return lane_fail(ln, B200_ERR_CAPACITY, "device arena exhausted: lower the batch size or raise B200_ARENA_MB / B200_SCRATCH_MB");
             z_used = pl.toff + tbytes;
             s_used += s_need;
             pl.soff_from_end = s_used;
-            stats.posting_bytes += o.posting_bytes;
+            ln.lst.posting_bytes += o.posting_bytes;
             uint64_t mb = (uint64_t)ld * 8 * (n_cols + o.n_pairs + o.n_costs + 2);
-            stats.matrix_bytes += mb;
+            ln.lst.matrix_bytes += mb;
             eval_bytes += mb;
             if (!pl.identity) compact_bytes += (uint64_t)q.p_rows * 8 + (uint64_t)ld * 12;
             fill_bytes += o.posting_bytes;
@@ -1972,7 +2051,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         }
         uint8_t *hb = ln.h_step;
         // pass 2 (parallel): write every activation's slice of the blob straight into pinned memory
-        pfor(NA, [&](size_t a) {
+        ln.pool->run(NA, [&](size_t a) {
             QState &q = *qs[act_q[a]];
             Level &L = q.levels.back();
             StepOut &o = q.pend;
@@ -2060,8 +2139,8 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         CU(ln.d_step.reserve(nbytes), "step buffer");
         cudaStream_t st = ln.stream;
         CU(cudaMemcpyAsync(ln.d_step.p, ln.h_step, nbytes, cudaMemcpyHostToDevice, st), "H2D step");
-        stats.h2d_bytes += nbytes;
-        stats.d2h_bytes += (size_t)res_words * 4 + 8;
+        ln.lst.h2d_bytes += nbytes;
+        ln.lst.d2h_bytes += (size_t)res_words * 4 + 8;
         size_t qcap = std::max<size_t>((size_t)n_jobs + ((size_t)1 << 20), (size_t)4 << 20);
         CU(ln.d_queue.reserve(qcap), "job queue");
         qcap = ln.d_queue.cap;
@@ -2080,7 +2159,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         if (n_emits) {
             size_t m0 = ln.mark();
             CU(launch_emit(st, reinterpret_cast<const EmitDesc *>(ln.d_step.p + o_emits), n_emits), "emit");
-            ln.time_kernel(stats, B200_K_EMIT, m0, ln.mark(), (uint64_t)n_emits * 64);
+            ln.time_kernel(ln.lst, B200_K_EMIT, m0, ln.mark(), (uint64_t)n_emits * 64);
         }
         if (NA) {
             CU(cudaMemsetAsync(ln.d_results.p, 0, (size_t)(res_words + 4) * 4, st), "zero results");
@@ -2090,22 +2169,22 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             size_t t0 = ln.mark();
             CU(launch_compact(st, dacts, (uint32_t)NA, ln.d_results.p), "compact");
             size_t t1 = ln.mark();
-            ln.time_kernel(stats, B200_K_COMPACT, t0, t1, compact_bytes);
+            ln.time_kernel(ln.lst, B200_K_COMPACT, t0, t1, compact_bytes);
             CU(launch_pair_probe(st, reinterpret_cast<const PairSet *>(ln.d_step.p + o_sets), n_sets, n_probes,
                                  reinterpret_cast<const uint32_t *>(ln.d_step.p + o_words), dix.pair_keys, hix.pair_keys.size(), hix.pair_list_base,
                                  dix.lists, dacts, ln.d_results.p, ln.d_queue.p, ln.d_qcount.p, (uint32_t)qcap),
                "pair probe");
             size_t t2 = ln.mark();
-            if (n_probes) ln.time_kernel(stats, B200_K_PAIR_PROBE, t1, t2, (uint64_t)n_probes * 8 * 23);
+            if (n_probes) ln.time_kernel(ln.lst, B200_K_PAIR_PROBE, t1, t2, (uint64_t)n_probes * 8 * 23);
             CU(launch_scatter(st, (uint32_t)sm_count * 8, ln.d_queue.p, ln.d_qcount.p, (uint32_t)qcap, dacts, ln.d_results.p, dix.lists, dix.pool), "scatter");
             size_t t3 = ln.mark();
-            ln.time_kernel(stats, B200_K_SCATTER, t2, t3, fill_bytes);
+            ln.time_kernel(ln.lst, B200_K_SCATTER, t2, t3, fill_bytes);
             CU(launch_eval(st, reinterpret_cast<const TileDesc *>(ln.d_step.p + o_tiles), n_tiles, dacts, ln.d_results.p,
                            reinterpret_cast<const ColOp *>(ln.d_step.p + o_colprog), reinterpret_cast<const DpState *>(ln.d_step.p + o_states),
                            reinterpret_cast<const DpEdge *>(ln.d_step.p + o_edges), reinterpret_cast<const uint16_t *>(ln.d_step.p + o_costs),
                            ln.d_pathbuf.p, ln.d_qcount.p + 1, (uint32_t)PATH_CAP),
                "eval paths");
-            ln.time_kernel(stats, B200_K_EVAL_PATHS, t3, ln.mark(), eval_bytes);
+            ln.time_kernel(ln.lst, B200_K_EVAL_PATHS, t3, ln.mark(), eval_bytes);
             CU(cudaMemcpyAsync(ln.h_results, ln.d_results.p, (size_t)res_words * 4, cudaMemcpyDeviceToHost, st), "D2H results");
             CU(cudaMemcpyAsync(ln.h_results + res_words, ln.d_qcount.p, 8, cudaMemcpyDeviceToHost, st), "D2H counters");
         }
@@ -2113,7 +2192,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         ln.res_words = res_words;
         ln.qcap = qcap;
         ln.inflight = true;
-        stats.host_ms[3] += ms_since(t_pack);
+        ln.lst.host_ms[3] += ms_since(t_pack);
         return 1;
     };
 
@@ -2125,20 +2204,20 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         {
             float ms = 0;
             cudaEventElapsedTime(&ms, ln.e0, ln.e1);
-            stats.device_ms += ms;
-            ln.resolve_timers(stats);
+            ln.lst.device_ms += ms;
+            ln.resolve_timers(ln.lst);
         }
         const std::vector<uint32_t> &act_q = ln.act_q;
         const uint32_t res_words = ln.res_words;
         if (!act_q.empty()) {
-            if (ln.h_results[res_words] > ln.qcap) return fail(B200_ERR_CAPACITY, "scatter job queue overflow");
+            if (ln.h_results[res_words] > ln.qcap) return lane_fail(ln, B200_ERR_CAPACITY, "scatter job queue overflow");
             uint32_t np = ln.h_results[res_words + 1];
-            if (np > PATH_CAP) return fail(B200_ERR_CAPACITY, "surviving-path buffer overflow");
+            if (np > PATH_CAP) return lane_fail(ln, B200_ERR_CAPACITY, "surviving-path buffer overflow");
             std::vector<PathOut> pouts(np);
             if (np) {
                 CU(cudaMemcpyAsync(pouts.data(), ln.d_pathbuf.p, (size_t)np * sizeof(PathOut), cudaMemcpyDeviceToHost, ln.stream), "D2H paths");
                 CU(cudaStreamSynchronize(ln.stream), "sync paths");
-                stats.d2h_bytes += (size_t)np * sizeof(PathOut);
+                ln.lst.d2h_bytes += (size_t)np * sizeof(PathOut);
             }
             for (size_t a = 0; a < act_q.size(); a++) qs[act_q[a]]->levels.back().surv.clear();
             for (auto &po : pouts) {
@@ -2149,10 +2228,10 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
                 L.surv.push_back(std::move(sp));
             }
         }
-        stats.host_ms[4] += ms_since(t_wait);
+        ln.lst.host_ms[4] += ms_since(t_wait);
         auto t_adv = clk::now();
         const bool dbg = getenv("B200_DEBUG") != nullptr;
-        pfor(act_q.size(), [&](size_t a) {
+        ln.pool->run(act_q.size(), [&](size_t a) {
             QState &q = *qs[act_q[a]];
             Level &L = q.levels.back();
             const uint32_t *res = ln.h_results + L.res_off;
@@ -2172,6 +2251,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
                 fprintf(stderr, "%s\n", msg.c_str());
             }
             try {
+                PROF(3);
                 advance(q);
             } catch (const TooComplex &t) {
                 q.status = B200_ERR_CAPACITY;
@@ -2180,27 +2260,45 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
                 q.want_activation = false;
             }
         });
-        stats.host_ms[5] += ms_since(t_adv);
+        ln.lst.host_ms[5] += ms_since(t_adv);
         return 0;
     };
 
-    for (unsigned l = 0; l < n_lanes; l++) {
-        int rc = launch(lanes[l]);
-        if (rc < 0) return rc;
-    }
-    for (;;) {
-        bool any = false;
-        for (unsigned l = 0; l < n_lanes; l++) {
-            Lane &ln = lanes[l];
-            if (!ln.inflight) continue;
-            any = true;
-            int rc = finish(ln);
-            if (rc < 0) return rc;
+    auto drive = [&](Lane &ln) -> int {
+        cudaError_t ce = cudaSetDevice(device);
+        if (ce != cudaSuccess) return cuda_fail(ce, "cudaSetDevice");
+        int rc = launch(ln);
+        while (rc > 0) {
+            rc = finish(ln);
+            if (rc < 0) break;
             rc = launch(ln);
-            if (rc < 0) return rc;
         }
-        if (!any) break;
+        return rc;
+    };
+    {
+        std::vector<std::thread> drivers;
+        for (unsigned l = 1; l < n_lanes; l++) drivers.emplace_back([&, l]() { lanes[l].rc = drive(lanes[l]); });
+        lanes[0].rc = drive(lanes[0]);
+        for (auto &t : drivers) t.join();
     }
+    for (unsigned l = 0; l < n_lanes; l++) {  // fold the lanes' statistics (host phases of different lanes overlap in time)
+        const b200_stats &x = lanes[l].lst;
+        stats.kernel_launches += x.kernel_launches;
+        stats.device_steps += x.device_steps;
+        stats.posting_bytes += x.posting_bytes;
+        stats.matrix_bytes += x.matrix_bytes;
+        stats.device_ms += x.device_ms;
+        stats.h2d_bytes += x.h2d_bytes;
+        stats.d2h_bytes += x.d2h_bytes;
+        for (int k = 0; k < B200_K_COUNT; k++) {
+            stats.kernel_ms[k] += x.kernel_ms[k];
+            stats.kernel_count[k] += x.kernel_count[k];
+            stats.kernel_bytes[k] += x.kernel_bytes[k];
+        }
+        for (int k = 3; k <= 5; k++) stats.host_ms[k] += x.host_ms[k] / n_lanes;  // mean over the concurrent lanes
+    }
+    for (unsigned l = 0; l < n_lanes; l++)
+        if (lanes[l].rc < 0) return lanes[l].rc;
     // ---- outputs
     t_ph = clk::now();
     std::vector<uint32_t> out_ids((size_t)NQ * std::max(1u, length));
@@ -2235,6 +2333,10 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             }
         }
     }
+    if (prof)
+        fprintf(stderr, "[b200 profile] thread-ms: build_from_paths %.2f  prepare_graph_rule %.2f  request_activation %.2f  advance(total) %.2f\n",
+                prof_ns[0] / 1e6, prof_ns[1] / 1e6, prof_ns[2] / 1e6, prof_ns[3] / 1e6);
+#undef PROF
     // tear the per-query state down off the critical path
     if (reaper.joinable()) reaper.join();
     {

@@ -83,12 +83,30 @@ __device__ __forceinline__ int banded_osa(const uint8_t *q, int m, const uint8_t
     return (b >= 0 && b <= 2 * k) ? c1[b] : INF;
 }
 
+// Character-class signature: bit (c & 31) for every byte.  If OSA(q, w) <= k then at most k classes of q are missing from w
+// (every edit removes at most one class; a transposition none), and — outside prefix mode — vice versa.  Sound with collisions.
+__device__ __forceinline__ uint32_t char_signature(const uint8_t *s, int n) {
+    uint32_t m = 0;
+    for (int i = 0; i < n; i++) m |= 1u << (s[i] & 31);
+    return m;
+}
+
 // grid.x: 256-word tiles of the dictionary; grid.y: chunks of LEV_TERMS_PER_CTA terms.
+// Two phases per group of 8 terms: (1) every thread filters its word against the 8 terms (length, first-letter rule, signature)
+// and queues the surviving (term, word) pairs in shared memory; (2) the queue is processed densely, one banded DP per thread —
+// the DP, which is the expensive part, runs on a few percent of the pairs and without divergence between matching and
+// non-matching lanes.  Match codes are collected per (term, 32-word group) and reported as ballot records.
+constexpr int LEV_TERM_GROUP = 8;
 __global__ void __launch_bounds__(256) lev_match_kernel(const uint8_t *__restrict__ dict_bytes, const uint32_t *__restrict__ dict_off,
                                                         uint32_t n_words, const LevTerm *__restrict__ terms, uint32_t n_terms,
                                                         LevRec *__restrict__ recs, uint32_t *__restrict__ rec_count) {
     __shared__ LevTerm sterms[LEV_TERMS_PER_CTA];
+    __shared__ uint32_t sterm_sig[LEV_TERMS_PER_CTA], sterm_meta[LEV_TERMS_PER_CTA];
     __shared__ uint8_t sbytes[8192];
+    __shared__ uint16_t s_woff[257];
+    __shared__ uint32_t s_queue[LEV_TERM_GROUP * 256];  // (term << 16) | word-in-tile | (same-first << 31)
+    __shared__ uint32_t s_qn;
+    __shared__ unsigned long long s_codes[LEV_TERM_GROUP][8];
     uint32_t t0 = blockIdx.y * LEV_TERMS_PER_CTA;
     uint32_t nt = min((uint32_t)LEV_TERMS_PER_CTA, n_terms - t0);
     {
@@ -100,50 +118,93 @@ __global__ void __launch_bounds__(256) lev_match_kernel(const uint8_t *__restric
     uint32_t wn = min(256u, n_words - w0);
     uint32_t byte0 = dict_off[w0], byte1 = dict_off[w0 + wn];
     bool in_smem = (byte1 - byte0) <= sizeof(sbytes);
-    if (in_smem)
+    if (in_smem) {
         for (uint32_t i = threadIdx.x; i < byte1 - byte0; i += blockDim.x) sbytes[i] = dict_bytes[byte0 + i];
+        for (uint32_t i = threadIdx.x; i <= wn; i += blockDim.x) s_woff[i] = (uint16_t)(dict_off[w0 + i] - byte0);
+    }
     __syncthreads();
+    if (threadIdx.x < nt) {
+        const LevTerm &T = sterms[threadIdx.x];
+        sterm_sig[threadIdx.x] = char_signature(T.q, T.len);
+        sterm_meta[threadIdx.x] = (uint32_t)T.len | ((uint32_t)(T.k_same + 1) << 8) | ((uint32_t)(T.k_diff + 1) << 12) |
+                                  ((uint32_t)(T.prefix ? 1 : 0) << 16) | ((uint32_t)T.q[0] << 24);
+    }
     uint32_t wid = w0 + threadIdx.x;
     bool valid = threadIdx.x < wn;
     uint32_t off = valid ? dict_off[wid] : byte0;
     int n = valid ? (int)(dict_off[wid + 1] - off) : 0;
     const uint8_t *w = in_smem ? (sbytes + (off - byte0)) : (dict_bytes + off);
     uint8_t w0c = n > 0 ? w[0] : 0, w1c = n > 1 ? w[1] : 0;
-    uint32_t lane = threadIdx.x & 31;
-    for (uint32_t t = 0; t < nt; t++) {
-        const LevTerm &T = sterms[t];
-        int code = 0;
+    const uint32_t wsig = char_signature(w, n);
+    for (uint32_t tg = 0; tg < nt; tg += LEV_TERM_GROUP) {
+        const uint32_t ng = min((uint32_t)LEV_TERM_GROUP, nt - tg);
+        if (threadIdx.x == 0) s_qn = 0;
+        if (threadIdx.x < LEV_TERM_GROUP * 8) s_codes[threadIdx.x >> 3][threadIdx.x & 7] = 0;
+        __syncthreads();
+        // phase 1: filter, most selective test first (the signature rejects ~95 % of the pairs with two shared-memory loads)
         if (valid && n > 0) {
-            int m = T.len;
-            bool sf = (T.q[0] == w0c);
-            int k = sf ? T.k_same : T.k_diff;
-            if (k >= 0) {
-                bool len_ok = T.prefix ? (n >= m - k) : (n >= m - k && n <= m + k);
+            for (uint32_t t = 0; t < ng; t++) {
+                const uint32_t tsig = sterm_sig[tg + t];
+                const uint32_t meta = sterm_meta[tg + t];  // len | (k_same+1) << 8 | (k_diff+1) << 12 | prefix << 16 | q0 << 24
+                const int kmax = (int)((meta >> 8) & 15) - 1;
+                if (__popc(tsig & ~wsig) > kmax) continue;
+                const bool prefix = (meta >> 16) & 1;
+                const bool sf = (uint8_t)(meta >> 24) == w0c;
+                const int k = sf ? kmax : (int)((meta >> 12) & 15) - 1;
+                if (k < 0) continue;
+                const int m = (int)(meta & 255);
+                bool ok = prefix ? (n >= m - k) : (n >= m - k && n <= m + k);
+                ok = ok && __popc(tsig & ~wsig) <= k && (prefix || __popc(wsig & ~tsig) <= k);
                 // different first char at distance <= 1: the single edit sits on the first position
-                if (len_ok && !sf && m >= 2) len_ok = (w1c == T.q[1]) || (w1c == T.q[0]) || (w0c == T.q[1]);
-                if (len_ok) {
-                    int d = banded_osa(T.q, m, w, n, k, T.prefix != 0);
-                    if (d <= k && d > 0) code = sf ? d : 3;
+                if (ok && !sf && m >= 2) {
+                    const LevTerm &T = sterms[tg + t];
+                    ok = (w1c == T.q[1]) || (w1c == T.q[0]) || (w0c == T.q[1]);
                 }
+                if (ok) s_queue[atomicAdd(&s_qn, 1u)] = (t << 16) | threadIdx.x | (sf ? 0x80000000u : 0u);
             }
         }
-        unsigned hit = __ballot_sync(0xffffffffu, code != 0);
-        if (hit) {
-            // assemble the 2-bit codes of the 32 lanes
-            unsigned long long mine = (unsigned long long)code << (2 * lane);
-#pragma unroll
-            for (int s = 16; s > 0; s >>= 1) mine |= __shfl_xor_sync(0xffffffffu, mine, s);
-            if (lane == 0) {
-                uint32_t slot = atomicAdd(&rec_count[t0 + t], 1u);
+        __syncthreads();
+        // phase 2: dense DP over the queue
+        const uint32_t qn = s_qn;
+        for (uint32_t i = threadIdx.x; i < qn; i += blockDim.x) {
+            const uint32_t e = s_queue[i];
+            const uint32_t t = (e >> 16) & 0x7fff, wi = e & 0xffff;
+            const bool sf = (e >> 31) != 0;
+            const LevTerm &T = sterms[tg + t];
+            const int k = sf ? T.k_same : T.k_diff;
+            const uint8_t *ww;
+            int wl;
+            if (in_smem) {
+                ww = sbytes + s_woff[wi];
+                wl = (int)s_woff[wi + 1] - (int)s_woff[wi];
+            } else {
+                uint32_t o = dict_off[w0 + wi];
+                ww = dict_bytes + o;
+                wl = (int)(dict_off[w0 + wi + 1] - o);
+            }
+            int d = banded_osa(T.q, T.len, ww, wl, k, T.prefix != 0);
+            if (d <= k && d > 0) {
+                unsigned long long code = sf ? (unsigned long long)d : 3ull;
+                atomicOr(&s_codes[t][wi >> 5], code << (2 * (wi & 31)));
+            }
+        }
+        __syncthreads();
+        // report: one record per (term, 32-word group) holding at least one match
+        if (threadIdx.x < ng * 8) {
+            const uint32_t t = threadIdx.x >> 3, g = threadIdx.x & 7;
+            const unsigned long long codes = s_codes[t][g];
+            if (codes) {
+                uint32_t slot = atomicAdd(&rec_count[t0 + tg + t], 1u);
                 if (slot < LEV_REC_CAP) {
                     LevRec r;
-                    r.base = w0 + (threadIdx.x & ~31u);
+                    r.base = w0 + g * 32;
                     r.pad = 0;
-                    r.codes = mine;
-                    recs[(size_t)(t0 + t) * LEV_REC_CAP + slot] = r;
+                    r.codes = codes;
+                    recs[(size_t)(t0 + tg + t) * LEV_REC_CAP + slot] = r;
                 }
             }
         }
+        __syncthreads();
     }
 }
 
@@ -214,46 +275,72 @@ __device__ __forceinline__ int find_row(const uint32_t *uw, uint32_t rows, uint3
     return (lo < rows && uw[lo] == w) ? (int)lo : -1;
 }
 
-// one CTA per activation: ordered compaction of the parent's non-zero bucket words
-__global__ void __launch_bounds__(256) act_compact_kernel(const ActDesc *__restrict__ acts, uint32_t *__restrict__ results) {
+// one CTA per activation: ordered compaction of the parent's non-zero bucket words.  Each iteration covers 2048 parent rows
+// (4 per thread, loads issued together) so that a 15 k-row parent needs 8 rounds of global-memory latency, not 61.
+constexpr int COMPACT_THREADS = 512, COMPACT_PER_THREAD = 4;
+__global__ void __launch_bounds__(COMPACT_THREADS) act_compact_kernel(const ActDesc *__restrict__ acts, uint32_t *__restrict__ results) {
     const ActDesc a = acts[blockIdx.x];
     if (!a.uw) {  // the activation works directly on the dense base universe (row j == word j): nothing to compact
         if (threadIdx.x == 0) results[a.res_off] = a.p_rows;
         return;
     }
-    __shared__ uint32_t warp_sums[8];
-    __shared__ uint32_t base;
-    if (threadIdx.x == 0) base = 0;
-    __syncthreads();
-    uint32_t lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-    for (uint32_t j0 = 0; j0 < a.p_rows; j0 += 256) {
-        uint32_t j = j0 + threadIdx.x;
-        unsigned long long v = 0;
-        if (j < a.p_rows) {
-            if (a.p_out) {
-                for (uint32_t c = a.p_col_lo; c < a.p_col_hi; c++) v |= a.p_out[(size_t)c * a.p_ld + j];
-            } else
-                v = a.p_ub[j];
-        }
-        unsigned m = __ballot_sync(0xffffffffu, v != 0);
-        uint32_t wcount = __popc(m), wpre = __popc(m & ((1u << lane) - 1));
-        if (lane == 0) warp_sums[wrp] = wcount;
-        __syncthreads();
-        uint32_t before = base;
-        for (uint32_t k = 0; k < wrp; k++) before += warp_sums[k];
-        if (v != 0) {
-            uint32_t at = before + wpre;
-            if (at < a.ld) {
-                a.uw[at] = a.p_uw ? a.p_uw[j] : j;
-                a.ub[at] = v;
+    constexpr int NW = COMPACT_THREADS / 32;
+    __shared__ uint32_t warp_sums[COMPACT_PER_THREAD][NW];
+    __shared__ uint32_t s_before[COMPACT_PER_THREAD][NW];
+    __shared__ uint32_t s_total;
+    const uint32_t lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    uint32_t base = 0;
+    for (uint32_t j0 = 0; j0 < a.p_rows; j0 += COMPACT_THREADS * COMPACT_PER_THREAD) {
+        unsigned long long v[COMPACT_PER_THREAD];
+        uint32_t src[COMPACT_PER_THREAD];
+#pragma unroll
+        for (int i = 0; i < COMPACT_PER_THREAD; i++) {  // sub-chunk i holds rows j0 + i*512 + tid: ordered by (i, warp, lane)
+            uint32_t j = j0 + (uint32_t)i * COMPACT_THREADS + threadIdx.x;
+            v[i] = 0;
+            src[i] = j;
+            if (j < a.p_rows) {
+                if (a.p_out) {
+                    for (uint32_t c = a.p_col_lo; c < a.p_col_hi; c++) v[i] |= a.p_out[(size_t)c * a.p_ld + j];
+                } else
+                    v[i] = a.p_ub[j];
+                if (a.p_uw) src[i] = a.p_uw[j];
             }
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t tot = 0;
-            for (int k = 0; k < 8; k++) tot += warp_sums[k];
-            base += tot;
+        uint32_t wpre[COMPACT_PER_THREAD];
+#pragma unroll
+        for (int i = 0; i < COMPACT_PER_THREAD; i++) {
+            unsigned m = __ballot_sync(0xffffffffu, v[i] != 0);
+            wpre[i] = __popc(m & ((1u << lane) - 1));
+            if (lane == 0) warp_sums[i][wrp] = __popc(m);
         }
+        __syncthreads();
+        if (wrp == 0) {  // exclusive scan of the 64 warp counts in (i, warp) order
+            uint32_t x0 = warp_sums[lane / NW][lane % NW], x1 = warp_sums[(lane + 32) / NW][(lane + 32) % NW];
+            uint32_t p0 = x0, p1 = x1;
+#pragma unroll
+            for (int sft = 1; sft < 32; sft <<= 1) {
+                uint32_t t0 = __shfl_up_sync(0xffffffffu, p0, sft), t1 = __shfl_up_sync(0xffffffffu, p1, sft);
+                if (lane >= (uint32_t)sft) {
+                    p0 += t0;
+                    p1 += t1;
+                }
+            }
+            uint32_t tot0 = __shfl_sync(0xffffffffu, p0, 31);
+            s_before[lane / NW][lane % NW] = p0 - x0;
+            s_before[(lane + 32) / NW][(lane + 32) % NW] = tot0 + p1 - x1;
+            if (lane == 31) s_total = tot0 + p1;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < COMPACT_PER_THREAD; i++)
+            if (v[i] != 0) {
+                uint32_t at = base + s_before[i][wrp] + wpre[i];
+                if (at < a.ld) {
+                    a.uw[at] = src[i];
+                    a.ub[at] = v[i];
+                }
+            }
+        base += s_total;
         __syncthreads();
     }
     if (threadIdx.x == 0) results[a.res_off] = min(base, a.ld);
@@ -453,9 +540,92 @@ __global__ void __launch_bounds__(128) eval_dp_kernel(const TileDesc *__restrict
     const TileDesc tile = tiles[blockIdx.x];
     const ActDesc &a = acts[tile.act];
     __shared__ uint32_t counts[MAX_COSTS + 1];
+    // the activation's state graph, staged once per CTA: the DP below touches it ~n_pairs * n_edges times per row
+    constexpr uint32_t SM_STATES = 64, SM_EDGES = 384;
+    __shared__ DpState s_states[SM_STATES];
+    __shared__ DpEdge s_edges[SM_EDGES];
     uint32_t rows = results[a.res_off];
     if (tile.row_begin >= rows) return;
+    const DpState *st = states + a.state_off;
+    const DpEdge *ed = edges + a.edge_off;
+    {
+        const uint32_t n_edges_total = st[a.n_states - 1].edge_begin;  // END carries the total
+        if (a.n_states <= SM_STATES && n_edges_total <= SM_EDGES) {
+            for (uint32_t i = threadIdx.x; i < a.n_states; i += blockDim.x) s_states[i] = st[i];
+            for (uint32_t i = threadIdx.x; i < n_edges_total; i += blockDim.x) s_edges[i] = ed[i];
+            st = s_states;
+            ed = s_edges;
+        }
+    }
     for (uint32_t i = threadIdx.x; i <= a.n_costs; i += blockDim.x) counts[i] = 0;
+    // Flatten the DP into a straight-line program in shared memory, once per CTA: for every (state, cost) pair in processing order
+    // (pair index descending = states in reverse topological order) a header {dst pair, n} followed by n ops {src pair, column}.
+    // The range checks and graph decoding are then paid once per CTA instead of once per row.
+    constexpr uint32_t SM_PAIRS = 512, SM_PROG = 2048;
+    __shared__ uint32_t s_prog[SM_PROG];
+    __shared__ uint16_t s_pair_state[SM_PAIRS], s_pair_cnt[SM_PAIRS], s_pair_off[SM_PAIRS];
+    __shared__ uint32_t s_prog_len;
+    __shared__ unsigned long long s_seen[64];  // path reports already made by this CTA (hashes)
+    const uint32_t END_STATE = a.n_states - 1;
+    const uint32_t n_pairs = (states + a.state_off)[END_STATE].pair_off + 1;  // from global: the shared copy is not complete yet
+    bool flat = (st == s_states) && n_pairs <= SM_PAIRS;
+    if (threadIdx.x < 64) s_seen[threadIdx.x] = 0;
+    __syncthreads();
+    if (flat) {
+        for (uint32_t sidx = threadIdx.x; sidx < END_STATE; sidx += blockDim.x) {
+            const DpState ss = st[sidx];
+            for (uint32_t k = 0; k < ss.rcount; k++) s_pair_state[ss.pair_off + k] = (uint16_t)sidx;
+        }
+        __syncthreads();
+        for (uint32_t pi = threadIdx.x; pi + 1 < n_pairs; pi += blockDim.x) {
+            const DpState ss = st[s_pair_state[pi]];
+            const int r = (int)ss.rmin + (int)(pi - ss.pair_off);
+            uint32_t c = 0;
+            for (uint32_t e = 0; e < ss.n_edges; e++) {
+                const DpEdge ee = ed[ss.edge_begin + e];
+                const DpState ds = st[ee.dst];
+                const int rr = r - (int)ee.cost;
+                c += (rr >= (int)ds.rmin && rr < (int)ds.rmin + (int)ds.rcount) ? 1u : 0u;
+            }
+            s_pair_cnt[pi] = (uint16_t)c;
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {  // offsets in processing order: pair n_pairs-2 first
+            const uint32_t total = n_pairs - 1, per = (total + 31) / 32;
+            const uint32_t q0 = threadIdx.x * per, q1 = min(total, q0 + per);  // q = position in processing order, pair = total-1-q
+            uint32_t sum = 0;
+            for (uint32_t q = q0; q < q1; q++) sum += 1u + s_pair_cnt[total - 1 - q];
+            uint32_t pre = sum;
+#pragma unroll
+            for (int sft = 1; sft < 32; sft <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, pre, sft);
+                if ((threadIdx.x & 31) >= (uint32_t)sft) pre += t;
+            }
+            uint32_t at = pre - sum;
+            for (uint32_t q = q0; q < q1; q++) {
+                s_pair_off[total - 1 - q] = (uint16_t)min(at, 0xffffu);
+                at += 1u + s_pair_cnt[total - 1 - q];
+            }
+            if (threadIdx.x == 31) s_prog_len = pre;
+        }
+        __syncthreads();
+        flat = s_prog_len <= SM_PROG;
+        if (flat) {
+            for (uint32_t pi = threadIdx.x; pi + 1 < n_pairs; pi += blockDim.x) {
+                const DpState ss = st[s_pair_state[pi]];
+                const int r = (int)ss.rmin + (int)(pi - ss.pair_off);
+                uint32_t at = s_pair_off[pi];
+                s_prog[at++] = pi | ((uint32_t)s_pair_cnt[pi] << 16);
+                for (uint32_t e = 0; e < ss.n_edges; e++) {
+                    const DpEdge ee = ed[ss.edge_begin + e];
+                    const DpState ds = st[ee.dst];
+                    const int rr = r - (int)ee.cost;
+                    if (rr >= (int)ds.rmin && rr < (int)ds.rmin + (int)ds.rcount)
+                        s_prog[at++] = (ds.pair_off + (uint32_t)(rr - (int)ds.rmin)) | ((uint32_t)ee.col << 16);
+                }
+            }
+        }
+    }
     __syncthreads();
     uint32_t j = tile.row_begin + threadIdx.x;
     if (j < rows) {
@@ -476,6 +646,7 @@ __global__ void __launch_bounds__(128) eval_dp_kernel(const TileDesc *__restrict
         if (a.all_conditional) {
             // a row that satisfies no condition at all cannot be on any path: it only contributes to the "rest" column
             unsigned long long any = 0;
+#pragma unroll 4
             for (uint32_t c = 0; c < a.n_cols; c++) any |= C[(size_t)c * ld + j];
             if (!any) {
                 for (uint32_t ci = 0; ci < a.n_costs; ci++) a.out[(size_t)ci * ld + j] = 0;
@@ -486,27 +657,63 @@ __global__ void __launch_bounds__(128) eval_dp_kernel(const TileDesc *__restrict
         }
         {
         unsigned long long *S = a.S;
-        const DpState *st = states + a.state_off;
-        const DpEdge *ed = edges + a.edge_off;
         const uint32_t END = a.n_states - 1;
-        // backward DP; END has the single pair (cost 0)
+        // backward DP; END has the single pair (cost 0).  All (cost, edge) terms of one state are independent: their S / C
+        // loads are issued in groups of 2 costs x 4 edges (predicated, no early-outs) so that a state costs about one
+        // round of L2 latency instead of one per term.
         S[(size_t)st[END].pair_off * ld + j] = u;
+        if (flat) {
+            const uint32_t plen = s_prog_len;
+            uint32_t i = 0;
+            while (i < plen) {
+                const uint32_t hdr = s_prog[i++];
+                const uint32_t nops = hdr >> 16;
+                unsigned long long acc = 0;
+                for (uint32_t e0 = 0; e0 < nops; e0 += 4) {
+                    unsigned long long vv[4], cc[4];
+#pragma unroll
+                    for (int x = 0; x < 4; x++) {
+                        const bool have = e0 + x < nops;
+                        const uint32_t op = s_prog[i + (have ? e0 + x : 0)];
+                        const uint32_t col = op >> 16;
+                        vv[x] = have ? S[(size_t)(op & 0xffff) * ld + j] : 0ull;
+                        cc[x] = (have && col != 0xffff) ? C[(size_t)col * ld + j] : ~0ull;
+                    }
+#pragma unroll
+                    for (int x = 0; x < 4; x++) acc |= vv[x] & cc[x];
+                }
+                S[(size_t)(hdr & 0xffff) * ld + j] = acc;
+                i += nops;
+            }
+        } else
         for (int s = (int)END - 1; s >= 0; s--) {
             const DpState ss = st[s];
-            for (uint32_t k = 0; k < ss.rcount; k++) {
-                uint32_t r = ss.rmin + k;
-                unsigned long long acc = 0;
-                for (uint32_t e = 0; e < ss.n_edges; e++) {
-                    const DpEdge ee = ed[ss.edge_begin + e];
-                    if (ee.cost > r) continue;
-                    const DpState ds = st[ee.dst];
-                    uint32_t rr = r - ee.cost;
-                    if (rr < ds.rmin || rr >= (uint32_t)ds.rmin + ds.rcount) continue;
-                    unsigned long long v = S[(size_t)(ds.pair_off + rr - ds.rmin) * ld + j];
-                    if (v && ee.col != 0xffff) v &= C[(size_t)ee.col * ld + j];
-                    acc |= v;
+            for (uint32_t k = 0; k < ss.rcount; k += 2) {
+                const uint32_t r0 = ss.rmin + k;
+                const bool two = k + 1 < ss.rcount;
+                unsigned long long acc0 = 0, acc1 = 0;
+                for (uint32_t e0 = 0; e0 < ss.n_edges; e0 += 4) {
+                    unsigned long long v0[4], v1[4], cc[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const bool have = e0 + i < ss.n_edges;
+                        const DpEdge ee = ed[ss.edge_begin + (have ? e0 + i : 0)];
+                        const DpState ds = st[ee.dst];
+                        const int rr0 = (int)r0 - (int)ee.cost, rr1 = rr0 + 1;
+                        const bool ok0 = have && rr0 >= (int)ds.rmin && rr0 < (int)ds.rmin + (int)ds.rcount;
+                        const bool ok1 = have && two && rr1 >= (int)ds.rmin && rr1 < (int)ds.rmin + (int)ds.rcount;
+                        v0[i] = ok0 ? S[(size_t)(ds.pair_off + (uint32_t)(rr0 - (int)ds.rmin)) * ld + j] : 0ull;
+                        v1[i] = ok1 ? S[(size_t)(ds.pair_off + (uint32_t)(rr1 - (int)ds.rmin)) * ld + j] : 0ull;
+                        cc[i] = ((ok0 || ok1) && ee.col != 0xffff) ? C[(size_t)ee.col * ld + j] : ~0ull;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        acc0 |= v0[i] & cc[i];
+                        acc1 |= v1[i] & cc[i];
+                    }
                 }
-                S[(size_t)(ss.pair_off + k) * ld + j] = acc;
+                S[(size_t)(ss.pair_off + k) * ld + j] = acc0;
+                if (two) S[(size_t)(ss.pair_off + k + 1) * ld + j] = acc1;
             }
         }
         // buckets: cheapest cost first
@@ -557,6 +764,21 @@ __global__ void __launch_bounds__(128) eval_dp_kernel(const TileDesc *__restrict
                             unsigned long long h = mix64(0x9e3779b97f4a7c15ull * (ci + 1));
                             for (int k = 0; k <= d; k++) h = mix64(h + 0xd6e8feb86659fd93ull * (unsigned long long)(pedges[k] + 1));
                             h |= 1ull;
+                            // every row of this CTA belongs to the same activation: report a path to the global table only once per CTA
+                            bool known = false;
+                            {
+                                uint32_t sl = (uint32_t)(h >> 20) & 63u;
+                                for (int probe = 0; probe < 8; probe++) {
+                                    unsigned long long prev = atomicCAS(&s_seen[sl], 0ull, h);
+                                    if (prev == h) {
+                                        known = true;
+                                        break;
+                                    }
+                                    if (prev == 0ull) break;  // we claimed it: go on to the global table
+                                    sl = (sl + 1) & 63u;
+                                }
+                            }
+                            if (known) continue;
                             uint32_t slot = (uint32_t)(h % a.tab_size);
                             bool fresh = false;
                             for (uint32_t probe = 0; probe < a.tab_size; probe++) {
@@ -824,7 +1046,7 @@ cudaError_t launch_lev(cudaStream_t s, const uint8_t *dict_bytes, const uint32_t
 
 cudaError_t launch_compact(cudaStream_t s, const ActDesc *acts, uint32_t n_acts, uint32_t *results) {
     if (!n_acts) return cudaSuccess;
-    act_compact_kernel<<<n_acts, 256, 0, s>>>(acts, results);
+    act_compact_kernel<<<n_acts, COMPACT_THREADS, 0, s>>>(acts, results);
     return cudaGetLastError();
 }
 cudaError_t launch_pair_probe(cudaStream_t s, const PairSet *sets, uint32_t n_sets, uint32_t n_probes, const uint32_t *wordpool,

@@ -10,6 +10,7 @@
 //            then matrix row tiles [64 rows x 64 halfs] through a 4-stage ring (B operand)
 //   warp 1   one thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128 queries, N=64 rows, K=16) into one of four TMEM accumulators
 //   warp 2   TMEM allocation (256 columns)
+//   warp 3   stages each row tile's docids (filtered rows marked) and inverse norms in shared memory, one tile ahead
 //   warps 4-7  epilogue: lane = query; tcgen05.ld of 64 fp32 dots, distance, compare with the query's running threshold, append
 //            survivors to the query's candidate run in L2-resident scratch; a warp-cooperative bitonic sort compacts a run to its
 //            k best whenever it fills up, which tightens the threshold.
@@ -31,6 +32,7 @@ constexpr int GN = 64;         // matrix rows per tile (UMMA N)
 constexpr int GK = 64;         // halfs per k-block = one 128-byte swizzle span
 constexpr int STAGES = 4;      // B ring
 constexpr int ACC_BUFS = 4;    // TMEM accumulators of GN columns each
+constexpr int META_BUFS = 2;   // row metadata (docid, inverse norm) staged per tile by warp 3
 constexpr int A_BLOCK = GM * GK * 2;  // 16 KB
 constexpr int B_BLOCK = GN * GK * 2;  // 8 KB
 constexpr int CAND_CAP = VEC_GEMM_CAND_CAP;
@@ -181,7 +183,10 @@ __global__ void __launch_bounds__(256, 1)
     uint8_t *sB = smem + (size_t)kblocks * A_BLOCK;
     uint64_t *bars = reinterpret_cast<uint64_t *>(sB + STAGES * B_BLOCK);
     uint64_t *a_full = bars, *b_full = bars + 1, *b_empty = b_full + STAGES, *acc_full = b_empty + STAGES, *acc_empty = acc_full + ACC_BUFS;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + ACC_BUFS);
+    uint64_t *meta_full = acc_empty + ACC_BUFS, *meta_empty = meta_full + META_BUFS;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(meta_empty + META_BUFS);
+    uint32_t *s_doc = reinterpret_cast<uint32_t *>(bars + 32);               // [META_BUFS][GN]
+    float *s_scale = reinterpret_cast<float *>(s_doc + META_BUFS * GN);      // [META_BUFS][GN]
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t qtile = blockIdx.x % n_qtiles, group = blockIdx.x / n_qtiles;
@@ -198,6 +203,10 @@ __global__ void __launch_bounds__(256, 1)
         for (int b = 0; b < ACC_BUFS; b++) {
             mbar_init(acc_full + b, 1);
             mbar_init(acc_empty + b, 4);
+        }
+        for (int b = 0; b < META_BUFS; b++) {
+            mbar_init(meta_full + b, 1);
+            mbar_init(meta_empty + b, 4);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -247,6 +256,27 @@ __global__ void __launch_bounds__(256, 1)
                 tc_commit(acc_full + buf);
             }
         }
+    } else if (warp == 3) {
+        uint32_t n = 0;
+        for (uint64_t t = tile_lo; t < tile_hi; t++, n++) {
+            const uint32_t mb = n % META_BUFS, mph = (n / META_BUFS) & 1;
+            mbar_wait(meta_empty + mb, mph ^ 1);
+#pragma unroll
+            for (int h = 0; h < GN / 32; h++) {
+                const uint64_t r = t * GN + (uint32_t)h * 32u + lane;
+                uint32_t doc = 0xffffffffu;
+                float sc = 0.f;
+                if (r < n_rows) {
+                    doc = __ldg(docids + r);
+                    sc = __ldg(inv_norm + r);
+                    if (cand && !((doc >> 6) < n_cand_words && ((__ldg(cand + (doc >> 6)) >> (doc & 63)) & 1))) doc = 0xffffffffu;
+                }
+                s_doc[mb * GN + h * 32 + lane] = doc;
+                s_scale[mb * GN + h * 32 + lane] = sc;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(meta_full + mb);
+        }
     } else if (warp >= 4) {
         const uint32_t w = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
         const uint32_t qrow = qtile * GM + w * 32 + lane;
@@ -268,26 +298,25 @@ __global__ void __launch_bounds__(256, 1)
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + buf);
-            const uint64_t r0 = t * GN;
-            const uint32_t n_valid = (uint32_t)((n_rows - r0) < (uint64_t)GN ? (n_rows - r0) : (uint64_t)GN);
+            const uint32_t mb = n % META_BUFS, mph = (n / META_BUFS) & 1;
+            mbar_wait(meta_full + mb, mph);
+            const uint32_t *tdoc = s_doc + mb * GN;
+            const float *tscale = s_scale + mb * GN;
 #pragma unroll
-            for (int j = 0; j < GN; j++) {  // fully unrolled: v[j] stays in registers
-                if ((uint32_t)j < n_valid) {
-                    const uint64_t r = r0 + j;
-                    const uint32_t doc = __ldg(docids + r);
-                    bool ok = true;
-                    if (cand) ok = (doc >> 6) < n_cand_words && ((__ldg(cand + (doc >> 6)) >> (doc & 63)) & 1);
-                    const float pn = __ldg(inv_norm + r) * qn;
-                    float dd = 0.f;
-                    if (pn > 0.f && isfinite(pn)) {
-                        float cs = __uint_as_float(v[j]) * pn;
-                        cs = fminf(1.f, fmaxf(-1.f, cs));
-                        dd = (1.f - cs) * 0.5f;
-                    }
-                    const unsigned long long key = ((unsigned long long)__float_as_uint(dd) << 32) | doc;
-                    if (ok && key < thr) my_run[cnt++] = key;
+            for (int j = 0; j < GN; j++) {  // fully unrolled: v[j] stays in registers; metadata reads are shared-memory broadcasts
+                const uint32_t doc = tdoc[j];
+                const float pn = tscale[j] * qn;
+                float dd = 0.f;
+                if (pn > 0.f && isfinite(pn)) {
+                    float cs = __uint_as_float(v[j]) * pn;
+                    cs = fminf(1.f, fmaxf(-1.f, cs));
+                    dd = (1.f - cs) * 0.5f;
                 }
+                const unsigned long long key = ((unsigned long long)__float_as_uint(dd) << 32) | doc;
+                if (doc != 0xffffffffu && key < thr) my_run[cnt++] = key;
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(meta_empty + mb);
             uint32_t need = __ballot_sync(0xffffffffu, cnt > (uint32_t)(CAND_CAP - GN));
             while (need) {
                 uint32_t l = __ffs(need) - 1;
@@ -409,7 +438,7 @@ bool make_map(CUtensorMap *m, const void *base, uint64_t rows, uint32_t d, uint3
 }
 }  // namespace
 
-size_t vec_gemm_smem_bytes(uint32_t d) { return (size_t)(d / GK) * A_BLOCK + STAGES * B_BLOCK + 256 + 1024; }
+size_t vec_gemm_smem_bytes(uint32_t d) { return (size_t)(d / GK) * A_BLOCK + STAGES * B_BLOCK + 256 + META_BUFS * GN * 8 + 1023; }
 
 bool vec_gemm_supported(uint32_t d, uint32_t limit) { return d % GK == 0 && d >= GK && d <= 768 && limit >= 1 && limit <= KMAX; }
 

@@ -116,7 +116,7 @@ class OracleIndex:
         l.orc_set_documents_ids(self._h, _p(image.documents_ids_cbo), len(image.documents_ids_cbo))
         self.n_fields = image.n_fields
         self.weights = list(weights) if weights is not None else list(range(image.n_fields))
-        self._settings = dict(criteria=list(criteria or DEFAULT_CRITERIA), authorize_typos=authorize_typos, one_typo=one_typo,
+        self._settings = dict(criteria=list(DEFAULT_CRITERIA if criteria is None else criteria), authorize_typos=authorize_typos, one_typo=one_typo,
                               two_typos=two_typos, prefix_search=prefix_search)
         self._push_settings()
         self.dim = 0

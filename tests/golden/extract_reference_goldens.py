@@ -236,6 +236,51 @@ def apply_setting(m, st):
     return True
 
 
+
+def query_criteria_cases():
+    """crates/milli/tests/search/query_criteria.rs:26-101 over crates/milli/tests/assets/test_set.ndjson: 17 documents carrying
+    their pre-computed per-rule ranks; the expected order is `expected_order` (crates/milli/tests/search/mod.rs:150-218): a stable
+    sort by each criterion's rank, documents with word_rank != 0 dropped under TermsMatchingStrategy::All.  Index settings:
+    tests/search/mod.rs:37-68 (searchable title+description, three synonyms).  Only the text criteria are transcribed (no
+    asc/desc/sort)."""
+    text = open("/root/reference/crates/milli/tests/assets/test_set.ndjson").read()
+    dec, i, docs = json.JSONDecoder(), 0, []
+    while True:
+        while i < len(text) and text[i].isspace():
+            i += 1
+        if i >= len(text):
+            break
+        o, i = dec.raw_decode(text, i)
+        docs.append(o)
+    index = {"searchable": ["title", "description"], "exact_attributes": [], "stop_words": [],
+             "docs": [{"id": k, "title": d["title"], "description": d["description"]} for k, d in enumerate(docs)]}
+    synonyms = {"hello": ["good morning"], "world": ["earth"], "america": ["the united states"]}
+    rank_key = {"words": "word_rank", "typo": "typo_rank", "proximity": "proximity_rank", "attribute": "attribute_rank", "exactness": "exact_rank"}
+    tests = [("none", 62, "all", []), ("words", 63, "last", ["words"]), ("attribute", 64, "all", ["attribute"]), ("typo", 65, "all", ["typo"]),
+             ("exactness", 66, "all", ["exactness"]), ("proximity", 67, "all", ["proximity"]),
+             ("default_criteria_order", 97, "last", ["words", "typo", "proximity", "attribute", "exactness"])]
+    out = []
+    for name, line, tms, criteria in tests:
+        groups = [list(range(len(docs)))]
+        for c in criteria:
+            nxt = []
+            for g in groups:
+                g = sorted(g, key=lambda k: docs[k][rank_key[c]])  # stable, like slice::sort_by_key
+                for k in g:  # linear_group_by_key
+                    if nxt and nxt[-1][0] in g and docs[nxt[-1][-1]][rank_key[c]] == docs[k][rank_key[c]]:
+                        nxt[-1].append(k)
+                    else:
+                        nxt.append([k])
+            groups = nxt
+        order = [k for g in groups for k in g]
+        if tms == "all":
+            order = [k for k in order if docs[k]["word_rank"] == 0]
+        out.append({"source": f"crates/milli/tests/search/query_criteria.rs:{line}", "test": name, "index": index,
+                    "settings": {"criteria": criteria, "synonyms": synonyms}, "tms": tms, "scoring": "skip", "limit": 17, "offset": 0,
+                    "query": "hello world america", "expected_ids": order})
+    return out
+
+
 def main():
     cases, skipped = [], 0
     for fname in FILES:
@@ -339,6 +384,7 @@ def main():
                         elif last_case is not None and last_query == cur["query"] and len(scores) == len(last_case["expected_ids"]):
                             last_case["expected_scores"] = scores
                             last_case["scores_source"] = rel
+    cases.extend(query_criteria_cases())
     # de-duplicate identical corpora into a table to keep the fixture small
     corpora, keyed = [], {}
     for c in cases:
