@@ -3,8 +3,8 @@
 //   crates/milli/src/search/new/query_term/{mod.rs,ntypo_subset.rs,parse_query.rs,compute_derivations.rs:170-253}
 //   crates/milli/src/search/new/query_graph.rs
 //   crates/milli/src/search/new/ranking_rule_graph/{build.rs,mod.rs} and the six rule directories
-// Scope: words, soft/hard separators, prefix, typos, n-grams, split words.  User phrases, the negative
-// operator and synonyms are reported as B200_ERR_UNSUPPORTED.
+// Scope: words, soft/hard separators, prefix, typos, n-grams, split words, user phrases, synonyms, the negative operator
+// (DESIGN.md §1 lists what is reported as B200_ERR_UNSUPPORTED).
 #pragma once
 #include <algorithm>
 #include <cstdint>
