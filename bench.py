@@ -44,6 +44,18 @@ def measured_peak_gbs():
     return 6650.0, "fallback"
 
 
+def ncu_traffic(kernel):
+    """dram bytes per launch of `kernel` from the committed ncu capture (profiles/*_traffic.json, see tools/profile3.sh), or None"""
+    names = {"eval_paths": "eval_dp_kernel", "scatter": "scatter_kernel", "lev_match": "lev_match_kernel", "act_compact": "act_compact_kernel",
+             "pair_probe": "pair_probe_kernel", "emit": "emit_kernel"}
+    try:
+        import glob
+        f = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))[-1]
+        return float(json.load(open(f))["kernels"][names[kernel]]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def measured_peak_tflops():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -270,7 +282,7 @@ def main():
     per_launch_ms = d["ms"] / d["count"]
     achieved = (d["bytes"] / d["count"]) / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_source": peak_kind, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "launches": int(d["count"]), "avg_launch_ms": per_launch_ms,
+                "frac": achieved / peak, "traffic": ncu_traffic(dom), "launches": int(d["count"]), "avg_launch_ms": per_launch_ms,
                 "algorithmic_bytes_per_launch": d["bytes"] / d["count"],
                 "kernel_time_share": {k: round(v["ms"] / max(1e-9, sum(x["ms"] for x in kern.values())), 4) for k, v in kern.items()}}
 

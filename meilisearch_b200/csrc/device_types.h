@@ -76,6 +76,10 @@ struct ActDesc {
     uint32_t tab_size, want_paths;
     uint32_t res_off;         // into results u32[]: [0] rows, [1..n_costs+1] counts
     uint32_t all_conditional; // every START->END path has at least one condition: rows whose columns are all zero match nothing
+    // per-query lookup table word index -> (tag << 20 | row), written by act_compact, read by scatter instead of a binary search in
+    // uw; nullptr = not available (then uw is searched).  Entries of other activations carry other tags.
+    uint32_t *row_tab;
+    uint32_t row_tag, pad_;
 };
 
 struct ColOp {  // executed per row before the paths

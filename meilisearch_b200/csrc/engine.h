@@ -239,6 +239,7 @@ struct Engine {
     DevBuf<uint32_t> d_qcount;   // [0] scatter jobs, [1] surviving paths
     DevBuf<PathOut> d_pathbuf;
     DevBuf<uint32_t> d_docids_out;  // n_queries x limit
+    DevBuf<uint32_t> d_rowtab;      // n_queries x n_words64: word -> (tag, row) of the query's current activation (ActDesc::row_tab)
     uint8_t *h_step = nullptr;      // pinned
     size_t h_step_cap = 0;
     uint32_t *h_results = nullptr;  // pinned

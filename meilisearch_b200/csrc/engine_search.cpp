@@ -416,6 +416,7 @@ struct QState {
     const uint32_t *p_uw = nullptr;
     const unsigned long long *p_ub = nullptr, *p_out = nullptr;
     uint32_t p_rows = 0, p_ld = 0, p_col = 0, p_cap = 0;
+    uint32_t act_counter = 0;  // tag of the query's current activation in its row lookup table
     explicit QState(const HostIndex &ix) : ctx(ix) {}
 };
 
@@ -1948,6 +1949,12 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         return fail(code, msg);
     };
     for (uint32_t i = 0; i < NQ; i++) lanes[i % n_lanes].members.push_back(i);
+    // per-query row lookup tables (scatter_kernel): zeroed once per batch, entries are tagged with the activation that wrote them
+    const bool use_rowtab = hix.n_words64 <= (1u << 20) && !getenv("B200_NO_ROWTAB");
+    if (use_rowtab) {
+        CU(d_rowtab.reserve((size_t)NQ * hix.n_words64), "row lookup tables");
+        CU(cudaMemsetAsync(d_rowtab.p, 0, (size_t)NQ * hix.n_words64 * 4, stream), "zero row lookup tables");
+    }
     // everything queued on the engine stream so far (derivations) must be visible to the lanes
     CU(cudaStreamSynchronize(stream), "sync");
     const size_t PATH_CAP = (size_t)1 << 20;
@@ -2084,6 +2091,12 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
                 d.uw = reinterpret_cast<uint32_t *>(pl.pb);
                 d.ub = reinterpret_cast<unsigned long long *>(pl.pb + (((size_t)ld * 4 + 255) & ~(size_t)255));
                 d.out = d.ub + (((size_t)ld + 31) & ~(size_t)31);
+            }
+            d.row_tab = nullptr;
+            d.row_tag = 0;
+            if (use_rowtab && !pl.identity && q.act_counter < 4094) {
+                d.row_tag = ++q.act_counter;
+                d.row_tab = d_rowtab.p + (size_t)act_q[a] * hix.n_words64;
             }
             L.uw = d.uw;
             L.ub = d.ub;

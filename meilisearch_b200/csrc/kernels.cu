@@ -263,6 +263,16 @@ __global__ void lev_finalize_kernel(LevRec *__restrict__ recs, const uint32_t *_
 }
 
 // ======================================================================================== activations
+// row of 64-document word `w` in an activation's universe, or -1
+__device__ __forceinline__ int find_row(const uint32_t *uw, uint32_t rows, uint32_t w);
+__device__ __forceinline__ int act_row(const ActDesc &a, uint32_t rows, uint32_t w) {
+    if (!a.uw) return w < rows ? (int)w : -1;
+    if (a.row_tab) {
+        uint32_t e = a.row_tab[w];
+        return (e >> 20) == a.row_tag ? (int)(e & 0xfffffu) : -1;
+    }
+    return find_row(a.uw, rows, w);
+}
 __device__ __forceinline__ int find_row(const uint32_t *uw, uint32_t rows, uint32_t w) {
     uint32_t lo = 0, hi = rows;
     while (lo < hi) {
@@ -338,6 +348,7 @@ __global__ void __launch_bounds__(COMPACT_THREADS) act_compact_kernel(const ActD
                 if (at < a.ld) {
                     a.uw[at] = src[i];
                     a.ub[at] = v[i];
+                    if (a.row_tab) a.row_tab[src[i]] = (a.row_tag << 20) | at;
                 }
             }
         base += s_total;
@@ -464,7 +475,7 @@ __device__ __forceinline__ void scatter_job_coop(const Job job, const ActDesc &a
     uint32_t e0 = job.chunk * JOB_CHUNK, e1 = min(lr.card, e0 + JOB_CHUNK);
     for (uint32_t e = e0 + lane; e < e1; e += 32) {
         uint32_t d = ids[e];
-        int j = a.uw ? find_row(a.uw, rows, d >> 6) : ((d >> 6) < rows ? (int)(d >> 6) : -1);
+        int j = act_row(a, rows, d >> 6);
         if (j >= 0) {
             unsigned long long bit = 1ull << (d & 63);
             if (a.ub[j] & bit) atomicOr(&col[j], bit);
@@ -500,7 +511,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(const Job *__restrict__ qu
             const uint32_t *ids = pool + lr.off;
             for (uint32_t e = 0; e < lr.card; e++) {
                 uint32_t d = ids[e];
-                int j = a.uw ? find_row(a.uw, rows, d >> 6) : ((d >> 6) < rows ? (int)(d >> 6) : -1);
+                int j = act_row(a, rows, d >> 6);
                 if (j >= 0) {
                     unsigned long long bit = 1ull << (d & 63);
                     if (a.ub[j] & bit) atomicOr(&col[j], bit);

@@ -28,7 +28,7 @@ cudaError_t launch_topk(cudaStream_t s, uint32_t n_q, const float *dist, const u
 #define VEC_GEMM_CAND_CAP 256
 #define VEC_GEMM_KMAX 128
 bool vec_gemm_supported(uint32_t d, uint32_t limit);
-size_t vec_gemm_smem_bytes(uint32_t d);
+size_t vec_gemm_smem_bytes(uint32_t d, bool ts);
 cudaError_t launch_vec_prep_queries(cudaStream_t s, const float *q, uint32_t n_q, uint32_t n_pad, uint32_t d, void *out_fp16, float *inv);
 // runs: n_qtiles*n_groups*128*VEC_GEMM_CAND_CAP u64 scratch; partial: n_qtiles*128*n_groups*VEC_GEMM_KMAX u64
 cudaError_t launch_vec_gemm_topk(cudaStream_t s, uint32_t sm_count, const void *mat_fp16, const float *inv_norm, const uint32_t *docids,

@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "kernels.h"
 
@@ -30,7 +31,9 @@ namespace {
 constexpr int GM = 128;        // queries per tile (UMMA M)
 constexpr int GN = 64;         // matrix rows per tile (UMMA N)
 constexpr int GK = 64;         // halfs per k-block = one 128-byte swizzle span
-constexpr int STAGES = 4;      // B ring
+constexpr int STAGES = 4;      // B ring when the query tile occupies shared memory (SS form)
+constexpr int STAGES_TS = 24;  // B ring when the query tile lives in TMEM (TS form): 192 KB in flight per SM
+constexpr int A_COLS = 384;    // TMEM columns of a 128 x 768 fp16 query tile (2 halfs per 32-bit column)
 constexpr int ACC_BUFS = 4;    // TMEM accumulators of GN columns each
 constexpr int META_BUFS = 2;   // row metadata (docid, inverse norm) staged per tile by warp 3
 constexpr int A_BLOCK = GM * GK * 2;  // 16 KB
@@ -95,6 +98,25 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t b
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
+        : "memory");
+}
+// A operand from tensor memory (lane = row, 32-bit column = two consecutive K elements), B from shared memory
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t *r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
+        "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *r) {
@@ -171,21 +193,29 @@ __device__ __forceinline__ void compact_run(unsigned long long *run, uint32_t c,
 
 }  // namespace
 
+// TS = true: the query tile is written to tensor memory once (tcgen05.st by the epilogue warps) and read by the MMA from there,
+// which leaves all of shared memory to the matrix ring (24 stages instead of 4: the stream is latency x bandwidth bound).
+template <bool TS>
 __global__ void __launch_bounds__(256, 1)
-    vec_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_m, uint64_t n_rows, uint32_t kblocks,
+    vec_gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_m, const __half *__restrict__ q_fp16,
+                         uint32_t d, uint64_t n_rows, uint32_t kblocks,
                          uint32_t n_qtiles, uint32_t n_groups, const float *__restrict__ inv_norm, const uint32_t *__restrict__ docids,
                          const float *__restrict__ q_inv_norm, const unsigned long long *__restrict__ cand, uint64_t n_cand_words, uint32_t kk,
                          unsigned long long *__restrict__ runs /* [cta][128][CAND_CAP] */,
                          unsigned long long *__restrict__ partial /* [n_qtiles*128][n_groups][KMAX] */) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int NST = TS ? STAGES_TS : STAGES;      // B ring depth
+    constexpr int NACC = TS ? 2 : ACC_BUFS;           // TMEM accumulators (TS: 384 columns hold the query tile, 128 are left)
+    constexpr uint32_t ACC_COL0 = TS ? A_COLS : 0;    // first accumulator column
+    constexpr uint32_t TMEM_COLS = TS ? 512 : ACC_BUFS * GN;
     uint8_t *sA = smem;
-    uint8_t *sB = smem + (size_t)kblocks * A_BLOCK;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + STAGES * B_BLOCK);
-    uint64_t *a_full = bars, *b_full = bars + 1, *b_empty = b_full + STAGES, *acc_full = b_empty + STAGES, *acc_empty = acc_full + ACC_BUFS;
-    uint64_t *meta_full = acc_empty + ACC_BUFS, *meta_empty = meta_full + META_BUFS;
+    uint8_t *sB = TS ? smem : smem + (size_t)kblocks * A_BLOCK;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + NST * B_BLOCK);
+    uint64_t *a_full = bars, *b_full = bars + 1, *b_empty = b_full + NST, *acc_full = b_empty + NST, *acc_empty = acc_full + NACC;
+    uint64_t *meta_full = acc_empty + NACC, *meta_empty = meta_full + META_BUFS;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(meta_empty + META_BUFS);
-    uint32_t *s_doc = reinterpret_cast<uint32_t *>(bars + 32);               // [META_BUFS][GN]
+    uint32_t *s_doc = reinterpret_cast<uint32_t *>(bars + 64);               // [META_BUFS][GN]
     float *s_scale = reinterpret_cast<float *>(s_doc + META_BUFS * GN);      // [META_BUFS][GN]
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -195,12 +225,12 @@ __global__ void __launch_bounds__(256, 1)
     const uint64_t tile_lo = n_tiles * group / n_groups, tile_hi = n_tiles * (group + 1) / n_groups;
 
     if (threadIdx.x == 0) {
-        mbar_init(a_full, 1);
-        for (int s = 0; s < STAGES; s++) {
+        mbar_init(a_full, TS ? 4 : 1);  // TS: one arrival per epilogue warp once its 32 query rows are in TMEM
+        for (int s = 0; s < NST; s++) {
             mbar_init(b_full + s, 1);
             mbar_init(b_empty + s, 1);
         }
-        for (int b = 0; b < ACC_BUFS; b++) {
+        for (int b = 0; b < NACC; b++) {
             mbar_init(acc_full + b, 1);
             mbar_init(acc_empty + b, 4);
         }
@@ -211,7 +241,7 @@ __global__ void __launch_bounds__(256, 1)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(ACC_BUFS * GN))
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -222,12 +252,15 @@ __global__ void __launch_bounds__(256, 1)
 
     if (warp == 0) {
         if (lane == 0) {
-            mbar_expect_tx(a_full, kblocks * A_BLOCK);
-            for (uint32_t kb = 0; kb < kblocks; kb++) tma_load_2d(sA + (size_t)kb * A_BLOCK, &tmap_q, a_full, (int32_t)(kb * GK), (int32_t)(qtile * GM));
+            if (!TS) {
+                mbar_expect_tx(a_full, kblocks * A_BLOCK);
+                for (uint32_t kb = 0; kb < kblocks; kb++)
+                    tma_load_2d(sA + (size_t)kb * A_BLOCK, &tmap_q, a_full, (int32_t)(kb * GK), (int32_t)(qtile * GM));
+            }
             uint32_t it = 0;
             for (uint64_t t = tile_lo; t < tile_hi; t++)
                 for (uint32_t kb = 0; kb < kblocks; kb++, it++) {
-                    uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                    uint32_t s = it % NST, ph = (it / NST) & 1;
                     mbar_wait(b_empty + s, ph ^ 1);
                     mbar_expect_tx(b_full + s, B_BLOCK);
                     tma_load_2d(sB + (size_t)s * B_BLOCK, &tmap_m, b_full + s, (int32_t)(kb * GK), (int32_t)(t * GN));
@@ -239,18 +272,24 @@ __global__ void __launch_bounds__(256, 1)
             tc_fence_after();
             uint32_t it = 0, n = 0;
             for (uint64_t t = tile_lo; t < tile_hi; t++, n++) {
-                uint32_t buf = n % ACC_BUFS, aph = (n / ACC_BUFS) & 1;
+                uint32_t buf = n % NACC, aph = (n / NACC) & 1;
                 mbar_wait(acc_empty + buf, aph ^ 1);
                 tc_fence_after();
-                uint32_t tmem_d = tmem_base + buf * GN;
+                uint32_t tmem_d = tmem_base + ACC_COL0 + buf * GN;
                 for (uint32_t kb = 0; kb < kblocks; kb++, it++) {
-                    uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                    uint32_t s = it % NST, ph = (it / NST) & 1;
                     mbar_wait(b_full + s, ph);
                     tc_fence_after();
-                    uint64_t ad = make_sdesc(smem_u32(sA + (size_t)kb * A_BLOCK));
                     uint64_t bd = make_sdesc(smem_u32(sB + (size_t)s * B_BLOCK));
+                    if (TS) {
 #pragma unroll
-                    for (uint32_t k = 0; k < GK / 16; k++) umma(tmem_d, ad + 2 * k, bd + 2 * k, (kb | k) != 0);  // +32 B per K=16 step
+                        for (uint32_t k = 0; k < GK / 16; k++)  // 8 TMEM columns (16 halfs) and 32 B of the B row per K=16 step
+                            umma_ts(tmem_d, tmem_base + kb * (GK / 2) + k * 8, bd + 2 * k, (kb | k) != 0);
+                    } else {
+                        uint64_t ad = make_sdesc(smem_u32(sA + (size_t)kb * A_BLOCK));
+#pragma unroll
+                        for (uint32_t k = 0; k < GK / 16; k++) umma(tmem_d, ad + 2 * k, bd + 2 * k, (kb | k) != 0);  // +32 B per K=16 step
+                    }
                     tc_commit(b_empty + s);
                 }
                 tc_commit(acc_full + buf);
@@ -283,15 +322,34 @@ __global__ void __launch_bounds__(256, 1)
         const float qn = q_inv_norm[qrow];
         unsigned long long *my_run = runs + ((size_t)blockIdx.x * GM + w * 32 + lane) * CAND_CAP;
         unsigned long long *warp_runs = runs + ((size_t)blockIdx.x * GM + w * 32) * CAND_CAP;
+        if (TS) {  // this thread's query row -> TMEM lane w*32+lane, columns [0, d/2)
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(q_fp16 + (size_t)qrow * d);
+            for (uint32_t c0 = 0; c0 < d / 2; c0 += 32) {
+                uint32_t regs[32];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    uint4 x = __ldg(reinterpret_cast<const uint4 *>(src + c0) + i);
+                    regs[4 * i] = x.x;
+                    regs[4 * i + 1] = x.y;
+                    regs[4 * i + 2] = x.z;
+                    regs[4 * i + 3] = x.w;
+                }
+                tmem_st32(tmem_base + ((w * 32u) << 16) + c0, regs);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full);
+        }
         uint32_t cnt = 0;
         unsigned long long thr = ~0ull;
         uint32_t n = 0;
         for (uint64_t t = tile_lo; t < tile_hi; t++, n++) {
-            uint32_t buf = n % ACC_BUFS, aph = (n / ACC_BUFS) & 1;
+            uint32_t buf = n % NACC, aph = (n / NACC) & 1;
             mbar_wait(acc_full + buf, aph);
             tc_fence_after();
             uint32_t v[GN];
-            uint32_t taddr = tmem_base + ((w * 32u) << 16) + buf * GN;
+            uint32_t taddr = tmem_base + ((w * 32u) << 16) + ACC_COL0 + buf * GN;
             tmem_ld32(taddr, v);
             tmem_ld32(taddr + 32, v + 32);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -354,7 +412,7 @@ __global__ void __launch_bounds__(256, 1)
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(ACC_BUFS * GN)) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -438,7 +496,9 @@ bool make_map(CUtensorMap *m, const void *base, uint64_t rows, uint32_t d, uint3
 }
 }  // namespace
 
-size_t vec_gemm_smem_bytes(uint32_t d) { return (size_t)(d / GK) * A_BLOCK + STAGES * B_BLOCK + 256 + META_BUFS * GN * 8 + 1023; }
+size_t vec_gemm_smem_bytes(uint32_t d, bool ts) {
+    return (ts ? (size_t)STAGES_TS * B_BLOCK : (size_t)(d / GK) * A_BLOCK + STAGES * B_BLOCK) + 512 + META_BUFS * GN * 8 + 1023;
+}
 
 bool vec_gemm_supported(uint32_t d, uint32_t limit) { return d % GK == 0 && d >= GK && d <= 768 && limit >= 1 && limit <= KMAX; }
 
@@ -454,11 +514,21 @@ cudaError_t launch_vec_gemm_topk(cudaStream_t s, uint32_t sm_count, const void *
     if (!vec_gemm_supported(d, k) || n_qtiles * n_groups > sm_count || n_groups == 0) return cudaErrorInvalidValue;
     CUtensorMap mq, mm;
     if (!make_map(&mq, q_fp16, (uint64_t)n_qtiles * GM, d, GM) || !make_map(&mm, mat_fp16, n_rows, d, GN)) return cudaErrorNotSupported;
-    size_t smem = vec_gemm_smem_bytes(d);
-    cudaError_t e = cudaFuncSetAttribute(vec_gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    vec_gemm_topk_kernel<<<n_qtiles * n_groups, 256, smem, s>>>(mq, mm, n_rows, d / GK, n_qtiles, n_groups, inv_norm, docids, q_inv_norm, cand,
-                                                                n_cand_words, k, runs, partial);
+    const bool ts = d % 64 == 0 && !(getenv("B200_VEC_GEMM_SS") && atoi(getenv("B200_VEC_GEMM_SS")) != 0);
+    size_t smem = vec_gemm_smem_bytes(d, ts);
+    const __half *qh = reinterpret_cast<const __half *>(q_fp16);
+    cudaError_t e;
+    if (ts) {
+        e = cudaFuncSetAttribute(vec_gemm_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        vec_gemm_topk_kernel<true><<<n_qtiles * n_groups, 256, smem, s>>>(mq, mm, qh, d, n_rows, d / GK, n_qtiles, n_groups, inv_norm, docids, q_inv_norm,
+                                                                          cand, n_cand_words, k, runs, partial);
+    } else {
+        e = cudaFuncSetAttribute(vec_gemm_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        vec_gemm_topk_kernel<false><<<n_qtiles * n_groups, 256, smem, s>>>(mq, mm, qh, d, n_rows, d / GK, n_qtiles, n_groups, inv_norm, docids, q_inv_norm,
+                                                                           cand, n_cand_words, k, runs, partial);
+    }
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     vec_merge_kernel<<<n_q, KMAX, 0, s>>>(partial, n_groups, k, out_ids, out_dist, out_n);

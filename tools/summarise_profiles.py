@@ -117,8 +117,35 @@ def full(tag):
         print("wrote", f"{tag}_{name}_full.md")
 
 
+def traffic(tag):
+    """gpurun_out/traffic.csv (ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum over tools/prof_keyword.py) ->
+    profiles/<tag>_traffic.json: mean DRAM bytes per launch of every kernel (all launches of the run); bench.py copies the
+    dominant kernel's figure into roofline.traffic."""
+    import json
+    path = os.path.join(SRC, "traffic.csv")
+    if not os.path.exists(path):
+        return
+    rows = read_ncu_csv(open(path, errors="replace").read())
+    per = defaultdict(lambda: defaultdict(float))
+    cnt = defaultdict(set)
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for r in rows:
+        k = short(r["Kernel Name"])
+        m = r["Metric Name"]
+        if m.startswith("dram__bytes"):
+            per[k][m] += float(r["Metric Value"].replace(",", "")) * scale.get(r.get("Metric Unit", "byte"), 1.0)
+            cnt[k].add(r["ID"])
+    out = {k: {"launches": len(cnt[k]), "dram_bytes_per_launch": (v["dram__bytes_read.sum"] + v["dram__bytes_write.sum"]) / max(1, len(cnt[k])),
+               "dram_read_per_launch": v["dram__bytes_read.sum"] / max(1, len(cnt[k])), "dram_write_per_launch": v["dram__bytes_write.sum"] / max(1, len(cnt[k]))}
+           for k, v in per.items()}
+    json.dump({"source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none python tools/prof_keyword.py (3 identical batches of cfg2)",
+               "kernels": out}, open(os.path.join(OUT, f"{tag}_traffic.json"), "w"), indent=1)
+    print("wrote", f"{tag}_traffic.json")
+
+
 if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     os.makedirs(OUT, exist_ok=True)
     launches(tag)
     full(tag)
+    traffic(tag)

@@ -14,6 +14,11 @@ n, d = int(os.environ.get("VEC_N", "1000000")), 768
 emb = rng.standard_normal((n, d), dtype=np.float32)
 ix.set_embeddings(emb)
 q = rng.standard_normal((8, d), dtype=np.float32)
+if os.environ.get("VEC_GEMM_ONLY"):
+    qq = rng.standard_normal((1024, d), dtype=np.float32)
+    for i in range(4):
+        ix.nns_by_vector(qq, 100)
+    sys.exit(0)
 for i in range(6):
     ix.nns_by_vector(q[:1], 100)
 ix.reset_stats()
