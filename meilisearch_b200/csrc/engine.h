@@ -62,7 +62,10 @@ struct WorkerPool {
     std::mutex mu;
     std::condition_variable cv_work;
     std::function<void(size_t)> fn;
-    std::atomic<size_t> next{0}, generation{0}, remaining{0};
+    // run(): announce (generation++), wait until no worker is still inside the previous job (entered == left), publish the job,
+    // set ready = generation.  A worker touches fn/n/next only between entered++ and left++ and only after re-checking that no
+    // newer job has been announced, so a late waker can never claim an index of a job it did not observe.
+    std::atomic<size_t> next{0}, generation{0}, ready{0}, remaining{0}, entered{0}, left{0};
     size_t n = 0;
     std::atomic<bool> stop{false};
     explicit WorkerPool(unsigned nt) {
@@ -70,40 +73,51 @@ struct WorkerPool {
             threads.emplace_back([this]() {
                 size_t seen = 0;
                 for (;;) {
-                    // spin ~200 us, then sleep
+                    // spin ~300 us, then sleep
                     bool got = false;
                     auto t0 = std::chrono::steady_clock::now();
                     for (int spin = 0;; spin++) {
                         if (stop.load(std::memory_order_acquire)) return;
-                        if (generation.load(std::memory_order_acquire) != seen) {
+                        if (ready.load(std::memory_order_acquire) != seen) {
                             got = true;
                             break;
                         }
-                        if ((spin & 63) == 63 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(200)) break;
+                        if ((spin & 63) == 63 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(300)) break;
 #if defined(__x86_64__)
                         __builtin_ia32_pause();
 #endif
                     }
                     if (!got) {
                         std::unique_lock<std::mutex> lk(mu);
-                        cv_work.wait(lk, [&] { return stop.load() || generation.load() != seen; });
+                        cv_work.wait(lk, [&] { return stop.load() || ready.load() != seen; });
                         if (stop.load()) return;
                     }
-                    seen = generation.load(std::memory_order_acquire);
-                    for (;;) {
-                        size_t i = next.fetch_add(1);
-                        if (i >= n) break;
-                        fn(i);
-                        remaining.fetch_sub(1, std::memory_order_acq_rel);
+                    const size_t g = ready.load(std::memory_order_acquire);
+                    entered.fetch_add(1, std::memory_order_acq_rel);
+                    if (generation.load(std::memory_order_acquire) == g) {
+                        for (;;) {
+                            size_t i = next.fetch_add(1);
+                            if (i >= n) break;
+                            fn(i);
+                            remaining.fetch_sub(1, std::memory_order_acq_rel);
+                        }
                     }
+                    left.fetch_add(1, std::memory_order_acq_rel);
+                    seen = g;
                 }
             });
     }
     void run(size_t count, std::function<void(size_t)> f) {
         if (count == 0) return;
-        if (threads.empty() || count == 1) {
+        if (threads.empty() || count < 4) {
             for (size_t i = 0; i < count; i++) f(i);
             return;
+        }
+        const size_t g = generation.fetch_add(1, std::memory_order_acq_rel) + 1;
+        while (entered.load(std::memory_order_acquire) != left.load(std::memory_order_acquire)) {
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
         }
         {
             std::lock_guard<std::mutex> lk(mu);
@@ -111,7 +125,7 @@ struct WorkerPool {
             n = count;
             next.store(0);
             remaining.store(count);
-            generation.fetch_add(1, std::memory_order_release);
+            ready.store(g, std::memory_order_release);
         }
         cv_work.notify_all();
         // the caller works too
@@ -153,7 +167,7 @@ struct Lane {
     size_t scratch_bytes = 0;
     std::vector<uint32_t> members, act_q;
     // a lane is driven by its own host thread with its own slice of the workers, of the arena and of the statistics
-    std::unique_ptr<WorkerPool> pool;
+    WorkerPool *pool = nullptr;  // the pool of the lane's driver (shared by the lanes that driver alternates between)
     uint8_t *arena = nullptr;
     size_t arena_bytes = 0, arena_used = 0;
     b200_stats lst{};
@@ -210,8 +224,9 @@ struct Lane {
 struct Engine {
     std::unique_ptr<WorkerPool> pool;
     std::thread reaper;  // frees the previous batch's per-query state in the background
-    static constexpr unsigned MAX_LANES = 4;
+    static constexpr unsigned MAX_LANES = 8, MAX_DRIVERS = 4;
     Lane lanes[MAX_LANES];
+    std::unique_ptr<WorkerPool> driver_pools[MAX_DRIVERS];
     int device = 0;
     cudaStream_t stream = nullptr;
     std::mutex mu;

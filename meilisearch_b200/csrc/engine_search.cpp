@@ -31,7 +31,7 @@ namespace b200 {
 
 namespace {
 
-enum RuleKind { RK_WORDS = 0, RK_TYPO, RK_PROXIMITY, RK_FID, RK_POSITION, RK_EXACTNESS, RK_EXACT_ATTRIBUTE, RK_RESOLVE };
+enum RuleKind { RK_WORDS = 0, RK_TYPO, RK_PROXIMITY, RK_FID, RK_POSITION, RK_EXACTNESS, RK_EXACT_ATTRIBUTE, RK_RESOLVE, RK_FREQ };
 
 struct UnsupportedQuery {
     std::string why;
@@ -53,6 +53,7 @@ struct QCtx {
     std::map<std::vector<int32_t>, uint32_t> phrase_ids;
     std::vector<uint32_t> neg_words;    // dictionary ranks of `-word` tokens (absent words exclude nothing)
     std::vector<uint32_t> neg_phrases;  // phrase ids of `-"..."`
+    std::vector<uint16_t> freq_weight;  // TermsMatchingStrategy::Frequency: removal weight per term id (query_graph.rs:303-344)
     explicit QCtx(const HostIndex &i) : ix(i) {}
     uint32_t intern_phrase(const EPhrase &p) {
         auto it = phrase_ids.find(p.words);
@@ -274,15 +275,16 @@ void remove_nodes_keep_edges(EGraph &g, const std::vector<uint16_t> &nodes) {  /
     }
 }
 
-// removal_order_for_terms_matching_strategy_last (:346-406): groups of nodes, cheapest removal first
-std::vector<std::vector<uint16_t>> removal_order_last(const QCtx &c, const EGraph &g) {
+// removal_order_for_terms_matching_strategy (query_graph.rs:379-406): groups of nodes, cheapest removal first.
+// Last: weight(term) = 1 + last - term (:346-377); Frequency: weight from the term frequencies (:303-344, QCtx::freq_weight).
+std::vector<std::vector<uint16_t>> removal_order(const QCtx &c, const EGraph &g, int tms) {
     int first = 255, last = 0;
     for (auto &n : g.nodes)
         if (n.kind == ND_TERM) {
             last = std::max<int>(last, n.term.t1);
             first = std::min<int>(first, n.term.t0);
         }
-    if (first >= last) return {};
+    if (tms == B200_TMS_LAST && first >= last) return {};
     std::map<uint16_t, std::vector<uint16_t>> groups;
     bool mandatory = false;
     for (uint16_t id = 0; id < g.nodes.size(); id++) {
@@ -294,7 +296,10 @@ std::vector<std::vector<uint16_t>> removal_order_last(const QCtx &c, const EGrap
             continue;
         }
         uint16_t cost = 0;
-        for (int t = n.term.t0; t <= n.term.t1; t++) cost = std::max<uint16_t>(cost, (uint16_t)(1 + last - t));
+        for (int t = n.term.t0; t <= n.term.t1; t++) {
+            uint16_t w = tms == B200_TMS_FREQUENCY ? ((size_t)t < c.freq_weight.size() ? c.freq_weight[t] : (uint16_t)1) : (uint16_t)(1 + last - t);
+            cost = std::max<uint16_t>(cost, w);
+        }
         groups[cost].push_back(id);
     }
     std::vector<std::vector<uint16_t>> res;
@@ -302,6 +307,7 @@ std::vector<std::vector<uint16_t>> removal_order_last(const QCtx &c, const EGrap
     if (!mandatory && !res.empty()) res.pop_back();
     return res;
 }
+std::vector<std::vector<uint16_t>> removal_order_last(const QCtx &c, const EGraph &g) { return removal_order(c, g, B200_TMS_LAST); }
 
 // ------------------------------------------------------------------------------------------------ activations
 struct ECond {
@@ -417,6 +423,8 @@ struct QState {
     const unsigned long long *p_ub = nullptr, *p_out = nullptr;
     uint32_t p_rows = 0, p_ld = 0, p_col = 0, p_cap = 0;
     uint32_t act_counter = 0;  // tag of the query's current activation in its row lookup table
+    std::vector<uint64_t> term_freq;  // Frequency: documents per term id, filled one device step per term before anything else
+    uint32_t n_term_ids = 0;
     explicit QState(const HostIndex &ix) : ctx(ix) {}
 };
 
@@ -911,8 +919,8 @@ void prepare_graph_rule(const QCtx &c, int rule, bool has_tms, int tms, Level &L
     uint16_t n = (uint16_t)qg.nodes.size();
     // cost of ignoring a node (graph_based_ranking_rule.rs:149-193)
     std::vector<int> ignore_cost(n, -1);
-    if (has_tms && tms == B200_TMS_LAST)
-        for (auto &grp : removal_order_last(c, qg))
+    if (has_tms && (tms == B200_TMS_LAST || tms == B200_TMS_FREQUENCY))
+        for (auto &grp : removal_order(c, qg, tms))
             for (auto nd : grp) ignore_cost[nd] = 1;
     CondTable ct;
     std::vector<EEdge> edges;
@@ -1006,9 +1014,9 @@ void prepare_graph_rule(const QCtx &c, int rule, bool has_tms, int tms, Level &L
     };
     std::vector<AEdge> aedges;
     std::vector<uint16_t> grp(n, 0);  // 1-based removal group, 0 = never removed
-    if (has_tms && tms == B200_TMS_LAST) {
+    if (has_tms && (tms == B200_TMS_LAST || tms == B200_TMS_FREQUENCY)) {
         uint16_t k = 1;
-        for (auto &g : removal_order_last(c, qg)) {
+        for (auto &g : removal_order(c, qg, tms)) {
             for (auto nd : g) grp[nd] = k;
             k++;
         }
@@ -1621,7 +1629,6 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
     const bool skip_scoring = scoring == 0;
     const uint32_t length = limit, from = offset;
     const int tms = b->terms_matching_strategy;
-    if (tms == B200_TMS_FREQUENCY) return fail(B200_ERR_UNSUPPORTED, "TermsMatchingStrategy::Frequency is not implemented on the device path");
     std::vector<std::unique_ptr<QState>> qs(NQ);
     for (uint32_t i = 0; i < NQ; i++) qs[i].reset(new QState(hix));
 
@@ -1731,6 +1738,47 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         q.p_col = p_col;
         q.p_cap = cap;
     };
+    // resolve_maximally_reduced_query_graph (search/new/mod.rs:273-301)
+    auto start_resolve = [&](QState &q) {
+        Level L;
+        L.kind = RK_RESOLVE;
+        L.graph = q.graph;
+        if (tms == B200_TMS_LAST || tms == B200_TMS_FREQUENCY) {
+            std::vector<uint16_t> rm;
+            for (auto &grp : removal_order(q.ctx, q.graph, tms))
+                for (auto nd : grp) rm.push_back(nd);
+            remove_nodes_keep_edges(L.graph, rm);
+        }
+        prepare_resolve(q.ctx, L);
+        request_activation(q, std::move(L), nullptr, dix.base_ub, nullptr, hix.n_words64, hix.n_words64, 0, hix.n_words64);
+    };
+    // Frequency (query_graph.rs:303-344): documents of term id t = union of the docids of every node covering t, counted over the
+    // whole index — one resolve-shaped activation START -> {covering nodes} -> END per term id
+    auto start_freq = [&](QState &q, uint32_t t) {
+        Level L;
+        L.kind = RK_FREQ;
+        L.rule_idx = (int)t;
+        EGraph &g = L.graph;
+        g.nodes.resize(2);
+        g.root = 0;
+        g.end = 1;
+        g.nodes[0].kind = ND_START;
+        g.nodes[1].kind = ND_END;
+        for (auto &nd : q.graph.nodes)
+            if (nd.kind == ND_TERM && nd.term.t0 <= t && t <= nd.term.t1) {
+                ENode x;
+                x.kind = ND_TERM;
+                x.term = nd.term;
+                uint16_t id = (uint16_t)g.nodes.size();
+                x.pred = {0};
+                x.succ = {1};
+                g.nodes.push_back(std::move(x));
+                sorted_insert(g.nodes[0].succ, id);
+                sorted_insert(g.nodes[1].pred, id);
+            }
+        prepare_resolve(q.ctx, L);
+        request_activation(q, std::move(L), nullptr, dix.base_ub, nullptr, hix.n_words64, hix.n_words64, 0, hix.n_words64);
+    };
     auto start_query = [&](QState &q) {
         q.rules = rules;
         if (q.placeholder) {
@@ -1751,18 +1799,17 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             q.done = true;
             return;
         }
-        // resolve_maximally_reduced_query_graph (search/new/mod.rs:273-301)
-        Level L;
-        L.kind = RK_RESOLVE;
-        L.graph = q.graph;
-        if (tms == B200_TMS_LAST) {
-            std::vector<uint16_t> rm;
-            for (auto &grp : removal_order_last(q.ctx, q.graph))
-                for (auto nd : grp) rm.push_back(nd);
-            remove_nodes_keep_edges(L.graph, rm);
+        if (tms == B200_TMS_FREQUENCY) {
+            q.n_term_ids = 0;
+            for (auto &nd : q.graph.nodes)
+                if (nd.kind == ND_TERM) q.n_term_ids = std::max<uint32_t>(q.n_term_ids, (uint32_t)nd.term.t1 + 1);
+            q.term_freq.clear();
+            if (q.n_term_ids > 0) {
+                start_freq(q, 0);
+                return;
+            }
         }
-        prepare_resolve(q.ctx, L);
-        request_activation(q, std::move(L), nullptr, dix.base_ub, nullptr, hix.n_words64, hix.n_words64, 0, hix.n_words64);
+        start_resolve(q);
     };
     std::vector<std::string> errs(NQ);
     t_ph = clk::now();
@@ -1825,6 +1872,27 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
                 } else if (q.levels.size() == 1)
                     q.rr_scores.clear();
             };
+            if (L.kind == RK_FREQ) {
+                const uint32_t t = (uint32_t)L.rule_idx;
+                q.term_freq.push_back(L.counts.empty() ? 0 : L.counts[0]);
+                q.levels.clear();
+                if (t + 1 < q.n_term_ids) {
+                    start_freq(q, t + 1);
+                    return;
+                }
+                // weights: most frequent term first (ties share a weight); a term matching nothing counts as the most frequent
+                std::vector<std::pair<uint8_t, uint64_t>> twf;
+                for (uint32_t i = 0; i < q.n_term_ids; i++) twf.push_back({(uint8_t)i, q.term_freq[i] == 0 ? UINT64_MAX : q.term_freq[i]});
+                std::stable_sort(twf.begin(), twf.end(), [](const auto &a, const auto &b2) { return a.second > b2.second; });
+                q.ctx.freq_weight.assign(q.n_term_ids, 1);
+                uint16_t weight = 1;
+                for (size_t i = 0; i < twf.size(); i++) {
+                    q.ctx.freq_weight[twf[i].first] = weight;
+                    if (i + 1 < twf.size() && twf[i].second != twf[i + 1].second) weight++;
+                }
+                start_resolve(q);
+                return;
+            }
             if (L.kind == RK_RESOLVE) {
                 // the resolve level is not a ranking rule: after it, start rule 0 on its bucket 0
                 if (L.cursor > 0) {
@@ -1912,18 +1980,23 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
 
     // ---- phase 4: step loop.  The batch is split over lanes; every lane has its own stream, device buffers, arena slice, host
     // driver thread and worker sub-pool, so the host phases of one lane overlap both the kernels and the host phases of the others.
-    unsigned n_lanes = NQ >= 64 ? 2 : 1;
-    if (const char *env = getenv("B200_LANES")) n_lanes = (unsigned)std::max(1, std::min((int)MAX_LANES, atoi(env)));
-    if (getenv("B200_SINGLE_LANE")) n_lanes = 1;
-    if (NQ < n_lanes) n_lanes = 1;
+    // Drivers are host threads; each alternates between its lanes (software pipeline: while one lane's kernels run, the driver packs
+    // and advances its other lane), and the drivers run concurrently.
+    unsigned n_drivers = NQ >= 64 ? 2 : 1, lanes_per_driver = NQ >= 256 ? 2 : 1;
+    if (const char *env = getenv("B200_DRIVERS")) n_drivers = (unsigned)std::max(1, std::min((int)MAX_DRIVERS, atoi(env)));
+    if (const char *env = getenv("B200_LANES_PER_DRIVER")) lanes_per_driver = (unsigned)std::max(1, atoi(env));
+    if (getenv("B200_SINGLE_LANE")) n_drivers = lanes_per_driver = 1;
+    unsigned n_lanes = std::min<unsigned>(MAX_LANES, n_drivers * lanes_per_driver);
+    if (NQ < n_lanes) n_lanes = n_drivers = lanes_per_driver = 1;
+    lanes_per_driver = n_lanes / n_drivers;
     {
         unsigned hw = std::thread::hardware_concurrency();
         const char *env = getenv("B200_HOST_THREADS");
-        unsigned nt = env ? (unsigned)atoi(env) : std::max(4u, std::min(64u, hw / 2));
-        unsigned per_lane = std::max(1u, nt / n_lanes);
-        for (unsigned l = 0; l < n_lanes; l++) {
-            Lane &ln = lanes[l];
-            if (!ln.pool || ln.pool->threads.size() + 1 != per_lane) ln.pool.reset(new WorkerPool(per_lane - 1));
+        unsigned nt = env ? (unsigned)atoi(env) : std::max(4u, std::min(32u, hw / 2));
+        unsigned per_driver = std::max(1u, nt / n_drivers);
+        for (unsigned dr = 0; dr < n_drivers; dr++) {
+            if (!driver_pools[dr] || driver_pools[dr]->threads.size() + 1 != per_driver) driver_pools[dr].reset(new WorkerPool(per_driver - 1));
+            for (unsigned k = 0; k < lanes_per_driver; k++) lanes[dr * lanes_per_driver + k].pool = driver_pools[dr].get();
         }
     }
     for (unsigned l = 0; l < n_lanes; l++) {
@@ -1968,6 +2041,9 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             if (qs[i]->want_activation) ln.act_q.push_back(i);
             if (!qs[i]->emits.empty()) emit_q.push_back(i);
         }
+        // longest first: the parallel-for over these queries ends when its slowest query does, and host time per query grows
+        // with the size of its query graph
+        std::stable_sort(ln.act_q.begin(), ln.act_q.end(), [&](uint32_t x, uint32_t y) { return qs[x]->graph.nodes.size() > qs[y]->graph.nodes.size(); });
         if (ln.act_q.empty() && emit_q.empty()) return 0;
         ln.lst.device_steps++;
         const std::vector<uint32_t> &act_q = ln.act_q;
@@ -2277,22 +2353,36 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         return 0;
     };
 
-    auto drive = [&](Lane &ln) -> int {
+    auto drive = [&](unsigned dr) -> int {
         cudaError_t ce = cudaSetDevice(device);
         if (ce != cudaSuccess) return cuda_fail(ce, "cudaSetDevice");
-        int rc = launch(ln);
-        while (rc > 0) {
-            rc = finish(ln);
-            if (rc < 0) break;
-            rc = launch(ln);
+        Lane *mine = lanes + dr * lanes_per_driver;
+        for (unsigned k = 0; k < lanes_per_driver; k++) {
+            int rc = launch(mine[k]);
+            if (rc < 0) return rc;
         }
-        return rc;
+        for (;;) {
+            bool any = false;
+            for (unsigned k = 0; k < lanes_per_driver; k++) {
+                Lane &ln = mine[k];
+                if (!ln.inflight) continue;
+                any = true;
+                int rc = finish(ln);
+                if (rc < 0) return rc;
+                rc = launch(ln);
+                if (rc < 0) return rc;
+            }
+            if (!any) return 0;
+        }
     };
     {
         std::vector<std::thread> drivers;
-        for (unsigned l = 1; l < n_lanes; l++) drivers.emplace_back([&, l]() { lanes[l].rc = drive(lanes[l]); });
-        lanes[0].rc = drive(lanes[0]);
+        std::vector<int> rcs(n_drivers, 0);
+        for (unsigned dr = 1; dr < n_drivers; dr++) drivers.emplace_back([&, dr]() { rcs[dr] = drive(dr); });
+        rcs[0] = drive(0);
         for (auto &t : drivers) t.join();
+        for (unsigned dr = 0; dr < n_drivers; dr++)
+            for (unsigned k = 0; k < lanes_per_driver; k++) lanes[dr * lanes_per_driver + k].rc = std::min(lanes[dr * lanes_per_driver + k].rc, rcs[dr]);
     }
     for (unsigned l = 0; l < n_lanes; l++) {  // fold the lanes' statistics (host phases of different lanes overlap in time)
         const b200_stats &x = lanes[l].lst;
@@ -2308,7 +2398,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             stats.kernel_count[k] += x.kernel_count[k];
             stats.kernel_bytes[k] += x.kernel_bytes[k];
         }
-        for (int k = 3; k <= 5; k++) stats.host_ms[k] += x.host_ms[k] / n_lanes;  // mean over the concurrent lanes
+        for (int k = 3; k <= 5; k++) stats.host_ms[k] += x.host_ms[k] / n_drivers;  // per driver thread (drivers run concurrently)
     }
     for (unsigned l = 0; l < n_lanes; l++)
         if (lanes[l].rc < 0) return lanes[l].rc;

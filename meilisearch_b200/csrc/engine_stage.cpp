@@ -241,7 +241,7 @@ int Engine::nns_batch(const float *queries, uint32_t n_q, uint32_t d, uint32_t l
                 uint32_t n_groups = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sm_count / n_qtiles, n_row_tiles));
                 CU(d_vq.reserve((size_t)nq * d + n_pad), "alloc queries");
                 CU(d_vq16.reserve((size_t)n_pad * d), "alloc fp16 queries");
-                CU(d_vruns.reserve((size_t)n_qtiles * n_groups * 128 * VEC_GEMM_CAND_CAP), "alloc candidate runs");
+                CU(d_vruns.reserve((size_t)n_qtiles * n_groups * 128 * VEC_GEMM_CAND_CAP + (size_t)n_pad * n_groups), "alloc candidate runs");
                 CU(d_vpartial.reserve((size_t)n_pad * n_groups * VEC_GEMM_KMAX), "alloc partial top-k");
                 CU(d_vsel_dist.reserve((size_t)n_pad * limit), "alloc selection");
                 CU(d_vsel_ids.reserve((size_t)n_pad * limit), "alloc selection");
@@ -253,7 +253,7 @@ int Engine::nns_batch(const float *queries, uint32_t n_q, uint32_t d, uint32_t l
                 stats.kernel_launches++;
                 size_t m0 = mark();
                 CU(launch_vec_gemm_topk(stream, (uint32_t)sm_count, dix.emb, dix.emb_inv_norm, dix.emb_docids, N, d, d_vq16.p, d_qinv, n_qtiles, n_groups,
-                                        d_c, n_cand_words, limit, d_vruns.p, d_vpartial.p, d_vsel_ids.p, d_vsel_dist.p, d_vsel_n.p, nq),
+                                        d_c, n_cand_words, limit, d_vruns.p + (size_t)n_qtiles * n_groups * 128 * VEC_GEMM_CAND_CAP, d_vruns.p, d_vpartial.p, d_vsel_ids.p, d_vsel_dist.p, d_vsel_n.p, nq),
                    "vec_gemm_topk");
                 size_t m1 = mark();
                 // algorithmic bytes: every query tile streams the matrix once (L2 absorbs the re-reads across tiles of the same rows)

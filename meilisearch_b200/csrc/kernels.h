@@ -33,6 +33,7 @@ cudaError_t launch_vec_prep_queries(cudaStream_t s, const float *q, uint32_t n_q
 // runs: n_qtiles*n_groups*128*VEC_GEMM_CAND_CAP u64 scratch; partial: n_qtiles*128*n_groups*VEC_GEMM_KMAX u64
 cudaError_t launch_vec_gemm_topk(cudaStream_t s, uint32_t sm_count, const void *mat_fp16, const float *inv_norm, const uint32_t *docids,
                                  uint64_t n_rows, uint32_t d, const void *q_fp16, const float *q_inv_norm, uint32_t n_qtiles, uint32_t n_groups,
-                                 const unsigned long long *cand, uint64_t n_cand_words, uint32_t k, unsigned long long *runs,
+                                 const unsigned long long *cand, uint64_t n_cand_words, uint32_t k, unsigned long long *gthr /* n_qtiles*128*n_groups u64 */,
+                                 unsigned long long *runs,
                                  unsigned long long *partial, uint32_t *out_ids, float *out_dist, uint32_t *out_n, uint32_t n_q);
 }  // namespace b200

@@ -20,7 +20,9 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "kernels.h"
 
@@ -67,6 +69,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         if (done) break;
         if (++spins > (1ull << 26)) __trap();  // a lost arrival must not hang the device
     }
+}
+__device__ __forceinline__ void mbar_wait_t(uint64_t *bar, uint32_t parity, unsigned long long &acc, bool on) {
+    if (!on) {
+        mbar_wait(bar, parity);
+        return;
+    }
+    long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += (unsigned long long)(clock64() - t0);
 }
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int32_t c0, int32_t c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
@@ -164,10 +175,85 @@ __device__ __forceinline__ void sort_size(unsigned long long (&k)[8], uint32_t l
     if constexpr (SIZE < 256) sort_size<SIZE * 2>(k, lane);
 }
 __device__ __forceinline__ void warp_sort256(unsigned long long (&k)[8], uint32_t lane) { sort_size<2>(k, lane); }
+// the same network applied to two arrays step by step (two independent dependency chains in flight)
+template <int SIZE, int J>
+__device__ __forceinline__ void sort_step2(unsigned long long (&a)[8], unsigned long long (&b)[8], uint32_t lane) {
+    if constexpr (J >= 32) {
+        constexpr int RJ = J >> 5;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            if ((i & RJ) == 0) {
+                cswap(a[i], a[i | RJ], ((i * 32) & SIZE) == 0);
+                cswap(b[i], b[i | RJ], ((i * 32) & SIZE) == 0);
+            }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t e = (uint32_t)i * 32u + lane;
+            const unsigned long long oa = __shfl_xor_sync(0xffffffffu, a[i], J), ob = __shfl_xor_sync(0xffffffffu, b[i], J);
+            const bool take_lo = (((e & (uint32_t)SIZE) == 0) == ((lane & (uint32_t)J) == 0));
+            const unsigned long long la = a[i] < oa ? a[i] : oa, ha = a[i] < oa ? oa : a[i];
+            const unsigned long long lb = b[i] < ob ? b[i] : ob, hb = b[i] < ob ? ob : b[i];
+            a[i] = take_lo ? la : ha;
+            b[i] = take_lo ? lb : hb;
+        }
+    }
+    if constexpr (J > 1) sort_step2<SIZE, J / 2>(a, b, lane);
+}
+template <int SIZE>
+__device__ __forceinline__ void sort_size2(unsigned long long (&a)[8], unsigned long long (&b)[8], uint32_t lane) {
+    sort_step2<SIZE, SIZE / 2>(a, b, lane);
+    if constexpr (SIZE < 256) sort_size2<SIZE * 2>(a, b, lane);
+}
+
+// Two runs at once: the two sorts are independent instruction streams, which roughly doubles the issue rate of the single warp
+// doing them (a lone bitonic sort is a chain of dependent shuffles).  run_b == nullptr: only run_a.
+__device__ __forceinline__ void compact_two(unsigned long long *run_a, uint32_t ca, unsigned long long *run_b, uint32_t cb, uint32_t kk, uint32_t kp,
+                                            uint32_t lane, uint32_t &na, unsigned long long &ta, unsigned long long &xa, uint32_t &nb,
+                                            unsigned long long &tb, unsigned long long &xb) {
+    unsigned long long ka[8], kb[8];
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint32_t e = (uint32_t)i * 32u + lane;
+        ka[i] = e < ca ? run_a[e] : ~0ull;
+        kb[i] = (run_b && e < cb) ? run_b[e] : ~0ull;
+    }
+    if (run_b) {
+        // interleaved step by step by the compiler: both arrays go through the same network
+        sort_size2<2>(ka, kb, lane);
+    } else
+        warp_sort256(ka, lane);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint32_t e = (uint32_t)i * 32u + lane;
+        if (e < kk) {
+            run_a[e] = ka[i];
+            if (run_b) run_b[e] = kb[i];
+        }
+    }
+    const uint32_t ri = (kk - 1) >> 5, rp = (kp - 1) >> 5;
+    unsigned long long ma = ri == 0 ? ka[0] : (ri == 1 ? ka[1] : (ri == 2 ? ka[2] : ka[3]));
+    unsigned long long mb = ri == 0 ? kb[0] : (ri == 1 ? kb[1] : (ri == 2 ? kb[2] : kb[3]));
+    unsigned long long pa = rp == 0 ? ka[0] : (rp == 1 ? ka[1] : (rp == 2 ? ka[2] : ka[3]));
+    unsigned long long pb = rp == 0 ? kb[0] : (rp == 1 ? kb[1] : (rp == 2 ? kb[2] : kb[3]));
+    ma = __shfl_sync(0xffffffffu, ma, (kk - 1) & 31);
+    mb = __shfl_sync(0xffffffffu, mb, (kk - 1) & 31);
+    pa = __shfl_sync(0xffffffffu, pa, (kp - 1) & 31);
+    pb = __shfl_sync(0xffffffffu, pb, (kp - 1) & 31);
+    na = ca < kk ? ca : kk;
+    ta = ca >= kk ? ma : ~0ull;
+    xa = ca >= kp ? pa : ~0ull;
+    nb = cb < kk ? cb : kk;
+    tb = cb >= kk ? mb : ~0ull;
+    xb = cb >= kp ? pb : ~0ull;
+    __syncwarp();
+}
 
 // Sort lane `l`'s candidate run and keep its `kk` smallest keys; returns (all lanes) the new count and threshold of that lane.
-__device__ __forceinline__ void compact_run(unsigned long long *run, uint32_t c, uint32_t kk, uint32_t lane, uint32_t &new_cnt,
-                                            unsigned long long &new_thr) {
+__device__ __forceinline__ void compact_run(unsigned long long *run, uint32_t c, uint32_t kk, uint32_t kp, uint32_t lane, uint32_t &new_cnt,
+                                            unsigned long long &new_thr, unsigned long long &kp_key) {
     unsigned long long k[8];
     __syncwarp();  // the owning lane's appends are visible to the whole warp
 #pragma unroll
@@ -186,9 +272,24 @@ __device__ __forceinline__ void compact_run(unsigned long long *run, uint32_t c,
     const uint32_t ri = (kk - 1) >> 5;  // < KMAX/32 = 4
     unsigned long long mine = ri == 0 ? k[0] : (ri == 1 ? k[1] : (ri == 2 ? k[2] : k[3]));
     unsigned long long kth = __shfl_sync(0xffffffffu, mine, (kk - 1) & 31);
+    const uint32_t rp = (kp - 1) >> 5;
+    unsigned long long minep = rp == 0 ? k[0] : (rp == 1 ? k[1] : (rp == 2 ? k[2] : k[3]));
+    unsigned long long kpth = __shfl_sync(0xffffffffu, minep, (kp - 1) & 31);
     new_cnt = c < kk ? c : kk;
     new_thr = c >= kk ? kth : ~0ull;
+    kp_key = c >= kp ? kpth : ~0ull;  // this slice's kp-th best so far
     __syncwarp();
+}
+
+// Smallest value of (dot x inverse row norm) a row needs in order to possibly have key < thr, with a safety margin for the
+// different rounding of the fast test: dd <= dd_thr  =>  cos >= 1 - 2 dd_thr  =>  dot*rn >= (1 - 2 dd_thr) / qn.
+__device__ __forceinline__ float reject_bound(unsigned long long thr, float qn) {
+    if (thr == ~0ull || !(qn > 0.f)) return __int_as_float(0xff800000);
+    const float dd_thr = __uint_as_float((uint32_t)(thr >> 32));
+    const float cs_min = 1.f - 2.f * dd_thr - 4e-7f;
+    if (cs_min <= -1.f) return __int_as_float(0xff800000);
+    const float x = cs_min / qn;
+    return x - fabsf(x) * 2e-6f - 1e-30f;
 }
 
 }  // namespace
@@ -201,8 +302,10 @@ __global__ void __launch_bounds__(256, 1)
                          uint32_t d, uint64_t n_rows, uint32_t kblocks,
                          uint32_t n_qtiles, uint32_t n_groups, const float *__restrict__ inv_norm, const uint32_t *__restrict__ docids,
                          const float *__restrict__ q_inv_norm, const unsigned long long *__restrict__ cand, uint64_t n_cand_words, uint32_t kk,
+                         unsigned long long *__restrict__ gthr /* [n_qtiles*128][n_groups], init ~0: each slice's ceil(k/n_groups)-th best key so far */,
                          unsigned long long *__restrict__ runs /* [cta][128][CAND_CAP] */,
-                         unsigned long long *__restrict__ partial /* [n_qtiles*128][n_groups][KMAX] */) {
+                         unsigned long long *__restrict__ partial /* [n_qtiles*128][n_groups][KMAX] */,
+                         unsigned long long *__restrict__ dbg /* optional [cta][8] cycle counters, see B200_VEC_DEBUG */) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr int NST = TS ? STAGES_TS : STAGES;      // B ring depth
@@ -258,27 +361,31 @@ __global__ void __launch_bounds__(256, 1)
                     tma_load_2d(sA + (size_t)kb * A_BLOCK, &tmap_q, a_full, (int32_t)(kb * GK), (int32_t)(qtile * GM));
             }
             uint32_t it = 0;
+            unsigned long long w_prod = 0;
             for (uint64_t t = tile_lo; t < tile_hi; t++)
                 for (uint32_t kb = 0; kb < kblocks; kb++, it++) {
                     uint32_t s = it % NST, ph = (it / NST) & 1;
-                    mbar_wait(b_empty + s, ph ^ 1);
+                    mbar_wait_t(b_empty + s, ph ^ 1, w_prod, dbg != nullptr);
                     mbar_expect_tx(b_full + s, B_BLOCK);
                     tma_load_2d(sB + (size_t)s * B_BLOCK, &tmap_m, b_full + s, (int32_t)(kb * GK), (int32_t)(t * GN));
                 }
+            if (dbg) dbg[blockIdx.x * 8 + 0] = w_prod;
         }
     } else if (warp == 1) {
         if (lane == 0) {
             mbar_wait(a_full, 0);
             tc_fence_after();
             uint32_t it = 0, n = 0;
+            unsigned long long w_acc = 0, w_b = 0;
+            const long long t_mma0 = clock64();
             for (uint64_t t = tile_lo; t < tile_hi; t++, n++) {
                 uint32_t buf = n % NACC, aph = (n / NACC) & 1;
-                mbar_wait(acc_empty + buf, aph ^ 1);
+                mbar_wait_t(acc_empty + buf, aph ^ 1, w_acc, dbg != nullptr);
                 tc_fence_after();
                 uint32_t tmem_d = tmem_base + ACC_COL0 + buf * GN;
                 for (uint32_t kb = 0; kb < kblocks; kb++, it++) {
                     uint32_t s = it % NST, ph = (it / NST) & 1;
-                    mbar_wait(b_full + s, ph);
+                    mbar_wait_t(b_full + s, ph, w_b, dbg != nullptr);
                     tc_fence_after();
                     uint64_t bd = make_sdesc(smem_u32(sB + (size_t)s * B_BLOCK));
                     if (TS) {
@@ -294,6 +401,11 @@ __global__ void __launch_bounds__(256, 1)
                 }
                 tc_commit(acc_full + buf);
             }
+            if (dbg) {
+                dbg[blockIdx.x * 8 + 1] = w_acc;
+                dbg[blockIdx.x * 8 + 2] = w_b;
+                dbg[blockIdx.x * 8 + 3] = (unsigned long long)(clock64() - t_mma0);
+            }
         }
     } else if (warp == 3) {
         uint32_t n = 0;
@@ -308,6 +420,7 @@ __global__ void __launch_bounds__(256, 1)
                 if (r < n_rows) {
                     doc = __ldg(docids + r);
                     sc = __ldg(inv_norm + r);
+                    if (!(sc > 0.f)) sc = __int_as_float(0x7f800000);  // zero norm: v*inf is NaN/inf, never fast-rejected; pn not finite -> distance 0
                     if (cand && !((doc >> 6) < n_cand_words && ((__ldg(cand + (doc >> 6)) >> (doc & 63)) & 1))) doc = 0xffffffffu;
                 }
                 s_doc[mb * GN + h * 32 + lane] = doc;
@@ -343,10 +456,14 @@ __global__ void __launch_bounds__(256, 1)
         }
         uint32_t cnt = 0;
         unsigned long long thr = ~0ull;
+        float tq = __int_as_float(0xff800000);  // -inf: nothing is rejected before a threshold exists
+        const uint32_t kp = (kk + n_groups - 1) / n_groups;  // per-slice share of the k best
         uint32_t n = 0;
+        unsigned long long w_full = 0, w_meta = 0, w_cmp = 0;
+        const long long t_epi0 = clock64();
         for (uint64_t t = tile_lo; t < tile_hi; t++, n++) {
             uint32_t buf = n % NACC, aph = (n / NACC) & 1;
-            mbar_wait(acc_full + buf, aph);
+            mbar_wait_t(acc_full + buf, aph, w_full, dbg != nullptr);
             tc_fence_after();
             uint32_t v[GN];
             uint32_t taddr = tmem_base + ((w * 32u) << 16) + ACC_COL0 + buf * GN;
@@ -357,36 +474,95 @@ __global__ void __launch_bounds__(256, 1)
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + buf);
             const uint32_t mb = n % META_BUFS, mph = (n / META_BUFS) & 1;
-            mbar_wait(meta_full + mb, mph);
+            mbar_wait_t(meta_full + mb, mph, w_meta, dbg != nullptr);
             const uint32_t *tdoc = s_doc + mb * GN;
             const float *tscale = s_scale + mb * GN;
+            // pass 1, branch-free: which of the 64 rows can possibly beat this query's threshold ("dot x inverse row norm" space)
+            uint32_t m_lo = 0, m_hi = 0;
 #pragma unroll
-            for (int j = 0; j < GN; j++) {  // fully unrolled: v[j] stays in registers; metadata reads are shared-memory broadcasts
-                const uint32_t doc = tdoc[j];
-                const float pn = tscale[j] * qn;
-                float dd = 0.f;
-                if (pn > 0.f && isfinite(pn)) {
-                    float cs = __uint_as_float(v[j]) * pn;
-                    cs = fminf(1.f, fmaxf(-1.f, cs));
-                    dd = (1.f - cs) * 0.5f;
+            for (int j = 0; j < 32; j++) {
+                m_lo |= (__uint_as_float(v[j]) * tscale[j] < tq) ? 0u : (1u << j);
+                m_hi |= (__uint_as_float(v[j + 32]) * tscale[j + 32] < tq) ? 0u : (1u << j);
+            }
+            // pass 2: exact distance + append, only for columns some lane of the warp flagged (warp-uniform branches, so v[j] keeps a
+            // static register index)
+            const uint32_t u_lo = __reduce_or_sync(0xffffffffu, m_lo), u_hi = __reduce_or_sync(0xffffffffu, m_hi);
+            if (u_lo | u_hi) {
+#pragma unroll
+                for (int g8 = 0; g8 < GN / 8; g8++) {  // convergence barriers are expensive: test 8 columns per warp-uniform branch
+                    const uint32_t um8 = ((g8 < 4 ? u_lo : u_hi) >> ((g8 & 3) * 8)) & 0xffu;
+                    if (um8) {
+#pragma unroll
+                        for (int jj = 0; jj < 8; jj++) {
+                            const int j = g8 * 8 + jj;
+                            const uint32_t mm = j < 32 ? m_lo : m_hi;
+                            if ((mm >> (j & 31)) & 1u) {
+                                const uint32_t doc = tdoc[j];
+                                const float pn = tscale[j] * qn;
+                                float dd = 0.f;
+                                if (pn > 0.f && isfinite(pn)) {
+                                    float cs = __uint_as_float(v[j]) * pn;
+                                    cs = fminf(1.f, fmaxf(-1.f, cs));
+                                    dd = (1.f - cs) * 0.5f;
+                                }
+                                const unsigned long long key = ((unsigned long long)__float_as_uint(dd) << 32) | doc;
+                                if (doc != 0xffffffffu && key < thr) my_run[cnt++] = key;
+                            }
+                        }
+                    }
                 }
-                const unsigned long long key = ((unsigned long long)__float_as_uint(dd) << 32) | doc;
-                if (doc != 0xffffffffu && key < thr) my_run[cnt++] = key;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(meta_empty + mb);
-            uint32_t need = __ballot_sync(0xffffffffu, cnt > (uint32_t)(CAND_CAP - GN));
+            bool changed = false;
+            const long long t_c0 = dbg ? clock64() : 0;
+            // compaction: when a run is nearly full — and once right after the first tile, so that every slice publishes an early
+            // bound (see below) instead of appending everything for three tiles
+            uint32_t need = __ballot_sync(0xffffffffu, cnt > (uint32_t)(CAND_CAP - GN) || (n == 0 && cnt >= kp));
             while (need) {
-                uint32_t l = __ffs(need) - 1;
+                const uint32_t l1 = __ffs(need) - 1;
                 need &= need - 1;
-                uint32_t c = __shfl_sync(0xffffffffu, cnt, l), nc;
-                unsigned long long nt;
-                compact_run(warp_runs + (size_t)l * CAND_CAP, c, kk, lane, nc, nt);
-                if (lane == l) {
-                    cnt = nc;
-                    thr = nt;
+                const bool two = need != 0;
+                const uint32_t l2 = two ? __ffs(need) - 1 : l1;
+                if (two) need &= need - 1;
+                const uint32_t c1 = __shfl_sync(0xffffffffu, cnt, l1), c2 = __shfl_sync(0xffffffffu, cnt, l2);
+                uint32_t n1, n2;
+                unsigned long long t1, t2, x1, x2;
+                compact_two(warp_runs + (size_t)l1 * CAND_CAP, c1, two ? warp_runs + (size_t)l2 * CAND_CAP : nullptr, c2, kk, kp, lane, n1, t1, x1, n2, t2,
+                            x2);
+                if (lane == l1 || (two && lane == l2)) {
+                    const bool first = lane == l1;
+                    cnt = first ? n1 : n2;
+                    const unsigned long long nt = first ? t1 : t2, xp = first ? x1 : x2;
+                    if (nt < thr) {
+                        thr = nt;
+                        changed = true;
+                    }
+                    // this slice holds kp = ceil(k / n_groups) keys <= xp; once every slice has published, the largest of their
+                    // xp is an upper bound of the global k-th key (n_groups * kp >= k keys are <= it)
+                    if (xp != ~0ull) gthr[(size_t)qrow * n_groups + group] = xp;
                 }
             }
+            if ((n & 3) == 1) {
+                const volatile unsigned long long *gx = gthr + (size_t)qrow * n_groups;
+                unsigned long long bound = 0;
+                for (uint32_t g = 0; g < n_groups; g++) {
+                    unsigned long long x = gx[g];
+                    bound = x > bound ? x : bound;
+                }
+                if (bound < thr) {
+                    thr = bound;
+                    changed = true;
+                }
+            }
+            if (changed) tq = reject_bound(thr, qn);
+            if (dbg) w_cmp += (unsigned long long)(clock64() - t_c0);
+        }
+        if (dbg && w == 0 && lane == 0) {
+            dbg[blockIdx.x * 8 + 4] = w_full;
+            dbg[blockIdx.x * 8 + 5] = w_meta;
+            dbg[blockIdx.x * 8 + 6] = w_cmp;
+            dbg[blockIdx.x * 8 + 7] = (unsigned long long)(clock64() - t_epi0);
         }
         // final: every lane's run sorted, its kk best written to this (query, group) slot
         __syncwarp();
@@ -509,11 +685,18 @@ cudaError_t launch_vec_prep_queries(cudaStream_t s, const float *q, uint32_t n_q
 
 cudaError_t launch_vec_gemm_topk(cudaStream_t s, uint32_t sm_count, const void *mat_fp16, const float *inv_norm, const uint32_t *docids, uint64_t n_rows,
                                  uint32_t d, const void *q_fp16, const float *q_inv_norm, uint32_t n_qtiles, uint32_t n_groups,
-                                 const unsigned long long *cand, uint64_t n_cand_words, uint32_t k, unsigned long long *runs,
+                                 const unsigned long long *cand, uint64_t n_cand_words, uint32_t k, unsigned long long *gthr, unsigned long long *runs,
                                  unsigned long long *partial, uint32_t *out_ids, float *out_dist, uint32_t *out_n, uint32_t n_q) {
     if (!vec_gemm_supported(d, k) || n_qtiles * n_groups > sm_count || n_groups == 0) return cudaErrorInvalidValue;
     CUtensorMap mq, mm;
     if (!make_map(&mq, q_fp16, (uint64_t)n_qtiles * GM, d, GM) || !make_map(&mm, mat_fp16, n_rows, d, GN)) return cudaErrorNotSupported;
+    cudaError_t em = cudaMemsetAsync(gthr, 0xff, (size_t)n_qtiles * GM * n_groups * 8, s);
+    if (em != cudaSuccess) return em;
+    unsigned long long *dbg = nullptr;
+    if (getenv("B200_VEC_DEBUG")) {
+        if (cudaMalloc((void **)&dbg, (size_t)n_qtiles * n_groups * 64) != cudaSuccess) dbg = nullptr;
+        if (dbg) cudaMemsetAsync(dbg, 0, (size_t)n_qtiles * n_groups * 64, s);
+    }
     const bool ts = d % 64 == 0 && !(getenv("B200_VEC_GEMM_SS") && atoi(getenv("B200_VEC_GEMM_SS")) != 0);
     size_t smem = vec_gemm_smem_bytes(d, ts);
     const __half *qh = reinterpret_cast<const __half *>(q_fp16);
@@ -522,15 +705,28 @@ cudaError_t launch_vec_gemm_topk(cudaStream_t s, uint32_t sm_count, const void *
         e = cudaFuncSetAttribute(vec_gemm_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         vec_gemm_topk_kernel<true><<<n_qtiles * n_groups, 256, smem, s>>>(mq, mm, qh, d, n_rows, d / GK, n_qtiles, n_groups, inv_norm, docids, q_inv_norm,
-                                                                          cand, n_cand_words, k, runs, partial);
+                                                                          cand, n_cand_words, k, gthr, runs, partial, dbg);
     } else {
         e = cudaFuncSetAttribute(vec_gemm_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         vec_gemm_topk_kernel<false><<<n_qtiles * n_groups, 256, smem, s>>>(mq, mm, qh, d, n_rows, d / GK, n_qtiles, n_groups, inv_norm, docids, q_inv_norm,
-                                                                           cand, n_cand_words, k, runs, partial);
+                                                                           cand, n_cand_words, k, gthr, runs, partial, dbg);
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    if (dbg) {
+        std::vector<unsigned long long> h((size_t)n_qtiles * n_groups * 8);
+        cudaStreamSynchronize(s);
+        cudaMemcpy(h.data(), dbg, h.size() * 8, cudaMemcpyDeviceToHost);
+        cudaFree(dbg);
+        double sum[8] = {0};
+        for (size_t c = 0; c < (size_t)n_qtiles * n_groups; c++)
+            for (int i = 0; i < 8; i++) sum[i] += (double)h[c * 8 + i];
+        const char *names[8] = {"producer wait b_empty", "mma wait acc_empty", "mma wait b_full", "mma total", "epi wait acc_full", "epi wait meta", "epi compaction", "epi total"};
+        fprintf(stderr, "[b200 vec debug] mean cycles per CTA (%u CTAs):", n_qtiles * n_groups);
+        for (int i = 0; i < 8; i++) fprintf(stderr, "  %s %.0f", names[i], sum[i] / (n_qtiles * n_groups));
+        fprintf(stderr, "\n");
+    }
     vec_merge_kernel<<<n_q, KMAX, 0, s>>>(partial, n_groups, k, out_ids, out_dist, out_n);
     return cudaGetLastError();
 }

@@ -1,6 +1,11 @@
-"""Multi-GPU plumbing for the query-sharded ("replicas only") deployment: every rank holds a full replica of the
-staged index and serves its own slice of the query stream; there is no collective on the data path.
-torch.distributed is used only to agree on timings and to gather results when one caller wants the whole batch back."""
+"""Multi-GPU plumbing.
+
+Keyword path — query-sharded ("replicas only"): every rank holds a full replica of the staged index and serves its own slice of
+the query stream; no collective on the data path; torch.distributed only agrees on timings and gathers results
+when one caller wants the whole batch back.
+
+Vector stage — optionally corpus-sharded by contiguous docid range (cfg 5): every rank scans its rows for the whole
+query batch and the per-shard top-k lists are exchanged with ONE all-gather (NCCL on GPUs, gloo in the CPU tests) and merged."""
 from __future__ import annotations
 
 import torch
@@ -44,3 +49,38 @@ def gather_hits(local_ids, n_total: int, limit: int, rank: int, world: int, devi
         a, b = shard_bounds(n_total, r, world)
         rows.append(out[r][: b - a])
     return torch.cat(rows, 0)
+
+
+# ---- corpus-sharded vector stage (cfg 5): shard g owns a contiguous docid range of the embedding matrix ----------
+def shard_rows(n_rows: int, rank: int, world: int):
+    """Contiguous row range [lo, hi) of the embedding matrix owned by `rank` (rows are in docid order)."""
+    return shard_bounds(n_rows, rank, world)
+
+
+def merge_sharded_topk(local_ids, local_dist, local_count, limit: int, device="cpu"):
+    """The one exchange step of the corpus-sharded path: every rank scanned ITS rows for the WHOLE query batch and holds, per
+    query, its local top-`limit` (ids, distances ascending, count).  One all-gather of B x limit x (u32 docid, f32 distance) per
+    rank, then a k-way merge by (distance, docid) — identical to the single-shard result because every global top-k entry is in
+    its shard's local top-k.  Returns (ids [B, limit] int64, dist [B, limit] float32, count [B] int64) on every rank."""
+    ids = torch.as_tensor(local_ids, device=device).to(torch.int64)
+    dst = torch.as_tensor(local_dist, device=device).to(torch.float32)
+    cnt = torch.as_tensor(local_count, device=device).to(torch.int64)
+    B = ids.shape[0]
+    col = torch.arange(limit, device=device)[None, :]
+    valid = col < cnt[:, None]
+    ids = torch.where(valid, ids, torch.full_like(ids, 0xFFFFFFFF))
+    dst = torch.where(valid, dst, torch.full_like(dst, float("inf")))
+    world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+    if world > 1:
+        g_ids = [torch.empty_like(ids) for _ in range(world)]
+        g_dst = [torch.empty_like(dst) for _ in range(world)]
+        dist.all_gather(g_ids, ids)
+        dist.all_gather(g_dst, dst)
+        ids, dst = torch.cat(g_ids, 1), torch.cat(g_dst, 1)
+    # order by (distance, docid): sort by docid first, then a stable sort by distance
+    o1 = torch.argsort(ids, dim=1, stable=True)
+    ids, dst = torch.gather(ids, 1, o1), torch.gather(dst, 1, o1)
+    o2 = torch.argsort(dst, dim=1, stable=True)
+    ids, dst = torch.gather(ids, 1, o2)[:, :limit], torch.gather(dst, 1, o2)[:, :limit]
+    count = torch.isfinite(dst).sum(1)
+    return ids, dst, count

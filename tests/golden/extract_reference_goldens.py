@@ -281,6 +281,28 @@ def query_criteria_cases():
     return out
 
 
+def matching_strategy_cases():
+    """crates/meilisearch/tests/search/matching_strategy.rs:16-140: 7 documents, default settings (every field searchable; serde_json
+    maps iterate in key order, so fid 0 = `id`, fid 1 = `title`), three queries under matchingStrategy last / all / frequency with
+    the `hits` snapshots.  External ids "1".."7" were inserted in order: internal docid = id - 1."""
+    path = "/root/reference/crates/meilisearch/tests/search/matching_strategy.rs"
+    src = open(path).read()
+    m = re.search(r"static SIMPLE_SEARCH_DOCUMENTS.*?json!\(\[(.*?)\]\)\s*\}\);", src, re.S)
+    docs = json.loads("[" + re.sub(r",(\s*[}\]])", r"\1", m.group(1)) + "]")
+    # `id` is a searchable text field here; the position in the list is the internal docid
+    index = {"searchable": ["id", "title"], "exact_attributes": [], "stop_words": [], "docs": [{"id": d["id"], "title": d["title"]} for d in docs]}
+    out = []
+    for sm in re.finditer(r'\.search\(json!\(\{"q": "([^"]*)", "matchingStrategy": "(\w+)".*?snapshot!\(response\["hits"\], @(?:r###)?"(.*?)"(?:###)?\);', src, re.S):
+        line = src.count("\n", 0, sm.start()) + 1
+        if line > 140:
+            break
+        hits = json.loads(sm.group(3))
+        out.append({"source": f"crates/meilisearch/tests/search/matching_strategy.rs:{line}", "test": "matching_strategy", "index": index,
+                    "settings": {}, "tms": sm.group(2), "scoring": "skip", "limit": 20, "offset": 0, "query": sm.group(1),
+                    "expected_ids": [int(h["id"]) - 1 for h in hits]})
+    return out
+
+
 def main():
     cases, skipped = [], 0
     for fname in FILES:
@@ -385,6 +407,7 @@ def main():
                             last_case["expected_scores"] = scores
                             last_case["scores_source"] = rel
     cases.extend(query_criteria_cases())
+    cases.extend(matching_strategy_cases())
     # de-duplicate identical corpora into a table to keep the fixture small
     corpora, keyed = [], {}
     for c in cases:

@@ -176,7 +176,7 @@ def test_reference_goldens_on_gpu(mb):
     assert ran == len(G["cases"])
 
 
-@pytest.mark.parametrize("tms,scoring", [("last", "detailed"), ("last", "skip"), ("all", "detailed")])
+@pytest.mark.parametrize("tms,scoring", [("last", "detailed"), ("last", "skip"), ("all", "detailed"), ("frequency", "detailed")])
 def test_keyword_batch_matches_oracle(mb, synth, tms, scoring):
     from oracle.pyoracle import OracleIndex
 

@@ -54,3 +54,46 @@ def test_shard_bounds_partition():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
             assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+
+
+def _vec_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from corpus.pyindexgen import IndexImage
+    from meilisearch_b200.parallel import merge_sharded_topk, shard_rows
+    from oracle.pyoracle import OracleIndex
+
+    rng = np.random.default_rng(5)
+    n, d, B, k = 4000, 32, 9, 10
+    emb = rng.standard_normal((n, d)).astype(np.float32)
+    emb[77] = emb[3001]  # an exact tie across the two shards
+    q = rng.standard_normal((B, d)).astype(np.float32)
+    q[0] = emb[77]
+    img = IndexImage(1)
+    img.add_text(0, 0, "doc")
+    img.build()
+    lo, hi = shard_rows(n, rank, world)
+    shard = OracleIndex(img)   # the oracle stands in for the per-GPU scan in this CPU test
+    shard.set_embeddings(emb[lo:hi], np.arange(lo, hi, dtype=np.uint32))
+    ids = np.full((B, k), 0xFFFFFFFF, np.int64)
+    dst = np.full((B, k), np.inf, np.float32)
+    cnt = np.zeros(B, np.int64)
+    for i in range(B):
+        oi, od = shard.nns(q[i], k)
+        ids[i, : len(oi)], dst[i, : len(oi)], cnt[i] = oi, od, len(oi)
+    m_ids, m_dst, m_cnt = merge_sharded_topk(ids, dst, cnt, k)
+    if rank == 0:
+        full = OracleIndex(img)
+        full.set_embeddings(emb, np.arange(n, dtype=np.uint32))
+        want = [full.nns(q[i], k) for i in range(B)]
+        ret["ok"] = all(m_ids[i, : m_cnt[i]].tolist() == want[i][0].tolist() and np.array_equal(m_dst[i, : m_cnt[i]].numpy(), want[i][1])
+                        for i in range(B))
+    dist.destroy_process_group()
+
+
+def test_corpus_sharded_vector_topk_world2():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_vec_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    assert ret["ok"]
