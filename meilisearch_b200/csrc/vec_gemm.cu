@@ -84,6 +84,14 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
                  "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
                  : "memory");
 }
+// one lane of a converged warp (the role loops run warp-convergent so that descriptors and ring counters live in uniform
+// registers; only the issuing instructions are predicated on the elected lane — a loop under `if (lane == 0)` pays a register ->
+// uniform-register move for every operand of every tcgen05.mma / TMA instruction)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {
@@ -175,81 +183,6 @@ __device__ __forceinline__ void sort_size(unsigned long long (&k)[8], uint32_t l
     if constexpr (SIZE < 256) sort_size<SIZE * 2>(k, lane);
 }
 __device__ __forceinline__ void warp_sort256(unsigned long long (&k)[8], uint32_t lane) { sort_size<2>(k, lane); }
-// the same network applied to two arrays step by step (two independent dependency chains in flight)
-template <int SIZE, int J>
-__device__ __forceinline__ void sort_step2(unsigned long long (&a)[8], unsigned long long (&b)[8], uint32_t lane) {
-    if constexpr (J >= 32) {
-        constexpr int RJ = J >> 5;
-#pragma unroll
-        for (int i = 0; i < 8; i++)
-            if ((i & RJ) == 0) {
-                cswap(a[i], a[i | RJ], ((i * 32) & SIZE) == 0);
-                cswap(b[i], b[i | RJ], ((i * 32) & SIZE) == 0);
-            }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const uint32_t e = (uint32_t)i * 32u + lane;
-            const unsigned long long oa = __shfl_xor_sync(0xffffffffu, a[i], J), ob = __shfl_xor_sync(0xffffffffu, b[i], J);
-            const bool take_lo = (((e & (uint32_t)SIZE) == 0) == ((lane & (uint32_t)J) == 0));
-            const unsigned long long la = a[i] < oa ? a[i] : oa, ha = a[i] < oa ? oa : a[i];
-            const unsigned long long lb = b[i] < ob ? b[i] : ob, hb = b[i] < ob ? ob : b[i];
-            a[i] = take_lo ? la : ha;
-            b[i] = take_lo ? lb : hb;
-        }
-    }
-    if constexpr (J > 1) sort_step2<SIZE, J / 2>(a, b, lane);
-}
-template <int SIZE>
-__device__ __forceinline__ void sort_size2(unsigned long long (&a)[8], unsigned long long (&b)[8], uint32_t lane) {
-    sort_step2<SIZE, SIZE / 2>(a, b, lane);
-    if constexpr (SIZE < 256) sort_size2<SIZE * 2>(a, b, lane);
-}
-
-// Two runs at once: the two sorts are independent instruction streams, which roughly doubles the issue rate of the single warp
-// doing them (a lone bitonic sort is a chain of dependent shuffles).  run_b == nullptr: only run_a.
-__device__ __forceinline__ void compact_two(unsigned long long *run_a, uint32_t ca, unsigned long long *run_b, uint32_t cb, uint32_t kk, uint32_t kp,
-                                            uint32_t lane, uint32_t &na, unsigned long long &ta, unsigned long long &xa, uint32_t &nb,
-                                            unsigned long long &tb, unsigned long long &xb) {
-    unsigned long long ka[8], kb[8];
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        uint32_t e = (uint32_t)i * 32u + lane;
-        ka[i] = e < ca ? run_a[e] : ~0ull;
-        kb[i] = (run_b && e < cb) ? run_b[e] : ~0ull;
-    }
-    if (run_b) {
-        // interleaved step by step by the compiler: both arrays go through the same network
-        sort_size2<2>(ka, kb, lane);
-    } else
-        warp_sort256(ka, lane);
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        uint32_t e = (uint32_t)i * 32u + lane;
-        if (e < kk) {
-            run_a[e] = ka[i];
-            if (run_b) run_b[e] = kb[i];
-        }
-    }
-    const uint32_t ri = (kk - 1) >> 5, rp = (kp - 1) >> 5;
-    unsigned long long ma = ri == 0 ? ka[0] : (ri == 1 ? ka[1] : (ri == 2 ? ka[2] : ka[3]));
-    unsigned long long mb = ri == 0 ? kb[0] : (ri == 1 ? kb[1] : (ri == 2 ? kb[2] : kb[3]));
-    unsigned long long pa = rp == 0 ? ka[0] : (rp == 1 ? ka[1] : (rp == 2 ? ka[2] : ka[3]));
-    unsigned long long pb = rp == 0 ? kb[0] : (rp == 1 ? kb[1] : (rp == 2 ? kb[2] : kb[3]));
-    ma = __shfl_sync(0xffffffffu, ma, (kk - 1) & 31);
-    mb = __shfl_sync(0xffffffffu, mb, (kk - 1) & 31);
-    pa = __shfl_sync(0xffffffffu, pa, (kp - 1) & 31);
-    pb = __shfl_sync(0xffffffffu, pb, (kp - 1) & 31);
-    na = ca < kk ? ca : kk;
-    ta = ca >= kk ? ma : ~0ull;
-    xa = ca >= kp ? pa : ~0ull;
-    nb = cb < kk ? cb : kk;
-    tb = cb >= kk ? mb : ~0ull;
-    xb = cb >= kp ? pb : ~0ull;
-    __syncwarp();
-}
 
 // Sort lane `l`'s candidate run and keep its `kk` smallest keys; returns (all lanes) the new count and threshold of that lane.
 __device__ __forceinline__ void compact_run(unsigned long long *run, uint32_t c, uint32_t kk, uint32_t kp, uint32_t lane, uint32_t &new_cnt,
@@ -305,11 +238,15 @@ __global__ void __launch_bounds__(256, 1)
                          unsigned long long *__restrict__ gthr /* [n_qtiles*128][n_groups], init ~0: each slice's ceil(k/n_groups)-th best key so far */,
                          unsigned long long *__restrict__ runs /* [cta][128][CAND_CAP] */,
                          unsigned long long *__restrict__ partial /* [n_qtiles*128][n_groups][KMAX] */,
-                         unsigned long long *__restrict__ dbg /* optional [cta][8] cycle counters, see B200_VEC_DEBUG */) {
+                         unsigned long long *__restrict__ dbg /* optional [cta][8] cycle counters, see B200_VEC_DEBUG */, uint32_t dbg_mode) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr int NST = TS ? STAGES_TS : STAGES;      // B ring depth
-    constexpr int NACC = TS ? 2 : ACC_BUFS;           // TMEM accumulators (TS: 384 columns hold the query tile, 128 are left)
+    constexpr int NACC = 2;                           // tile buffers in TMEM
+    // SS: every tile accumulates into KS = 2 accumulators (even / odd k-blocks) that the epilogue adds: consecutive MMAs into one
+    // accumulator serialise on its latency (~100 cycles at N = 64), two independent chains keep the tensor pipe busy
+    constexpr int KS = TS ? 1 : 2;
+    const uint32_t ks = (KS == 2 && kblocks >= 2) ? 2u : 1u;  // a single k-block leaves the odd accumulator unused
     constexpr uint32_t ACC_COL0 = TS ? A_COLS : 0;    // first accumulator column
     constexpr uint32_t TMEM_COLS = TS ? 512 : ACC_BUFS * GN;
     uint8_t *sA = smem;
@@ -354,57 +291,97 @@ __global__ void __launch_bounds__(256, 1)
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            if (!TS) {
-                mbar_expect_tx(a_full, kblocks * A_BLOCK);
-                for (uint32_t kb = 0; kb < kblocks; kb++)
-                    tma_load_2d(sA + (size_t)kb * A_BLOCK, &tmap_q, a_full, (int32_t)(kb * GK), (int32_t)(qtile * GM));
-            }
-            uint32_t it = 0;
-            unsigned long long w_prod = 0;
-            for (uint64_t t = tile_lo; t < tile_hi; t++)
-                for (uint32_t kb = 0; kb < kblocks; kb++, it++) {
-                    uint32_t s = it % NST, ph = (it / NST) & 1;
-                    mbar_wait_t(b_empty + s, ph ^ 1, w_prod, dbg != nullptr);
+        const bool leader = elect_one();
+        if (!TS && leader) {
+            mbar_expect_tx(a_full, kblocks * A_BLOCK);
+            for (uint32_t kb = 0; kb < kblocks; kb++) tma_load_2d(sA + (size_t)kb * A_BLOCK, &tmap_q, a_full, (int32_t)(kb * GK), (int32_t)(qtile * GM));
+        }
+        uint32_t s = 0, ph = 0;
+        unsigned long long w_prod = 0;
+        for (uint64_t t = tile_lo; t < tile_hi; t++)
+            for (uint32_t kb = 0; kb < kblocks; kb++) {
+                mbar_wait_t(b_empty + s, ph ^ 1, w_prod, false);
+                if (leader) {
                     mbar_expect_tx(b_full + s, B_BLOCK);
                     tma_load_2d(sB + (size_t)s * B_BLOCK, &tmap_m, b_full + s, (int32_t)(kb * GK), (int32_t)(t * GN));
                 }
-            if (dbg) dbg[blockIdx.x * 8 + 0] = w_prod;
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
+                __syncwarp();
+                if (++s == (uint32_t)NST) {
+                    s = 0;
+                    ph ^= 1;
+                }
+            }
+    } else if (warp == 1 || warp == 2) {
+        // Two MMA issuers (one thread each), alternating tiles: at N = 64 a K-block is only 4 x 32 cycles of tensor work, less than
+        // what one thread needs to wait for the stage, build the descriptors and issue — one issuer alone leaves the tensor pipe idle
+        // two thirds of the time.  Issuer p owns tile buffer p and the ring stages of the tiles of its parity.
+        {
+            const bool leader = elect_one();
+            const uint32_t par = warp - 1;
+            // mbarrier parity waits are only unambiguous one phase ahead: with two issuers a ring stage must always come back to
+            // the issuer that consumed its previous phase, i.e. the ring must hold a whole number of tile PAIRS
+            const bool dual = (uint32_t)NST % (2 * kblocks) == 0;
+            const uint32_t step = dual ? 2 : 1;
+            if (par == 0 || dual) {
             mbar_wait(a_full, 0);
             tc_fence_after();
-            uint32_t it = 0, n = 0;
+            uint32_t s = 0, ph = 0;  // ring position of this issuer's next stage
+            if (par) {
+                s += kblocks;
+                while (s >= (uint32_t)NST) {
+                    s -= NST;
+                    ph ^= 1;
+                }
+            }
+            const uint64_t bd0 = make_sdesc(smem_u32(sB));
+            const uint64_t ad0 = TS ? 0ull : make_sdesc(smem_u32(sA));
             unsigned long long w_acc = 0, w_b = 0;
             const long long t_mma0 = clock64();
-            for (uint64_t t = tile_lo; t < tile_hi; t++, n++) {
-                uint32_t buf = n % NACC, aph = (n / NACC) & 1;
+            uint32_t n = par;
+            for (uint64_t t = tile_lo + par; t < tile_hi; t += step, n += step) {
+                const uint32_t buf = n & 1, aph = (n >> 1) & 1;
                 mbar_wait_t(acc_empty + buf, aph ^ 1, w_acc, dbg != nullptr);
                 tc_fence_after();
-                uint32_t tmem_d = tmem_base + ACC_COL0 + buf * GN;
-                for (uint32_t kb = 0; kb < kblocks; kb++, it++) {
-                    uint32_t s = it % NST, ph = (it / NST) & 1;
+                const uint32_t tmem_d = tmem_base + ACC_COL0 + buf * (KS * GN);
+                for (uint32_t kb = 0; kb < kblocks; kb++) {
                     mbar_wait_t(b_full + s, ph, w_b, dbg != nullptr);
                     tc_fence_after();
-                    uint64_t bd = make_sdesc(smem_u32(sB + (size_t)s * B_BLOCK));
+                    const uint64_t bd = bd0 + (uint64_t)s * (B_BLOCK >> 4);
                     if (TS) {
 #pragma unroll
                         for (uint32_t k = 0; k < GK / 16; k++)  // 8 TMEM columns (16 halfs) and 32 B of the B row per K=16 step
-                            umma_ts(tmem_d, tmem_base + kb * (GK / 2) + k * 8, bd + 2 * k, (kb | k) != 0);
+                            if (leader) umma_ts(tmem_d, tmem_base + kb * (GK / 2) + k * 8, bd + 2 * k, (kb | k) != 0);
                     } else {
-                        uint64_t ad = make_sdesc(smem_u32(sA + (size_t)kb * A_BLOCK));
+                        const uint64_t ad = ad0 + (uint64_t)kb * (A_BLOCK >> 4);
+                        const uint32_t acc = tmem_d + (kb & (ks - 1)) * GN;  // even / odd k-blocks: two accumulation chains
 #pragma unroll
-                        for (uint32_t k = 0; k < GK / 16; k++) umma(tmem_d, ad + 2 * k, bd + 2 * k, (kb | k) != 0);  // +32 B per K=16 step
+                        for (uint32_t k = 0; k < GK / 16; k++)
+                            if (leader) umma(acc, ad + 2 * k, bd + 2 * k, (kb >= ks) || k != 0);  // +32 B per K=16 step
                     }
-                    tc_commit(b_empty + s);
+                    if (leader) tc_commit(b_empty + s);
+                    __syncwarp();
+                    if (++s == (uint32_t)NST) {
+                        s = 0;
+                        ph ^= 1;
+                    }
                 }
-                tc_commit(acc_full + buf);
+                if (leader) tc_commit(acc_full + buf);
+                __syncwarp();
+                if (dual) {
+                    s += kblocks;  // the other issuer's tile
+                    while (s >= (uint32_t)NST) {
+                        s -= NST;
+                        ph ^= 1;
+                    }
+                }
             }
-            if (dbg) {
-                dbg[blockIdx.x * 8 + 1] = w_acc;
-                dbg[blockIdx.x * 8 + 2] = w_b;
+            if (dbg && par == 0 && leader) {
                 dbg[blockIdx.x * 8 + 3] = (unsigned long long)(clock64() - t_mma0);
+                if (dbg_mode == 2) {
+                    dbg[blockIdx.x * 8 + 1] = w_acc;
+                    dbg[blockIdx.x * 8 + 2] = w_b;
+                }
+            }
             }
         }
     } else if (warp == 3) {
@@ -458,25 +435,43 @@ __global__ void __launch_bounds__(256, 1)
         unsigned long long thr = ~0ull;
         float tq = __int_as_float(0xff800000);  // -inf: nothing is rejected before a threshold exists
         const uint32_t kp = (kk + n_groups - 1) / n_groups;  // per-slice share of the k best
+        // When kp is small the slice's kp best keys live in registers, so its published bound is always current (it does not
+        // wait for a run compaction) and the shared threshold tightens with every candidate.
+        constexpr int KP_REG = 8;
+        const bool reg_best = kp <= (uint32_t)KP_REG;
+        unsigned long long best[KP_REG];
+#pragma unroll
+        for (int i = 0; i < KP_REG; i++) best[i] = ~0ull;
+        unsigned long long published = ~0ull;
         uint32_t n = 0;
-        unsigned long long w_full = 0, w_meta = 0, w_cmp = 0;
+        unsigned long long w_full = 0, w_meta = 0, w_cmp = 0, w_ld = 0, w_p1 = 0, w_p2 = 0, w_flag = 0, w_mine = 0;
         const long long t_epi0 = clock64();
         for (uint64_t t = tile_lo; t < tile_hi; t++, n++) {
             uint32_t buf = n % NACC, aph = (n / NACC) & 1;
             mbar_wait_t(acc_full + buf, aph, w_full, dbg != nullptr);
             tc_fence_after();
+            const long long t_l0 = dbg ? clock64() : 0;
             uint32_t v[GN];
-            uint32_t taddr = tmem_base + ((w * 32u) << 16) + ACC_COL0 + buf * GN;
+            uint32_t taddr = tmem_base + ((w * 32u) << 16) + ACC_COL0 + buf * (KS * GN);
             tmem_ld32(taddr, v);
             tmem_ld32(taddr + 32, v + 32);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty + buf);
+            if (ks == 2) {  // add the odd-k-block accumulator
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    uint32_t o[32];
+                    tmem_ld32(taddr + GN + h * 32, o);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int i = 0; i < 32; i++) v[h * 32 + i] = __float_as_uint(__uint_as_float(v[h * 32 + i]) + __uint_as_float(o[i]));
+                }
+            }
+            if (dbg) w_ld += (unsigned long long)(clock64() - t_l0);
             const uint32_t mb = n % META_BUFS, mph = (n / META_BUFS) & 1;
             mbar_wait_t(meta_full + mb, mph, w_meta, dbg != nullptr);
             const uint32_t *tdoc = s_doc + mb * GN;
             const float *tscale = s_scale + mb * GN;
+            const long long t_p0 = dbg ? clock64() : 0;
             // pass 1, branch-free: which of the 64 rows can possibly beat this query's threshold ("dot x inverse row norm" space)
             uint32_t m_lo = 0, m_hi = 0;
 #pragma unroll
@@ -484,71 +479,112 @@ __global__ void __launch_bounds__(256, 1)
                 m_lo |= (__uint_as_float(v[j]) * tscale[j] < tq) ? 0u : (1u << j);
                 m_hi |= (__uint_as_float(v[j + 32]) * tscale[j + 32] < tq) ? 0u : (1u << j);
             }
-            // pass 2: exact distance + append, only for columns some lane of the warp flagged (warp-uniform branches, so v[j] keeps a
-            // static register index)
-            const uint32_t u_lo = __reduce_or_sync(0xffffffffu, m_lo), u_hi = __reduce_or_sync(0xffffffffu, m_hi);
-            if (u_lo | u_hi) {
+            uint32_t u_lo = __reduce_or_sync(0xffffffffu, m_lo), u_hi = __reduce_or_sync(0xffffffffu, m_hi);
+            const long long t_p1 = dbg ? clock64() : 0;
+            if (dbg) {
+                w_p1 += (unsigned long long)(t_p1 - t_p0);
+                w_flag += __popc(u_lo) + __popc(u_hi);
+                w_mine += __popc(m_lo) + __popc(m_hi);
+            }
+            // pass 2: exact distance + append for the (rare) columns some lane flagged.  A compact loop over the set bits — the dot is
+            // re-read from tensor memory with a one-column tcgen05.ld — instead of 64 unrolled copies: the hot loop stays small
+            // enough for the instruction cache.
+            while (u_lo | u_hi) {  // warp-uniform; up to four flagged columns per round share one tcgen05.wait::ld
+                uint32_t js[4], vv[4], vo[4];
+                int nj = 0;
 #pragma unroll
-                for (int g8 = 0; g8 < GN / 8; g8++) {  // convergence barriers are expensive: test 8 columns per warp-uniform branch
-                    const uint32_t um8 = ((g8 < 4 ? u_lo : u_hi) >> ((g8 & 3) * 8)) & 0xffu;
-                    if (um8) {
+                for (int q = 0; q < 4; q++) {
+                    js[q] = 0;
+                    vv[q] = vo[q] = 0;
+                    if (u_lo | u_hi) {
+                        const uint32_t j = u_lo ? (uint32_t)__ffs(u_lo) - 1u : 32u + (uint32_t)__ffs(u_hi) - 1u;
+                        if (u_lo)
+                            u_lo &= u_lo - 1;
+                        else
+                            u_hi &= u_hi - 1;
+                        js[q] = j;
+                        nj = q + 1;
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(vv[q]) : "r"(taddr + j) : "memory");
+                        if (ks == 2) asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(vo[q]) : "r"(taddr + GN + j) : "memory");
+                    }
+                }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                        for (int jj = 0; jj < 8; jj++) {
-                            const int j = g8 * 8 + jj;
-                            const uint32_t mm = j < 32 ? m_lo : m_hi;
-                            if ((mm >> (j & 31)) & 1u) {
-                                const uint32_t doc = tdoc[j];
-                                const float pn = tscale[j] * qn;
-                                float dd = 0.f;
-                                if (pn > 0.f && isfinite(pn)) {
-                                    float cs = __uint_as_float(v[j]) * pn;
-                                    cs = fminf(1.f, fmaxf(-1.f, cs));
-                                    dd = (1.f - cs) * 0.5f;
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t j = js[q];
+                    const uint32_t mm = j < 32 ? m_lo : m_hi;
+                    if (q < nj && ((mm >> (j & 31)) & 1u)) {
+                        const float dot = ks == 2 ? __uint_as_float(vv[q]) + __uint_as_float(vo[q]) : __uint_as_float(vv[q]);
+                        const uint32_t doc = tdoc[j];
+                        const float pn = tscale[j] * qn;
+                        float dd = 0.f;
+                        if (pn > 0.f && isfinite(pn)) {
+                            float cs = dot * pn;
+                            cs = fminf(1.f, fmaxf(-1.f, cs));
+                            dd = (1.f - cs) * 0.5f;
+                        }
+                        const unsigned long long key = ((unsigned long long)__float_as_uint(dd) << 32) | doc;
+                        if (doc != 0xffffffffu && key < thr) {
+                            my_run[cnt++] = key;
+                            if (reg_best) {  // sorted insertion (ascending), the largest falls off
+                                unsigned long long x = key;
+#pragma unroll
+                                for (int i = 0; i < KP_REG; i++) {
+                                    const unsigned long long lo = x < best[i] ? x : best[i], hi = x < best[i] ? best[i] : x;
+                                    best[i] = lo;
+                                    x = hi;
                                 }
-                                const unsigned long long key = ((unsigned long long)__float_as_uint(dd) << 32) | doc;
-                                if (doc != 0xffffffffu && key < thr) my_run[cnt++] = key;
                             }
                         }
                     }
                 }
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + buf);
             __syncwarp();
             if (lane == 0) mbar_arrive(meta_empty + mb);
+            if (dbg) w_p2 += (unsigned long long)(clock64() - t_p1);
             bool changed = false;
             const long long t_c0 = dbg ? clock64() : 0;
             // compaction: when a run is nearly full — and once right after the first tile, so that every slice publishes an early
             // bound (see below) instead of appending everything for three tiles
-            uint32_t need = __ballot_sync(0xffffffffu, cnt > (uint32_t)(CAND_CAP - GN) || (n == 0 && cnt >= kp));
+            uint32_t need = __ballot_sync(0xffffffffu, cnt > (uint32_t)(CAND_CAP - GN) || (!reg_best && n == 0 && cnt >= kp));
             while (need) {
-                const uint32_t l1 = __ffs(need) - 1;
+                uint32_t l = __ffs(need) - 1;
                 need &= need - 1;
-                const bool two = need != 0;
-                const uint32_t l2 = two ? __ffs(need) - 1 : l1;
-                if (two) need &= need - 1;
-                const uint32_t c1 = __shfl_sync(0xffffffffu, cnt, l1), c2 = __shfl_sync(0xffffffffu, cnt, l2);
-                uint32_t n1, n2;
-                unsigned long long t1, t2, x1, x2;
-                compact_two(warp_runs + (size_t)l1 * CAND_CAP, c1, two ? warp_runs + (size_t)l2 * CAND_CAP : nullptr, c2, kk, kp, lane, n1, t1, x1, n2, t2,
-                            x2);
-                if (lane == l1 || (two && lane == l2)) {
-                    const bool first = lane == l1;
-                    cnt = first ? n1 : n2;
-                    const unsigned long long nt = first ? t1 : t2, xp = first ? x1 : x2;
+                uint32_t c = __shfl_sync(0xffffffffu, cnt, l), nc;
+                unsigned long long nt, xp;
+                compact_run(warp_runs + (size_t)l * CAND_CAP, c, kk, kp, lane, nc, nt, xp);
+                if (lane == l) {
+                    cnt = nc;
                     if (nt < thr) {
                         thr = nt;
                         changed = true;
                     }
                     // this slice holds kp = ceil(k / n_groups) keys <= xp; once every slice has published, the largest of their
                     // xp is an upper bound of the global k-th key (n_groups * kp >= k keys are <= it)
-                    if (xp != ~0ull) gthr[(size_t)qrow * n_groups + group] = xp;
+                    if (!reg_best && xp != ~0ull) gthr[(size_t)qrow * n_groups + group] = xp;
                 }
             }
-            if ((n & 3) == 1) {
-                const volatile unsigned long long *gx = gthr + (size_t)qrow * n_groups;
+            if (reg_best) {
+                unsigned long long x = best[0];
+#pragma unroll
+                for (int i = 1; i < KP_REG; i++) x = (uint32_t)i < kp ? best[i] : x;  // best[kp-1]
+                if (x < published) {
+                    published = x;
+                    __stcg(gthr + (size_t)qrow * n_groups + group, x);
+                }
+            }
+            if (n < 8 || (n & 7) == 1) {  // every tile while the bound still moves fast, then every eighth
+                const unsigned long long *gx = gthr + (size_t)qrow * n_groups;
                 unsigned long long bound = 0;
-                for (uint32_t g = 0; g < n_groups; g++) {
-                    unsigned long long x = gx[g];
-                    bound = x > bound ? x : bound;
+                for (uint32_t g0 = 0; g0 < n_groups; g0 += 6) {
+                    unsigned long long x[6];
+#pragma unroll
+                    for (int i = 0; i < 6; i++) x[i] = g0 + i < n_groups ? __ldcg(gx + g0 + i) : 0ull;  // L2 reads, issued together
+#pragma unroll
+                    for (int i = 0; i < 6; i++) bound = x[i] > bound ? x[i] : bound;
                 }
                 if (bound < thr) {
                     thr = bound;
@@ -559,10 +595,15 @@ __global__ void __launch_bounds__(256, 1)
             if (dbg) w_cmp += (unsigned long long)(clock64() - t_c0);
         }
         if (dbg && w == 0 && lane == 0) {
-            dbg[blockIdx.x * 8 + 4] = w_full;
-            dbg[blockIdx.x * 8 + 5] = w_meta;
+            dbg[blockIdx.x * 8 + 4] = w_flag;
+            dbg[blockIdx.x * 8 + 5] = w_mine;
             dbg[blockIdx.x * 8 + 6] = w_cmp;
             dbg[blockIdx.x * 8 + 7] = (unsigned long long)(clock64() - t_epi0);
+            dbg[blockIdx.x * 8 + 0] = w_ld;
+            if (dbg_mode != 2) {
+                dbg[blockIdx.x * 8 + 1] = w_p1;
+                dbg[blockIdx.x * 8 + 2] = w_p2;
+            }
         }
         // final: every lane's run sorted, its kk best written to this (query, group) slot
         __syncwarp();
@@ -693,11 +734,13 @@ cudaError_t launch_vec_gemm_topk(cudaStream_t s, uint32_t sm_count, const void *
     cudaError_t em = cudaMemsetAsync(gthr, 0xff, (size_t)n_qtiles * GM * n_groups * 8, s);
     if (em != cudaSuccess) return em;
     unsigned long long *dbg = nullptr;
-    if (getenv("B200_VEC_DEBUG")) {
+    const uint32_t dbg_mode = getenv("B200_VEC_DEBUG") ? (uint32_t)atoi(getenv("B200_VEC_DEBUG")) : 0;
+    if (dbg_mode) {
         if (cudaMalloc((void **)&dbg, (size_t)n_qtiles * n_groups * 64) != cudaSuccess) dbg = nullptr;
         if (dbg) cudaMemsetAsync(dbg, 0, (size_t)n_qtiles * n_groups * 64, s);
     }
-    const bool ts = d % 64 == 0 && !(getenv("B200_VEC_GEMM_SS") && atoi(getenv("B200_VEC_GEMM_SS")) != 0);
+    // default: TMEM-resident query tile (deep matrix ring); B200_VEC_GEMM_TS=0 keeps the query tile in shared memory (k-split accumulators)
+    const bool ts = d % 64 == 0 && !(getenv("B200_VEC_GEMM_TS") && atoi(getenv("B200_VEC_GEMM_TS")) == 0);
     size_t smem = vec_gemm_smem_bytes(d, ts);
     const __half *qh = reinterpret_cast<const __half *>(q_fp16);
     cudaError_t e;
@@ -705,12 +748,12 @@ cudaError_t launch_vec_gemm_topk(cudaStream_t s, uint32_t sm_count, const void *
         e = cudaFuncSetAttribute(vec_gemm_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         vec_gemm_topk_kernel<true><<<n_qtiles * n_groups, 256, smem, s>>>(mq, mm, qh, d, n_rows, d / GK, n_qtiles, n_groups, inv_norm, docids, q_inv_norm,
-                                                                          cand, n_cand_words, k, gthr, runs, partial, dbg);
+                                                                          cand, n_cand_words, k, gthr, runs, partial, dbg, dbg_mode);
     } else {
         e = cudaFuncSetAttribute(vec_gemm_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         vec_gemm_topk_kernel<false><<<n_qtiles * n_groups, 256, smem, s>>>(mq, mm, qh, d, n_rows, d / GK, n_qtiles, n_groups, inv_norm, docids, q_inv_norm,
-                                                                           cand, n_cand_words, k, gthr, runs, partial, dbg);
+                                                                           cand, n_cand_words, k, gthr, runs, partial, dbg, dbg_mode);
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -722,7 +765,7 @@ cudaError_t launch_vec_gemm_topk(cudaStream_t s, uint32_t sm_count, const void *
         double sum[8] = {0};
         for (size_t c = 0; c < (size_t)n_qtiles * n_groups; c++)
             for (int i = 0; i < 8; i++) sum[i] += (double)h[c * 8 + i];
-        const char *names[8] = {"producer wait b_empty", "mma wait acc_empty", "mma wait b_full", "mma total", "epi wait acc_full", "epi wait meta", "epi compaction", "epi total"};
+        const char *names[8] = {"epi tmem ld", dbg_mode == 2 ? "mma wait acc_empty" : "epi pass1", dbg_mode == 2 ? "mma wait b_full" : "epi pass2", "mma total", "warp0 flagged columns", "lane0 flagged", "epi compaction", "epi total"};
         fprintf(stderr, "[b200 vec debug] mean cycles per CTA (%u CTAs):", n_qtiles * n_groups);
         for (int i = 0; i < 8; i++) fprintf(stderr, "  %s %.0f", names[i], sum[i] / (n_qtiles * n_groups));
         fprintf(stderr, "\n");
