@@ -343,7 +343,7 @@ def main():
         "config": workload_config(args, img),
         "e2e": {"value": total_q / wall, "unit": "queries/s", "ms_per_step": 1e3 * wall / args.steps, "p50_batch_ms": 1e3 * float(np.median(lat)),
                 "h2d_bytes_per_step": int(st_e2e["h2d_bytes"] / args.steps), "d2h_bytes_per_step": int(st_e2e["d2h_bytes"] / args.steps),
-                "device_steps_per_batch": st_e2e["device_steps"] / args.steps, "lanes": os.environ.get("B200_DRIVERS", "2") + "x" + os.environ.get("B200_LANES_PER_DRIVER", "2")},
+                "device_steps_per_batch": st_e2e["device_steps"] / args.steps, "lanes": os.environ.get("B200_DRIVERS", "2") + "x" + os.environ.get("B200_LANES_PER_DRIVER", "1")},
         "gpu_launches": int(st_e2e["kernel_launches"]),
         "clocks": clocks,
         "roofline": roofline,

@@ -308,11 +308,12 @@ int Engine::search_batch(const b200_query_batch *b, b200_results *r) {
         fill_values(h);
         return h;
     };
-    for (uint32_t q = 0; q < NQ; q++) {
+    auto merge_one = [&](size_t qi) {
+        const uint32_t q = (uint32_t)qi;
         if (r->status) r->status[q] = kw.status[q];
         if (kw.status[q] != 0) {
             r->n_hits[q] = 0;
-            continue;
+            return;
         }
         std::vector<Hit> K, V;
         for (uint32_t i = 0; i < kw.n_hits[q]; i++) K.push_back(load(kw, q, i));
@@ -369,7 +370,12 @@ int Engine::search_batch(const b200_query_batch *b, b200_results *r) {
                 }
             }
         }
-    }
+    };
+    // the merges of different queries are independent: spread them over the worker pool
+    if (pool)
+        pool->run(NQ, merge_one);
+    else
+        for (uint32_t q = 0; q < NQ; q++) merge_one(q);
     return B200_OK;
 }
 

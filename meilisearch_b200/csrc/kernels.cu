@@ -680,18 +680,17 @@ __global__ void __launch_bounds__(128) eval_dp_kernel(const TileDesc *__restrict
                 const uint32_t hdr = s_prog[i++];
                 const uint32_t nops = hdr >> 16;
                 unsigned long long acc = 0;
-                for (uint32_t e0 = 0; e0 < nops; e0 += 4) {
-                    unsigned long long vv[4], cc[4];
+                for (uint32_t e0 = 0; e0 < nops; e0 += 2) {  // most groups have one or two ops
+                    unsigned long long vv[2], cc[2];
 #pragma unroll
-                    for (int x = 0; x < 4; x++) {
+                    for (int x = 0; x < 2; x++) {
                         const bool have = e0 + x < nops;
                         const uint32_t op = s_prog[i + (have ? e0 + x : 0)];
                         const uint32_t col = op >> 16;
                         vv[x] = have ? S[(size_t)(op & 0xffff) * ld + j] : 0ull;
                         cc[x] = (have && col != 0xffff) ? C[(size_t)col * ld + j] : ~0ull;
                     }
-#pragma unroll
-                    for (int x = 0; x < 4; x++) acc |= vv[x] & cc[x];
+                    acc |= (vv[0] & cc[0]) | (vv[1] & cc[1]);
                 }
                 S[(size_t)(hdr & 0xffff) * ld + j] = acc;
                 i += nops;
