@@ -255,8 +255,9 @@ __global__ void __launch_bounds__(256, 1)
     uint64_t *a_full = bars, *b_full = bars + 1, *b_empty = b_full + NST, *acc_full = b_empty + NST, *acc_empty = acc_full + NACC;
     uint64_t *meta_full = acc_empty + NACC, *meta_empty = meta_full + META_BUFS;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(meta_empty + META_BUFS);
-    uint32_t *s_doc = reinterpret_cast<uint32_t *>(bars + 64);               // [META_BUFS][GN]
-    float *s_scale = reinterpret_cast<float *>(s_doc + META_BUFS * GN);      // [META_BUFS][GN]
+    // row metadata ring: static shared memory, so that the epilogue reads it with (vectorisable) LDS instead of generic loads
+    __shared__ __align__(16) uint32_t s_doc[META_BUFS * GN];
+    __shared__ __align__(16) float s_scale[META_BUFS * GN];
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t qtile = blockIdx.x % n_qtiles, group = blockIdx.x / n_qtiles;
@@ -442,7 +443,7 @@ __global__ void __launch_bounds__(256, 1)
         unsigned long long best[KP_REG];
 #pragma unroll
         for (int i = 0; i < KP_REG; i++) best[i] = ~0ull;
-        unsigned long long published = ~0ull;
+        unsigned long long published = ~0ull, best_kp = ~0ull;  // best_kp == best[kp - 1]
         uint32_t n = 0;
         unsigned long long w_full = 0, w_meta = 0, w_cmp = 0, w_ld = 0, w_p1 = 0, w_p2 = 0, w_flag = 0, w_mine = 0;
         const long long t_epi0 = clock64();
@@ -526,7 +527,7 @@ __global__ void __launch_bounds__(256, 1)
                         const unsigned long long key = ((unsigned long long)__float_as_uint(dd) << 32) | doc;
                         if (doc != 0xffffffffu && key < thr) {
                             my_run[cnt++] = key;
-                            if (reg_best) {  // sorted insertion (ascending), the largest falls off
+                            if (reg_best && key < best_kp) {  // improves this slice's kp best: sorted insertion, the largest falls off
                                 unsigned long long x = key;
 #pragma unroll
                                 for (int i = 0; i < KP_REG; i++) {
@@ -534,6 +535,9 @@ __global__ void __launch_bounds__(256, 1)
                                     best[i] = lo;
                                     x = hi;
                                 }
+                                best_kp = best[0];
+#pragma unroll
+                                for (int i = 1; i < KP_REG; i++) best_kp = (uint32_t)i < kp ? best[i] : best_kp;
                             }
                         }
                     }
@@ -567,16 +571,11 @@ __global__ void __launch_bounds__(256, 1)
                     if (!reg_best && xp != ~0ull) gthr[(size_t)qrow * n_groups + group] = xp;
                 }
             }
-            if (reg_best) {
-                unsigned long long x = best[0];
-#pragma unroll
-                for (int i = 1; i < KP_REG; i++) x = (uint32_t)i < kp ? best[i] : x;  // best[kp-1]
-                if (x < published) {
-                    published = x;
-                    __stcg(gthr + (size_t)qrow * n_groups + group, x);
-                }
+            if (reg_best && best_kp < published) {
+                published = best_kp;
+                __stcg(gthr + (size_t)qrow * n_groups + group, best_kp);
             }
-            if (n < 8 || (n & 7) == 1) {  // every tile while the bound still moves fast, then every eighth
+            if (n < 8 || (n < 64 && (n & 3) == 1) || (n & 15) == 1) {  // every tile while the bound still moves fast, then ever more rarely
                 const unsigned long long *gx = gthr + (size_t)qrow * n_groups;
                 unsigned long long bound = 0;
                 for (uint32_t g0 = 0; g0 < n_groups; g0 += 6) {
@@ -714,7 +713,7 @@ bool make_map(CUtensorMap *m, const void *base, uint64_t rows, uint32_t d, uint3
 }  // namespace
 
 size_t vec_gemm_smem_bytes(uint32_t d, bool ts) {
-    return (ts ? (size_t)STAGES_TS * B_BLOCK : (size_t)(d / GK) * A_BLOCK + STAGES * B_BLOCK) + 512 + META_BUFS * GN * 8 + 1023;
+    return (ts ? (size_t)STAGES_TS * B_BLOCK : (size_t)(d / GK) * A_BLOCK + STAGES * B_BLOCK) + 512 + 1023;  // + 1 KB static (row metadata)
 }
 
 bool vec_gemm_supported(uint32_t d, uint32_t limit) { return d % GK == 0 && d >= GK && d <= 768 && limit >= 1 && limit <= KMAX; }
