@@ -246,6 +246,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    # ranks share the host: keep the per-rank worker pools inside the machine's cores
+    os.environ.setdefault("B200_HOST_THREADS", str(max(8, min(32, (os.cpu_count() or 64) // max(1, world)))))
     img, batches = build_workload(args, rank)
     t = time.time()
     ix = mb.Index(img, device=local_rank)
@@ -343,7 +345,7 @@ def main():
         "config": workload_config(args, img),
         "e2e": {"value": total_q / wall, "unit": "queries/s", "ms_per_step": 1e3 * wall / args.steps, "p50_batch_ms": 1e3 * float(np.median(lat)),
                 "h2d_bytes_per_step": int(st_e2e["h2d_bytes"] / args.steps), "d2h_bytes_per_step": int(st_e2e["d2h_bytes"] / args.steps),
-                "device_steps_per_batch": st_e2e["device_steps"] / args.steps, "lanes": os.environ.get("B200_DRIVERS", "2") + "x" + os.environ.get("B200_LANES_PER_DRIVER", "1")},
+                "device_steps_per_batch": st_e2e["device_steps"] / args.steps, "lanes": os.environ.get("B200_DRIVERS", "4") + "x" + os.environ.get("B200_LANES_PER_DRIVER", "1")},
         "gpu_launches": int(st_e2e["kernel_launches"]),
         "clocks": clocks,
         "roofline": roofline,

@@ -1982,7 +1982,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
     // driver thread and worker sub-pool, so the host phases of one lane overlap both the kernels and the host phases of the others.
     // Drivers are host threads; each alternates between its lanes (software pipeline: while one lane's kernels run, the driver packs
     // and advances its other lane), and the drivers run concurrently.
-    unsigned n_drivers = NQ >= 64 ? 2 : 1, lanes_per_driver = 1;
+    unsigned n_drivers = NQ >= 512 ? 4 : (NQ >= 64 ? 2 : 1), lanes_per_driver = 1;
     if (const char *env = getenv("B200_DRIVERS")) n_drivers = (unsigned)std::max(1, std::min((int)MAX_DRIVERS, atoi(env)));
     if (const char *env = getenv("B200_LANES_PER_DRIVER")) lanes_per_driver = (unsigned)std::max(1, atoi(env));
     if (getenv("B200_SINGLE_LANE")) n_drivers = lanes_per_driver = 1;

@@ -543,7 +543,7 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
 }
 
 // thread per row (64 documents): column program, backward DP over the state graph, buckets, first-match walk
-__global__ void __launch_bounds__(128) eval_dp_kernel(const TileDesc *__restrict__ tiles, const ActDesc *__restrict__ acts,
+__global__ void __launch_bounds__(128, 10) eval_dp_kernel(const TileDesc *__restrict__ tiles, const ActDesc *__restrict__ acts,
                                                       uint32_t *__restrict__ results, const ColOp *__restrict__ colprog,
                                                       const DpState *__restrict__ states, const DpEdge *__restrict__ edges,
                                                       const uint16_t *__restrict__ costpool, PathOut *__restrict__ pathbuf,
