@@ -113,4 +113,12 @@ struct TileDesc {
     uint32_t act, row_begin;
 };
 
+// one segment of COMPACT_SEG parent rows of an activation's compaction (act_count_kernel / act_compact_kernel)
+constexpr uint32_t COMPACT_SEG = 8192;
+struct CompactTile {
+    uint32_t act, seg;
+    uint32_t first_tile;  // index of the activation's segment 0 in the tile list (segment counts are stored per tile)
+    uint32_t n_seg;
+};
+
 }  // namespace b200

@@ -156,7 +156,7 @@ struct Lane {
     cudaStream_t stream = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     DevBuf<uint8_t> d_step;
-    DevBuf<uint32_t> d_results, d_qcount;
+    DevBuf<uint32_t> d_results, d_qcount, d_segcount;
     DevBuf<Job> d_queue;
     DevBuf<PathOut> d_pathbuf;
     uint8_t *h_step = nullptr;
@@ -211,6 +211,7 @@ struct Lane {
         d_results.release();
         d_qcount.release();
         d_queue.release();
+        d_segcount.release();
         d_pathbuf.release();
         if (h_step) cudaFreeHost(h_step);
         if (h_results) cudaFreeHost(h_results);

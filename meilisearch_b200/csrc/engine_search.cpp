@@ -2050,7 +2050,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         const size_t NA = act_q.size();
         // pass 1 (serial, light): sizes, offsets, device memory
         struct Plan {
-            uint32_t jobs, sets, words, colprog, states, edges, costs, tiles, probes, res_off;
+            uint32_t jobs, sets, words, colprog, states, edges, costs, tiles, probes, res_off, ctiles, n_seg;
             uint32_t ld;
             uint8_t *pb;
             size_t coff, toff, soff_from_end;
@@ -2058,6 +2058,8 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         };
         std::vector<Plan> plan(NA);
         uint32_t n_jobs = 0, n_sets = 0, n_words = 0, n_colprog = 0, n_states = 0, n_edges = 0, n_costs_tot = 0, n_tiles = 0, n_probes = 0, res_words = 0;
+        uint32_t n_ctiles = 0;
+        bool multi_segment = false;
         size_t z_used = 0, s_used = 0;
         uint64_t compact_bytes = 0, eval_bytes = 0, fill_bytes = 0;
         for (size_t a = 0; a < NA; a++) {
@@ -2087,6 +2089,10 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             for (auto &ps : o.pairsets) n_probes += ps.n_left * ps.n_right;
             res_words += 2 + o.n_costs;
             pl.identity = !q.p_uw && !q.p_out;  // first activation of a query: the universe is the dense documents bitmap itself
+            pl.n_seg = pl.identity ? 1u : std::max(1u, (q.p_rows + COMPACT_SEG - 1) / COMPACT_SEG);
+            pl.ctiles = n_ctiles;
+            n_ctiles += pl.n_seg;
+            multi_segment = multi_segment || pl.n_seg > 1;
             uint32_t n_cols = std::max(1u, o.n_cols);
             uint32_t tab_size = o.want_paths ? 4096 : 1;
             size_t persist = pl.identity ? (size_t)ld * 8 * (o.n_costs + 1) : (size_t)ld * 4 + 256 + (size_t)ld * 8 + 256 + (size_t)ld * 8 * (o.n_costs + 1);
@@ -2124,7 +2130,8 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         size_t o_acts = section(NA * sizeof(ActDesc)), o_sets = section((size_t)n_sets * sizeof(PairSet)), o_words = section((size_t)n_words * 4),
                o_colprog = section((size_t)n_colprog * sizeof(ColOp)), o_states = section((size_t)n_states * sizeof(DpState)),
                o_edges = section((size_t)n_edges * sizeof(DpEdge)), o_costs = section((size_t)n_costs_tot * 2),
-               o_tiles = section((size_t)n_tiles * sizeof(TileDesc)), o_emits = section((size_t)n_emits * sizeof(EmitDesc)),
+               o_tiles = section((size_t)n_tiles * sizeof(TileDesc)), o_ctiles = section((size_t)n_ctiles * sizeof(CompactTile)),
+               o_emits = section((size_t)n_emits * sizeof(EmitDesc)),
                o_jobs = section((size_t)n_jobs * sizeof(Job)), o_nstatic = section(16);
         size_t nbytes = off + 16;
         if (nbytes > ln.h_step_cap) {
@@ -2208,6 +2215,8 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             }
             TileDesc *td = reinterpret_cast<TileDesc *>(hb + o_tiles) + pl.tiles;
             for (uint32_t r0 = 0, k = 0; r0 < ld; r0 += 128, k++) td[k] = TileDesc{(uint32_t)a, r0};
+            CompactTile *ct = reinterpret_cast<CompactTile *>(hb + o_ctiles) + pl.ctiles;
+            for (uint32_t sg = 0; sg < pl.n_seg; sg++) ct[sg] = CompactTile{(uint32_t)a, sg, pl.ctiles, pl.n_seg};
             q.want_activation = false;
         });
         {
@@ -2256,7 +2265,11 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             CU(ln.d_pathbuf.reserve(PATH_CAP), "path buffer");
             CU(cudaMemsetAsync(ln.d_qcount.p + 1, 0, 4, st), "zero path count");
             size_t t0 = ln.mark();
-            CU(launch_compact(st, dacts, (uint32_t)NA, ln.d_results.p), "compact");
+            CU(ln.d_segcount.reserve(n_ctiles + 1), "segment counts");
+            CU(launch_compact(st, reinterpret_cast<const CompactTile *>(ln.d_step.p + o_ctiles), n_ctiles, multi_segment, dacts, ln.d_segcount.p,
+                              ln.d_results.p),
+               "compact");
+            if (multi_segment) ln.lst.kernel_launches++;  // act_count_kernel
             size_t t1 = ln.mark();
             ln.time_kernel(ln.lst, B200_K_COMPACT, t0, t1, compact_bytes);
             CU(launch_pair_probe(st, reinterpret_cast<const PairSet *>(ln.d_step.p + o_sets), n_sets, n_probes,

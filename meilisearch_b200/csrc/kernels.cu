@@ -285,13 +285,51 @@ __device__ __forceinline__ int find_row(const uint32_t *uw, uint32_t rows, uint3
     return (lo < rows && uw[lo] == w) ? (int)lo : -1;
 }
 
-// one CTA per activation: ordered compaction of the parent's non-zero bucket words.  Each iteration covers 2048 parent rows
-// (4 per thread, loads issued together) so that a 15 k-row parent needs 8 rounds of global-memory latency, not 61.
+// Ordered compaction of the parent's non-zero bucket words, split into segments of COMPACT_SEG parent rows (one CTA each) so that a
+// 150 k-row parent is compacted by 19 CTAs instead of one.  Pass 1 (act_count_kernel) counts the surviving rows of every segment;
+// pass 2 starts each segment at the sum of the earlier segments' counts and compacts it in rounds of 2048 rows (4 per thread, loads
+// issued together).
 constexpr int COMPACT_THREADS = 512, COMPACT_PER_THREAD = 4;
-__global__ void __launch_bounds__(COMPACT_THREADS) act_compact_kernel(const ActDesc *__restrict__ acts, uint32_t *__restrict__ results) {
-    const ActDesc a = acts[blockIdx.x];
+__device__ __forceinline__ unsigned long long compact_row_value(const ActDesc &a, uint32_t j) {
+    if (!a.p_out) return a.p_ub[j];
+    unsigned long long v = 0;
+    for (uint32_t c = a.p_col_lo; c < a.p_col_hi; c++) v |= a.p_out[(size_t)c * a.p_ld + j];
+    return v;
+}
+__global__ void __launch_bounds__(COMPACT_THREADS) act_count_kernel(const CompactTile *__restrict__ tiles, const ActDesc *__restrict__ acts,
+                                                                    uint32_t *__restrict__ seg_count) {
+    const CompactTile t = tiles[blockIdx.x];
+    const ActDesc &a = acts[t.act];
+    if (t.n_seg <= 1) return;  // single segment: pass 2 needs no base
+    __shared__ uint32_t warp_sums[COMPACT_THREADS / 32];
+    const uint32_t r0 = t.seg * COMPACT_SEG, r1 = min(a.p_rows, r0 + COMPACT_SEG);
+    uint32_t c = 0;
+    for (uint32_t j0 = r0; j0 < r1; j0 += COMPACT_THREADS * COMPACT_PER_THREAD) {
+        unsigned long long v[COMPACT_PER_THREAD];
+#pragma unroll
+        for (int i = 0; i < COMPACT_PER_THREAD; i++) {
+            uint32_t j = j0 + (uint32_t)i * COMPACT_THREADS + threadIdx.x;
+            v[i] = j < r1 ? compact_row_value(a, j) : 0ull;
+        }
+#pragma unroll
+        for (int i = 0; i < COMPACT_PER_THREAD; i++) c += v[i] != 0 ? 1u : 0u;
+    }
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) c += __shfl_xor_sync(0xffffffffu, c, sft);
+    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int k = 0; k < COMPACT_THREADS / 32; k++) tot += warp_sums[k];
+        seg_count[blockIdx.x] = tot;
+    }
+}
+__global__ void __launch_bounds__(COMPACT_THREADS) act_compact_kernel(const CompactTile *__restrict__ tiles, const ActDesc *__restrict__ acts,
+                                                                      const uint32_t *__restrict__ seg_count, uint32_t *__restrict__ results) {
+    const CompactTile t = tiles[blockIdx.x];
+    const ActDesc a = acts[t.act];
     if (!a.uw) {  // the activation works directly on the dense base universe (row j == word j): nothing to compact
-        if (threadIdx.x == 0) results[a.res_off] = a.p_rows;
+        if (threadIdx.x == 0 && t.seg == 0) results[a.res_off] = a.p_rows;
         return;
     }
     constexpr int NW = COMPACT_THREADS / 32;
@@ -300,7 +338,9 @@ __global__ void __launch_bounds__(COMPACT_THREADS) act_compact_kernel(const ActD
     __shared__ uint32_t s_total;
     const uint32_t lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
     uint32_t base = 0;
-    for (uint32_t j0 = 0; j0 < a.p_rows; j0 += COMPACT_THREADS * COMPACT_PER_THREAD) {
+    for (uint32_t sg = 0; sg < t.seg; sg++) base += seg_count[t.first_tile + sg];  // <= a few dozen
+    const uint32_t r0 = t.seg * COMPACT_SEG, r1 = min(a.p_rows, r0 + COMPACT_SEG);
+    for (uint32_t j0 = r0; j0 < r1; j0 += COMPACT_THREADS * COMPACT_PER_THREAD) {
         unsigned long long v[COMPACT_PER_THREAD];
         uint32_t src[COMPACT_PER_THREAD];
 #pragma unroll
@@ -308,11 +348,8 @@ __global__ void __launch_bounds__(COMPACT_THREADS) act_compact_kernel(const ActD
             uint32_t j = j0 + (uint32_t)i * COMPACT_THREADS + threadIdx.x;
             v[i] = 0;
             src[i] = j;
-            if (j < a.p_rows) {
-                if (a.p_out) {
-                    for (uint32_t c = a.p_col_lo; c < a.p_col_hi; c++) v[i] |= a.p_out[(size_t)c * a.p_ld + j];
-                } else
-                    v[i] = a.p_ub[j];
+            if (j < r1) {
+                v[i] = compact_row_value(a, j);
                 if (a.p_uw) src[i] = a.p_uw[j];
             }
         }
@@ -354,7 +391,7 @@ __global__ void __launch_bounds__(COMPACT_THREADS) act_compact_kernel(const ActD
         base += s_total;
         __syncthreads();
     }
-    if (threadIdx.x == 0) results[a.res_off] = min(base, a.ld);
+    if (threadIdx.x == 0 && t.seg + 1 == t.n_seg) results[a.res_off] = min(base, a.ld);
 }
 
 __device__ __forceinline__ int64_t pair_lower_bound(const unsigned long long *keys, uint64_t n, unsigned long long k) {
@@ -834,46 +871,59 @@ __global__ void __launch_bounds__(128, 10) eval_dp_kernel(const TileDesc *__rest
         if (counts[i]) atomicAdd(&results[a.res_off + 1 + i], counts[i]);
 }
 
-// one warp per emission: ascending docids of OR(out[col_lo..col_hi)), skipping `skip`, taking `take`
+// one warp per emission: ascending docids of OR(out[col_lo..col_hi)), skipping `skip`, taking `take`.
+// 256 rows per round — 8 consecutive rows per lane, loads issued together — because a sparse bucket of a large universe is a long
+// scan (a 20-document bucket of a 150 k-row universe) whose cost is the number of dependent global-memory round trips.
+constexpr int EMIT_ROWS_PER_LANE = 8;
 __global__ void __launch_bounds__(128) emit_kernel(const EmitDesc *__restrict__ emits, uint32_t n_emits) {
     uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (e >= n_emits) return;
     const EmitDesc d = emits[e];
     uint32_t lane = threadIdx.x & 31;
-    uint32_t seen = 0, written = 0;
-    for (uint32_t j0 = 0; j0 < d.rows && written < d.take; j0 += 32) {
-        uint32_t j = j0 + lane;
-        unsigned long long v = 0;
-        if (j < d.rows) {
-            if (d.out) {
-                for (uint32_t c = d.col_lo; c < d.col_hi; c++) v |= d.out[(size_t)c * d.ld + j];
-            } else
-                v = d.ub[j];
+    uint32_t seen = 0;  // documents of the bucket in the rows before this round
+    for (uint32_t j0 = 0; j0 < d.rows && seen < d.skip + d.take; j0 += 32 * EMIT_ROWS_PER_LANE) {
+        const uint32_t jb = j0 + lane * EMIT_ROWS_PER_LANE;
+        unsigned long long v[EMIT_ROWS_PER_LANE];
+#pragma unroll
+        for (int i = 0; i < EMIT_ROWS_PER_LANE; i++) {
+            const uint32_t j = jb + i;
+            v[i] = 0;
+            if (j < d.rows) {
+                if (d.out) {
+                    for (uint32_t c = d.col_lo; c < d.col_hi; c++) v[i] |= d.out[(size_t)c * d.ld + j];
+                } else
+                    v[i] = d.ub[j];
+            }
         }
-        uint32_t pc = (uint32_t)__popcll(v);
+        uint32_t pc = 0;
+#pragma unroll
+        for (int i = 0; i < EMIT_ROWS_PER_LANE; i++) pc += (uint32_t)__popcll(v[i]);
         uint32_t pre = pc;
 #pragma unroll
         for (int s = 1; s < 32; s <<= 1) {
             uint32_t t = __shfl_up_sync(0xffffffffu, pre, s);
             if (lane >= (uint32_t)s) pre += t;
         }
-        uint32_t total = __shfl_sync(0xffffffffu, pre, 31);
-        uint32_t first = seen + pre - pc;  // rank of this lane's first doc within the bucket
-        if (v) {
-            uint32_t base = d.uw ? d.uw[j] : j;
-            uint32_t rk = first;
-            while (v) {
-                uint32_t bit = (uint32_t)__ffsll((long long)v) - 1;
-                v &= v - 1;
-                if (rk >= d.skip) {
-                    uint32_t o = rk - d.skip;
-                    if (o < d.take) d.dst[o] = base * 64 + bit;
+        const uint32_t total = __shfl_sync(0xffffffffu, pre, 31);
+        uint32_t rk = seen + pre - pc;  // rank of this lane's first document within the bucket
+        if (pc && rk < d.skip + d.take && rk + pc > d.skip) {
+#pragma unroll
+            for (int i = 0; i < EMIT_ROWS_PER_LANE; i++) {
+                unsigned long long x = v[i];
+                if (!x) continue;
+                const uint32_t base = d.uw ? d.uw[jb + i] : jb + i;
+                while (x) {
+                    uint32_t bit = (uint32_t)__ffsll((long long)x) - 1;
+                    x &= x - 1;
+                    if (rk >= d.skip) {
+                        uint32_t o = rk - d.skip;
+                        if (o < d.take) d.dst[o] = base * 64 + bit;
+                    }
+                    rk++;
                 }
-                rk++;
             }
         }
         seen += total;
-        written = seen > d.skip ? seen - d.skip : 0;
     }
 }
 
@@ -1054,9 +1104,11 @@ cudaError_t launch_lev(cudaStream_t s, const uint8_t *dict_bytes, const uint32_t
     return cudaGetLastError();
 }
 
-cudaError_t launch_compact(cudaStream_t s, const ActDesc *acts, uint32_t n_acts, uint32_t *results) {
-    if (!n_acts) return cudaSuccess;
-    act_compact_kernel<<<n_acts, COMPACT_THREADS, 0, s>>>(acts, results);
+cudaError_t launch_compact(cudaStream_t s, const CompactTile *tiles, uint32_t n_tiles, bool multi_segment, const ActDesc *acts,
+                           uint32_t *seg_count, uint32_t *results) {
+    if (!n_tiles) return cudaSuccess;
+    if (multi_segment) act_count_kernel<<<n_tiles, COMPACT_THREADS, 0, s>>>(tiles, acts, seg_count);
+    act_compact_kernel<<<n_tiles, COMPACT_THREADS, 0, s>>>(tiles, acts, seg_count, results);
     return cudaGetLastError();
 }
 cudaError_t launch_pair_probe(cudaStream_t s, const PairSet *sets, uint32_t n_sets, uint32_t n_probes, const uint32_t *wordpool,

@@ -54,6 +54,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// BACKOFF > 0: sleep that many nanoseconds after a failed poll — the single-thread roles share their scheduler with an epilogue
+// warp, and a tight polling loop takes half of its issue slots
+template <int BACKOFF = 0>
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
@@ -67,16 +70,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             : "r"(addr), "r"(parity)
             : "memory");
         if (done) break;
+        if (BACKOFF > 0) __nanosleep(BACKOFF);
         if (++spins > (1ull << 26)) __trap();  // a lost arrival must not hang the device
     }
 }
+template <int BACKOFF = 0>
 __device__ __forceinline__ void mbar_wait_t(uint64_t *bar, uint32_t parity, unsigned long long &acc, bool on) {
     if (!on) {
-        mbar_wait(bar, parity);
+        mbar_wait<BACKOFF>(bar, parity);
         return;
     }
     long long t0 = clock64();
-    mbar_wait(bar, parity);
+    mbar_wait<BACKOFF>(bar, parity);
     acc += (unsigned long long)(clock64() - t0);
 }
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int32_t c0, int32_t c1) {
@@ -301,7 +306,7 @@ __global__ void __launch_bounds__(256, 1)
         unsigned long long w_prod = 0;
         for (uint64_t t = tile_lo; t < tile_hi; t++)
             for (uint32_t kb = 0; kb < kblocks; kb++) {
-                mbar_wait_t(b_empty + s, ph ^ 1, w_prod, false);
+                mbar_wait_t<128>(b_empty + s, ph ^ 1, w_prod, false);
                 if (leader) {
                     mbar_expect_tx(b_full + s, B_BLOCK);
                     tma_load_2d(sB + (size_t)s * B_BLOCK, &tmap_m, b_full + s, (int32_t)(kb * GK), (int32_t)(t * GN));
@@ -341,11 +346,11 @@ __global__ void __launch_bounds__(256, 1)
             uint32_t n = par;
             for (uint64_t t = tile_lo + par; t < tile_hi; t += step, n += step) {
                 const uint32_t buf = n & 1, aph = (n >> 1) & 1;
-                mbar_wait_t(acc_empty + buf, aph ^ 1, w_acc, dbg != nullptr);
+                mbar_wait_t<32>(acc_empty + buf, aph ^ 1, w_acc, dbg != nullptr);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + ACC_COL0 + buf * (KS * GN);
                 for (uint32_t kb = 0; kb < kblocks; kb++) {
-                    mbar_wait_t(b_full + s, ph, w_b, dbg != nullptr);
+                    mbar_wait_t<32>(b_full + s, ph, w_b, dbg != nullptr);
                     tc_fence_after();
                     const uint64_t bd = bd0 + (uint64_t)s * (B_BLOCK >> 4);
                     if (TS) {
@@ -389,7 +394,7 @@ __global__ void __launch_bounds__(256, 1)
         uint32_t n = 0;
         for (uint64_t t = tile_lo; t < tile_hi; t++, n++) {
             const uint32_t mb = n % META_BUFS, mph = (n / META_BUFS) & 1;
-            mbar_wait(meta_empty + mb, mph ^ 1);
+            mbar_wait<128>(meta_empty + mb, mph ^ 1);
 #pragma unroll
             for (int h = 0; h < GN / 32; h++) {
                 const uint64_t r = t * GN + (uint32_t)h * 32u + lane;

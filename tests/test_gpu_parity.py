@@ -274,3 +274,20 @@ def test_unsupported_is_reported_not_faked(mb, synth):
     assert res.status[2] == -4 and res.n_hits[2] == 0
     # with the default words_limit (10) the same long query is in scope
     assert ix.search().query([long_query]).execute().status[0] == 0
+
+
+def test_large_universe_matches_oracle(mb):
+    """More than 8192 x 64 documents: universes span several compaction segments and the emit scan runs many rounds."""
+    from oracle.pyoracle import OracleIndex
+    from tests.helpers import synthetic_image
+
+    img = synthetic_image(700_000, 60_000, seed=0xB201)
+    queries = img.synthetic_queries(48, seed=9)
+    tokens = mb.TokenBatch(queries)
+    got = mb.Index(img).search().query(tokens).scoring_strategy("detailed").execute()
+    want = OracleIndex(img).search_batch(tokens, scoring="detailed", n_threads=8)
+    for q in range(len(queries)):
+        assert got.status[q] == 0
+        assert got.ids(q) == want.ids(q), queries[q]
+        assert got.scores(q) == want.scores(q), queries[q]
+        assert int(got.n_candidates[q]) == int(want.n_candidates[q])
