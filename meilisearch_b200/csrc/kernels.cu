@@ -107,13 +107,7 @@ __global__ void __launch_bounds__(256) lev_match_kernel(const uint8_t *__restric
     __shared__ uint32_t s_queue[LEV_TERM_GROUP * 256];  // (term << 16) | word-in-tile | (same-first << 31)
     __shared__ uint32_t s_qn;
     __shared__ unsigned long long s_codes[LEV_TERM_GROUP][8];
-    uint32_t t0 = blockIdx.y * LEV_TERMS_PER_CTA;
-    uint32_t nt = min((uint32_t)LEV_TERMS_PER_CTA, n_terms - t0);
-    {
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(terms + t0);
-        uint32_t *dst = reinterpret_cast<uint32_t *>(sterms);
-        for (uint32_t i = threadIdx.x; i < nt * sizeof(LevTerm) / 4; i += blockDim.x) dst[i] = src[i];
-    }
+    // the CTA stages its 256 dictionary words once and sweeps the term chunks blockIdx.y, blockIdx.y + gridDim.y, ... over them
     uint32_t w0 = blockIdx.x * 256;
     uint32_t wn = min(256u, n_words - w0);
     uint32_t byte0 = dict_off[w0], byte1 = dict_off[w0 + wn];
@@ -123,12 +117,6 @@ __global__ void __launch_bounds__(256) lev_match_kernel(const uint8_t *__restric
         for (uint32_t i = threadIdx.x; i <= wn; i += blockDim.x) s_woff[i] = (uint16_t)(dict_off[w0 + i] - byte0);
     }
     __syncthreads();
-    if (threadIdx.x < nt) {
-        const LevTerm &T = sterms[threadIdx.x];
-        sterm_sig[threadIdx.x] = char_signature(T.q, T.len);
-        sterm_meta[threadIdx.x] = (uint32_t)T.len | ((uint32_t)(T.k_same + 1) << 8) | ((uint32_t)(T.k_diff + 1) << 12) |
-                                  ((uint32_t)(T.prefix ? 1 : 0) << 16) | ((uint32_t)T.q[0] << 24);
-    }
     uint32_t wid = w0 + threadIdx.x;
     bool valid = threadIdx.x < wn;
     uint32_t off = valid ? dict_off[wid] : byte0;
@@ -136,6 +124,23 @@ __global__ void __launch_bounds__(256) lev_match_kernel(const uint8_t *__restric
     const uint8_t *w = in_smem ? (sbytes + (off - byte0)) : (dict_bytes + off);
     uint8_t w0c = n > 0 ? w[0] : 0, w1c = n > 1 ? w[1] : 0;
     const uint32_t wsig = char_signature(w, n);
+    const uint32_t n_chunks = (n_terms + LEV_TERMS_PER_CTA - 1) / LEV_TERMS_PER_CTA;
+    for (uint32_t chunk = blockIdx.y; chunk < n_chunks; chunk += gridDim.y) {
+    const uint32_t t0 = chunk * LEV_TERMS_PER_CTA;
+    const uint32_t nt = min((uint32_t)LEV_TERMS_PER_CTA, n_terms - t0);
+    __syncthreads();  // the previous chunk's terms are no longer read
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(terms + t0);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(sterms);
+        for (uint32_t i = threadIdx.x; i < nt * sizeof(LevTerm) / 4; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < nt) {
+        const LevTerm &T = sterms[threadIdx.x];
+        sterm_sig[threadIdx.x] = char_signature(T.q, T.len);
+        sterm_meta[threadIdx.x] = (uint32_t)T.len | ((uint32_t)(T.k_same + 1) << 8) | ((uint32_t)(T.k_diff + 1) << 12) |
+                                  ((uint32_t)(T.prefix ? 1 : 0) << 16) | ((uint32_t)T.q[0] << 24);
+    }
     for (uint32_t tg = 0; tg < nt; tg += LEV_TERM_GROUP) {
         const uint32_t ng = min((uint32_t)LEV_TERM_GROUP, nt - tg);
         if (threadIdx.x == 0) s_qn = 0;
@@ -205,6 +210,7 @@ __global__ void __launch_bounds__(256) lev_match_kernel(const uint8_t *__restric
             }
         }
         __syncthreads();
+    }
     }
 }
 
@@ -479,9 +485,24 @@ __device__ __forceinline__ void scatter_job_coop(const Job job, const ActDesc &a
     if (lr.dense) {
         const unsigned long long *words = reinterpret_cast<const unsigned long long *>(pool + lr.off);
         uint32_t r0 = job.chunk * JOB_CHUNK, r1 = min(rows, r0 + JOB_CHUNK);
-        for (uint32_t j = r0 + lane; j < r1; j += 32) {
-            unsigned long long v = words[a.uw ? a.uw[j] : j] & a.ub[j];
-            if (v) atomicOr(&col[j], v);
+        // four rows per lane and round: the three dependent loads (row -> word index -> list word, universe word) of the four rows
+        // are in flight together
+        for (uint32_t j0 = r0 + lane; j0 < r1; j0 += 128) {
+            uint32_t wi[4];
+            unsigned long long ubv[4], lw[4];
+#pragma unroll
+            for (int x = 0; x < 4; x++) {
+                const uint32_t j = j0 + 32 * x;
+                wi[x] = j < r1 ? (a.uw ? a.uw[j] : j) : 0;
+                ubv[x] = j < r1 ? a.ub[j] : 0ull;
+            }
+#pragma unroll
+            for (int x = 0; x < 4; x++) lw[x] = ubv[x] ? words[wi[x]] : 0ull;
+#pragma unroll
+            for (int x = 0; x < 4; x++) {
+                const unsigned long long v = lw[x] & ubv[x];
+                if (v) atomicOr(&col[j0 + 32 * x], v);
+            }
         }
         return;
     }
@@ -510,12 +531,20 @@ __device__ __forceinline__ void scatter_job_coop(const Job job, const ActDesc &a
         return;
     }
     uint32_t e0 = job.chunk * JOB_CHUNK, e1 = min(lr.card, e0 + JOB_CHUNK);
-    for (uint32_t e = e0 + lane; e < e1; e += 32) {
-        uint32_t d = ids[e];
-        int j = act_row(a, rows, d >> 6);
-        if (j >= 0) {
-            unsigned long long bit = 1ull << (d & 63);
-            if (a.ub[j] & bit) atomicOr(&col[j], bit);
+    for (uint32_t eb = e0 + lane; eb < e1; eb += 128) {  // four docids per lane and round, their lookups in flight together
+        uint32_t d[4];
+        int jr[4];
+        unsigned long long ubv[4];
+#pragma unroll
+        for (int x = 0; x < 4; x++) d[x] = eb + 32 * x < e1 ? ids[eb + 32 * x] : 0xffffffffu;
+#pragma unroll
+        for (int x = 0; x < 4; x++) jr[x] = d[x] != 0xffffffffu ? act_row(a, rows, d[x] >> 6) : -1;
+#pragma unroll
+        for (int x = 0; x < 4; x++) ubv[x] = jr[x] >= 0 ? a.ub[jr[x]] : 0ull;
+#pragma unroll
+        for (int x = 0; x < 4; x++) {
+            const unsigned long long bit = 1ull << (d[x] & 63);
+            if (ubv[x] & bit) atomicOr(&col[jr[x]], bit);
         }
     }
 }
@@ -1098,7 +1127,8 @@ cudaError_t launch_lev(cudaStream_t s, const uint8_t *dict_bytes, const uint32_t
                        uint32_t *n_two, int32_t *status) {
     if (n_terms == 0 || n_words == 0) return cudaSuccess;
     CK(cudaMemsetAsync(rec_count, 0, sizeof(uint32_t) * n_terms, s));
-    dim3 grid((n_words + 255) / 256, (n_terms + LEV_TERMS_PER_CTA - 1) / LEV_TERMS_PER_CTA);
+    const uint32_t n_chunks = (n_terms + LEV_TERMS_PER_CTA - 1) / LEV_TERMS_PER_CTA;
+    dim3 grid((n_words + 255) / 256, n_chunks < 8 ? n_chunks : 8);  // every CTA sweeps n_chunks / 8 term chunks over its word tile
     lev_match_kernel<<<grid, 256, 0, s>>>(dict_bytes, dict_off, n_words, terms, n_terms, recs, rec_count);
     lev_finalize_kernel<<<(n_terms + 63) / 64, 64, 0, s>>>(recs, rec_count, terms, n_terms, one_out, n_one, two_out, n_two, status);
     return cudaGetLastError();
