@@ -224,7 +224,8 @@ struct Lane {
 
 struct Engine {
     std::unique_ptr<WorkerPool> pool;
-    std::thread reaper;  // frees the previous batch's per-query state in the background
+    std::vector<std::thread> reapers;  // free the previous batch's per-query state in the background (several: one thread cannot
+                                       // free a batch's worth of small allocations within the next batch's time)
     static constexpr unsigned MAX_LANES = 8, MAX_DRIVERS = 4;
     Lane lanes[MAX_LANES];
     std::unique_ptr<WorkerPool> driver_pools[MAX_DRIVERS];

@@ -2454,10 +2454,16 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
                 prof_ns[0] / 1e6, prof_ns[1] / 1e6, prof_ns[2] / 1e6, prof_ns[3] / 1e6);
 #undef PROF
     // tear the per-query state down off the critical path
-    if (reaper.joinable()) reaper.join();
+    for (auto &t : reapers)
+        if (t.joinable()) t.join();
+    reapers.clear();
     {
-        auto *dead = new std::vector<std::unique_ptr<QState>>(std::move(qs));
-        reaper = std::thread([dead]() { delete dead; });
+        const size_t n_reapers = 4, per = (qs.size() + n_reapers - 1) / n_reapers;
+        for (size_t r0 = 0; r0 < qs.size(); r0 += std::max<size_t>(1, per)) {
+            auto *dead = new std::vector<std::unique_ptr<QState>>();
+            for (size_t i = r0; i < std::min(qs.size(), r0 + per); i++) dead->push_back(std::move(qs[i]));
+            reapers.emplace_back([dead]() { delete dead; });
+        }
     }
     stats.host_ms[6] += ms_since(t_ph);
     stats.host_ms[7] += ms_since(t_total);

@@ -28,7 +28,9 @@ static cudaError_t upload(T **dst, const T *src, size_t n) {
 }
 
 Engine::~Engine() {
-    if (reaper.joinable()) reaper.join();
+    for (auto &t : reapers)
+        if (t.joinable()) t.join();
+    reapers.clear();
     cudaSetDevice(device);
     for (void *p : {(void *)dix.dict_bytes, (void *)dix.dict_off, (void *)dix.pool, (void *)dix.lists, (void *)dix.pair_keys, (void *)dix.base_ub,
                     (void *)dix.emb, (void *)dix.emb_inv_norm, (void *)dix.emb_docids, (void *)arena, (void *)scratch})
