@@ -99,6 +99,16 @@ int b200_stage_distribution(b200_index *, int enabled, float mean, float sigma);
 int b200_derive_batch(b200_index *, uint32_t n_words, const char *words, const uint32_t *word_off, const uint8_t *max_typo,
                       const uint8_t *is_prefix, uint32_t *one_out, uint32_t *n_one, uint32_t *two_out, uint32_t *n_two);
 
+/* ---- S2: condition resolver (union-shaped conditions) ---------------------------------- */
+/* Replaces the posting-list part of G::resolve_condition as called by ConditionDocIdsCache::get_computed_condition
+ * (crates/milli/src/search/new/ranking_rule_graph/condition_docids_cache.rs:34-57; the unions are
+ * compute_query_term_subset_docids, crates/milli/src/search/new/resolve_query_graph.rs:33-59): out = (OR of the posting lists of
+ * `db` at key indices key_index[0..n_keys)) AND universe.  db: the b200_stage_db id; a key index is the position of the key in the
+ * database as staged (LMDB order).  universe: dense little-endian u64 words over docids, NULL = all documents; out: the same
+ * shape, ceil((max docid + 1) / 64) words. */
+int b200_union_postings(b200_index *, int db, const uint32_t *key_index, uint32_t n_keys, const uint64_t *universe, uint64_t n_universe_words,
+                        uint64_t *out);
+
 /* ---- S4: vector store ------------------------------------------------------------------ */
 /* Replaces VectorStore::nns_by_vector (crates/milli/src/vector/store.rs:638-675) for a batch of queries:
  * exact scan, ascending distance (1 - cos)/2, ties by ascending docid.

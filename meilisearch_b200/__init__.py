@@ -93,6 +93,7 @@ def load_library():
         l.b200_stage_embeddings.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
         l.b200_stage_distribution.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float]
         l.b200_derive_batch.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_void_p] * 4
+        l.b200_union_postings.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
         l.b200_nns_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
         l.b200_search_batch.argtypes = [C.c_void_p, C.POINTER(_Batch), C.POINTER(_Results)]
         l.b200_get_stats.argtypes = [C.c_void_p, C.POINTER(_Stats)]
@@ -103,7 +104,7 @@ def load_library():
 
 SYMBOLS = ["b200_open", "b200_close", "b200_last_error", "b200_open_error", "b200_stage_dictionary", "b200_stage_db",
            "b200_stage_documents_ids", "b200_stage_settings", "b200_stage_synonyms", "b200_stage_finish", "b200_stage_embeddings", "b200_stage_distribution",
-           "b200_derive_batch", "b200_nns_batch", "b200_search_batch", "b200_get_stats", "b200_reset_stats"]
+           "b200_derive_batch", "b200_union_postings", "b200_nns_batch", "b200_search_batch", "b200_get_stats", "b200_reset_stats"]
 
 
 def _p(a):
@@ -170,6 +171,7 @@ class Index:
         """image: anything with dict_bytes/dict_offsets/n_words, dbs[i].{key_bytes,key_offsets,val_bytes,val_offsets,n_keys},
         documents_ids_cbo, n_fields — i.e. the LMDB databases in their on-disk formats."""
         l = self._l
+        self._n_docs = int(image.n_docs)
         self._ck(l.b200_stage_dictionary(self._h, _p(image.dict_bytes), _p(image.dict_offsets), image.n_words))
         for i, db in enumerate(image.dbs):
             self._ck(l.b200_stage_db(self._h, i, db.n_keys, _p(db.key_bytes), _p(db.key_offsets), _p(db.val_bytes), _p(db.val_offsets)))
@@ -212,6 +214,15 @@ class Index:
         return [(one[i, : n1[i]].copy(), two[i, : n2[i]].copy()) for i in range(n)]
 
     # S4 — VectorStore::nns_by_vector (vector/store.rs:638-675)
+    def union_postings(self, db, key_indices, universe=None):
+        """S2: (OR of the posting lists of database `db` at the given key positions) AND universe, as dense u64 words."""
+        keys = np.ascontiguousarray(key_indices, np.uint32)
+        n_words = (self._n_docs + 63) // 64
+        out = np.zeros(n_words, np.uint64)
+        uni = None if universe is None else np.ascontiguousarray(universe, np.uint64)
+        self._ck(self._l.b200_union_postings(self._h, int(db), _p(keys), len(keys), _p(uni), 0 if uni is None else len(uni), _p(out)))
+        return out
+
     def nns_by_vector(self, queries, limit, candidates=None):
         q = np.ascontiguousarray(np.atleast_2d(queries), np.float32)
         n = q.shape[0]

@@ -144,6 +144,11 @@ int b200_nns_batch(b200_index *h, const float *q, uint32_t n_q, uint32_t d, uint
     std::lock_guard<std::mutex> g(h->e.mu);
     return h->e.nns_batch(q, n_q, d, limit, cand, ncw, ids, dist, n_out);
 }
+int b200_union_postings(b200_index *h, int db, const uint32_t *key_index, uint32_t n_keys, const uint64_t *universe, uint64_t n_universe_words,
+                        uint64_t *out) {
+    std::lock_guard<std::mutex> g(h->e.mu);
+    return h->e.union_postings(db, key_index, n_keys, universe, n_universe_words, out);
+}
 int b200_search_batch(b200_index *h, const b200_query_batch *b, b200_results *r) {
     std::lock_guard<std::mutex> g(h->e.mu);
     if (!h->e.staged) return h->e.fail(B200_ERR_STATE, "search before b200_stage_finish");

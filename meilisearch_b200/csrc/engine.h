@@ -300,6 +300,8 @@ struct Engine {
     int nns_batch(const float *queries, uint32_t n_q, uint32_t d, uint32_t limit, const uint64_t *cand, uint64_t n_cand_words, uint32_t *ids_out,
                   float *dist_out, uint32_t *n_out);
     int search_batch(const b200_query_batch *b, b200_results *r);
+    int union_postings(int db, const uint32_t *key_index, uint32_t n_keys, const uint64_t *universe, uint64_t n_universe_words, uint64_t *out);
+    DevBuf<uint8_t> d_s2;  // S2 scratch: universe | column | ActDesc | jobs | counters
     int keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t offset, uint32_t limit, int scoring);
     int semantic_batch(const b200_query_batch *b, b200_results *r, uint32_t offset, uint32_t limit);
     ~Engine();

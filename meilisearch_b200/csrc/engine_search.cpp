@@ -690,7 +690,7 @@ uint16_t bucketed_position(uint16_t rel) {  // lib.rs:248-260
 struct CondTable {
     std::vector<ECond> items;
     CondTable() { items.reserve(48); }
-    uint32_t insert(ECond c) {
+    uint32_t insert(ECond &&c) {
         items.push_back(std::move(c));
         return (uint32_t)items.size() - 1;
     }
@@ -729,7 +729,7 @@ std::vector<std::pair<uint32_t, uint32_t>> build_edges(const QCtx &c, int rule, 
                 if (n != 1) x.term.ts.one = ESubset{};
                 if (n != 2) x.term.ts.two = ESubset{};
                 x.end_subset = x.term;
-                edges.push_back({n + bc, ct.insert(x)});
+                edges.push_back({n + bc, ct.insert(std::move(x))});
             }
             break;
         }
@@ -746,7 +746,7 @@ std::vector<std::pair<uint32_t, uint32_t>> build_edges(const QCtx &c, int rule, 
                 x.cost = (uint8_t)(cost + 1);
                 x.has_start = true;
                 x.start_subset = *from;
-                edges.push_back({cost, ct.insert(x)});
+                edges.push_back({cost, ct.insert(std::move(x))});
             }
             edges.push_back({3 + rmax, base_id()});
             break;
@@ -771,7 +771,7 @@ std::vector<std::pair<uint32_t, uint32_t>> build_edges(const QCtx &c, int rule, 
                 ECond x = base();
                 x.has_fid = true;
                 x.fid = fid;
-                edges.push_back({(uint32_t)weight * to.n_term_ids(), ct.insert(x)});
+                edges.push_back({(uint32_t)weight * to.n_term_ids(), ct.insert(std::move(x))});
             }
             uint16_t mw = c.ix.settings.max_weight();
             if (cur_max < mw) edges.push_back({(uint32_t)mw * to.n_term_ids(), ct.insert(base())});
@@ -800,7 +800,7 @@ std::vector<std::pair<uint32_t, uint32_t>> build_edges(const QCtx &c, int rule, 
             for (auto &kv : by_cost) {
                 ECond x = base();
                 x.positions = kv.second;
-                edges.push_back({kv.first, ct.insert(x)});
+                edges.push_back({kv.first, ct.insert(std::move(x))});
             }
             if (!by_cost.count(max_cost)) edges.push_back({max_cost, ct.insert(base())});
             break;
@@ -820,7 +820,7 @@ std::vector<std::pair<uint32_t, uint32_t>> build_edges(const QCtx &c, int rule, 
                 }
                 e.end_subset.ts.mandatory = true;
             }
-            uint32_t ei = ct.insert(e), ai = ct.insert(base());
+            uint32_t ei = ct.insert(std::move(e)), ai = ct.insert(base());
             edges.push_back({0, ei});
             edges.push_back({to.n_term_ids(), ai});
             break;

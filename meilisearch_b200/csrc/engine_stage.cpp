@@ -115,8 +115,10 @@ int Engine::stage_finish() {
         const char *v = getenv(name);
         return v ? (size_t)atoll(v) << 20 : dflt;
     };
-    arena_bytes = env_mb("B200_ARENA_MB", std::min<size_t>(free_b / 4, (size_t)24 << 30));
-    scratch_bytes = env_mb("B200_SCRATCH_MB", std::min<size_t>(free_b / 8, (size_t)12 << 30));
+    // sized for 180 GB of HBM: a sixth of what is free each (capped; two handles can coexist), the rest stays for the embeddings staged afterwards and
+    // the row lookup tables; a 10 M-document index at batch 256 needs ~ 30 GB of scratch for its widest rule step
+    arena_bytes = env_mb("B200_ARENA_MB", std::min<size_t>(free_b / 6, (size_t)32 << 30));
+    scratch_bytes = env_mb("B200_SCRATCH_MB", std::min<size_t>(free_b / 6, (size_t)40 << 30));
     CU(cudaMalloc((void **)&arena, arena_bytes), "alloc arena");
     CU(cudaMalloc((void **)&scratch, scratch_bytes), "alloc scratch");
     staged = true;
@@ -338,6 +340,67 @@ int Engine::nns_batch(const float *queries, uint32_t n_q, uint32_t d, uint32_t l
         }
     }
     (void)total_ms;
+    return B200_OK;
+}
+
+// S2: OR of posting lists, restricted to a universe — what ConditionDocIdsCache::get_computed_condition
+// (crates/milli/src/search/new/ranking_rule_graph/condition_docids_cache.rs:34-57) obtains from G::resolve_condition for the
+// union-shaped conditions (compute_query_term_subset_docids, resolve_query_graph.rs:33-59: `docids |= list` for every derivation,
+// then `& universe`).  One scatter_kernel launch over the dense universe.
+int Engine::union_postings(int db, const uint32_t *key_index, uint32_t n_keys, const uint64_t *universe, uint64_t n_universe_words, uint64_t *out) {
+    if (!staged) return fail(B200_ERR_STATE, "union_postings before b200_stage_finish");
+    if (db < 0 || db >= 10) return fail(B200_ERR_INVALID, "union_postings: unknown database id");
+    if (db == 4 && hix.pair_keys.size() != hix.db_keys[4])
+        return fail(B200_ERR_UNSUPPORTED, "union_postings: word_pair_proximity keys were dropped at staging, key indices are not stable");
+    CU(cudaSetDevice(device), "cudaSetDevice");
+    const uint64_t W = hix.n_words64;
+    if (universe && n_universe_words < W) return fail(B200_ERR_INVALID, "union_postings: universe bitmap shorter than the document range");
+    std::vector<Job> jobs;
+    for (uint32_t i = 0; i < n_keys; i++) {
+        if (key_index[i] >= hix.db_keys[db]) return fail(B200_ERR_INVALID, "union_postings: key index out of range");
+        const uint32_t list = hix.db_first[db] + key_index[i];
+        const ListRef &lr = hix.lists[list];
+        if (!lr.card) continue;
+        const uint64_t units = lr.dense ? W : lr.card;
+        for (uint32_t k = 0; k < (units + JOB_CHUNK - 1) / JOB_CHUNK; k++) jobs.push_back(Job{0, 0, list, k});
+    }
+    const size_t o_ub = 0, o_col = o_ub + W * 8, o_act = (o_col + W * 8 + 255) & ~(size_t)255, o_res = o_act + ((sizeof(ActDesc) + 255) & ~(size_t)255),
+                 o_jobs = o_res + 256, total = o_jobs + std::max<size_t>(1, jobs.size()) * sizeof(Job);
+    CU(d_s2.reserve(total), "alloc S2 scratch");
+    uint8_t *base = d_s2.p;
+    if (universe)
+        CU(cudaMemcpyAsync(base + o_ub, universe, W * 8, cudaMemcpyHostToDevice, stream), "H2D universe");
+    else
+        CU(cudaMemcpyAsync(base + o_ub, dix.base_ub, W * 8, cudaMemcpyDeviceToDevice, stream), "universe");
+    CU(cudaMemsetAsync(base + o_col, 0, W * 8, stream), "zero column");
+    ActDesc a;
+    memset(&a, 0, sizeof a);
+    a.ub = reinterpret_cast<unsigned long long *>(base + o_ub);
+    a.C = reinterpret_cast<unsigned long long *>(base + o_col);
+    a.ld = (uint32_t)W;
+    a.n_cols = 1;
+    a.res_off = 0;
+    uint32_t counters[4] = {(uint32_t)W, 0, 0, 0};      // results[0] = rows
+    uint32_t qcount[4] = {(uint32_t)jobs.size(), 0, 0, 0};
+    CU(cudaMemcpyAsync(base + o_act, &a, sizeof a, cudaMemcpyHostToDevice, stream), "H2D activation");
+    CU(cudaMemcpyAsync(base + o_res, counters, sizeof counters, cudaMemcpyHostToDevice, stream), "H2D rows");
+    CU(cudaMemcpyAsync(base + o_res + 64, qcount, sizeof qcount, cudaMemcpyHostToDevice, stream), "H2D job count");
+    if (!jobs.empty()) {
+        CU(cudaMemcpyAsync(base + o_jobs, jobs.data(), jobs.size() * sizeof(Job), cudaMemcpyHostToDevice, stream), "H2D jobs");
+        size_t m0 = mark();
+        CU(launch_scatter(stream, (uint32_t)sm_count * 8, reinterpret_cast<const Job *>(base + o_jobs), reinterpret_cast<const uint32_t *>(base + o_res + 64),
+                          (uint32_t)jobs.size(), reinterpret_cast<const ActDesc *>(base + o_act), reinterpret_cast<const uint32_t *>(base + o_res),
+                          dix.lists, dix.pool),
+           "scatter");
+        uint64_t bytes = 0;
+        for (auto &j : jobs) bytes += hix.lists[j.list].dense ? (uint64_t)JOB_CHUNK * 8 : (uint64_t)std::min<uint32_t>(JOB_CHUNK, hix.lists[j.list].card) * 4;
+        time_kernel(B200_K_SCATTER, m0, mark(), bytes);
+    }
+    CU(cudaMemcpyAsync(out, base + o_col, W * 8, cudaMemcpyDeviceToHost, stream), "D2H column");
+    CU(cudaStreamSynchronize(stream), "sync");
+    resolve_timers();
+    stats.h2d_bytes += (universe ? W * 8 : 0) + jobs.size() * sizeof(Job) + sizeof a;
+    stats.d2h_bytes += W * 8;
     return B200_OK;
 }
 

@@ -57,10 +57,15 @@ uint32_t cbo_decode_append(const uint8_t *p, size_t n, std::vector<uint32_t> &ou
 
 struct Builder {
     HostIndex &ix;
+    const RawDb *dbs_base = nullptr;
     explicit Builder(HostIndex &i) : ix(i) {}
     // decode values [k0,k1) of a db in parallel, then append to the pool in key order; returns first list id
     uint32_t add_lists(const RawDb &db, const std::vector<uint8_t> &keep /* per key: 1 = stage */) {
         uint64_t n = db.n;
+        if (dbs_base && &db >= dbs_base && &db < dbs_base + 10) {
+            ix.db_first[&db - dbs_base] = (uint32_t)ix.lists.size();
+            ix.db_keys[&db - dbs_base] = (uint32_t)n;
+        }
         unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
         std::vector<std::vector<uint32_t>> parts(nt);
         std::vector<std::vector<uint32_t>> cards(nt);
@@ -139,6 +144,7 @@ void build_host_index(const std::vector<uint8_t> &dict_bytes, const std::vector<
     ix.lists.clear();
     ix.pool.clear();
     Builder b(ix);
+    b.dbs_base = dbs;
     std::vector<uint8_t> all;
 
     auto word_of_key = [&](const RawDb &db, uint64_t i, size_t trim) -> int64_t {

@@ -73,6 +73,9 @@ struct HostIndex {
     std::vector<uint64_t> pair_keys;
     uint32_t pair_list_base = 0;
     std::map<uint32_t, uint32_t> fwc_list;  // fid<<8|count -> list
+    // list id of key i of database db = db_first[db] + i (keys in LMDB order); db_keys[db] = number of staged keys.
+    // (word_pair_proximity keys naming unknown words are dropped at staging: for that db the mapping only holds when none was.)
+    uint32_t db_first[10] = {0}, db_keys[10] = {0};
 
     Settings settings;
 

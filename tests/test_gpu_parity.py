@@ -291,3 +291,28 @@ def test_large_universe_matches_oracle(mb):
         assert got.ids(q) == want.ids(q), queries[q]
         assert got.scores(q) == want.scores(q), queries[q]
         assert int(got.n_candidates[q]) == int(want.n_candidates[q])
+
+
+def test_union_postings_matches_decoded_lists(mb, synth):
+    """S2 (b200_union_postings): OR of posting lists AND universe, against the CBO values decoded by the oracle's codec."""
+    from oracle.pyoracle import cbo_decode
+
+    ix = mb.Index(synth)
+    rng = np.random.default_rng(3)
+    n_words = (synth.n_docs + 63) // 64
+    for db in (0, 4, 5):  # word_docids, word_pair_proximity_docids, word_position_docids
+        view = synth.dbs[db]
+        n_keys = int(view.n_keys)
+        # a mix of the longest lists (dense on the device) and random ones
+        lens = np.diff(np.asarray(view.val_offsets))
+        keys = np.unique(np.concatenate([np.argsort(lens)[-3:], rng.integers(0, n_keys, 40)])).astype(np.uint32)
+        want = np.zeros(n_words, np.uint64)
+        for k in keys:
+            ids = cbo_decode(view.val(int(k)))
+            np.bitwise_or.at(want, ids >> 6, np.uint64(1) << (ids & 63).astype(np.uint64))
+        got = ix.union_postings(db, keys)
+        assert np.array_equal(got, want), db
+        universe = rng.integers(0, 2**63, n_words, dtype=np.uint64)
+        got_u = ix.union_postings(db, keys, universe)
+        assert np.array_equal(got_u, want & universe), db
+    assert np.array_equal(ix.union_postings(0, np.zeros(0, np.uint32)), np.zeros(n_words, np.uint64))
