@@ -1645,14 +1645,15 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         }
     });
     stats.host_ms[0] += ms_since(t_ph);
-    // ---- phase 2: typo derivations for every term of the batch in one device sweep
-    {
-        t_ph = clk::now();
+    // ---- phase 2 (per wave, see below): typo derivations for every term of queries [lo, hi) in one device sweep
+    auto derive_range = [&](uint32_t lo, uint32_t hi) -> int {
+        auto t_ph = clk::now();
         std::vector<char> wbytes;
         std::vector<uint32_t> woff{0};
         std::vector<uint8_t> mt, ip;
         std::unordered_map<std::string, int32_t> slot_of;
-        for (auto &qp : qs) {
+        for (uint32_t qi = lo; qi < hi; qi++) {
+            auto &qp = qs[qi];
             if (qp->done) continue;
             for (auto &t : qp->ctx.terms) {
                 if (t.empty_term || t.max_lev == 0) continue;
@@ -1687,8 +1688,8 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         }
         stats.host_ms[1] += ms_since(t_ph);
         t_ph = clk::now();
-        pfor(NQ, [&](size_t i) {
-            QState &q = *qs[i];
+        pfor(hi - lo, [&](size_t i) {
+            QState &q = *qs[lo + i];
             if (q.done) return;
             for (auto &t : q.ctx.terms) {
                 if (t.empty_term) continue;
@@ -1701,7 +1702,8 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             }
         });
         stats.host_ms[2] += ms_since(t_ph);
-    }
+        return B200_OK;
+    };
     // ---- result buffers
     CU(d_docids_out.reserve((size_t)NQ * std::max(1u, length)), "alloc results");
     // optional host profile (B200_PROFILE=1): summed thread time per section, printed per batch
@@ -1811,21 +1813,21 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         }
         start_resolve(q);
     };
-    std::vector<std::string> errs(NQ);
-    t_ph = clk::now();
-    pfor(NQ, [&](size_t i) {
-        QState &q = *qs[i];
-        if (q.done) return;
-        try {
-            start_query(q);
-        } catch (const TooComplex &t) {
-            q.status = B200_ERR_CAPACITY;
-            q.error = t.why;
-            q.done = true;
-        }
-    });
-
-    stats.host_ms[5] += ms_since(t_ph);
+    auto start_range = [&](uint32_t lo, uint32_t hi) {
+        auto t_ph = clk::now();
+        pfor(hi - lo, [&](size_t i) {
+            QState &q = *qs[lo + i];
+            if (q.done) return;
+            try {
+                start_query(q);
+            } catch (const TooComplex &t) {
+                q.status = B200_ERR_CAPACITY;
+                q.error = t.why;
+                q.done = true;
+            }
+        });
+        stats.host_ms[5] += ms_since(t_ph);
+    };
     // advance one query's bucket sort until it needs the device again (bucket_sort.rs:193-330)
     auto emit_bucket = [&](QState &q, Level &L, uint32_t col_lo, uint32_t col_hi, uint64_t count) {
         if (count == 0) return;
@@ -2021,15 +2023,16 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         ln.error = msg;
         return fail(code, msg);
     };
-    for (uint32_t i = 0; i < NQ; i++) lanes[i % n_lanes].members.push_back(i);
+    // contiguous query ranges per lane, so that the first half of the drivers can start while the second half's terms are derived
+    auto lane_lo = [&](unsigned l) { return (uint32_t)((uint64_t)NQ * l / n_lanes); };
+    for (unsigned l = 0; l < n_lanes; l++)
+        for (uint32_t i = lane_lo(l); i < lane_lo(l + 1); i++) lanes[l].members.push_back(i);
     // per-query row lookup tables (scatter_kernel): zeroed once per batch, entries are tagged with the activation that wrote them
     const bool use_rowtab = hix.n_words64 <= (1u << 20) && !getenv("B200_NO_ROWTAB");
     if (use_rowtab) {
         CU(d_rowtab.reserve((size_t)NQ * hix.n_words64), "row lookup tables");
         CU(cudaMemsetAsync(d_rowtab.p, 0, (size_t)NQ * hix.n_words64 * 4, stream), "zero row lookup tables");
     }
-    // everything queued on the engine stream so far (derivations) must be visible to the lanes
-    CU(cudaStreamSynchronize(stream), "sync");
     const size_t PATH_CAP = (size_t)1 << 20;
 
     // pack the pending work of a lane and enqueue it (no synchronisation). returns <0 on error, 0 idle, 1 launched
@@ -2389,11 +2392,28 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         }
     };
     {
+        // Waves: a driver starts stepping as soon as the terms of ITS queries are derived, while the main thread derives the next
+        // driver's (the derivation sweep is serial device + host work at the head of the call).  B200_WAVES caps the number of waves.
         std::vector<std::thread> drivers;
         std::vector<int> rcs(n_drivers, 0);
-        for (unsigned dr = 1; dr < n_drivers; dr++) drivers.emplace_back([&, dr]() { rcs[dr] = drive(dr); });
-        rcs[0] = drive(0);
+        unsigned n_waves = n_drivers;
+        if (const char *env = getenv("B200_WAVES")) n_waves = (unsigned)std::max(1, std::min((int)n_drivers, atoi(env)));
+        int rc_prep = B200_OK;
+        for (unsigned wv = 0; wv < n_waves && rc_prep == B200_OK; wv++) {
+            const unsigned d0 = n_drivers * wv / n_waves, d1 = n_drivers * (wv + 1) / n_waves;
+            const uint32_t lo = lane_lo(d0 * lanes_per_driver), hi = lane_lo(d1 * lanes_per_driver);
+            rc_prep = derive_range(lo, hi);
+            if (rc_prep != B200_OK) break;
+            start_range(lo, hi);
+            cudaError_t ce = cudaStreamSynchronize(stream);  // row-table memset and derivations visible to the lanes
+            if (ce != cudaSuccess) {
+                rc_prep = cuda_fail(ce, "sync");
+                break;
+            }
+            for (unsigned dr = d0; dr < d1; dr++) drivers.emplace_back([&, dr]() { rcs[dr] = drive(dr); });
+        }
         for (auto &t : drivers) t.join();
+        if (rc_prep != B200_OK) return rc_prep;
         for (unsigned dr = 0; dr < n_drivers; dr++)
             for (unsigned k = 0; k < lanes_per_driver; k++) lanes[dr * lanes_per_driver + k].rc = std::min(lanes[dr * lanes_per_driver + k].rc, rcs[dr]);
     }
