@@ -2396,7 +2396,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         // driver's (the derivation sweep is serial device + host work at the head of the call).  B200_WAVES caps the number of waves.
         std::vector<std::thread> drivers;
         std::vector<int> rcs(n_drivers, 0);
-        unsigned n_waves = n_drivers;
+        unsigned n_waves = std::min(2u, n_drivers);
         if (const char *env = getenv("B200_WAVES")) n_waves = (unsigned)std::max(1, std::min((int)n_drivers, atoi(env)));
         int rc_prep = B200_OK;
         for (unsigned wv = 0; wv < n_waves && rc_prep == B200_OK; wv++) {
