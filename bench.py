@@ -274,6 +274,7 @@ def main():
         log(f"parity: {parity}")
 
     sampler = ClockSampler(local_rank)
+    os.environ["B200_KERNEL_TIMERS"] = "0"  # the e2e region runs as production would: no per-kernel event records
     ix.reset_stats()
     if world > 1:
         dist.barrier()
@@ -295,6 +296,7 @@ def main():
     # second timed region, software pipeline off (one lane): kernels of different lanes no longer overlap, so the CUDA-event
     # intervals are clean.  `value` and the roofline come from this pass; `e2e` from the pipelined pass above.
     os.environ["B200_SINGLE_LANE"] = "1"
+    os.environ["B200_KERNEL_TIMERS"] = "1"
     step(args.warmup)
     ix.reset_stats()
     torch.cuda.synchronize()

@@ -183,7 +183,9 @@ struct Lane {
     std::vector<cudaEvent_t> ev_pool;
     std::vector<Timed> timed;
     size_t ev_used = 0;
+    bool timing = true;  // per-kernel CUDA-event timing (B200_KERNEL_TIMERS=0 turns the ~10 event records per step off)
     size_t mark() {
+        if (!timing) return 0;
         if (ev_used == ev_pool.size()) {
             cudaEvent_t e;
             cudaEventCreate(&e);
@@ -193,7 +195,7 @@ struct Lane {
         return ev_used++;
     }
     void time_kernel(b200_stats &st, int cls, size_t a, size_t b, uint64_t bytes) {
-        timed.push_back(Timed{cls, a, b});
+        if (timing) timed.push_back(Timed{cls, a, b});
         st.kernel_count[cls]++;
         st.kernel_bytes[cls] += bytes;
         st.kernel_launches++;

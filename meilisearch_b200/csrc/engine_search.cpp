@@ -1921,6 +1921,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
                     PROF(1);
                     prepare_graph_rule(q.ctx, C.kind, C.kind == RK_WORDS, tms, C);
                 }
+                if ((size_t)C.rule_idx + 1 == n_rules) C.want_paths = false;  // nothing descends from the last rule: its buckets are emitted as they are
                 uint32_t cap = (uint32_t)std::min<uint64_t>(cnt, L.rows);
                 request_activation(q, std::move(C), L.uw, L.ub, L.out, L.rows, L.ld, 0, cap);
                 return;
@@ -1973,6 +1974,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
                 PROF(1);
                 prepare_graph_rule(q.ctx, C.kind, false, tms, C);
             }
+            if ((size_t)C.rule_idx + 1 == n_rules) C.want_paths = false;  // nothing descends from the last rule
             uint32_t cap = (uint32_t)std::min<uint64_t>(cnt, L.rows);
             request_activation(q, std::move(C), L.uw, L.ub, L.out, L.rows, L.ld, (uint32_t)ci, cap);
             return;
@@ -2013,6 +2015,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         ln.arena = arena + (((arena_bytes / n_lanes) * l) & ~(size_t)255);
         ln.arena_bytes = (arena_bytes / n_lanes) & ~(size_t)255;
         ln.arena_used = 0;
+        ln.timing = !(getenv("B200_KERNEL_TIMERS") && atoi(getenv("B200_KERNEL_TIMERS")) == 0);
         ln.lst = b200_stats{};
         ln.rc = 0;
         ln.error.clear();
@@ -2256,7 +2259,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         CU(cudaMemcpyAsync(ln.d_qcount.p, ln.d_step.p + o_nstatic, 4, cudaMemcpyDeviceToDevice, st), "job count");
         const ActDesc *dacts = reinterpret_cast<const ActDesc *>(ln.d_step.p + o_acts);
         // 1. emissions queued before this step's activations
-        CU(cudaEventRecord(ln.e0, st), "event");
+        if (ln.timing) CU(cudaEventRecord(ln.e0, st), "event");
         if (n_emits) {
             size_t m0 = ln.mark();
             CU(launch_emit(st, reinterpret_cast<const EmitDesc *>(ln.d_step.p + o_emits), n_emits), "emit");
@@ -2293,7 +2296,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             CU(cudaMemcpyAsync(ln.h_results, ln.d_results.p, (size_t)res_words * 4, cudaMemcpyDeviceToHost, st), "D2H results");
             CU(cudaMemcpyAsync(ln.h_results + res_words, ln.d_qcount.p, 8, cudaMemcpyDeviceToHost, st), "D2H counters");
         }
-        CU(cudaEventRecord(ln.e1, st), "event");
+        if (ln.timing) CU(cudaEventRecord(ln.e1, st), "event");
         ln.res_words = res_words;
         ln.qcap = qcap;
         ln.inflight = true;
@@ -2308,7 +2311,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         ln.inflight = false;
         {
             float ms = 0;
-            cudaEventElapsedTime(&ms, ln.e0, ln.e1);
+            if (ln.timing) cudaEventElapsedTime(&ms, ln.e0, ln.e1);
             ln.lst.device_ms += ms;
             ln.resolve_timers(ln.lst);
         }
