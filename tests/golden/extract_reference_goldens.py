@@ -303,6 +303,39 @@ def matching_strategy_cases():
     return out
 
 
+def typo_tolerance_count_cases():
+    """crates/milli/tests/search/typo_tolerance.rs:18-357: known-answer tests on `documents_ids.len()` (test_set.ndjson with criteria
+    [Typo] and the three synonyms of tests/search/mod.rs:37-68, or two inline documents).  Only the hit COUNT is asserted by the
+    reference, so these are kept apart from the ordered goldens (`count_cases`, oracle-only)."""
+    text = open("/root/reference/crates/milli/tests/assets/test_set.ndjson").read()
+    dec, i, docs = json.JSONDecoder(), 0, []
+    while True:
+        while i < len(text) and text[i].isspace():
+            i += 1
+        if i >= len(text):
+            break
+        o, i = dec.raw_decode(text, i)
+        docs.append(o)
+    def test_set(exact_attributes=()):
+        return {"searchable": ["title", "description"], "exact_attributes": list(exact_attributes), "stop_words": [],
+                "docs": [{"id": k, "title": d["title"], "description": d["description"]} for k, d in enumerate(docs)]}
+    synonyms = {"hello": ["good morning"], "world": ["earth"], "america": ["the united states"]}
+    two_docs = {"searchable": ["id", "data"], "exact_attributes": [], "stop_words": [],
+                "docs": [{"id": "1", "data": "zealand"}, {"id": "2", "data": "zearand"}]}
+    src = "crates/milli/tests/search/typo_tolerance.rs"
+    base = {"criteria": ["typo"], "synonyms": synonyms}
+    rows = [
+        (43, test_set(), dict(base), "zeal", 1), (60, test_set(), dict(base), "zean", 0),
+        (95, test_set(), dict(base, one_typo=4), "zean", 1),
+        (123, test_set(), dict(base), "zealand", 1), (140, test_set(), dict(base), "zealemd", 0),
+        (175, test_set(), dict(base, two_typos=7), "zealemd", 1),
+        (255, two_docs, {}, "zealand", 2), (292, two_docs, {"exact_words": ["zealand"]}, "zealand", 1),
+        (321, test_set(), dict(base), "antebelum", 1), (356, test_set(["description"]), dict(base), "antebelum", 0),
+    ]
+    return [{"source": f"{src}:{line}", "test": "typo_tolerance", "index": index, "settings": st, "tms": "last", "scoring": "skip", "limit": 10,
+             "offset": 0, "query": q, "expected_count": n} for line, index, st, q, n in rows]
+
+
 def main():
     cases, skipped = [], 0
     for fname in FILES:
@@ -416,8 +449,15 @@ def main():
             keyed[k] = len(corpora)
             corpora.append(c["index"])
         c["index"] = keyed[k]
+    count_cases = typo_tolerance_count_cases()
+    for c in count_cases:
+        k = json.dumps(c["index"], sort_keys=True)
+        if k not in keyed:
+            keyed[k] = len(corpora)
+            corpora.append(c["index"])
+        c["index"] = keyed[k]
     json.dump({"generated_by": "tests/golden/extract_reference_goldens.py", "reference": "meilisearch v1.50.0 @ 5cb2f2e",
-               "corpora": corpora, "cases": cases}, open(OUT, "w"), indent=0)
+               "corpora": corpora, "cases": cases, "count_cases": count_cases}, open(OUT, "w"), indent=0)
     print(f"{len(cases)} cases, {len(corpora)} corpora, {skipped} skipped -> {OUT}")
     by = {}
     for c in cases:

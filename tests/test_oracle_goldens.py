@@ -33,6 +33,18 @@ def test_reference_golden(case):
         assert got == case["expected_scores"], case["scores_source"]
 
 
+@pytest.mark.parametrize("case", G.get("count_cases", []), ids=[c["source"].split("/")[-1] + ":" + c["query"] for c in G.get("count_cases", [])])
+def test_reference_hit_counts(case):
+    """crates/milli/tests/search/typo_tolerance.rs asserts only `documents_ids.len()`."""
+    img = _image(case["index"])
+    s = case["settings"]
+    ix = OracleIndex(img, criteria=s.get("criteria"), authorize_typos=s.get("authorize_typos", True),
+                     one_typo=s.get("one_typo", 5), two_typos=s.get("two_typos", 9))
+    ix.update_settings(exact_words=s.get("exact_words", []), synonyms=s.get("synonyms", {}))
+    r = ix.search_batch(TokenBatch([case["query"]], img.stop_words), tms=case["tms"], scoring=case["scoring"], limit=case["limit"])
+    assert len(r.ids(0)) == case["expected_count"], case["source"]
+
+
 def test_typo_bucketing_scores():
     # crates/milli/src/search/new/tests/snapshots/milli__search__new__tests__typo__typo_bucketing-5.snap:
     # Typo{typo_count, max_typo_count=5} = 0,0,1,1,2,5  (SURVEY.md Appendix C.1)
