@@ -1,7 +1,10 @@
 // indexgen — see indexgen.h. Test/bench infrastructure standing in for milli's indexer.
 #include "indexgen.h"
 
+#include <omp.h>
+
 #include <algorithm>
+#include <parallel/algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -263,22 +266,51 @@ void ig_add_synthetic(ig_builder *b, uint32_t n_docs, uint32_t vocab, double zip
         uint32_t k = (uint32_t)(std::lower_bound(cdf.begin(), cdf.end(), u) - cdf.begin());
         return k >= vocab ? vocab - 1 : k;
     };
+    (void)draw;
+    // Every document has its own generator (seeded by seed and docid), so the corpus does not depend on the number of threads:
+    // pass 1 draws the field lengths, pass 2 fills the preallocated token arrays in parallel.
     uint32_t base = b->max_doc_plus1;
-    b->toks.reserve(b->toks.size() + (size_t)n_docs * (len_lo + len_hi) / 2);
+    const uint32_t nf = std::min<uint32_t>(b->n_fields, 2);
+    auto doc_rng = [&](uint32_t d) { return Rng(seed ^ (0xD6E8FEB86659FD93ull * ((uint64_t)d + 1))); };
+    std::vector<uint64_t> tok_off((size_t)n_docs + 1, 0), f0_off((size_t)n_docs + 1, 0);
+#pragma omp parallel for schedule(static)
     for (uint32_t d = 0; d < n_docs; d++) {
-        uint32_t doc = base + d;
-        b->all_docs.push_back(doc);
-        for (uint32_t f = 0; f < b->n_fields && f < 2; f++) {
-            uint32_t len = f == 0 ? len_lo + r.below(len_hi - len_lo + 1) : 20 + r.below(61);
+        Rng rd = doc_rng(d);
+        uint32_t l0 = len_lo + rd.below(len_hi - len_lo + 1), l1 = nf > 1 ? 20 + rd.below(61) : 0;
+        tok_off[d + 1] = l0 + l1;
+        f0_off[d + 1] = l0;
+    }
+    for (uint32_t d = 0; d < n_docs; d++) {
+        tok_off[d + 1] += tok_off[d];
+        f0_off[d + 1] += f0_off[d];
+    }
+    const size_t tok_base = b->toks.size(), f0_base = b->syn_doc_words.size();
+    b->toks.resize(tok_base + tok_off[n_docs]);
+    b->syn_doc_words.resize(f0_base + f0_off[n_docs]);
+    b->syn_doc_off.resize(b->syn_doc_off.size() + n_docs);
+    const size_t sdo_base = b->syn_doc_off.size() - n_docs;
+    b->all_docs.resize(b->all_docs.size() + n_docs);
+    const size_t ad_base = b->all_docs.size() - n_docs;
+#pragma omp parallel for schedule(static)
+    for (uint32_t d = 0; d < n_docs; d++) {
+        Rng rd = doc_rng(d);
+        const uint32_t doc = base + d;
+        uint32_t lens[2] = {len_lo + rd.below(len_hi - len_lo + 1), nf > 1 ? 20 + rd.below(61) : 0};
+        Tok *tk = b->toks.data() + tok_base + tok_off[d];
+        uint32_t *sw = b->syn_doc_words.data() + f0_base + f0_off[d];
+        for (uint32_t f = 0; f < nf; f++) {
             uint32_t pos = 0;
-            for (uint32_t k = 0; k < len; k++) {
-                uint32_t rank = draw();
-                if (k > 0) pos += (r.below(100) < 5) ? 8 : 1;
-                b->toks.push_back({vid[rank], doc, (uint16_t)f, (uint16_t)pos});
-                if (f == 0) b->syn_doc_words.push_back(vid[rank]);
+            for (uint32_t k = 0; k < lens[f]; k++) {
+                double u = rd.unit() * acc;
+                uint32_t rank = (uint32_t)(std::lower_bound(cdf.begin(), cdf.end(), u) - cdf.begin());
+                if (rank >= vocab) rank = vocab - 1;
+                if (k > 0) pos += (rd.below(100) < 5) ? 8 : 1;
+                *tk++ = Tok{vid[rank], doc, (uint16_t)f, (uint16_t)pos};
+                if (f == 0) *sw++ = vid[rank];
             }
         }
-        b->syn_doc_off.push_back((uint32_t)b->syn_doc_words.size());
+        b->syn_doc_off[sdo_base + d] = (uint32_t)(f0_base + f0_off[d + 1]);
+        b->all_docs[ad_base + d] = doc;
     }
     b->max_doc_plus1 = base + n_docs;
 }
@@ -329,18 +361,45 @@ static void put_be16(std::vector<uint8_t> &k, uint16_t v) {
 // Emit a db from (key tuple -> sorted docs) given tuples sorted by (a, b, doc); key writer gets (a,b).
 template <class KeyFn>
 static void emit_db(Db &db, std::vector<std::pair<uint64_t, uint32_t>> &tuples, KeyFn key_fn) {
-    std::sort(tuples.begin(), tuples.end());
+    __gnu_parallel::sort(tuples.begin(), tuples.end());
     tuples.erase(std::unique(tuples.begin(), tuples.end()), tuples.end());
-    std::vector<uint32_t> ids;
-    size_t i = 0, n = tuples.size();
-    while (i < n) {
-        size_t j = i;
-        ids.clear();
-        while (j < n && tuples[j].first == tuples[i].first) ids.push_back(tuples[j++].second);
-        key_fn(tuples[i].first, db.keys);
-        cbo_encode(ids.data(), ids.size(), db.vals);
-        db.end_entry();
-        i = j;
+    const size_t n = tuples.size();
+    // the key ranges are encoded in parallel into per-thread databases and concatenated in order
+    const int T = std::max(1, std::min<int>(omp_get_max_threads(), (int)(n / 65536) + 1));
+    std::vector<size_t> cut(T + 1, n);
+    cut[0] = 0;
+    for (int t = 1; t < T; t++) {
+        size_t c = n * (size_t)t / (size_t)T;
+        while (c < n && c > 0 && tuples[c].first == tuples[c - 1].first) c++;
+        cut[t] = std::max(c, cut[t - 1]);
+    }
+    std::vector<Db> parts(T);
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+    for (int t = 0; t < T; t++) {
+        Db &part = parts[t];
+        std::vector<uint32_t> ids;
+        size_t i = cut[t];
+        const size_t e = cut[t + 1];
+        while (i < e) {
+            size_t j = i;
+            ids.clear();
+            while (j < e && tuples[j].first == tuples[i].first) ids.push_back(tuples[j++].second);
+            key_fn(tuples[i].first, part.keys);
+            cbo_encode(ids.data(), ids.size(), part.vals);
+            part.end_entry();
+            i = j;
+        }
+    }
+    for (auto &part : parts) {
+        const uint64_t kb = db.keys.size(), vb = db.vals.size();
+        db.keys.insert(db.keys.end(), part.keys.begin(), part.keys.end());
+        db.vals.insert(db.vals.end(), part.vals.begin(), part.vals.end());
+        for (size_t k = 1; k < part.koff.size(); k++) {
+            db.koff.push_back(kb + part.koff[k]);
+            db.voff.push_back(vb + part.voff[k]);
+        }
+        Db().keys.swap(part.keys);
+        Db().vals.swap(part.vals);
     }
 }
 }  // extern "C++"
@@ -350,7 +409,7 @@ void ig_build(ig_builder *b) {
     size_t nw = b->words.size();
     std::vector<uint32_t> order(nw);
     for (uint32_t i = 0; i < nw; i++) order[i] = i;
-    std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return b->words[x] < b->words[y]; });
+    __gnu_parallel::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return b->words[x] < b->words[y]; });
     // only words that actually occur are in the dictionary
     std::vector<uint8_t> used(nw, 0);
     for (auto &t : b->toks) used[t.word] = 1;
@@ -376,24 +435,38 @@ void ig_build(ig_builder *b) {
 
     // 2. word_docids / exact_word_docids / word_fid / word_position / fid_word_count
     std::vector<std::pair<uint64_t, uint32_t>> t_word, t_exact, t_fid, t_pos, t_cnt;
-    t_word.reserve(b->toks.size());
-    t_fid.reserve(b->toks.size());
-    t_pos.reserve(b->toks.size());
     // sort tokens by (doc, fid, pos) for pair extraction and counts
-    std::sort(b->toks.begin(), b->toks.end(), [](const Tok &x, const Tok &y) {
-        if (x.doc != y.doc) return x.doc < y.doc;
-        if (x.fid != y.fid) return x.fid < y.fid;
-        return x.pos < y.pos;
-    });
-    for (auto &t : b->toks) t.word = rank[t.word];
+    {
+        auto tok_less = [](const Tok &x, const Tok &y) {
+            if (x.doc != y.doc) return x.doc < y.doc;
+            if (x.fid != y.fid) return x.fid < y.fid;
+            return x.pos < y.pos;
+        };
+        if (!std::is_sorted(b->toks.begin(), b->toks.end(), tok_less)) __gnu_parallel::stable_sort(b->toks.begin(), b->toks.end(), tok_less);
+    }
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < b->toks.size(); i++) b->toks[i].word = rank[b->toks[i].word];
     std::vector<std::pair<uint64_t, uint32_t>> t_pair;  // key = prox<<42 | w1<<21 | w2
     if (W >= (1u << 21)) {
         fprintf(stderr, "indexgen: vocabulary too large for packed pair keys\n");
         abort();
     }
+    const int T = std::max(1, omp_get_max_threads());
+    std::vector<std::vector<std::pair<uint64_t, uint32_t>>> p_word(T), p_exact(T), p_fid(T), p_pos(T), p_cnt(T), p_pair(T);
+#pragma omp parallel num_threads(T)
     {
-        size_t n = b->toks.size();
-        size_t i = 0;
+        const int tid = omp_get_thread_num();
+        auto &t_word = p_word[tid];
+        auto &t_exact = p_exact[tid];
+        auto &t_fid = p_fid[tid];
+        auto &t_pos = p_pos[tid];
+        auto &t_cnt = p_cnt[tid];
+        auto &t_pair = p_pair[tid];
+        const size_t ntok = b->toks.size();
+        // this thread's token range, moved to document boundaries
+        size_t i = ntok * (size_t)tid / (size_t)T, n = ntok * (size_t)(tid + 1) / (size_t)T;
+        while (i > 0 && i < ntok && b->toks[i].doc == b->toks[i - 1].doc) i++;
+        while (n > 0 && n < ntok && b->toks[n].doc == b->toks[n - 1].doc) n++;
         std::vector<std::pair<uint64_t, uint8_t>> docpairs;  // (w1<<21|w2, prox)
         while (i < n) {
             size_t dj = i;
@@ -429,6 +502,23 @@ void ig_build(ig_builder *b) {
             i = dj;
         }
     }
+    auto gather = [&](std::vector<std::vector<std::pair<uint64_t, uint32_t>>> &parts, std::vector<std::pair<uint64_t, uint32_t>> &out) {
+        size_t tot = 0;
+        std::vector<size_t> at(parts.size() + 1, 0);
+        for (size_t t = 0; t < parts.size(); t++) at[t + 1] = (tot += parts[t].size());
+        out.resize(tot);
+#pragma omp parallel for schedule(static, 1)
+        for (size_t t = 0; t < parts.size(); t++) {
+            std::copy(parts[t].begin(), parts[t].end(), out.begin() + at[t]);
+            std::vector<std::pair<uint64_t, uint32_t>>().swap(parts[t]);
+        }
+    };
+    gather(p_word, t_word);
+    gather(p_exact, t_exact);
+    gather(p_fid, t_fid);
+    gather(p_pos, t_pos);
+    gather(p_cnt, t_cnt);
+    gather(p_pair, t_pair);
     auto key_word = [&](uint64_t k, std::vector<uint8_t> &out) { wkey((uint32_t)k, out); };
     auto key_word_u16 = [&](uint64_t k, std::vector<uint8_t> &out) {
         wkey((uint32_t)(k >> 16), out);
@@ -450,6 +540,7 @@ void ig_build(ig_builder *b) {
         out.push_back(0);
         wkey((uint32_t)(k & 0x1fffff), out);
     });
+    std::vector<std::pair<uint64_t, uint32_t>>().swap(t_pair);
 
     // 3. prefix dbs: every 1..4-byte prefix shared by >= 100 dictionary words (word_fst_builder.rs:100-131)
     struct Pfx {
@@ -505,6 +596,93 @@ void ig_build(ig_builder *b) {
     build_prefix(t_fid, 16, b->dbs[IG_DB_WORD_PREFIX_FID_DOCIDS], true);
     build_prefix(t_pos, 16, b->dbs[IG_DB_WORD_PREFIX_POSITION_DOCIDS], true);
     std::vector<Tok>().swap(b->toks);
+}
+
+// Query generation from a persisted corpus (the arrays ig_query_source exposes): same stream as ig_synthetic_queries.
+static char *queries_from_arrays(const uint8_t *word_bytes, const uint64_t *word_off, const uint32_t *doc_off, uint32_t n_docs,
+                                 const uint32_t *doc_words, uint32_t n, uint64_t seed, int with_typos) {
+    Rng r(seed ^ 0xC0FFEEull);
+    std::string out;
+    for (uint32_t q = 0; q < n; q++) {
+        uint32_t d, len;
+        do {
+            d = r.below(n_docs);
+            len = doc_off[d + 1] - doc_off[d];
+        } while (len < 2);
+        uint32_t want = 2 + r.below(3);
+        if (want > len) want = len;
+        uint32_t start = r.below(len - want + 1);
+        for (uint32_t k = 0; k < want; k++) {
+            uint32_t wid = doc_words[doc_off[d] + start + k];
+            std::string w((const char *)word_bytes + word_off[wid], (size_t)(word_off[wid + 1] - word_off[wid]));
+            if (with_typos) {
+                uint32_t e = r.below(100);
+                uint32_t edits = e < 40 ? 0 : (e < 80 ? 1 : 2);
+                for (uint32_t t = 0; t < edits; t++) {
+                    std::string m = mutate(w, r);
+                    if (!m.empty()) w = m;
+                }
+                if (k + 1 == want && r.below(100) < 30 && w.size() > 2) w = w.substr(0, 2 + r.below((uint32_t)w.size() - 2));
+            }
+            if (k) out.push_back(' ');
+            out += w;
+        }
+        out.push_back('\n');
+    }
+    char *p = (char *)malloc(out.size() + 1);
+    memcpy(p, out.c_str(), out.size() + 1);
+    return p;
+}
+char *ig_queries_from_arrays(const uint8_t *word_bytes, const uint64_t *word_off, const uint32_t *doc_off, uint32_t n_docs,
+                             const uint32_t *doc_words, uint32_t n, uint64_t seed, int with_typos) {
+    return queries_from_arrays(word_bytes, word_off, doc_off, n_docs, doc_words, n, seed, with_typos);
+}
+// The arrays ig_queries_from_arrays needs, for the on-disk cache of a synthetic corpus: interned words (by intern id) and the
+// field-0 word ids of every synthetic document.  The byte/offset buffers are malloc'ed; free them with ig_free_str.
+void ig_query_source(const ig_builder *b, uint8_t **word_bytes, uint64_t **word_off, uint64_t *n_words, const uint32_t **doc_off,
+                     uint64_t *n_docs, const uint32_t **doc_words, uint64_t *n_doc_words) {
+    uint64_t tot = 0;
+    for (auto &w : b->words) tot += w.size();
+    uint8_t *wb = (uint8_t *)malloc(tot + 1);
+    uint64_t *wo = (uint64_t *)malloc((b->words.size() + 1) * 8);
+    uint64_t at = 0;
+    for (size_t i = 0; i < b->words.size(); i++) {
+        wo[i] = at;
+        memcpy(wb + at, b->words[i].data(), b->words[i].size());
+        at += b->words[i].size();
+    }
+    wo[b->words.size()] = at;
+    *word_bytes = wb;
+    *word_off = wo;
+    *n_words = b->words.size();
+    *doc_off = b->syn_doc_off.data();
+    *n_docs = b->syn_doc_off.size() - 1;
+    *doc_words = b->syn_doc_words.data();
+    *n_doc_words = b->syn_doc_words.size();
+}
+
+// cfg 4 embeddings: rows i.i.d. N(0,1) then L2-normalised, stored fp16.  Row r has its own generator (seed, r), so
+// any row range can be produced by any number of threads; `out` holds n x d IEEE binary16 values for rows [first_row, first_row+n).
+void ig_fill_embeddings_f16(uint16_t *out, uint64_t first_row, uint64_t n, uint32_t d, uint64_t seed) {
+#pragma omp parallel
+    {
+        std::vector<float> v(d + 1);
+#pragma omp for schedule(static)
+        for (uint64_t r = 0; r < n; r++) {
+            Rng g(seed ^ (0xA24BAED4963EE407ull * (first_row + r + 1)));
+            double ss = 0;
+            for (uint32_t i = 0; i < d; i += 2) {  // Box-Muller, two values per pair of uniforms
+                double u1 = 1.0 - g.unit(), u2 = g.unit();
+                double rad = std::sqrt(-2.0 * std::log(u1)), ang = 6.283185307179586 * u2;
+                v[i] = (float)(rad * std::cos(ang));
+                v[i + 1] = (float)(rad * std::sin(ang));
+            }
+            for (uint32_t i = 0; i < d; i++) ss += (double)v[i] * v[i];
+            const float inv = ss > 0 ? (float)(1.0 / std::sqrt(ss)) : 0.f;
+            _Float16 *o = reinterpret_cast<_Float16 *>(out + r * d);
+            for (uint32_t i = 0; i < d; i++) o[i] = (_Float16)(v[i] * inv);
+        }
+    }
 }
 
 uint32_t ig_n_docs(const ig_builder *b) { return b->max_doc_plus1; }

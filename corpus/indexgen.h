@@ -63,6 +63,15 @@ void ig_add_synthetic(ig_builder *, uint32_t n_docs, uint32_t vocab, double zipf
  * last word truncated to a prefix with p=0.3. Returns a malloc'ed '\n'-joined buffer. */
 char *ig_synthetic_queries(ig_builder *, uint32_t n, uint64_t seed, int with_typos);
 void ig_free_str(char *);
+/* Same query stream as ig_synthetic_queries, from the arrays of ig_query_source (so that a corpus cached on disk can still
+ * produce queries): words by intern id (bytes + n_words+1 offsets), field-0 word ids of every document (n_docs+1 offsets). */
+char *ig_queries_from_arrays(const uint8_t *word_bytes, const uint64_t *word_off, const uint32_t *doc_off, uint32_t n_docs,
+                             const uint32_t *doc_words, uint32_t n, uint64_t seed, int with_typos);
+void ig_query_source(const ig_builder *, uint8_t **word_bytes, uint64_t **word_off, uint64_t *n_words, const uint32_t **doc_off,
+                     uint64_t *n_docs, const uint32_t **doc_words, uint64_t *n_doc_words);
+/* SURVEY §8(d) cfg 4 embeddings: rows [first_row, first_row + n) of an i.i.d. N(0,1), L2-normalised matrix as IEEE binary16;
+ * deterministic in (seed, row), multi-threaded. */
+void ig_fill_embeddings_f16(uint16_t *out, uint64_t first_row, uint64_t n, uint32_t d, uint64_t seed);
 /* sort + build every database */
 void ig_build(ig_builder *);
 uint32_t ig_n_docs(const ig_builder *);        /* max docid + 1 */

@@ -84,6 +84,9 @@ int b200_stage_finish(b200_index *);
 /* Replaces the arroy/hannoy item nodes read by VectorStore (crates/milli/src/vector/store.rs:1427-1434):
  * one f32[d] vector per row + its docid.  Stored on device as fp16 rows + f32 inverse norms. */
 int b200_stage_embeddings(b200_index *, const float *vectors, uint64_t n, uint32_t d, const uint32_t *docids);
+/* Same store from rows that are already IEEE binary16 (a quantised store, or a corpus generated as fp16): no f32 round trip;
+ * the inverse norms are those of the fp16 values. */
+int b200_stage_embeddings_f16(b200_index *, const uint16_t *rows_fp16, uint64_t n, uint32_t d, const uint32_t *docids);
 /* Embedder `distribution` (crates/milli/src/vector/distribution.rs): enabled=0 disables the shift. */
 int b200_stage_distribution(b200_index *, int enabled, float mean, float sigma);
 
@@ -176,6 +179,10 @@ typedef struct {
     double host_ms[8];            /* wall time of the host phases of b200_search_batch: 0 parse, 1 derive (incl. device), 2 term finalisation,
                                      3 step packing, 4 step device wait, 5 bucket-sort advance, 6 result copy, 7 total */
     uint64_t hbm_bytes_staged;
+    uint64_t deferred;            /* ranking-rule activations that had to wait for a later device step (scratch / arena full) */
+    uint64_t arena_peak_bytes;    /* high-water mark of the per-batch level storage (universes + bucket columns) */
+    uint64_t eval_class_launches[5]; /* eval_dp launches per DP-table class: <= 24 / 56 / 112 / 216 slots in shared memory, [4] = global matrices */
+    uint64_t eval_class_tiles[5];    /* 128-row tiles evaluated per class */
 } b200_stats;
 int b200_get_stats(b200_index *, b200_stats *out);
 int b200_reset_stats(b200_index *);

@@ -54,7 +54,8 @@ class _Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("device_steps", C.c_uint64), ("posting_bytes", C.c_uint64), ("matrix_bytes", C.c_uint64),
                 ("dictionary_bytes", C.c_uint64), ("vector_bytes", C.c_uint64), ("kernel_ms", C.c_double * 10),
                 ("kernel_count", C.c_uint64 * 10), ("kernel_bytes", C.c_uint64 * 10), ("device_ms", C.c_double), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("host_ms", C.c_double * 8),
-                ("hbm_bytes_staged", C.c_uint64)]
+                ("hbm_bytes_staged", C.c_uint64), ("deferred", C.c_uint64), ("arena_peak_bytes", C.c_uint64),
+                ("eval_class_launches", C.c_uint64 * 5), ("eval_class_tiles", C.c_uint64 * 5)]
 
 
 KERNELS = ["lev_match", "act_compact", "pair_probe", "scatter", "eval_paths", "emit", "vec_dist", "topk_select", "vec_gemm_topk", "vec_merge"]
@@ -91,6 +92,7 @@ def load_library():
         l.b200_stage_synonyms.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p)]
         l.b200_stage_finish.argtypes = [C.c_void_p]
         l.b200_stage_embeddings.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
+        l.b200_stage_embeddings_f16.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
         l.b200_stage_distribution.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float]
         l.b200_derive_batch.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_void_p] * 4
         l.b200_union_postings.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
@@ -103,7 +105,7 @@ def load_library():
 
 
 SYMBOLS = ["b200_open", "b200_close", "b200_last_error", "b200_open_error", "b200_stage_dictionary", "b200_stage_db",
-           "b200_stage_documents_ids", "b200_stage_settings", "b200_stage_synonyms", "b200_stage_finish", "b200_stage_embeddings", "b200_stage_distribution",
+           "b200_stage_documents_ids", "b200_stage_settings", "b200_stage_synonyms", "b200_stage_finish", "b200_stage_embeddings", "b200_stage_embeddings_f16", "b200_stage_distribution",
            "b200_derive_batch", "b200_union_postings", "b200_nns_batch", "b200_search_batch", "b200_get_stats", "b200_reset_stats"]
 
 
@@ -190,9 +192,14 @@ class Index:
         self.n_fields = image.n_fields
 
     def set_embeddings(self, matrix, docids=None, distribution=None):
-        m = np.ascontiguousarray(matrix, np.float32)
+        """f32 rows (converted to fp16 on the device), or a float16 matrix staged as it is."""
         ids = None if docids is None else np.ascontiguousarray(docids, np.uint32)
-        self._ck(self._l.b200_stage_embeddings(self._h, _p(m), m.shape[0], m.shape[1], _p(ids)))
+        if getattr(matrix, "dtype", None) == np.float16:
+            m = np.ascontiguousarray(matrix)
+            self._ck(self._l.b200_stage_embeddings_f16(self._h, _p(m), m.shape[0], m.shape[1], _p(ids)))
+        else:
+            m = np.ascontiguousarray(matrix, np.float32)
+            self._ck(self._l.b200_stage_embeddings(self._h, _p(m), m.shape[0], m.shape[1], _p(ids)))
         self.dim = m.shape[1]
         if distribution:
             self._ck(self._l.b200_stage_distribution(self._h, 1, distribution[0], distribution[1]))
@@ -239,7 +246,9 @@ class Index:
     def stats(self):
         s = _Stats()
         self._l.b200_get_stats(self._h, C.byref(s))
-        d = {n: getattr(s, n) for n, _ in _Stats._fields_ if not n.startswith("kernel_") and n != "host_ms"}
+        d = {n: getattr(s, n) for n, _ in _Stats._fields_ if not n.startswith("kernel_") and not n.startswith("eval_class") and n != "host_ms"}
+        d["eval_class_launches"] = list(s.eval_class_launches)
+        d["eval_class_tiles"] = list(s.eval_class_tiles)
         d["host_ms"] = dict(zip(["parse", "derive", "terms", "pack", "device_wait", "advance", "results", "total"], list(s.host_ms)))
         d["kernel_launches"] = s.kernel_launches
         d["kernels"] = {KERNELS[i]: {"ms": s.kernel_ms[i], "count": s.kernel_count[i], "bytes": s.kernel_bytes[i]} for i in range(len(KERNELS))}

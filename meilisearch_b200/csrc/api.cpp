@@ -125,7 +125,11 @@ int b200_stage_finish(b200_index *h) {
 }
 int b200_stage_embeddings(b200_index *h, const float *v, uint64_t n, uint32_t d, const uint32_t *docids) {
     std::lock_guard<std::mutex> g(h->e.mu);
-    return h->e.stage_embeddings(v, n, d, docids);
+    return h->e.stage_embeddings(v, nullptr, n, d, docids);
+}
+int b200_stage_embeddings_f16(b200_index *h, const uint16_t *rows, uint64_t n, uint32_t d, const uint32_t *docids) {
+    std::lock_guard<std::mutex> g(h->e.mu);
+    return h->e.stage_embeddings(nullptr, rows, n, d, docids);
 }
 int b200_stage_distribution(b200_index *h, int enabled, float mean, float sigma) {
     std::lock_guard<std::mutex> g(h->e.mu);

@@ -73,6 +73,7 @@ struct ActDesc {
     uint32_t ld, n_cols, n_costs, n_states;
     uint32_t state_off, edge_off, cost_off;  // into DpState[], DpEdge[], u16 cost_vals[]
     uint32_t colprog_off, colprog_len;
+    uint32_t prog_off, prog_len;  // DP program, u32 ops in the step's program pool; prog_len is a multiple of 4
     uint32_t tab_size, want_paths;
     uint32_t res_off;         // into results u32[]: [0] rows, [1..n_costs+1] counts
     uint32_t all_conditional; // every START->END path has at least one condition: rows whose columns are all zero match nothing
@@ -111,7 +112,21 @@ struct EmitDesc {  // append the first docids of OR(out[col_lo..col_hi)) to a re
 
 struct TileDesc {
     uint32_t act, row_begin;
+    uint32_t rows_per_thread, pad;  // the tile covers 128 * rows_per_thread rows
 };
+// eval_dp_kernel keeps a row's condition words and DP table in thread-private shared-memory slots ([slot][128 rows] u64 = 1 KB per
+// slot and CTA); a step's tiles are binned by the slot count (n_cols + n_pairs) of their activation, one launch per class; wider
+// activations use the global-memory variant.
+constexpr uint32_t EVAL_CLASSES = 4;
+constexpr uint32_t EVAL_CLASS_SLOTS[EVAL_CLASSES] = {24, 56, 112, 216};
+inline uint32_t eval_class(uint32_t slots) {
+    for (uint32_t c = 0; c < EVAL_CLASSES; c++)
+        if (slots <= EVAL_CLASS_SLOTS[c]) return c;
+    return EVAL_CLASSES;
+}
+// DP program ops (built by the host, emit_activation_work): src slot | last-of-pair << 15 | condition slot << 16.  Slots of a row:
+// [0, n_cols) condition columns, [n_cols, n_cols + n_pairs) DP table, then the constants ZERO and ONES.
+constexpr uint32_t EVAL_EXTRA_SLOTS = 2;
 
 // one segment of COMPACT_SEG parent rows of an activation's compaction (act_count_kernel / act_compact_kernel)
 constexpr uint32_t COMPACT_SEG = 8192;

@@ -5,6 +5,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <functional>
+#include <map>
 #include <mutex>
 #include <thread>
 #include <atomic>
@@ -151,10 +152,56 @@ struct WorkerPool {
     }
 };
 
+// Host-side first-fit allocator over a lane's slice of the device arena.  Blocks are the persistent buffers of one ranking-rule
+// level (universe rows + bucket columns); they are returned when bucket_sort leaves the level, so the live set follows the
+// depth-first descent of the queries instead of growing for the whole batch.
+struct ArenaAlloc {
+    std::map<size_t, size_t> free_;  // offset -> length, non-adjacent
+    size_t total = 0, used = 0, peak = 0;
+    void reset(size_t bytes) {
+        free_.clear();
+        total = bytes;
+        used = peak = 0;
+        if (bytes) free_[0] = bytes;
+    }
+    size_t take(size_t bytes) {  // SIZE_MAX when nothing fits
+        bytes = (bytes + 255) & ~(size_t)255;
+        for (auto it = free_.begin(); it != free_.end(); ++it)
+            if (it->second >= bytes) {
+                size_t off = it->first, rest = it->second - bytes;
+                free_.erase(it);
+                if (rest) free_[off + bytes] = rest;
+                used += bytes;
+                peak = std::max(peak, used);
+                return off;
+            }
+        return SIZE_MAX;
+    }
+    void give(size_t off, size_t bytes) {
+        bytes = (bytes + 255) & ~(size_t)255;
+        used -= bytes;
+        auto nx = free_.lower_bound(off);
+        if (nx != free_.end() && off + bytes == nx->first) {
+            bytes += nx->second;
+            nx = free_.erase(nx);
+        }
+        if (nx != free_.begin()) {
+            auto pv = std::prev(nx);
+            if (pv->first + pv->second == off) {
+                pv->second += bytes;
+                return;
+            }
+        }
+        free_[off] = bytes;
+    }
+};
+
 // One software-pipeline lane of the step loop: own stream, step buffers, scratch slice and kernel timers.
 struct Lane {
     cudaStream_t stream = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaStream_t cls_stream[EVAL_CLASSES + 1] = {};  // eval_dp classes 1.. run beside class 0 (forked from / joined into `stream`)
+    cudaEvent_t ev_fork = nullptr, ev_join[EVAL_CLASSES + 1] = {};
     DevBuf<uint8_t> d_step;
     DevBuf<uint32_t> d_results, d_qcount, d_segcount;
     DevBuf<Job> d_queue;
@@ -169,7 +216,8 @@ struct Lane {
     // a lane is driven by its own host thread with its own slice of the workers, of the arena and of the statistics
     WorkerPool *pool = nullptr;  // the pool of the lane's driver (shared by the lanes that driver alternates between)
     uint8_t *arena = nullptr;
-    size_t arena_bytes = 0, arena_used = 0;
+    size_t arena_bytes = 0;
+    ArenaAlloc alloc;
     b200_stats lst{};
     int rc = 0;
     std::string error;
@@ -220,6 +268,11 @@ struct Lane {
         for (auto e : ev_pool) cudaEventDestroy(e);
         if (e0) cudaEventDestroy(e0);
         if (e1) cudaEventDestroy(e1);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        for (auto e : ev_join)
+            if (e) cudaEventDestroy(e);
+        for (auto cs : cls_stream)
+            if (cs) cudaStreamDestroy(cs);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -296,7 +349,7 @@ struct Engine {
     int cuda_fail(cudaError_t e, const char *what) { return fail(B200_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e)); }
 
     int stage_finish();
-    int stage_embeddings(const float *vectors, uint64_t n, uint32_t d, const uint32_t *docids);
+    int stage_embeddings(const float *vectors, const uint16_t *half_rows, uint64_t n, uint32_t d, const uint32_t *docids);
     int derive_batch(uint32_t n, const char *words, const uint32_t *off, const uint8_t *max_typo, const uint8_t *is_prefix, uint32_t *one_out,
                      uint32_t *n_one, uint32_t *two_out, uint32_t *n_two);
     int nns_batch(const float *queries, uint32_t n_q, uint32_t d, uint32_t limit, const uint64_t *cand, uint64_t n_cand_words, uint32_t *ids_out,

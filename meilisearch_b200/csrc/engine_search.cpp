@@ -370,6 +370,7 @@ struct StepOut {  // per-activation device work, appended to the step blob by th
     std::vector<DpState> dp_states;   // edge_begin relative to dp_edges
     std::vector<DpEdge> dp_edges;
     std::vector<uint16_t> cost_vals;
+    std::vector<uint32_t> prog;       // DP program for eval_dp_kernel (device_types.h: EVAL_COL_*)
     uint32_t n_cols = 0, n_costs = 0, n_pairs = 0, want_paths = 0, all_conditional = 0;
     uint64_t posting_bytes = 0;
 };
@@ -392,6 +393,7 @@ struct Level {
     uint32_t *uw = nullptr;
     unsigned long long *ub = nullptr, *out = nullptr;
     uint32_t ld = 0, rows = 0, res_off = 0;
+    size_t a_off = SIZE_MAX, a_len = 0;  // the level's block in its lane's arena (uw | ub | out)
     std::vector<uint32_t> counts;  // per cost idx, last = unmatched
     size_t cursor = 0;
     uint64_t universe_count = 0;
@@ -423,8 +425,25 @@ struct QState {
     const unsigned long long *p_ub = nullptr, *p_out = nullptr;
     uint32_t p_rows = 0, p_ld = 0, p_col = 0, p_cap = 0;
     uint32_t act_counter = 0;  // tag of the query's current activation in its row lookup table
+    uint32_t tab_shift = 0;           // the pending activation's path de-duplication table is 4096 << tab_shift slots
+    size_t demand = 0;                // device bytes the pending activation asked for (capacity diagnostics)
     std::vector<uint64_t> term_freq;  // Frequency: documents per term id, filled one device step per term before anything else
     uint32_t n_term_ids = 0;
+    // arena blocks of levels bucket_sort has left; the lane's driver returns them to its allocator at the start of its next step
+    // (the emissions queued by the same advance() still read them: they run first on the lane's stream, before any new owner writes)
+    std::vector<std::pair<size_t, size_t>> freed;
+    void release_level(Level &L) {
+        if (L.a_off != SIZE_MAX) freed.emplace_back(L.a_off, L.a_len);
+        L.a_off = SIZE_MAX;
+    }
+    void pop_level() {
+        release_level(levels.back());
+        levels.pop_back();
+    }
+    void drop_levels() {
+        for (auto &L : levels) release_level(L);
+        levels.clear();
+    }
     explicit QState(const HostIndex &ix) : ctx(ix) {}
 };
 
@@ -1319,6 +1338,29 @@ void emit_activation_work(const QCtx &c, Level &L, StepOut &o) {
         o.dp_edges.push_back(DpEdge{e.dst, (uint16_t)e.cost, e.cond >= 0 ? L.conds[e.cond].col : (uint16_t)0xffff, 0});
     }
     for (auto cv : L.cost_vals) o.cost_vals.push_back((uint16_t)cv);
+    // The DP as a straight-line program over the row's slots (condition columns first, then the (state, cost) pairs): pairs in
+    // descending order = states in reverse topological order; one op per feasible edge, the last one of a pair flagged.
+    const uint32_t n_cols = std::max(1u, o.n_cols), n_pairs = o.n_pairs;
+    if (n_cols + n_pairs + EVAL_EXTRA_SLOTS > 0x7ffe) throw TooComplex{"ranking-rule step with more than 32764 columns"};
+    const uint32_t zero_slot = n_cols + n_pairs, ones_slot = zero_slot + 1;
+    o.prog.clear();
+    for (int sidx = (int)o.dp_states.size() - 2; sidx >= 0; sidx--) {  // END (last state) is the seed, not computed
+        const DpState &ss = o.dp_states[sidx];
+        for (int k = (int)ss.rcount - 1; k >= 0; k--) {
+            const int r = (int)ss.rmin + k;
+            const size_t first = o.prog.size();
+            for (uint32_t e = 0; e < ss.n_edges; e++) {
+                const DpEdge &ee = o.dp_edges[ss.edge_begin + e];
+                const DpState &ds = o.dp_states[ee.dst];
+                const int rr = r - (int)ee.cost;
+                if (rr < (int)ds.rmin || rr >= (int)ds.rmin + (int)ds.rcount) continue;
+                o.prog.push_back((n_cols + ds.pair_off + (uint32_t)(rr - (int)ds.rmin)) | ((ee.col == 0xffff ? ones_slot : (uint32_t)ee.col) << 16));
+            }
+            if (o.prog.size() == first) o.prog.push_back(zero_slot | (zero_slot << 16));
+            o.prog.back() |= 0x8000u;
+        }
+    }
+    while (o.prog.size() % 4) o.prog.push_back(zero_slot | (zero_slot << 16));
 }
 
 // located_query_terms_from_tokens (parse_query.rs:28-202)
@@ -1867,7 +1909,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             size_t cur = q.levels.size() - 1;  // level index; rule index = cur - 1 (level 0 = resolve)
             Level &L = q.levels[cur];
             auto back = [&]() {
-                q.levels.pop_back();
+                q.pop_level();
                 if (!q.levels.empty() && q.levels.size() - 1 >= 1) {
                     size_t rule_cur = q.levels.size() - 2;
                     if (q.rr_scores.size() > rule_cur) q.rr_scores.pop_back();
@@ -1877,7 +1919,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             if (L.kind == RK_FREQ) {
                 const uint32_t t = (uint32_t)L.rule_idx;
                 q.term_freq.push_back(L.counts.empty() ? 0 : L.counts[0]);
-                q.levels.clear();
+                q.drop_levels();
                 if (t + 1 < q.n_term_ids) {
                     start_freq(q, t + 1);
                     return;
@@ -1898,19 +1940,19 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             if (L.kind == RK_RESOLVE) {
                 // the resolve level is not a ranking rule: after it, start rule 0 on its bucket 0
                 if (L.cursor > 0) {
-                    q.levels.clear();
+                    q.drop_levels();
                     break;
                 }
                 L.cursor = 1;
                 q.n_candidates = L.counts[0];
                 uint64_t cnt = L.counts[0];
                 if (cnt < from) {  // bucket_sort.rs:52-64
-                    q.levels.clear();
+                    q.drop_levels();
                     break;
                 }
                 if (n_rules == 0) {
                     emit_bucket(q, L, 0, 1, cnt);
-                    q.levels.clear();
+                    q.drop_levels();
                     break;
                 }
                 Level C;
@@ -1979,6 +2021,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             request_activation(q, std::move(C), L.uw, L.ub, L.out, L.rows, L.ld, (uint32_t)ci, cap);
             return;
         }
+        q.drop_levels();
         q.done = true;
     };
 
@@ -2009,12 +2052,17 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             CU(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking), "lane stream");
             CU(cudaEventCreate(&ln.e0), "lane event");
             CU(cudaEventCreate(&ln.e1), "lane event");
+            CU(cudaEventCreateWithFlags(&ln.ev_fork, cudaEventDisableTiming), "lane event");
+            for (uint32_t c = 1; c <= EVAL_CLASSES; c++) {
+                CU(cudaStreamCreateWithFlags(&ln.cls_stream[c], cudaStreamNonBlocking), "class stream");
+                CU(cudaEventCreateWithFlags(&ln.ev_join[c], cudaEventDisableTiming), "lane event");
+            }
         }
         ln.scratch = scratch + (((scratch_bytes / n_lanes) * l) & ~(size_t)255);
         ln.scratch_bytes = (scratch_bytes / n_lanes) & ~(size_t)255;
         ln.arena = arena + (((arena_bytes / n_lanes) * l) & ~(size_t)255);
         ln.arena_bytes = (arena_bytes / n_lanes) & ~(size_t)255;
-        ln.arena_used = 0;
+        ln.alloc.reset(ln.arena_bytes);
         ln.timing = !(getenv("B200_KERNEL_TIMERS") && atoi(getenv("B200_KERNEL_TIMERS")) == 0);
         ln.lst = b200_stats{};
         ln.rc = 0;
@@ -2037,41 +2085,50 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         CU(cudaMemsetAsync(d_rowtab.p, 0, (size_t)NQ * hix.n_words64 * 4, stream), "zero row lookup tables");
     }
     const size_t PATH_CAP = (size_t)1 << 20;
+    const uint32_t eval_rpt_big = getenv("B200_EVAL_RPT") ? (uint32_t)std::max(1, std::min(8, atoi(getenv("B200_EVAL_RPT")))) : 1;
 
     // pack the pending work of a lane and enqueue it (no synchronisation). returns <0 on error, 0 idle, 1 launched
     auto launch = [&](Lane &ln) -> int {
         auto t_pack = clk::now();
         ln.act_q.clear();
-        std::vector<uint32_t> emit_q;
+        std::vector<uint32_t> emit_q, cand_q;
         for (auto i : ln.members) {
-            if (qs[i]->want_activation) ln.act_q.push_back(i);
-            if (!qs[i]->emits.empty()) emit_q.push_back(i);
+            QState &q = *qs[i];
+            for (auto &f : q.freed) ln.alloc.give(f.first, f.second);  // levels left since the lane's previous step
+            q.freed.clear();
+            if (q.want_activation) cand_q.push_back(i);
+            if (!q.emits.empty()) emit_q.push_back(i);
         }
         // longest first: the parallel-for over these queries ends when its slowest query does, and host time per query grows
         // with the size of its query graph
-        std::stable_sort(ln.act_q.begin(), ln.act_q.end(), [&](uint32_t x, uint32_t y) { return qs[x]->graph.nodes.size() > qs[y]->graph.nodes.size(); });
-        if (ln.act_q.empty() && emit_q.empty()) return 0;
-        ln.lst.device_steps++;
-        const std::vector<uint32_t> &act_q = ln.act_q;
-        const size_t NA = act_q.size();
+        std::stable_sort(cand_q.begin(), cand_q.end(), [&](uint32_t x, uint32_t y) { return qs[x]->graph.nodes.size() > qs[y]->graph.nodes.size(); });
+        if (cand_q.empty() && emit_q.empty()) return 0;
         // pass 1 (serial, light): sizes, offsets, device memory
         struct Plan {
-            uint32_t jobs, sets, words, colprog, states, edges, costs, tiles, probes, res_off, ctiles, n_seg;
-            uint32_t ld;
+            uint32_t jobs, sets, words, colprog, states, edges, costs, tiles, probes, res_off, ctiles, n_seg, prog;
+            uint32_t ld, cls, tab_size, rpt;
             uint8_t *pb;
             size_t coff, toff, soff_from_end;
             bool identity;
         };
-        std::vector<Plan> plan(NA);
-        uint32_t n_jobs = 0, n_sets = 0, n_words = 0, n_colprog = 0, n_states = 0, n_edges = 0, n_costs_tot = 0, n_tiles = 0, n_probes = 0, res_words = 0;
-        uint32_t n_ctiles = 0;
+        std::vector<Plan> plan;
+        plan.reserve(cand_q.size());
+        uint32_t n_jobs = 0, n_sets = 0, n_words = 0, n_colprog = 0, n_states = 0, n_edges = 0, n_costs_tot = 0, n_tiles = 0, n_probes = 0, res_words = 0, n_prog = 0;
+        uint32_t n_ctiles = 0, n_tiles_cls[EVAL_CLASSES + 1] = {};
         bool multi_segment = false;
         size_t z_used = 0, s_used = 0;
         uint64_t compact_bytes = 0, eval_bytes = 0, fill_bytes = 0;
-        for (size_t a = 0; a < NA; a++) {
-            QState &q = *qs[act_q[a]];
+        // An activation joins the step when its per-step scratch (condition matrix, DP table, path table) and its persistent block
+        // (universe rows + bucket columns) fit; otherwise it waits for a later step of the lane (scratch is reused every step, the
+        // arena is refilled as queries leave levels).  New queries (first activation) are only admitted while the arena is less
+        // than ~60 % full, so that the queries already descending can finish.  When nothing at all fits and the lane is idle, the
+        // waiting query with the largest demand fails alone with B200_ERR_CAPACITY and the others go on.
+        bool admit_all = false;
+    plan_again:
+        for (size_t ci = 0; ci < cand_q.size(); ci++) {
+            QState &q = *qs[cand_q[ci]];
             StepOut &o = q.pend;
-            Plan &pl = plan[a];
+            Plan pl{};
             pl.jobs = n_jobs;
             pl.sets = n_sets;
             pl.words = n_words;
@@ -2079,11 +2136,36 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             pl.states = n_states;
             pl.edges = n_edges;
             pl.costs = n_costs_tot;
-            pl.tiles = n_tiles;
+            pl.prog = n_prog;
             pl.probes = n_probes;
             pl.res_off = res_words;
             uint32_t ld = std::max(1u, q.p_cap);
             pl.ld = ld;
+            pl.identity = !q.p_uw && !q.p_out;  // first activation of a query: the universe is the dense documents bitmap itself
+            uint32_t n_cols = std::max(1u, o.n_cols);
+            uint32_t tab_size = o.want_paths ? 4096u << q.tab_shift : 1;
+            pl.tab_size = tab_size;
+            pl.cls = eval_class(n_cols + o.n_pairs + EVAL_EXTRA_SLOTS);
+            pl.rpt = 1;  // rows per thread: > 1 only pays for grids far larger than the GPU (measured: it lengthens the tail of small grids)
+            if (eval_rpt_big > 1 && pl.cls == 0 && ld >= 65536) pl.rpt = eval_rpt_big;
+            const uint32_t my_tiles = (ld + 128 * pl.rpt - 1) / (128 * pl.rpt);
+            size_t persist = pl.identity ? (size_t)ld * 8 * (o.n_costs + 1) : (size_t)ld * 4 + 256 + (size_t)ld * 8 + 256 + (size_t)ld * 8 * (o.n_costs + 1);
+            size_t cbytes = (size_t)ld * 8 * n_cols, sbytes = pl.cls < EVAL_CLASSES ? 0 : (size_t)ld * 8 * o.n_pairs, tbytes = (size_t)tab_size * 8;
+            // zeroed zone (condition matrix + path table) grows from the front of the lane's scratch, the DP table from the back
+            pl.coff = (z_used + 255) & ~(size_t)255;
+            pl.toff = (pl.coff + cbytes + 255) & ~(size_t)255;
+            size_t s_need = (sbytes + 255) & ~(size_t)255;
+            q.demand = persist + cbytes + tbytes + s_need;
+            if (pl.toff + tbytes + s_need + s_used > ln.scratch_bytes) continue;                                   // next step
+            if (pl.identity && !admit_all && ln.alloc.used * 5 > ln.alloc.total * 3 && q.levels.size() <= 1) continue;  // admission
+            size_t aoff = ln.alloc.take(persist);
+            if (aoff == SIZE_MAX) continue;
+            pl.pb = ln.arena + aoff;
+            {
+                Level &L = q.levels.back();
+                L.a_off = aoff;
+                L.a_len = persist;
+            }
             n_jobs += (uint32_t)o.jobs.size();
             n_sets += (uint32_t)o.pairsets.size();
             n_words += (uint32_t)o.words.size();
@@ -2091,39 +2173,59 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             n_states += (uint32_t)o.dp_states.size();
             n_edges += (uint32_t)o.dp_edges.size();
             n_costs_tot += (uint32_t)o.cost_vals.size();
-            n_tiles += (ld + 127) / 128;
+            n_prog += (uint32_t)o.prog.size();
+            pl.tiles = n_tiles_cls[pl.cls];  // within its class; the class bases are added below
+            n_tiles_cls[pl.cls] += my_tiles;
+            n_tiles += my_tiles;
             for (auto &ps : o.pairsets) n_probes += ps.n_left * ps.n_right;
-            res_words += 2 + o.n_costs;
-            pl.identity = !q.p_uw && !q.p_out;  // first activation of a query: the universe is the dense documents bitmap itself
+            res_words += 3 + o.n_costs;  // rows | n_costs + 1 bucket counts | path-table saturation flag
             pl.n_seg = pl.identity ? 1u : std::max(1u, (q.p_rows + COMPACT_SEG - 1) / COMPACT_SEG);
             pl.ctiles = n_ctiles;
             n_ctiles += pl.n_seg;
             multi_segment = multi_segment || pl.n_seg > 1;
-            uint32_t n_cols = std::max(1u, o.n_cols);
-            uint32_t tab_size = o.want_paths ? 4096 : 1;
-            size_t persist = pl.identity ? (size_t)ld * 8 * (o.n_costs + 1) : (size_t)ld * 4 + 256 + (size_t)ld * 8 + 256 + (size_t)ld * 8 * (o.n_costs + 1);
-            {
-                size_t aoff = (ln.arena_used + 255) & ~(size_t)255;
-                pl.pb = aoff + persist <= ln.arena_bytes ? ln.arena + aoff : nullptr;
-                if (pl.pb) ln.arena_used = aoff + persist;
-            }
-            size_t cbytes = (size_t)ld * 8 * n_cols, sbytes = (size_t)ld * 8 * o.n_pairs, tbytes = (size_t)tab_size * 8;
-            // zeroed zone (condition matrix + path table) grows from the front of the lane's scratch, the DP table from the back
-            pl.coff = (z_used + 255) & ~(size_t)255;
-            pl.toff = (pl.coff + cbytes + 255) & ~(size_t)255;
-            size_t s_need = (sbytes + 255) & ~(size_t)255;
-            if (!pl.pb || pl.toff + tbytes + s_need + s_used > ln.scratch_bytes)
-                return lane_fail(ln, B200_ERR_CAPACITY, "device arena exhausted: lower the batch size or raise B200_ARENA_MB / B200_SCRATCH_MB");
             z_used = pl.toff + tbytes;
             s_used += s_need;
             pl.soff_from_end = s_used;
+            ln.act_q.push_back(cand_q[ci]);
             ln.lst.posting_bytes += o.posting_bytes;
-            uint64_t mb = (uint64_t)ld * 8 * (n_cols + o.n_pairs + o.n_costs + 2);
+            // algorithmic bytes of the evaluation: condition columns in, universe word in, bucket columns out (the DP table is on-chip)
+            uint64_t mb = (uint64_t)ld * 8 * (n_cols + o.n_costs + 2);
             ln.lst.matrix_bytes += mb;
             eval_bytes += mb;
             if (!pl.identity) compact_bytes += (uint64_t)q.p_rows * 8 + (uint64_t)ld * 12;
             fill_bytes += o.posting_bytes;
+            plan.push_back(pl);
         }
+        if (ln.act_q.empty() && emit_q.empty()) {
+            // the lane is idle (launch is only called between its steps) and nothing fits
+            if (!admit_all) {
+                admit_all = true;
+                goto plan_again;
+            }
+            uint32_t worst = cand_q[0];
+            for (auto i : cand_q)
+                if (qs[i]->demand > qs[worst]->demand) worst = i;
+            QState &q = *qs[worst];
+            q.status = B200_ERR_CAPACITY;
+            q.error = "a single ranking-rule step of this query needs more device memory than the lane owns (B200_ARENA_MB / B200_SCRATCH_MB)";
+            q.want_activation = false;
+            q.drop_levels();
+            q.done = true;
+            for (auto &f : q.freed) ln.alloc.give(f.first, f.second);
+            q.freed.clear();
+            cand_q.erase(std::find(cand_q.begin(), cand_q.end(), worst));
+            ln.lst.deferred++;
+            if (cand_q.empty()) return 0;
+            admit_all = false;
+            goto plan_again;
+        }
+        ln.lst.deferred += cand_q.size() - ln.act_q.size();
+        uint32_t tile_base[EVAL_CLASSES + 2] = {};
+        for (uint32_t c = 0; c <= EVAL_CLASSES; c++) tile_base[c + 1] = tile_base[c] + n_tiles_cls[c];
+        for (auto &pl : plan) pl.tiles += tile_base[pl.cls];
+        ln.lst.device_steps++;
+        const std::vector<uint32_t> &act_q = ln.act_q;
+        const size_t NA = act_q.size();
         uint32_t n_emits = 0;
         for (auto qi : emit_q) n_emits += (uint32_t)qs[qi]->emits.size();
         // section offsets inside the step blob
@@ -2135,7 +2237,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         };
         size_t o_acts = section(NA * sizeof(ActDesc)), o_sets = section((size_t)n_sets * sizeof(PairSet)), o_words = section((size_t)n_words * 4),
                o_colprog = section((size_t)n_colprog * sizeof(ColOp)), o_states = section((size_t)n_states * sizeof(DpState)),
-               o_edges = section((size_t)n_edges * sizeof(DpEdge)), o_costs = section((size_t)n_costs_tot * 2),
+               o_edges = section((size_t)n_edges * sizeof(DpEdge)), o_costs = section((size_t)n_costs_tot * 2), o_prog = section((size_t)n_prog * 4),
                o_tiles = section((size_t)n_tiles * sizeof(TileDesc)), o_ctiles = section((size_t)n_ctiles * sizeof(CompactTile)),
                o_emits = section((size_t)n_emits * sizeof(EmitDesc)),
                o_jobs = section((size_t)n_jobs * sizeof(Job)), o_nstatic = section(16);
@@ -2167,7 +2269,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             d.n_costs = o.n_costs;
             d.n_states = (uint32_t)o.dp_states.size();
             d.want_paths = o.want_paths;
-            d.tab_size = o.want_paths ? 4096 : 1;
+            d.tab_size = pl.tab_size;
             d.all_conditional = o.all_conditional;
             d.S = reinterpret_cast<unsigned long long *>(ln.scratch + ln.scratch_bytes - pl.soff_from_end);
             d.tab = reinterpret_cast<unsigned long long *>(ln.scratch + pl.toff);
@@ -2196,6 +2298,9 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             d.state_off = pl.states;
             d.edge_off = pl.edges;
             d.cost_off = pl.costs;
+            d.prog_off = pl.prog;
+            d.prog_len = (uint32_t)o.prog.size();
+            if (!o.prog.empty()) memcpy(hb + o_prog + (size_t)pl.prog * 4, o.prog.data(), o.prog.size() * 4);
             d.res_off = pl.res_off;
             L.res_off = pl.res_off;
             memcpy(hb + o_acts + a * sizeof(ActDesc), &d, sizeof d);
@@ -2220,7 +2325,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
                 pb += sd[k].n_left * sd[k].n_right;
             }
             TileDesc *td = reinterpret_cast<TileDesc *>(hb + o_tiles) + pl.tiles;
-            for (uint32_t r0 = 0, k = 0; r0 < ld; r0 += 128, k++) td[k] = TileDesc{(uint32_t)a, r0};
+            for (uint32_t r0 = 0, k = 0; r0 < ld; r0 += 128 * pl.rpt, k++) td[k] = TileDesc{(uint32_t)a, r0, pl.rpt, 0};
             CompactTile *ct = reinterpret_cast<CompactTile *>(hb + o_ctiles) + pl.ctiles;
             for (uint32_t sg = 0; sg < pl.n_seg; sg++) ct[sg] = CompactTile{(uint32_t)a, sg, pl.ctiles, pl.n_seg};
             q.want_activation = false;
@@ -2287,11 +2392,28 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             CU(launch_scatter(st, (uint32_t)sm_count * 8, ln.d_queue.p, ln.d_qcount.p, (uint32_t)qcap, dacts, ln.d_results.p, dix.lists, dix.pool), "scatter");
             size_t t3 = ln.mark();
             ln.time_kernel(ln.lst, B200_K_SCATTER, t2, t3, fill_bytes);
-            CU(launch_eval(st, reinterpret_cast<const TileDesc *>(ln.d_step.p + o_tiles), n_tiles, dacts, ln.d_results.p,
-                           reinterpret_cast<const ColOp *>(ln.d_step.p + o_colprog), reinterpret_cast<const DpState *>(ln.d_step.p + o_states),
-                           reinterpret_cast<const DpEdge *>(ln.d_step.p + o_edges), reinterpret_cast<const uint16_t *>(ln.d_step.p + o_costs),
-                           ln.d_pathbuf.p, ln.d_qcount.p + 1, (uint32_t)PATH_CAP),
-               "eval paths");
+            // the classes are independent (different activations): class 0 stays on the lane's stream, the others run beside it on
+            // forked streams and are joined before the results are copied back
+            uint32_t n_forked = 0;
+            for (uint32_t c = 1; c <= EVAL_CLASSES; c++) n_forked += n_tiles_cls[c] ? 1 : 0;
+            if (n_forked) CU(cudaEventRecord(ln.ev_fork, st), "fork");
+            for (uint32_t c = 0; c <= EVAL_CLASSES; c++) {
+                if (!n_tiles_cls[c]) continue;
+                cudaStream_t cs = c == 0 ? st : ln.cls_stream[c];
+                if (c) CU(cudaStreamWaitEvent(cs, ln.ev_fork, 0), "fork wait");
+                CU(launch_eval(cs, (int)c, reinterpret_cast<const TileDesc *>(ln.d_step.p + o_tiles) + tile_base[c], n_tiles_cls[c], dacts, ln.d_results.p,
+                               reinterpret_cast<const ColOp *>(ln.d_step.p + o_colprog), reinterpret_cast<const DpState *>(ln.d_step.p + o_states),
+                               reinterpret_cast<const DpEdge *>(ln.d_step.p + o_edges), reinterpret_cast<const uint16_t *>(ln.d_step.p + o_costs),
+                               reinterpret_cast<const uint32_t *>(ln.d_step.p + o_prog), ln.d_pathbuf.p, ln.d_qcount.p + 1, (uint32_t)PATH_CAP),
+                   "eval paths");
+                ln.lst.eval_class_launches[c]++;
+                ln.lst.eval_class_tiles[c] += n_tiles_cls[c];
+                if (c) {
+                    ln.lst.kernel_launches++;
+                    CU(cudaEventRecord(ln.ev_join[c], cs), "join");
+                    CU(cudaStreamWaitEvent(st, ln.ev_join[c], 0), "join wait");
+                }
+            }
             ln.time_kernel(ln.lst, B200_K_EVAL_PATHS, t3, ln.mark(), eval_bytes);
             CU(cudaMemcpyAsync(ln.h_results, ln.d_results.p, (size_t)res_words * 4, cudaMemcpyDeviceToHost, st), "D2H results");
             CU(cudaMemcpyAsync(ln.h_results + res_words, ln.d_qcount.p, 8, cudaMemcpyDeviceToHost, st), "D2H counters");
@@ -2349,6 +2471,22 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             L.universe_count = 0;
             for (auto c : L.counts) L.universe_count += c;
             L.cursor = 0;
+            if (res[1 + nc + 1] != 0) {
+                // more distinct surviving paths than the de-duplication table holds: some were not reported.  Run the activation again
+                // with a table 16x larger (its work description q.pend is still in place); give up at 16 M slots.
+                q.release_level(L);
+                if (q.tab_shift >= 12) {
+                    q.status = B200_ERR_CAPACITY;
+                    q.error = "more distinct surviving paths in one ranking-rule step than the device path table holds";
+                    q.drop_levels();
+                    q.done = true;
+                    return;
+                }
+                q.tab_shift += 4;
+                q.want_activation = true;
+                return;
+            }
+            q.tab_shift = 0;
             if (dbg) {
                 std::string msg = "[b200 debug] q" + std::to_string(act_q[a]) + " level " + std::to_string(q.levels.size() - 1) + " kind " +
                                   std::to_string(L.kind) + " rows " + std::to_string(L.rows) + "/" + std::to_string(L.ld) + " states " +
@@ -2429,6 +2567,12 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         stats.device_ms += x.device_ms;
         stats.h2d_bytes += x.h2d_bytes;
         stats.d2h_bytes += x.d2h_bytes;
+        stats.deferred += x.deferred;
+        for (int k = 0; k < 5; k++) {
+            stats.eval_class_launches[k] += x.eval_class_launches[k];
+            stats.eval_class_tiles[k] += x.eval_class_tiles[k];
+        }
+        stats.arena_peak_bytes = std::max<uint64_t>(stats.arena_peak_bytes, lanes[l].alloc.peak * n_lanes);
         for (int k = 0; k < B200_K_COUNT; k++) {
             stats.kernel_ms[k] += x.kernel_ms[k];
             stats.kernel_count[k] += x.kernel_count[k];

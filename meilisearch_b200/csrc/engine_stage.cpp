@@ -125,37 +125,56 @@ int Engine::stage_finish() {
     return B200_OK;
 }
 
-int Engine::stage_embeddings(const float *vectors, uint64_t n, uint32_t d, const uint32_t *docids) {
+// The vector store: fp16 rows + f32 inverse norms + docids.  f32 input (what arroy/hannoy item nodes hold) is converted on the
+// device, chunk by chunk; `half_rows` non-null = the caller already holds IEEE binary16 rows.
+int Engine::stage_embeddings(const float *vectors, const uint16_t *half_rows, uint64_t n, uint32_t d, const uint32_t *docids) {
     CU(cudaSetDevice(device), "cudaSetDevice");
     if (d == 0 || d % 8 != 0) return fail(B200_ERR_INVALID, "embedding dimension must be a positive multiple of 8");
+    if (!vectors && !half_rows && n) return fail(B200_ERR_INVALID, "embeddings: null matrix");
     for (void *p : {(void *)dix.emb, (void *)dix.emb_inv_norm, (void *)dix.emb_docids})
         if (p) cudaFree(p);
     dix.emb = nullptr;
     dix.emb_inv_norm = nullptr;
     dix.emb_docids = nullptr;
-    // fp16 rows + inverse norms computed from the fp32 input (the norm arroy stores in the item header)
-    std::vector<__half> h((size_t)n * d);
-    std::vector<float> inv(n);
-    for (uint64_t r = 0; r < n; r++) {
-        double s = 0;
-        const float *v = vectors + r * d;
-        for (uint32_t i = 0; i < d; i++) {
-            s += (double)v[i] * v[i];
-            h[r * d + i] = __float2half_rn(v[i]);
+    dix.emb_n = 0;
+    const size_t rows_alloc = std::max<uint64_t>(n, 1);
+    CU(cudaMalloc(&dix.emb, rows_alloc * d * 2), "alloc embeddings");
+    CU(cudaMalloc((void **)&dix.emb_inv_norm, rows_alloc * 4), "alloc norms");
+    CU(cudaMalloc((void **)&dix.emb_docids, rows_alloc * 4), "alloc embedding docids");
+    uint8_t *dm = reinterpret_cast<uint8_t *>(dix.emb);
+    const uint64_t chunk = std::max<uint64_t>(1, ((uint64_t)256 << 20) / ((uint64_t)d * 4));  // rows per 256 MB of f32
+    if (half_rows) {
+        for (uint64_t r0 = 0; r0 < n; r0 += chunk * 2) {
+            const uint64_t nr = std::min<uint64_t>(chunk * 2, n - r0);
+            CU(cudaMemcpyAsync(dm + r0 * d * 2, half_rows + r0 * d, nr * d * 2, cudaMemcpyHostToDevice, stream), "H2D embeddings");
         }
-        float nrm = (float)std::sqrt(s);
-        inv[r] = nrm > 0.f ? 1.0f / nrm : 0.f;
+        CU(launch_emb_norm_f16(stream, dix.emb, dix.emb_inv_norm, n, d), "embedding norms");
+    } else {
+        float *stage = nullptr;
+        CU(cudaMalloc((void **)&stage, std::min<uint64_t>(chunk, rows_alloc) * d * 4), "alloc embedding staging");
+        for (uint64_t r0 = 0; r0 < n; r0 += chunk) {
+            const uint64_t nr = std::min<uint64_t>(chunk, n - r0);
+            cudaError_t e = cudaMemcpyAsync(stage, vectors + r0 * d, nr * d * 4, cudaMemcpyHostToDevice, stream);
+            if (e == cudaSuccess) e = launch_emb_from_f32(stream, stage, dm + r0 * d * 2, dix.emb_inv_norm + r0, nr, d);
+            if (e != cudaSuccess) {
+                cudaFree(stage);
+                return cuda_fail(e, "convert embeddings");
+            }
+        }
+        cudaStreamSynchronize(stream);
+        cudaFree(stage);
     }
-    __half *dm = nullptr;
-    CU(upload(&dm, h.data(), h.size()), "upload embeddings");
-    dix.emb = dm;
-    CU(upload(&dix.emb_inv_norm, inv.data(), inv.size()), "upload norms");
-    std::vector<uint32_t> ids(n);
-    for (uint64_t r = 0; r < n; r++) ids[r] = docids ? docids[r] : (uint32_t)r;
-    CU(upload(&dix.emb_docids, ids.data(), ids.size()), "upload embedding docids");
+    if (docids)
+        CU(cudaMemcpyAsync(dix.emb_docids, docids, n * 4, cudaMemcpyHostToDevice, stream), "H2D embedding docids");
+    else {
+        std::vector<uint32_t> ids(n);
+        for (uint64_t r = 0; r < n; r++) ids[r] = (uint32_t)r;
+        CU(cudaMemcpy(dix.emb_docids, ids.data(), n * 4, cudaMemcpyHostToDevice), "H2D embedding docids");
+    }
+    CU(cudaStreamSynchronize(stream), "sync");
     dix.emb_n = n;
     dix.emb_d = d;
-    stats.hbm_bytes_staged += h.size() * 2 + inv.size() * 4 + ids.size() * 4;
+    stats.hbm_bytes_staged += n * d * 2 + n * 8;
     return B200_OK;
 }
 
@@ -399,6 +418,8 @@ int Engine::union_postings(int db, const uint32_t *key_index, uint32_t n_keys, c
     CU(cudaMemcpyAsync(out, base + o_col, W * 8, cudaMemcpyDeviceToHost, stream), "D2H column");
     CU(cudaStreamSynchronize(stream), "sync");
     resolve_timers();
+    // scatter_kernel does not consult the universe for sparse lists (inside the engine the DP masks with it): apply it here
+    for (uint64_t w = 0; w < W; w++) out[w] &= universe ? universe[w] : hix.base_ub[w];
     stats.h2d_bytes += (universe ? W * 8 : 0) + jobs.size() * sizeof(Job) + sizeof a;
     stats.d2h_bytes += W * 8;
     return B200_OK;

@@ -531,21 +531,19 @@ __device__ __forceinline__ void scatter_job_coop(const Job job, const ActDesc &a
         return;
     }
     uint32_t e0 = job.chunk * JOB_CHUNK, e1 = min(lr.card, e0 + JOB_CHUNK);
-    for (uint32_t eb = e0 + lane; eb < e1; eb += 128) {  // four docids per lane and round, their lookups in flight together
-        uint32_t d[4];
-        int jr[4];
-        unsigned long long ubv[4];
+    // Eight docids per lane and round, their row lookups in flight together.  The universe word is NOT consulted here: a document
+    // outside the universe can never leave the DP (S[END] = universe word and every S value is an AND chain down to it), so stray
+    // bits in a condition column are harmless and the dependent chain is docid -> row -> fire-and-forget reduction.
+    for (uint32_t eb = e0 + lane; eb < e1; eb += 256) {
+        uint32_t d[8];
+        int jr[8];
 #pragma unroll
-        for (int x = 0; x < 4; x++) d[x] = eb + 32 * x < e1 ? ids[eb + 32 * x] : 0xffffffffu;
+        for (int x = 0; x < 8; x++) d[x] = eb + 32 * x < e1 ? ids[eb + 32 * x] : 0xffffffffu;
 #pragma unroll
-        for (int x = 0; x < 4; x++) jr[x] = d[x] != 0xffffffffu ? act_row(a, rows, d[x] >> 6) : -1;
+        for (int x = 0; x < 8; x++) jr[x] = d[x] != 0xffffffffu ? act_row(a, rows, d[x] >> 6) : -1;
 #pragma unroll
-        for (int x = 0; x < 4; x++) ubv[x] = jr[x] >= 0 ? a.ub[jr[x]] : 0ull;
-#pragma unroll
-        for (int x = 0; x < 4; x++) {
-            const unsigned long long bit = 1ull << (d[x] & 63);
-            if (ubv[x] & bit) atomicOr(&col[jr[x]], bit);
-        }
+        for (int x = 0; x < 8; x++)
+            if (jr[x] >= 0) atomicOr(&col[jr[x]], 1ull << (d[x] & 63));
     }
 }
 
@@ -575,13 +573,16 @@ __global__ void __launch_bounds__(256) scatter_kernel(const Job *__restrict__ qu
             const ActDesc &a = acts[job.act];
             unsigned long long *col = a.C + (size_t)job.col * a.ld;
             const uint32_t *ids = pool + lr.off;
-            for (uint32_t e = 0; e < lr.card; e++) {
-                uint32_t d = ids[e];
-                int j = act_row(a, rows, d >> 6);
-                if (j >= 0) {
-                    unsigned long long bit = 1ull << (d & 63);
-                    if (a.ub[j] & bit) atomicOr(&col[j], bit);
-                }
+            for (uint32_t e0 = 0; e0 < lr.card; e0 += 4) {  // lookups of four docids in flight together; no universe check (see below)
+                uint32_t d[4];
+                int j[4];
+#pragma unroll
+                for (int x = 0; x < 4; x++) d[x] = e0 + x < lr.card ? ids[e0 + x] : 0xffffffffu;
+#pragma unroll
+                for (int x = 0; x < 4; x++) j[x] = d[x] != 0xffffffffu ? act_row(a, rows, d[x] >> 6) : -1;
+#pragma unroll
+                for (int x = 0; x < 4; x++)
+                    if (j[x] >= 0) atomicOr(&col[j[x]], 1ull << (d[x] & 63));
             }
         }
         unsigned big = __ballot_sync(0xffffffffu, live && !small);
@@ -608,24 +609,40 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
     return x;
 }
 
-// thread per row (64 documents): column program, backward DP over the state graph, buckets, first-match walk
-__global__ void __launch_bounds__(128, 10) eval_dp_kernel(const TileDesc *__restrict__ tiles, const ActDesc *__restrict__ acts,
+// thread per row (64 documents): column program, backward DP over the state graph, buckets, first-match walk.
+//
+// Every thread owns `n_cols + n_pairs` 64-bit *slots*: first the condition columns of its row, then the DP table
+// S[(state, cost) pair].  SMEM = true keeps the slots in shared memory, [slot][thread] (thread-private, conflict-free, no
+// barriers): the thread first loads all its condition words from global memory (independent, coalesced loads: one round of
+// latency), runs the column program on them, and from then on the DP, the buckets and the walk touch shared memory only.  Global
+// traffic = condition columns in + universe word in + bucket columns out, i.e. the algorithmic bytes.  The host bins the tiles of
+// a step by slot count (EVAL_CLASS_SLOTS) and launches one grid per class with that much dynamic shared memory; SMEM = false
+// (more slots than fit) works on the global matrices C and S directly.
+//
+// The DP is a straight-line program built by the host once per activation (emit_activation_work): one 32-bit op per
+// (pair, feasible edge) in processing order (pairs descending = states in reverse topological order):
+// {src slot : 15 | last-of-pair : 1 | condition slot : 16}; acc |= slot[src] & slot[cond]; on `last` the accumulator is stored to
+// the current destination pair, which then steps down.  Ops are consumed four at a time.
+template <bool SMEM>
+__global__ void __launch_bounds__(128, SMEM ? 5 : 8) eval_dp_kernel(const TileDesc *__restrict__ tiles, const ActDesc *__restrict__ acts,
                                                       uint32_t *__restrict__ results, const ColOp *__restrict__ colprog,
                                                       const DpState *__restrict__ states, const DpEdge *__restrict__ edges,
-                                                      const uint16_t *__restrict__ costpool, PathOut *__restrict__ pathbuf,
-                                                      uint32_t *__restrict__ path_count, uint32_t path_cap) {
+                                                      const uint16_t *__restrict__ costpool, const uint32_t *__restrict__ progpool,
+                                                      PathOut *__restrict__ pathbuf, uint32_t *__restrict__ path_count, uint32_t path_cap) {
+    extern __shared__ unsigned long long s_slot[];  // SMEM: [n_cols + n_pairs][128]
     const TileDesc tile = tiles[blockIdx.x];
     const ActDesc &a = acts[tile.act];
     __shared__ uint32_t counts[MAX_COSTS + 1];
-    // the activation's state graph, staged once per CTA: the DP below touches it ~n_pairs * n_edges times per row
+    // the activation's state graph for the walk, staged once per CTA
     constexpr uint32_t SM_STATES = 64, SM_EDGES = 384;
     __shared__ DpState s_states[SM_STATES];
     __shared__ DpEdge s_edges[SM_EDGES];
+    __shared__ unsigned long long s_seen[64];  // path reports already made by this CTA (hashes)
     uint32_t rows = results[a.res_off];
     if (tile.row_begin >= rows) return;
     const DpState *st = states + a.state_off;
     const DpEdge *ed = edges + a.edge_off;
-    {
+    if (a.want_paths) {
         const uint32_t n_edges_total = st[a.n_states - 1].edge_begin;  // END carries the total
         if (a.n_states <= SM_STATES && n_edges_total <= SM_EDGES) {
             for (uint32_t i = threadIdx.x; i < a.n_states; i += blockDim.x) s_states[i] = st[i];
@@ -633,99 +650,71 @@ __global__ void __launch_bounds__(128, 10) eval_dp_kernel(const TileDesc *__rest
             st = s_states;
             ed = s_edges;
         }
+        if (threadIdx.x < 64) s_seen[threadIdx.x] = 0;
     }
     for (uint32_t i = threadIdx.x; i <= a.n_costs; i += blockDim.x) counts[i] = 0;
-    // Flatten the DP into a straight-line program in shared memory, once per CTA: for every (state, cost) pair in processing order
-    // (pair index descending = states in reverse topological order) a header {dst pair, n} followed by n ops {src pair, column}.
-    // The range checks and graph decoding are then paid once per CTA instead of once per row.
-    constexpr uint32_t SM_PAIRS = 512, SM_PROG = 2048;
-    __shared__ uint32_t s_prog[SM_PROG];
-    __shared__ uint16_t s_pair_state[SM_PAIRS], s_pair_cnt[SM_PAIRS], s_pair_off[SM_PAIRS];
-    __shared__ uint32_t s_prog_len;
-    __shared__ unsigned long long s_seen[64];  // path reports already made by this CTA (hashes)
-    const uint32_t END_STATE = a.n_states - 1;
-    const uint32_t n_pairs = (states + a.state_off)[END_STATE].pair_off + 1;  // from global: the shared copy is not complete yet
-    bool flat = (st == s_states) && n_pairs <= SM_PAIRS;
-    if (threadIdx.x < 64) s_seen[threadIdx.x] = 0;
     __syncthreads();
-    if (flat) {
-        for (uint32_t sidx = threadIdx.x; sidx < END_STATE; sidx += blockDim.x) {
-            const DpState ss = st[sidx];
-            for (uint32_t k = 0; k < ss.rcount; k++) s_pair_state[ss.pair_off + k] = (uint16_t)sidx;
-        }
-        __syncthreads();
-        for (uint32_t pi = threadIdx.x; pi + 1 < n_pairs; pi += blockDim.x) {
-            const DpState ss = st[s_pair_state[pi]];
-            const int r = (int)ss.rmin + (int)(pi - ss.pair_off);
-            uint32_t c = 0;
-            for (uint32_t e = 0; e < ss.n_edges; e++) {
-                const DpEdge ee = ed[ss.edge_begin + e];
-                const DpState ds = st[ee.dst];
-                const int rr = r - (int)ee.cost;
-                c += (rr >= (int)ds.rmin && rr < (int)ds.rmin + (int)ds.rcount) ? 1u : 0u;
-            }
-            s_pair_cnt[pi] = (uint16_t)c;
-        }
-        __syncthreads();
-        if (threadIdx.x < 32) {  // offsets in processing order: pair n_pairs-2 first
-            const uint32_t total = n_pairs - 1, per = (total + 31) / 32;
-            const uint32_t q0 = threadIdx.x * per, q1 = min(total, q0 + per);  // q = position in processing order, pair = total-1-q
-            uint32_t sum = 0;
-            for (uint32_t q = q0; q < q1; q++) sum += 1u + s_pair_cnt[total - 1 - q];
-            uint32_t pre = sum;
-#pragma unroll
-            for (int sft = 1; sft < 32; sft <<= 1) {
-                uint32_t t = __shfl_up_sync(0xffffffffu, pre, sft);
-                if ((threadIdx.x & 31) >= (uint32_t)sft) pre += t;
-            }
-            uint32_t at = pre - sum;
-            for (uint32_t q = q0; q < q1; q++) {
-                s_pair_off[total - 1 - q] = (uint16_t)min(at, 0xffffu);
-                at += 1u + s_pair_cnt[total - 1 - q];
-            }
-            if (threadIdx.x == 31) s_prog_len = pre;
-        }
-        __syncthreads();
-        flat = s_prog_len <= SM_PROG;
-        if (flat) {
-            for (uint32_t pi = threadIdx.x; pi + 1 < n_pairs; pi += blockDim.x) {
-                const DpState ss = st[s_pair_state[pi]];
-                const int r = (int)ss.rmin + (int)(pi - ss.pair_off);
-                uint32_t at = s_pair_off[pi];
-                s_prog[at++] = pi | ((uint32_t)s_pair_cnt[pi] << 16);
-                for (uint32_t e = 0; e < ss.n_edges; e++) {
-                    const DpEdge ee = ed[ss.edge_begin + e];
-                    const DpState ds = st[ee.dst];
-                    const int rr = r - (int)ee.cost;
-                    if (rr >= (int)ds.rmin && rr < (int)ds.rmin + (int)ds.rcount)
-                        s_prog[at++] = (ds.pair_off + (uint32_t)(rr - (int)ds.rmin)) | ((uint32_t)ee.col << 16);
-                }
-            }
-        }
+    const uint32_t END = a.n_states - 1;
+    const uint32_t n_cols = a.n_cols;
+    const uint32_t n_pairs = (states + a.state_off)[END].pair_off + 1;
+    // a thread evaluates `rows_per_thread` rows one after the other (rows j, j + 128, ...: coalesced per round), re-using its slots,
+    // so that the per-CTA setup above is paid once per 128 * rows_per_thread rows of a large activation
+    const uint32_t ZERO_SLOT = n_cols + n_pairs, ONES_SLOT = n_cols + n_pairs + 1;
+    if (SMEM) {
+        s_slot[(size_t)ZERO_SLOT * 128 + threadIdx.x] = 0ull;
+        s_slot[(size_t)ONES_SLOT * 128 + threadIdx.x] = ~0ull;
     }
-    __syncthreads();
-    uint32_t j = tile.row_begin + threadIdx.x;
+    for (uint32_t rr_ = 0; rr_ < tile.rows_per_thread; rr_++) {
+    const uint32_t j = tile.row_begin + rr_ * 128 + threadIdx.x;
     if (j < rows) {
         const size_t ld = a.ld;
         unsigned long long *C = a.C;
+        unsigned long long *Sg = a.S;
+        unsigned long long g_const[2] = {0ull, ~0ull};
+#define SLOT(k) (*(SMEM ? &s_slot[(size_t)(k) * 128 + threadIdx.x] : ((k) < n_cols ? &C[(size_t)(k) * ld + j] : ((k) < ZERO_SLOT ? &Sg[(size_t)((k) - n_cols) * ld + j] : &g_const[(k) - ZERO_SLOT]))))
+        const unsigned long long u = a.ub[j];
+        if (SMEM) {
+            unsigned long long any = 0;
+            uint32_t c = 0;
+            for (; c + 8 <= n_cols; c += 8) {
+                unsigned long long v[8];
+#pragma unroll
+                for (int x = 0; x < 8; x++) v[x] = C[(size_t)(c + x) * ld + j];
+#pragma unroll
+                for (int x = 0; x < 8; x++) {
+                    s_slot[(size_t)(c + x) * 128 + threadIdx.x] = v[x];
+                    any |= v[x];
+                }
+            }
+            for (; c < n_cols; c++) {
+                const unsigned long long v = C[(size_t)c * ld + j];
+                s_slot[(size_t)c * 128 + threadIdx.x] = v;
+                any |= v;
+            }
+            if (a.all_conditional && !(any & u)) {
+                // a row that satisfies no condition at all cannot be on any path: it only contributes to the "rest" column
+                for (uint32_t ci = 0; ci < a.n_costs; ci++) a.out[(size_t)ci * ld + j] = 0;
+                a.out[(size_t)a.n_costs * ld + j] = u;
+                if (u) atomicAdd(&counts[a.n_costs], (uint32_t)__popcll(u));
+                goto row_done;
+            }
+        }
         for (uint32_t i = 0; i < a.colprog_len; i++) {
             const ColOp op = colprog[a.colprog_off + i];
-            unsigned long long x = C[(size_t)op.a * ld + j], r;
+            unsigned long long x = SLOT(op.a), r;
             if (op.op == 3)
                 r = x;
             else {
-                unsigned long long y = C[(size_t)op.b * ld + j];
+                unsigned long long y = SLOT(op.b);
                 r = op.op == 0 ? (x & y) : (op.op == 1 ? (x | y) : (x & ~y));
             }
-            C[(size_t)op.dst * ld + j] = r;
+            SLOT(op.dst) = r;
         }
-        const unsigned long long u = a.ub[j];
-        if (a.all_conditional) {
-            // a row that satisfies no condition at all cannot be on any path: it only contributes to the "rest" column
+        if (!SMEM && a.all_conditional) {
             unsigned long long any = 0;
 #pragma unroll 4
-            for (uint32_t c = 0; c < a.n_cols; c++) any |= C[(size_t)c * ld + j];
-            if (!any) {
+            for (uint32_t c = 0; c < n_cols; c++) any |= C[(size_t)c * ld + j];
+            if (!(any & u)) {
                 for (uint32_t ci = 0; ci < a.n_costs; ci++) a.out[(size_t)ci * ld + j] = 0;
                 a.out[(size_t)a.n_costs * ld + j] = u;
                 if (u) atomicAdd(&counts[a.n_costs], (uint32_t)__popcll(u));
@@ -733,63 +722,29 @@ __global__ void __launch_bounds__(128, 10) eval_dp_kernel(const TileDesc *__rest
             }
         }
         {
-        unsigned long long *S = a.S;
-        const uint32_t END = a.n_states - 1;
-        // backward DP; END has the single pair (cost 0).  All (cost, edge) terms of one state are independent: their S / C
-        // loads are issued in groups of 2 costs x 4 edges (predicated, no early-outs) so that a state costs about one
-        // round of L2 latency instead of one per term.
-        S[(size_t)st[END].pair_off * ld + j] = u;
-        if (flat) {
-            const uint32_t plen = s_prog_len;
-            uint32_t i = 0;
-            while (i < plen) {
-                const uint32_t hdr = s_prog[i++];
-                const uint32_t nops = hdr >> 16;
-                unsigned long long acc = 0;
-                for (uint32_t e0 = 0; e0 < nops; e0 += 2) {  // most groups have one or two ops
-                    unsigned long long vv[2], cc[2];
+        SLOT(n_cols + n_pairs - 1) = u;  // END has the single pair (cost 0), the last one
+        {
+            const uint32_t *prog = progpool + a.prog_off;
+            const uint32_t plen = a.prog_len;  // multiple of 4 (padded with no-ops)
+            uint32_t dst = n_cols + n_pairs - 2;
+            unsigned long long acc = 0;
+            for (uint32_t i = 0; i < plen; i += 4) {
+                const uint4 o4 = __ldg(reinterpret_cast<const uint4 *>(prog + i));
+                const uint32_t op[4] = {o4.x, o4.y, o4.z, o4.w};
+                unsigned long long cc[4], sv[4];
 #pragma unroll
-                    for (int x = 0; x < 2; x++) {
-                        const bool have = e0 + x < nops;
-                        const uint32_t op = s_prog[i + (have ? e0 + x : 0)];
-                        const uint32_t col = op >> 16;
-                        vv[x] = have ? S[(size_t)(op & 0xffff) * ld + j] : 0ull;
-                        cc[x] = (have && col != 0xffff) ? C[(size_t)col * ld + j] : ~0ull;
-                    }
-                    acc |= (vv[0] & cc[0]) | (vv[1] & cc[1]);
-                }
-                S[(size_t)(hdr & 0xffff) * ld + j] = acc;
-                i += nops;
-            }
-        } else
-        for (int s = (int)END - 1; s >= 0; s--) {
-            const DpState ss = st[s];
-            for (uint32_t k = 0; k < ss.rcount; k += 2) {
-                const uint32_t r0 = ss.rmin + k;
-                const bool two = k + 1 < ss.rcount;
-                unsigned long long acc0 = 0, acc1 = 0;
-                for (uint32_t e0 = 0; e0 < ss.n_edges; e0 += 4) {
-                    unsigned long long v0[4], v1[4], cc[4];
+                for (int x = 0; x < 4; x++) cc[x] = SLOT(op[x] >> 16);  // a condition slot, or the constant ZERO / ONES slot
+                // sources written inside this group of four are re-read after the store (in-order per thread): read them one by one
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const bool have = e0 + i < ss.n_edges;
-                        const DpEdge ee = ed[ss.edge_begin + (have ? e0 + i : 0)];
-                        const DpState ds = st[ee.dst];
-                        const int rr0 = (int)r0 - (int)ee.cost, rr1 = rr0 + 1;
-                        const bool ok0 = have && rr0 >= (int)ds.rmin && rr0 < (int)ds.rmin + (int)ds.rcount;
-                        const bool ok1 = have && two && rr1 >= (int)ds.rmin && rr1 < (int)ds.rmin + (int)ds.rcount;
-                        v0[i] = ok0 ? S[(size_t)(ds.pair_off + (uint32_t)(rr0 - (int)ds.rmin)) * ld + j] : 0ull;
-                        v1[i] = ok1 ? S[(size_t)(ds.pair_off + (uint32_t)(rr1 - (int)ds.rmin)) * ld + j] : 0ull;
-                        cc[i] = ((ok0 || ok1) && ee.col != 0xffff) ? C[(size_t)ee.col * ld + j] : ~0ull;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        acc0 |= v0[i] & cc[i];
-                        acc1 |= v1[i] & cc[i];
+                for (int x = 0; x < 4; x++) {
+                    sv[x] = SLOT(op[x] & 0x7fffu);
+                    acc |= sv[x] & cc[x];
+                    if (op[x] & 0x8000u) {
+                        SLOT(dst) = acc;
+                        acc = 0;
+                        dst--;
                     }
                 }
-                S[(size_t)(ss.pair_off + k) * ld + j] = acc0;
-                if (two) S[(size_t)(ss.pair_off + k + 1) * ld + j] = acc1;
             }
         }
         // buckets: cheapest cost first
@@ -799,7 +754,7 @@ __global__ void __launch_bounds__(128, 10) eval_dp_kernel(const TileDesc *__rest
         for (uint32_t ci = 0; ci < a.n_costs; ci++) {
             uint32_t r = cost_vals[ci];
             unsigned long long b = 0;
-            if (r >= root.rmin && r < (uint32_t)root.rmin + root.rcount) b = S[(size_t)(root.pair_off + r - root.rmin) * ld + j] & ~taken;
+            if (r >= root.rmin && r < (uint32_t)root.rmin + root.rcount) b = SLOT(n_cols + root.pair_off + r - root.rmin) & ~taken;
             a.out[(size_t)ci * ld + j] = b;
             if (b) {
                 taken |= b;
@@ -830,8 +785,8 @@ __global__ void __launch_bounds__(128, 10) eval_dp_kernel(const TileDesc *__rest
                         uint32_t rr = f.r - ee.cost;
                         const DpState ds = st[ee.dst];
                         if (rr < ds.rmin || rr >= (uint32_t)ds.rmin + ds.rcount) continue;
-                        unsigned long long take = f.mask & S[(size_t)(ds.pair_off + rr - ds.rmin) * ld + j];
-                        if (take && ee.col != 0xffff) take &= C[(size_t)ee.col * ld + j];
+                        unsigned long long take = f.mask & SLOT(n_cols + ds.pair_off + rr - ds.rmin);
+                        if (take && ee.col != 0xffff) take &= SLOT(ee.col);
                         if (!take) continue;
                         f.mask &= ~take;
                         pedges[d] = (uint16_t)eidx;
@@ -856,17 +811,21 @@ __global__ void __launch_bounds__(128, 10) eval_dp_kernel(const TileDesc *__rest
                             }
                             if (known) continue;
                             uint32_t slot = (uint32_t)(h % a.tab_size);
-                            bool fresh = false;
+                            int fresh = -1;  // 1 new, 0 known, -1 table full
                             for (uint32_t probe = 0; probe < a.tab_size; probe++) {
                                 unsigned long long prev = atomicCAS(&a.tab[slot], 0ull, h);
                                 if (prev == 0ull) {
-                                    fresh = true;
+                                    fresh = 1;
                                     break;
                                 }
-                                if (prev == h) break;
+                                if (prev == h) {
+                                    fresh = 0;
+                                    break;
+                                }
                                 slot = slot + 1 == a.tab_size ? 0 : slot + 1;
                             }
-                            if (fresh) {
+                            if (fresh < 0) atomicOr(&results[a.res_off + 1 + a.n_costs + 1], 1u);  // dedup table saturated: the host reruns the step
+                            if (fresh > 0) {
                                 uint32_t at = atomicAdd(path_count, 1u);
                                 if (at < path_cap) {
                                     PathOut po;
@@ -894,6 +853,8 @@ __global__ void __launch_bounds__(128, 10) eval_dp_kernel(const TileDesc *__rest
         if (rest) atomicAdd(&counts[a.n_costs], (uint32_t)__popcll(rest));
         }
     row_done:;
+#undef SLOT
+    }
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i <= a.n_costs; i += blockDim.x)
@@ -1115,6 +1076,52 @@ __global__ void __launch_bounds__(1024) topk_select_kernel(const float *__restri
     }
 }
 
+// ---- staging of the vector store: fp16 rows + f32 inverse norms, one warp per row
+__global__ void __launch_bounds__(256) emb_from_f32_kernel(const float *__restrict__ in, __half *__restrict__ out, float *__restrict__ inv_norm,
+                                                           uint64_t n, uint32_t d) {
+    const uint64_t r = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    if (r >= n) return;
+    const uint32_t lane = threadIdx.x & 31;
+    float ss = 0.f;
+    for (uint32_t i = lane; i < d; i += 32) {
+        const float v = in[r * d + i];
+        ss = fmaf(v, v, ss);
+        out[r * d + i] = __float2half_rn(v);
+    }
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, sft);
+    if (lane == 0) {
+        const float nrm = sqrtf(ss);
+        inv_norm[r] = nrm > 0.f ? 1.0f / nrm : 0.f;
+    }
+}
+__global__ void __launch_bounds__(256) emb_norm_f16_kernel(const __half *__restrict__ rows, float *__restrict__ inv_norm, uint64_t n, uint32_t d) {
+    const uint64_t r = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    if (r >= n) return;
+    const uint32_t lane = threadIdx.x & 31;
+    float ss = 0.f;
+    for (uint32_t i = lane; i < d; i += 32) {
+        const float v = __half2float(rows[r * d + i]);
+        ss = fmaf(v, v, ss);
+    }
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, sft);
+    if (lane == 0) {
+        const float nrm = sqrtf(ss);
+        inv_norm[r] = nrm > 0.f ? 1.0f / nrm : 0.f;
+    }
+}
+cudaError_t launch_emb_from_f32(cudaStream_t s, const float *in, void *out_fp16, float *inv_norm, uint64_t n, uint32_t d) {
+    if (!n) return cudaSuccess;
+    emb_from_f32_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, s>>>(in, reinterpret_cast<__half *>(out_fp16), inv_norm, n, d);
+    return cudaGetLastError();
+}
+cudaError_t launch_emb_norm_f16(cudaStream_t s, const void *rows_fp16, float *inv_norm, uint64_t n, uint32_t d) {
+    if (!n) return cudaSuccess;
+    emb_norm_f16_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, s>>>(reinterpret_cast<const __half *>(rows_fp16), inv_norm, n, d);
+    return cudaGetLastError();
+}
+
 // ======================================================================================== launch wrappers
 #define CK(x)                          \
     do {                               \
@@ -1154,11 +1161,21 @@ cudaError_t launch_scatter(cudaStream_t s, uint32_t n_ctas, const Job *queue, co
     scatter_kernel<<<n_ctas, 256, 0, s>>>(queue, qcount, qcap, acts, results, lists, pool);
     return cudaGetLastError();
 }
-cudaError_t launch_eval(cudaStream_t s, const TileDesc *tiles, uint32_t n_tiles, const ActDesc *acts, uint32_t *results, const ColOp *colprog,
-                        const DpState *states, const DpEdge *edges, const uint16_t *costpool, PathOut *pathbuf, uint32_t *path_count,
-                        uint32_t path_cap) {
+cudaError_t launch_eval(cudaStream_t s, int cls, const TileDesc *tiles, uint32_t n_tiles, const ActDesc *acts, uint32_t *results,
+                        const ColOp *colprog, const DpState *states, const DpEdge *edges, const uint16_t *costpool, const uint32_t *progpool,
+                        PathOut *pathbuf, uint32_t *path_count, uint32_t path_cap) {
     if (!n_tiles) return cudaSuccess;
-    eval_dp_kernel<<<n_tiles, 128, 0, s>>>(tiles, acts, results, colprog, states, edges, costpool, pathbuf, path_count, path_cap);
+    if (cls >= (int)EVAL_CLASSES) {
+        eval_dp_kernel<false><<<n_tiles, 128, 0, s>>>(tiles, acts, results, colprog, states, edges, costpool, progpool, pathbuf, path_count, path_cap);
+        return cudaGetLastError();
+    }
+    static bool attr_done = false;
+    if (!attr_done) {
+        CK(cudaFuncSetAttribute(eval_dp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EVAL_CLASS_SLOTS[EVAL_CLASSES - 1] * 1024)));
+        attr_done = true;
+    }
+    eval_dp_kernel<true><<<n_tiles, 128, (size_t)EVAL_CLASS_SLOTS[cls] * 1024, s>>>(tiles, acts, results, colprog, states, edges, costpool, progpool,
+                                                                                pathbuf, path_count, path_cap);
     return cudaGetLastError();
 }
 cudaError_t launch_emit(cudaStream_t s, const EmitDesc *emits, uint32_t n_emits) {

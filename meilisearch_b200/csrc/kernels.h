@@ -16,15 +16,20 @@ cudaError_t launch_pair_probe(cudaStream_t s, const PairSet *sets, uint32_t n_se
                               const ActDesc *acts, const uint32_t *results, Job *queue, uint32_t *qcount, uint32_t qcap);
 cudaError_t launch_scatter(cudaStream_t s, uint32_t n_ctas, const Job *queue, const uint32_t *qcount, uint32_t qcap, const ActDesc *acts,
                            const uint32_t *results, const DListRef *lists, const uint32_t *pool);
-cudaError_t launch_eval(cudaStream_t s, const TileDesc *tiles, uint32_t n_tiles, const ActDesc *acts, uint32_t *results, const ColOp *colprog,
-                        const DpState *states, const DpEdge *edges, const uint16_t *costpool, PathOut *pathbuf, uint32_t *path_count,
-                        uint32_t path_cap);
+// cls: eval_class() of the tiles' activations (EVAL_CLASSES = DP table in global scratch)
+cudaError_t launch_eval(cudaStream_t s, int cls, const TileDesc *tiles, uint32_t n_tiles, const ActDesc *acts, uint32_t *results, const ColOp *colprog,
+                        const DpState *states, const DpEdge *edges, const uint16_t *costpool, const uint32_t *progpool, PathOut *pathbuf,
+                        uint32_t *path_count, uint32_t path_cap);
 cudaError_t launch_emit(cudaStream_t s, const EmitDesc *emits, uint32_t n_emits);
 cudaError_t launch_vec_dist(cudaStream_t s, int n_ctas, int qt, const void *mat_fp16, const float *inv_norm, const uint32_t *docids,
                             uint64_t n_rows, uint32_t d, const float *queries, const float *q_inv_norm, const unsigned long long *cand,
                             uint64_t n_cand_words, float *dist);
 cudaError_t launch_topk(cudaStream_t s, uint32_t n_q, const float *dist, const uint32_t *docids, uint64_t n_rows, uint32_t k, uint32_t tie_cap,
                         float *out_dist, uint32_t *out_ids, uint32_t *out_n);
+
+// staging of the vector store: f32 rows -> fp16 rows + inverse norms; inverse norms of fp16 rows
+cudaError_t launch_emb_from_f32(cudaStream_t s, const float *in, void *out_fp16, float *inv_norm, uint64_t n, uint32_t d);
+cudaError_t launch_emb_norm_f16(cudaStream_t s, const void *rows_fp16, float *inv_norm, uint64_t n, uint32_t d);
 
 // ---- vec_gemm.cu: batched vector stage on tcgen05 (queries x matrix^T with the top-k fused into the epilogue)
 #define VEC_GEMM_CAND_CAP 256

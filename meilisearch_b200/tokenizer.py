@@ -69,3 +69,15 @@ class TokenBatch:
         self.token_kind = np.asarray(kinds, dtype=np.uint8) if kinds else np.zeros(1, np.uint8)
         self.lemma_off = np.asarray(offs, dtype=np.uint32)
         self.lemma_bytes = np.frombuffer(b"".join(chunks) + b"\0", dtype=np.uint8).copy()
+
+    def head(self, n):
+        """the first n queries as a batch of their own (shares no buffers with self)"""
+        n = min(n, self.n_queries)
+        t = TokenBatch.__new__(TokenBatch)
+        t.n_queries = n
+        t.token_begin = self.token_begin[: n + 1].copy()
+        nt = int(t.token_begin[-1])
+        t.token_kind = self.token_kind[: max(nt, 1)].copy()
+        t.lemma_off = self.lemma_off[: nt + 1].copy()
+        t.lemma_bytes = self.lemma_bytes.copy()
+        return t

@@ -98,8 +98,21 @@ struct Index {
     // vector store: one embedding per row, cosine
     uint32_t dim = 0;
     std::vector<float> embeddings;
+    std::vector<uint16_t> embeddings_f16;  // alternative storage (IEEE binary16 rows) for large stores; `embeddings` is then empty
     std::vector<float> emb_norms;
     std::vector<uint32_t> emb_docids;
+    // Whole-universe nearest neighbours of the current batch's query vectors, computed by one blocked pass over the store
+    // (batch_nns, rules.h) instead of one full scan per query: query vector pointer -> ascending (docid, distance).
+    // Read-only while queries run.
+    mutable std::map<const float *, std::vector<std::pair<uint32_t, float>>> nns_cache;
+    float emb_at(size_t r, uint32_t i) const {
+        if (!embeddings_f16.empty()) {
+            _Float16 h;
+            memcpy(&h, &embeddings_f16[r * dim + i], 2);
+            return (float)h;
+        }
+        return embeddings[r * dim + i];
+    }
     bool has_distribution = false;
     float dist_mean = 0, dist_sigma = 0;
 

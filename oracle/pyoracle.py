@@ -54,6 +54,7 @@ def lib():
         l.orc_clear_synonyms.argtypes = [C.c_void_p]
         l.orc_add_synonym.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
         l.orc_set_embeddings.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
+        l.orc_set_embeddings_f16.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint32]
         l.orc_set_distribution.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float]
         l.orc_search_batch.restype = C.c_int
         l.orc_search_batch.argtypes = [C.c_void_p, C.POINTER(_Batch), C.POINTER(_Out), C.c_uint32, C.c_char_p, C.c_uint32]
@@ -144,9 +145,13 @@ class OracleIndex:
                     self._l.orc_add_synonym(self._h, k.encode(), v.encode())
 
     def set_embeddings(self, matrix, docids=None, distribution=None):
-        m = np.ascontiguousarray(matrix, np.float32)
-        ids = np.arange(m.shape[0], dtype=np.uint32) if docids is None else np.ascontiguousarray(docids, np.uint32)
-        self._l.orc_set_embeddings(self._h, _p(m), m.shape[0], m.shape[1], _p(ids))
+        ids = np.arange(matrix.shape[0], dtype=np.uint32) if docids is None else np.ascontiguousarray(docids, np.uint32)
+        if getattr(matrix, "dtype", None) == np.float16:
+            m = np.ascontiguousarray(matrix)
+            self._l.orc_set_embeddings_f16(self._h, _p(m), m.shape[0], m.shape[1], _p(ids), os.cpu_count() or 1)
+        else:
+            m = np.ascontiguousarray(matrix, np.float32)
+            self._l.orc_set_embeddings(self._h, _p(m), m.shape[0], m.shape[1], _p(ids))
         self.dim = m.shape[1]
         if distribution:
             self._l.orc_set_distribution(self._h, 1, distribution[0], distribution[1])

@@ -882,31 +882,131 @@ struct ExactAttributeRule : RankingRule {
 // arroy/hannoy `Cosine` (arroy 0.6.4 / hannoy 0.1.3, not vendored): distance = (1 - cos)/2 in f32, cos clamped to [-1,1],
 // 0 when either norm is ~0.  Exact scan (the reference is approximate).  Ordering contract:
 // vector/store.rs:1059,1090 (ascending distance).
-inline std::vector<std::pair<uint32_t, float>> nns_by_vector(const Index &ix, const float *q, size_t limit, const Bitmap *filter) {
+// 8-lane partial sums (GCC vector extension): the dot product of a query with a row, as arroy/hannoy compute it with SIMD
+// (their summation order is not specified either; results are compared with a 1e-4 relative tolerance)
+typedef float orc_v8 __attribute__((vector_size(32)));
+inline float dot_f32(const float *a, const float *b, uint32_t d) {
+    orc_v8 acc = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t i = 0;
+    for (; i + 8 <= d; i += 8) {
+        orc_v8 x, y;
+        memcpy(&x, a + i, 32);
+        memcpy(&y, b + i, 32);
+        acc += x * y;
+    }
+    float s = ((acc[0] + acc[4]) + (acc[1] + acc[5])) + ((acc[2] + acc[6]) + (acc[3] + acc[7]));
+    for (; i < d; i++) s += a[i] * b[i];
+    return s;
+}
+inline float cosine_distance(float dot, float qn, float vn) {
+    float pnqn = qn * vn;
+    if (pnqn > 1.1920929e-7f) {
+        float cs = dot / pnqn;
+        cs = std::max(-1.0f, std::min(1.0f, cs));
+        return (1.0f - cs) / 2.0f;
+    }
+    return 0.0f;
+}
+inline std::vector<std::pair<uint32_t, float>> nns_by_vector(const Index &ix, const float *q, size_t limit, const Bitmap *filter,
+                                                             const float *cache_key = nullptr) {
+    // served from the batch pass when the call covers every stored embedding (execute_hybrid / semantic search over documents_ids)
+    if (!ix.nns_cache.empty()) {
+        auto it = ix.nns_cache.find(cache_key ? cache_key : q);
+        if (it != ix.nns_cache.end() && (limit <= it->second.size() || it->second.size() == ix.emb_docids.size()) &&
+            (!filter || filter->len() >= ix.documents_ids.len())) {
+            std::vector<std::pair<uint32_t, float>> r(it->second.begin(), it->second.begin() + std::min(limit, it->second.size()));
+            return r;
+        }
+    }
     std::vector<std::pair<uint32_t, float>> res;
     uint32_t d = ix.dim;
     float qn = 0;
     for (uint32_t i = 0; i < d; i++) qn += q[i] * q[i];
     qn = std::sqrt(qn);
     size_t n = ix.emb_docids.size();
+    std::vector<float> row(d);
     for (size_t r = 0; r < n; r++) {
         uint32_t doc = ix.emb_docids[r];
         if (filter && !filter->contains(doc)) continue;
-        const float *v = ix.embeddings.data() + r * d;
+        const float *v;
+        if (ix.embeddings_f16.empty())
+            v = ix.embeddings.data() + r * d;
+        else {
+            for (uint32_t i = 0; i < d; i++) row[i] = ix.emb_at(r, i);
+            v = row.data();
+        }
         float dot = 0;
         for (uint32_t i = 0; i < d; i++) dot += q[i] * v[i];
-        float pnqn = qn * ix.emb_norms[r];
-        float dist = 0.0f;
-        if (pnqn > 1.1920929e-7f) {
-            float cs = dot / pnqn;
-            cs = std::max(-1.0f, std::min(1.0f, cs));
-            dist = (1.0f - cs) / 2.0f;
-        }
-        res.push_back({doc, dist});
+        res.push_back({doc, cosine_distance(dot, qn, ix.emb_norms[r])});
     }
     std::sort(res.begin(), res.end(), [](auto &a, auto &b) { return a.second != b.second ? a.second < b.second : a.first < b.first; });
     if (res.size() > limit) res.resize(limit);
     return res;
+}
+// One blocked pass over the store for a whole batch of query vectors (the shape of the scan is ours; every distance is the same
+// arroy/hannoy `Cosine` as above): row blocks are spread over threads, every thread keeps the k best (distance, docid) of every
+// query, the per-thread lists are merged.  Fills ix.nns_cache.
+inline void batch_nns(const Index &ix, const float *queries, uint32_t nq, size_t k, unsigned n_threads) {
+    ix.nns_cache.clear();
+    const uint32_t d = ix.dim;
+    const size_t n = ix.emb_docids.size();
+    if (!nq || !n || !d) return;
+    std::vector<float> qn(nq);
+    for (uint32_t q = 0; q < nq; q++) {
+        float s = 0;
+        for (uint32_t i = 0; i < d; i++) s += queries[(size_t)q * d + i] * queries[(size_t)q * d + i];
+        qn[q] = std::sqrt(s);
+    }
+    n_threads = std::max(1u, n_threads);
+    typedef std::pair<float, uint32_t> DK;  // (distance, docid): the nns ordering
+    std::vector<std::vector<std::vector<DK>>> best(n_threads, std::vector<std::vector<DK>>(nq));
+    const size_t BLOCK = 256;
+    std::atomic<size_t> next{0};
+    auto worker = [&](unsigned t) {
+        std::vector<float> blk(BLOCK * d);
+        auto &mine = best[t];
+        for (auto &h : mine) h.reserve(k + 1);
+        for (;;) {
+            const size_t r0 = next.fetch_add(BLOCK);
+            if (r0 >= n) break;
+            const size_t nr = std::min(BLOCK, n - r0);
+            const float *rows;
+            if (ix.embeddings_f16.empty())
+                rows = ix.embeddings.data() + r0 * d;
+            else {
+                for (size_t r = 0; r < nr; r++)
+                    for (uint32_t i = 0; i < d; i++) blk[r * d + i] = ix.emb_at(r0 + r, i);
+                rows = blk.data();
+            }
+            for (uint32_t q = 0; q < nq; q++) {
+                const float *qv = queries + (size_t)q * d;
+                auto &h = mine[q];  // max-heap on (distance, docid) of the k best so far
+                for (size_t r = 0; r < nr; r++) {
+                    DK cand{cosine_distance(dot_f32(qv, rows + r * d, d), qn[q], ix.emb_norms[r0 + r]), ix.emb_docids[r0 + r]};
+                    if (h.size() < k) {
+                        h.push_back(cand);
+                        std::push_heap(h.begin(), h.end());
+                    } else if (cand < h.front()) {
+                        std::pop_heap(h.begin(), h.end());
+                        h.back() = cand;
+                        std::push_heap(h.begin(), h.end());
+                    }
+                }
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < n_threads; t++) th.emplace_back(worker, t);
+    worker(0);
+    for (auto &x : th) x.join();
+    for (uint32_t q = 0; q < nq; q++) {
+        std::vector<DK> all;
+        for (unsigned t = 0; t < n_threads; t++) all.insert(all.end(), best[t][q].begin(), best[t][q].end());
+        std::sort(all.begin(), all.end());
+        if (all.size() > k) all.resize(k);
+        auto &out = ix.nns_cache[queries + (size_t)q * d];
+        for (auto &x : all) out.push_back({x.second, x.first});
+    }
 }
 inline float distribution_shift(float mean, float sigma, float score) {  // vector/distribution.rs:103-130
     float factor = 0.4f / sigma;
@@ -918,13 +1018,14 @@ inline float distribution_shift(float mean, float sigma, float score) {  // vect
 }
 struct VectorSortRule : RankingRule {
     std::vector<float> target;
+    const float *source = nullptr;  // the caller's vector (key of Index::nns_cache)
     Bitmap vector_candidates;
     size_t limit;
     std::vector<std::pair<uint32_t, float>> cached;
     size_t cursor = 0;
     VectorSortRule(std::vector<float> t, Bitmap c, size_t l) : target(std::move(t)), vector_candidates(std::move(c)), limit(l) {}
     size_t fill_buffer(Ctx &ctx, const Bitmap &cands) {
-        cached = nns_by_vector(ctx.index, target.data(), limit, &cands);
+        cached = nns_by_vector(ctx.index, target.data(), limit, &cands, source);
         cursor = 0;
         return cached.size();
     }
