@@ -14,7 +14,7 @@ def test_header_symbols_exported():
     mb.build_library()
     lib = mb.load_library()
     hdr = open(os.path.join(ROOT, "include", "b200milli.h")).read()
-    declared = set(re.findall(r"\b(b200_[a-z_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", hdr))
     assert declared, "no declarations parsed"
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in b200milli.h but not exported"
