@@ -74,8 +74,11 @@ struct ActDesc {
     uint32_t state_off, edge_off, cost_off;  // into DpState[], DpEdge[], u16 cost_vals[]
     uint32_t colprog_off, colprog_len;
     uint32_t prog_off, prog_len;  // DP program, u32 ops in the step's program pool; prog_len is a multiple of 4
+    uint32_t n_pairs;             // (state, cost) pairs of the DP table; START's pairs come first, END's single pair last
+    uint32_t root_rmin, root_rcount;  // START's cost range
+    uint32_t need;                // documents bucket_sort can still use from this activation (hits left + offset left), saturating
     uint32_t tab_size, want_paths;
-    uint32_t res_off;         // into results u32[]: [0] rows, [1..n_costs+1] counts
+    uint32_t res_off;         // into results u32[]: [0] rows, [1..n_costs+1] counts, then: path-table saturation flag, last walked bucket
     uint32_t all_conditional; // every START->END path has at least one condition: rows whose columns are all zero match nothing
     // per-query lookup table word index -> (tag << 20 | row), written by act_compact, read by scatter instead of a binary search in
     // uw; nullptr = not available (then uw is searched).  Entries of other activations carry other tags.

@@ -206,6 +206,7 @@ struct Lane {
     DevBuf<uint32_t> d_results, d_qcount, d_segcount;
     DevBuf<Job> d_queue;
     DevBuf<PathOut> d_pathbuf;
+    DevBuf<unsigned long long> d_tile_summary;  // 2 u64 per eval tile: its non-empty buckets (eval_dp_kernel -> walk_kernel)
     uint8_t *h_step = nullptr;
     size_t h_step_cap = 0;
     uint32_t *h_results = nullptr;
@@ -263,6 +264,7 @@ struct Lane {
         d_queue.release();
         d_segcount.release();
         d_pathbuf.release();
+        d_tile_summary.release();
         if (h_step) cudaFreeHost(h_step);
         if (h_results) cudaFreeHost(h_results);
         for (auto e : ev_pool) cudaEventDestroy(e);

@@ -393,6 +393,7 @@ struct Level {
     uint32_t *uw = nullptr;
     unsigned long long *ub = nullptr, *out = nullptr;
     uint32_t ld = 0, rows = 0, res_off = 0;
+    uint32_t walked_m = 0;               // last bucket whose surviving paths were computed (walk_kernel)
     size_t a_off = SIZE_MAX, a_len = 0;  // the level's block in its lane's arena (uw | ub | out)
     std::vector<uint32_t> counts;  // per cost idx, last = unmatched
     size_t cursor = 0;
@@ -425,6 +426,7 @@ struct QState {
     const unsigned long long *p_ub = nullptr, *p_out = nullptr;
     uint32_t p_rows = 0, p_ld = 0, p_col = 0, p_cap = 0;
     uint32_t act_counter = 0;  // tag of the query's current activation in its row lookup table
+    uint32_t need = 1;                // documents the pending activation can still contribute (ActDesc::need)
     uint32_t tab_shift = 0;           // the pending activation's path de-duplication table is 4096 << tab_shift slots
     size_t demand = 0;                // device bytes the pending activation asked for (capacity diagnostics)
     std::vector<uint64_t> term_freq;  // Frequency: documents per term id, filled one device step per term before anything else
@@ -1774,6 +1776,10 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         emit_activation_work(q.ctx, L, q.pend);
         q.levels.push_back(std::move(L));
         q.want_activation = true;
+        // what bucket_sort can still use from this activation: the hits it has to return plus the offset it has to skip; the walk
+        // (pass 2) only looks at the cheapest buckets that together hold that many documents
+        q.need = (uint32_t)std::min<uint64_t>(0xffffffffull, (from > q.cur_offset ? from - q.cur_offset : 0) + (uint64_t)(length - std::min(length, q.n_results)));
+        if (q.need == 0) q.need = 1;
         q.p_uw = p_uw;
         q.p_ub = p_ub;
         q.p_out = p_out;
@@ -1999,6 +2005,13 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             else {
                 // the paths that took at least one document, in visiting order (= lexicographic in edge ids)
                 PROF(0);
+                if (ci > L.walked_m) {  // cannot happen: buckets 0..walked_m hold every document the query still needed
+                    q.status = B200_ERR_STATE;
+                    q.error = "internal: descent into a bucket whose surviving paths were not computed";
+                    q.drop_levels();
+                    q.done = true;
+                    return;
+                }
                 std::vector<const SurvPath *> sp;
                 for (auto &p : L.surv)
                     if (p.cost_idx == ci) sp.push_back(&p);
@@ -2085,6 +2098,14 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         CU(cudaMemsetAsync(d_rowtab.p, 0, (size_t)NQ * hix.n_words64 * 4, stream), "zero row lookup tables");
     }
     const size_t PATH_CAP = (size_t)1 << 20;
+    struct WorkHist {
+        std::mutex mu;
+        uint64_t lists[4][33][2] = {};  // [universe class][log2 card | 32 = dense] -> {lists, stored bytes}
+        uint64_t eval[10][4][4] = {};   // [rule kind][universe class] -> {activations, rows(ld), rows x program ops, rows x columns}
+        uint64_t probes[4] = {};
+    };
+    std::unique_ptr<WorkHist> work_hist_holder(getenv("B200_WORK_HIST") ? new WorkHist() : nullptr);
+    WorkHist *work_hist = work_hist_holder.get();
     const uint32_t eval_rpt_big = getenv("B200_EVAL_RPT") ? (uint32_t)std::max(1, std::min(8, atoi(getenv("B200_EVAL_RPT")))) : 1;
 
     // pack the pending work of a lane and enqueue it (no synchronisation). returns <0 on error, 0 idle, 1 launched
@@ -2115,6 +2136,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         plan.reserve(cand_q.size());
         uint32_t n_jobs = 0, n_sets = 0, n_words = 0, n_colprog = 0, n_states = 0, n_edges = 0, n_costs_tot = 0, n_tiles = 0, n_probes = 0, res_words = 0, n_prog = 0;
         uint32_t n_ctiles = 0, n_tiles_cls[EVAL_CLASSES + 1] = {};
+        bool want_paths_cls[EVAL_CLASSES + 1] = {};
         bool multi_segment = false;
         size_t z_used = 0, s_used = 0;
         uint64_t compact_bytes = 0, eval_bytes = 0, fill_bytes = 0;
@@ -2174,11 +2196,12 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             n_edges += (uint32_t)o.dp_edges.size();
             n_costs_tot += (uint32_t)o.cost_vals.size();
             n_prog += (uint32_t)o.prog.size();
+            want_paths_cls[pl.cls] = want_paths_cls[pl.cls] || o.want_paths;
             pl.tiles = n_tiles_cls[pl.cls];  // within its class; the class bases are added below
             n_tiles_cls[pl.cls] += my_tiles;
             n_tiles += my_tiles;
             for (auto &ps : o.pairsets) n_probes += ps.n_left * ps.n_right;
-            res_words += 3 + o.n_costs;  // rows | n_costs + 1 bucket counts | path-table saturation flag
+            res_words += 4 + o.n_costs;  // rows | n_costs + 1 bucket counts | path-table saturation flag | last walked bucket
             pl.n_seg = pl.identity ? 1u : std::max(1u, (q.p_rows + COMPACT_SEG - 1) / COMPACT_SEG);
             pl.ctiles = n_ctiles;
             n_ctiles += pl.n_seg;
@@ -2194,6 +2217,26 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             eval_bytes += mb;
             if (!pl.identity) compact_bytes += (uint64_t)q.p_rows * 8 + (uint64_t)ld * 12;
             fill_bytes += o.posting_bytes;
+            if (work_hist) {  // B200_WORK_HIST=1: where the step's work comes from (developer statistics, see tools/)
+                const int kind = q.levels.back().kind;
+                const int ub = ld >= 65536 ? 3 : (ld >= 4096 ? 2 : (ld >= 128 ? 1 : 0));
+                std::lock_guard<std::mutex> g(work_hist->mu);
+                for (auto &jb : o.jobs) {
+                    if (jb.chunk) continue;
+                    const ListRef &lr = hix.lists[jb.list];
+                    int cb = 0;
+                    while ((1u << cb) < lr.card && cb < 31) cb++;
+                    auto &cell = work_hist->lists[ub][lr.dense ? 32 : cb];
+                    cell[0]++;
+                    cell[1] += lr.dense ? (uint64_t)hix.n_words64 * 8 : (uint64_t)lr.card * 4;
+                }
+                auto &ev = work_hist->eval[kind][ub];
+                ev[0]++;
+                ev[1] += ld;
+                ev[2] += (uint64_t)ld * o.prog.size();
+                ev[3] += (uint64_t)ld * n_cols;
+                for (auto &ps : o.pairsets) work_hist->probes[ub] += (uint64_t)ps.n_left * ps.n_right;
+            }
             plan.push_back(pl);
         }
         if (ln.act_q.empty() && emit_q.empty()) {
@@ -2300,6 +2343,10 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             d.cost_off = pl.costs;
             d.prog_off = pl.prog;
             d.prog_len = (uint32_t)o.prog.size();
+            d.n_pairs = o.n_pairs;
+            d.need = q.need;
+            d.root_rmin = o.dp_states.empty() ? 0 : o.dp_states[0].rmin;
+            d.root_rcount = o.dp_states.empty() ? 0 : o.dp_states[0].rcount;
             if (!o.prog.empty()) memcpy(hb + o_prog + (size_t)pl.prog * 4, o.prog.data(), o.prog.size() * 4);
             d.res_off = pl.res_off;
             L.res_off = pl.res_off;
@@ -2374,7 +2421,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             CU(cudaMemsetAsync(ln.d_results.p, 0, (size_t)(res_words + 4) * 4, st), "zero results");
             CU(cudaMemsetAsync(ln.scratch, 0, z_used, st), "zero condition matrix");
             CU(ln.d_pathbuf.reserve(PATH_CAP), "path buffer");
-            CU(cudaMemsetAsync(ln.d_qcount.p + 1, 0, 4, st), "zero path count");
+            CU(cudaMemsetAsync(ln.d_qcount.p + 1, 0, 12, st), "zero path count, scatter cursor, walk count");
             size_t t0 = ln.mark();
             CU(ln.d_segcount.reserve(n_ctiles + 1), "segment counts");
             CU(launch_compact(st, reinterpret_cast<const CompactTile *>(ln.d_step.p + o_ctiles), n_ctiles, multi_segment, dacts, ln.d_segcount.p,
@@ -2389,11 +2436,12 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
                "pair probe");
             size_t t2 = ln.mark();
             if (n_probes) ln.time_kernel(ln.lst, B200_K_PAIR_PROBE, t1, t2, (uint64_t)n_probes * 8 * 23);
-            CU(launch_scatter(st, (uint32_t)sm_count * 8, ln.d_queue.p, ln.d_qcount.p, (uint32_t)qcap, dacts, ln.d_results.p, dix.lists, dix.pool), "scatter");
+            CU(launch_scatter(st, (uint32_t)sm_count * 5, ln.d_queue.p, ln.d_qcount.p, (uint32_t)qcap, dacts, ln.d_results.p, dix.lists, dix.pool), "scatter");
             size_t t3 = ln.mark();
             ln.time_kernel(ln.lst, B200_K_SCATTER, t2, t3, fill_bytes);
             // the classes are independent (different activations): class 0 stays on the lane's stream, the others run beside it on
             // forked streams and are joined before the results are copied back
+            CU(ln.d_tile_summary.reserve(2 * (size_t)n_tiles + 2), "tile summaries");
             uint32_t n_forked = 0;
             for (uint32_t c = 1; c <= EVAL_CLASSES; c++) n_forked += n_tiles_cls[c] ? 1 : 0;
             if (n_forked) CU(cudaEventRecord(ln.ev_fork, st), "fork");
@@ -2401,11 +2449,20 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
                 if (!n_tiles_cls[c]) continue;
                 cudaStream_t cs = c == 0 ? st : ln.cls_stream[c];
                 if (c) CU(cudaStreamWaitEvent(cs, ln.ev_fork, 0), "fork wait");
-                CU(launch_eval(cs, (int)c, reinterpret_cast<const TileDesc *>(ln.d_step.p + o_tiles) + tile_base[c], n_tiles_cls[c], dacts, ln.d_results.p,
-                               reinterpret_cast<const ColOp *>(ln.d_step.p + o_colprog), reinterpret_cast<const DpState *>(ln.d_step.p + o_states),
-                               reinterpret_cast<const DpEdge *>(ln.d_step.p + o_edges), reinterpret_cast<const uint16_t *>(ln.d_step.p + o_costs),
-                               reinterpret_cast<const uint32_t *>(ln.d_step.p + o_prog), ln.d_pathbuf.p, ln.d_qcount.p + 1, (uint32_t)PATH_CAP),
-                   "eval paths");
+                const TileDesc *tl = reinterpret_cast<const TileDesc *>(ln.d_step.p + o_tiles) + tile_base[c];
+                CU(launch_eval(cs, (int)c, tl, n_tiles_cls[c], dacts, ln.d_results.p, reinterpret_cast<const ColOp *>(ln.d_step.p + o_colprog),
+                               reinterpret_cast<const uint16_t *>(ln.d_step.p + o_costs), reinterpret_cast<const uint32_t *>(ln.d_step.p + o_prog),
+                               ln.d_tile_summary.p + 2 * (size_t)tile_base[c]),
+                   "eval");
+                // pass 2 right behind it on the same stream: all tiles of an activation are in one class, so its counts are final
+                if (want_paths_cls[c]) {
+                    CU(launch_walk(cs, (int)c, tl, n_tiles_cls[c], dacts, ln.d_results.p, reinterpret_cast<const ColOp *>(ln.d_step.p + o_colprog),
+                                   reinterpret_cast<const DpState *>(ln.d_step.p + o_states), reinterpret_cast<const DpEdge *>(ln.d_step.p + o_edges),
+                                   reinterpret_cast<const uint16_t *>(ln.d_step.p + o_costs), reinterpret_cast<const uint32_t *>(ln.d_step.p + o_prog),
+                                   ln.d_tile_summary.p + 2 * (size_t)tile_base[c], ln.d_pathbuf.p, ln.d_qcount.p + 1, (uint32_t)PATH_CAP),
+                       "walk");
+                    ln.lst.kernel_launches++;
+                }
                 ln.lst.eval_class_launches[c]++;
                 ln.lst.eval_class_tiles[c] += n_tiles_cls[c];
                 if (c) {
@@ -2416,7 +2473,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             }
             ln.time_kernel(ln.lst, B200_K_EVAL_PATHS, t3, ln.mark(), eval_bytes);
             CU(cudaMemcpyAsync(ln.h_results, ln.d_results.p, (size_t)res_words * 4, cudaMemcpyDeviceToHost, st), "D2H results");
-            CU(cudaMemcpyAsync(ln.h_results + res_words, ln.d_qcount.p, 8, cudaMemcpyDeviceToHost, st), "D2H counters");
+            CU(cudaMemcpyAsync(ln.h_results + res_words, ln.d_qcount.p, 16, cudaMemcpyDeviceToHost, st), "D2H counters");
         }
         if (ln.timing) CU(cudaEventRecord(ln.e1, st), "event");
         ln.res_words = res_words;
@@ -2471,6 +2528,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             L.universe_count = 0;
             for (auto c : L.counts) L.universe_count += c;
             L.cursor = 0;
+            L.walked_m = res[1 + nc + 2];
             if (res[1 + nc + 1] != 0) {
                 // more distinct surviving paths than the de-duplication table holds: some were not reported.  Run the activation again
                 // with a table 16x larger (its work description q.pend is still in place); give up at 16 M slots.
@@ -2615,6 +2673,23 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
                 }
             }
         }
+    }
+    if (work_hist) {
+        static const char *ucls[4] = {"ld<128", "ld<4096", "ld<65536", "ld>=65536"};
+        static const char *kinds[10] = {"words", "typo", "proximity", "fid", "position", "exactness", "exact_attr", "resolve", "freq", "?"};
+        for (int u = 0; u < 4; u++) {
+            fprintf(stderr, "[b200 work] scatter lists, universe %s (pair probes %llu):\n", ucls[u], (unsigned long long)work_hist->probes[u]);
+            for (int c = 0; c < 33; c++)
+                if (work_hist->lists[u][c][0])
+                    fprintf(stderr, "    %s%-2d lists %9llu  bytes %8.1f MB\n", c == 32 ? "dense " : "card<=2^", c == 32 ? 0 : c,
+                            (unsigned long long)work_hist->lists[u][c][0], work_hist->lists[u][c][1] / 1e6);
+        }
+        for (int k = 0; k < 10; k++)
+            for (int u = 0; u < 4; u++)
+                if (work_hist->eval[k][u][0])
+                    fprintf(stderr, "[b200 work] eval %-10s %-10s acts %7llu rows %10llu row*ops %12llu row*cols %11llu\n", kinds[k], ucls[u],
+                            (unsigned long long)work_hist->eval[k][u][0], (unsigned long long)work_hist->eval[k][u][1],
+                            (unsigned long long)work_hist->eval[k][u][2], (unsigned long long)work_hist->eval[k][u][3]);
     }
     if (prof)
         fprintf(stderr, "[b200 profile] thread-ms: build_from_paths %.2f  prepare_graph_rule %.2f  request_activation %.2f  advance(total) %.2f\n",

@@ -407,7 +407,7 @@ int Engine::union_postings(int db, const uint32_t *key_index, uint32_t n_keys, c
     if (!jobs.empty()) {
         CU(cudaMemcpyAsync(base + o_jobs, jobs.data(), jobs.size() * sizeof(Job), cudaMemcpyHostToDevice, stream), "H2D jobs");
         size_t m0 = mark();
-        CU(launch_scatter(stream, (uint32_t)sm_count * 8, reinterpret_cast<const Job *>(base + o_jobs), reinterpret_cast<const uint32_t *>(base + o_res + 64),
+        CU(launch_scatter(stream, (uint32_t)sm_count * 5, reinterpret_cast<const Job *>(base + o_jobs), reinterpret_cast<uint32_t *>(base + o_res + 64),
                           (uint32_t)jobs.size(), reinterpret_cast<const ActDesc *>(base + o_act), reinterpret_cast<const uint32_t *>(base + o_res),
                           dix.lists, dix.pool),
            "scatter");

@@ -92,7 +92,12 @@ struct Builder {
         for (auto &e : errs)
             if (!e.empty()) throw std::runtime_error(e);
         uint32_t first = (uint32_t)ix.lists.size();
-        uint32_t dense_min = ix.n_docs / 32;
+        // A list is stored as a dense bitmap over the docid space when card > n_docs / 128 (B200_DENSE_DIV): a bitmap costs
+        // n_docs / 8 bytes, i.e. at most 4x the sorted-docid form at that density, and turns the scatter of the list into a coalesced
+        // gather by universe row instead of one random row lookup per docid.
+        uint32_t dense_div = 128;
+        if (const char *env = getenv("B200_DENSE_DIV")) dense_div = (uint32_t)std::max(8, atoi(env));
+        uint32_t dense_min = ix.n_docs / dense_div;
         for (unsigned t = 0; t < nt; t++) {
             size_t at = 0;
             for (uint32_t c : cards[t]) {

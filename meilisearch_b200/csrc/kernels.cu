@@ -16,6 +16,8 @@
 #include "device_types.h"
 #include "kernels.h"
 
+#include <algorithm>
+
 namespace b200 {
 
 // ======================================================================================== lev
@@ -508,9 +510,10 @@ __device__ __forceinline__ void scatter_job_coop(const Job job, const ActDesc &a
     }
     const uint32_t *ids = pool + lr.off;
     if (a.uw && (unsigned long long)rows * 16ull < lr.card) {
-        // universe much smaller than the list: walk the rows and binary-search the list (chunk 0 does it all)
-        if (job.chunk != 0) return;
-        for (uint32_t j = lane; j < rows; j += 32) {
+        // universe much smaller than the list: walk the rows and binary-search the list; the rows are dealt round-robin to the
+        // list's chunks (every chunk of the list has a job), so a 100-chunk list searches with 100 warps
+        const uint32_t n_chunks = (lr.card + JOB_CHUNK - 1) / JOB_CHUNK;
+        for (uint32_t j = job.chunk * 32 + lane; j < rows; j += 32 * n_chunks) {
             uint32_t w = a.uw[j];
             uint32_t lo = 0, hi = lr.card, key = w << 6;
             while (lo < hi) {
@@ -547,18 +550,23 @@ __device__ __forceinline__ void scatter_job_coop(const Job job, const ActDesc &a
     }
 }
 
-__global__ void __launch_bounds__(256) scatter_kernel(const Job *__restrict__ queue, const uint32_t *__restrict__ qcount, uint32_t qcap,
+__global__ void __launch_bounds__(256) scatter_kernel(const Job *__restrict__ queue, uint32_t *__restrict__ qcount, uint32_t qcap,
                                                       const ActDesc *__restrict__ acts, const uint32_t *__restrict__ results,
                                                       const DListRef *__restrict__ lists, const uint32_t *__restrict__ pool) {
-    uint32_t n_jobs = min(*qcount, qcap);
-    uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
-    uint32_t lane = threadIdx.x & 31;
-    // job (k*32 + lane) * warps_total + warp: neighbouring jobs (e.g. the chunks of one long list) go to different warps
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    for (uint32_t k = 0; (unsigned long long)k * 32ull * warps_total + warp < n_jobs; k++) {
-        unsigned long long jb64 = ((unsigned long long)k * 32ull + lane) * warps_total + warp;
-        bool have = jb64 < n_jobs;
-        uint32_t jb = (uint32_t)jb64;
+    const uint32_t n_jobs = min(qcount[0], qcap);
+    const uint32_t lane = threadIdx.x & 31;
+    // Persistent warps pull 32 jobs at a time from a shared cursor (qcount[2], zeroed by the host): the cost of a job ranges from
+    // one docid to a 2048-element chunk, so a static split leaves most warps idle behind the few that drew long lists.
+    // A grab g covers the jobs g, g + n_grabs, g + 2 n_grabs, ...: neighbouring jobs (the chunks of one long list) go to different
+    // warps, and the 32 jobs of one grab come from all over the step.
+    const uint32_t n_grabs = (n_jobs + 31) / 32;
+    for (;;) {
+        uint32_t g = 0;
+        if (lane == 0) g = atomicAdd(&qcount[2], 1u);
+        g = __shfl_sync(0xffffffffu, g, 0);
+        if (g >= n_grabs) break;
+        const uint32_t jb = lane * n_grabs + g;
+        const bool have = jb < n_jobs;
         Job job{0, 0, 0, 0};
         DListRef lr{0, 0, 0};
         uint32_t rows = 0;
@@ -609,71 +617,164 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
     return x;
 }
 
-// thread per row (64 documents): column program, backward DP over the state graph, buckets, first-match walk.
-//
-// Every thread owns `n_cols + n_pairs` 64-bit *slots*: first the condition columns of its row, then the DP table
-// S[(state, cost) pair].  SMEM = true keeps the slots in shared memory, [slot][thread] (thread-private, conflict-free, no
-// barriers): the thread first loads all its condition words from global memory (independent, coalesced loads: one round of
-// latency), runs the column program on them, and from then on the DP, the buckets and the walk touch shared memory only.  Global
-// traffic = condition columns in + universe word in + bucket columns out, i.e. the algorithmic bytes.  The host bins the tiles of
-// a step by slot count (EVAL_CLASS_SLOTS) and launches one grid per class with that much dynamic shared memory; SMEM = false
-// (more slots than fit) works on the global matrices C and S directly.
+// ---- evaluation of an activation: column program, backward DP over the state graph, buckets, counts, surviving paths.
+// Thread per row (64 documents).  Every thread owns `n_cols + n_pairs + 2` 64-bit *slots*: the condition columns of its row, the
+// DP table S[(state, cost) pair], and the constants ZERO / ONES.  SMEM = true keeps the slots in shared memory, [slot][thread]
+// (thread-private, conflict-free, no barriers): the thread first loads all its condition words from global memory (independent,
+// coalesced loads: one round of latency), runs the column program on them, and from then on the DP, the buckets and the walk
+// touch shared memory only.  Global traffic = condition columns in + universe word in + bucket columns out, i.e. the algorithmic
+// bytes.  The host bins the tiles of a step by slot count (EVAL_CLASS_SLOTS) and launches one grid per class with that much
+// dynamic shared memory; SMEM = false (more slots than fit) works on the global matrices C and S directly.
 //
 // The DP is a straight-line program built by the host once per activation (emit_activation_work): one 32-bit op per
 // (pair, feasible edge) in processing order (pairs descending = states in reverse topological order):
 // {src slot : 15 | last-of-pair : 1 | condition slot : 16}; acc |= slot[src] & slot[cond]; on `last` the accumulator is stored to
 // the current destination pair, which then steps down.  Ops are consumed four at a time.
-template <bool SMEM>
-__global__ void __launch_bounds__(128, SMEM ? 5 : 8) eval_dp_kernel(const TileDesc *__restrict__ tiles, const ActDesc *__restrict__ acts,
-                                                      uint32_t *__restrict__ results, const ColOp *__restrict__ colprog,
-                                                      const DpState *__restrict__ states, const DpEdge *__restrict__ edges,
-                                                      const uint16_t *__restrict__ costpool, const uint32_t *__restrict__ progpool,
-                                                      PathOut *__restrict__ pathbuf, uint32_t *__restrict__ path_count, uint32_t path_cap) {
-    extern __shared__ unsigned long long s_slot[];  // SMEM: [n_cols + n_pairs][128]
-    const TileDesc tile = tiles[blockIdx.x];
-    const ActDesc &a = acts[tile.act];
-    __shared__ uint32_t counts[MAX_COSTS + 1];
-    // the activation's state graph for the walk, staged once per CTA
-    constexpr uint32_t SM_STATES = 64, SM_EDGES = 384;
-    __shared__ DpState s_states[SM_STATES];
-    __shared__ DpEdge s_edges[SM_EDGES];
-    __shared__ unsigned long long s_seen[64];  // path reports already made by this CTA (hashes)
-    uint32_t rows = results[a.res_off];
-    if (tile.row_begin >= rows) return;
-    const DpState *st = states + a.state_off;
-    const DpEdge *ed = edges + a.edge_off;
-    if (a.want_paths) {
-        const uint32_t n_edges_total = st[a.n_states - 1].edge_begin;  // END carries the total
-        if (a.n_states <= SM_STATES && n_edges_total <= SM_EDGES) {
-            for (uint32_t i = threadIdx.x; i < a.n_states; i += blockDim.x) s_states[i] = st[i];
-            for (uint32_t i = threadIdx.x; i < n_edges_total; i += blockDim.x) s_edges[i] = ed[i];
-            st = s_states;
-            ed = s_edges;
-        }
-        if (threadIdx.x < 64) s_seen[threadIdx.x] = 0;
+//
+// Surviving paths (graph_based_ranking_rule.rs:340-353: the host rebuilds the next query graph from the paths that took at
+// least one document) are the business of walk_kernel, which runs after this kernel over the same tiles: this kernel leaves, per
+// tile, the set of its non-empty buckets (tile_summary), so that whole tiles are skipped there.
+constexpr int WALK_SPARSE = 8;
+__device__ __forceinline__ void load_act(ActDesc *dst, const ActDesc *src) {
+    static_assert(sizeof(ActDesc) % 4 == 0, "ActDesc is copied word by word");
+    const uint32_t *s = reinterpret_cast<const uint32_t *>(src);
+    uint32_t *d = reinterpret_cast<uint32_t *>(dst);
+    for (uint32_t i = threadIdx.x; i < sizeof(ActDesc) / 4; i += blockDim.x) d[i] = s[i];
+}
+// insert h into the activation's global table; 1 new, 0 known, -1 table full
+__device__ __forceinline__ int tab_insert(const ActDesc &a, unsigned long long h) {
+    uint32_t slot = (uint32_t)(h % a.tab_size);
+    for (uint32_t probe = 0; probe < a.tab_size; probe++) {
+        unsigned long long prev = atomicCAS(&a.tab[slot], 0ull, h);
+        if (prev == 0ull) return 1;
+        if (prev == h) return 0;
+        slot = slot + 1 == a.tab_size ? 0 : slot + 1;
     }
-    for (uint32_t i = threadIdx.x; i <= a.n_costs; i += blockDim.x) counts[i] = 0;
+    return -1;
+}
+// The walk of one row: `slot(k)` reads the row's slot k (condition columns after the column program, then the DP table).
+template <class SlotFn>
+__device__ __forceinline__ void walk_row(const ActDesc &a, uint32_t act_i, uint32_t last_bucket, const DpState *st, const DpEdge *ed,
+                                         const uint16_t *cost_vals, size_t j, SlotFn slot, unsigned long long *s_seen /* 64 */, uint32_t *results, PathOut *pathbuf,
+                                         uint32_t *path_count, uint32_t path_cap) {
+    const uint32_t END = a.n_states - 1, n_cols = a.n_cols;
+    for (uint32_t ci = 0; ci <= last_bucket && ci < a.n_costs; ci++) {
+        const unsigned long long b = a.out[(size_t)ci * a.ld + j];
+        if (!b) continue;
+        struct Frame {
+            unsigned long long mask;
+            uint16_t state, e, r;
+        } stack[MAX_WALK];
+        uint16_t pedges[MAX_WALK];
+        int d = 0;
+        stack[0].mask = b;
+        stack[0].state = 0;
+        stack[0].e = 0;
+        stack[0].r = cost_vals[ci];
+        while (d >= 0) {
+            Frame &f = stack[d];
+            const DpState fs = st[f.state];
+            if (f.mask == 0 || f.e >= fs.n_edges) {
+                d--;
+                continue;
+            }
+            uint32_t eidx = fs.edge_begin + f.e;
+            const DpEdge ee = ed[eidx];
+            f.e++;
+            if (ee.cost > f.r) continue;
+            uint32_t rr = f.r - ee.cost;
+            const DpState ds = st[ee.dst];
+            if (rr < ds.rmin || rr >= (uint32_t)ds.rmin + ds.rcount) continue;
+            unsigned long long take = f.mask & slot(n_cols + ds.pair_off + rr - ds.rmin);
+            if (take && ee.col != 0xffff) take &= slot(ee.col);
+            if (!take) continue;
+            f.mask &= ~take;
+            pedges[d] = (uint16_t)eidx;
+            if (ee.dst == END) {
+                // a complete path: report it once per activation
+                unsigned long long h = mix64(0x9e3779b97f4a7c15ull * (ci + 1));
+                for (int k = 0; k <= d; k++) h = mix64(h + 0xd6e8feb86659fd93ull * (unsigned long long)(pedges[k] + 1));
+                h = (h & ~2ull) | 1ull;  // bit 1 clear: a path (signatures have it set)
+                bool known = false;
+                {
+                    // the local filter may be shared by rows of different activations (walk_kernel): its key carries the activation
+                    const unsigned long long hl = (h ^ (0x9e3779b97f4a7c15ull * (unsigned long long)(act_i + 1))) | 1ull;
+                    uint32_t sl = (uint32_t)(hl >> 20) & 63u;
+                    for (int probe = 0; probe < 8; probe++) {
+                        unsigned long long prev = atomicCAS(&s_seen[sl], 0ull, hl);
+                        if (prev == hl) {
+                            known = true;
+                            break;
+                        }
+                        if (prev == 0ull) break;  // we claimed it: go on to the global table
+                        sl = (sl + 1) & 63u;
+                    }
+                }
+                if (known) continue;
+                const int fresh = tab_insert(a, h);
+                if (fresh < 0) atomicOr(&results[a.res_off + 1 + a.n_costs + 1], 1u);  // table saturated: the host reruns the step
+                if (fresh > 0) {
+                    uint32_t at = atomicAdd(path_count, 1u);
+                    if (at < path_cap) {
+                        PathOut po;
+                        po.act = act_i;
+                        po.cost_idx = (uint16_t)ci;
+                        po.len = (uint16_t)(d + 1);
+                        for (int k = 0; k < (int)MAX_WALK; k++) po.edges[k] = k <= d ? pedges[k] : 0;
+                        pathbuf[at] = po;
+                    }
+                }
+                continue;
+            }
+            if (d + 1 >= (int)MAX_WALK) continue;  // host guarantees path length <= MAX_WALK
+            d++;
+            stack[d].mask = take;
+            stack[d].state = ee.dst;
+            stack[d].e = 0;
+            stack[d].r = (uint16_t)rr;
+        }
+    }
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(128, 8) eval_dp_kernel(const TileDesc *__restrict__ tiles, const ActDesc *__restrict__ acts,
+                                                      uint32_t *__restrict__ results, const ColOp *__restrict__ colprog,
+                                                      const uint16_t *__restrict__ costpool, const uint32_t *__restrict__ progpool,
+                                                      unsigned long long *__restrict__ tile_summary) {
+    extern __shared__ unsigned long long s_slot[];  // SMEM: [n_cols + n_pairs + 2][128]
+    const TileDesc tile = tiles[blockIdx.x];
+    __shared__ ActDesc a;
+    __shared__ uint32_t counts[MAX_COSTS + 1];
+    load_act(&a, &acts[tile.act]);
+    for (uint32_t i = threadIdx.x; i <= MAX_COSTS; i += blockDim.x) counts[i] = 0;
     __syncthreads();
-    const uint32_t END = a.n_states - 1;
-    const uint32_t n_cols = a.n_cols;
-    const uint32_t n_pairs = (states + a.state_off)[END].pair_off + 1;
-    // a thread evaluates `rows_per_thread` rows one after the other (rows j, j + 128, ...: coalesced per round), re-using its slots,
-    // so that the per-CTA setup above is paid once per 128 * rows_per_thread rows of a large activation
+    const uint32_t rows = results[a.res_off];
+    if (tile.row_begin >= rows) {
+        if (threadIdx.x < 2) tile_summary[2 * (size_t)blockIdx.x + threadIdx.x] = 0ull;
+        return;
+    }
+    const uint32_t n_cols = a.n_cols, n_pairs = a.n_pairs, n_costs = a.n_costs;
     const uint32_t ZERO_SLOT = n_cols + n_pairs, ONES_SLOT = n_cols + n_pairs + 1;
+    const size_t ld = a.ld;
+    unsigned long long *const C = a.C;
+    unsigned long long *const Sg = a.S;
+    unsigned long long *const out = a.out;
+    const uint32_t *const prog = progpool + a.prog_off;
+    const uint16_t *const cost_vals = costpool + a.cost_off;
+    const uint32_t lane = threadIdx.x & 31;
     if (SMEM) {
         s_slot[(size_t)ZERO_SLOT * 128 + threadIdx.x] = 0ull;
         s_slot[(size_t)ONES_SLOT * 128 + threadIdx.x] = ~0ull;
     }
     for (uint32_t rr_ = 0; rr_ < tile.rows_per_thread; rr_++) {
-    const uint32_t j = tile.row_begin + rr_ * 128 + threadIdx.x;
-    if (j < rows) {
-        const size_t ld = a.ld;
-        unsigned long long *C = a.C;
-        unsigned long long *Sg = a.S;
+        const uint32_t j = tile.row_begin + rr_ * 128 + threadIdx.x;
+        if (tile.row_begin + rr_ * 128 >= rows) break;  // uniform
+        const bool active = j < rows;
         unsigned long long g_const[2] = {0ull, ~0ull};
 #define SLOT(k) (*(SMEM ? &s_slot[(size_t)(k) * 128 + threadIdx.x] : ((k) < n_cols ? &C[(size_t)(k) * ld + j] : ((k) < ZERO_SLOT ? &Sg[(size_t)((k) - n_cols) * ld + j] : &g_const[(k) - ZERO_SLOT]))))
-        const unsigned long long u = a.ub[j];
-        if (SMEM) {
+        const unsigned long long u = active ? a.ub[j] : 0ull;
+        bool run = active;
+        if (SMEM && active) {
             unsigned long long any = 0;
             uint32_t c = 0;
             for (; c + 8 <= n_cols; c += 8) {
@@ -691,54 +792,43 @@ __global__ void __launch_bounds__(128, SMEM ? 5 : 8) eval_dp_kernel(const TileDe
                 s_slot[(size_t)c * 128 + threadIdx.x] = v;
                 any |= v;
             }
-            if (a.all_conditional && !(any & u)) {
-                // a row that satisfies no condition at all cannot be on any path: it only contributes to the "rest" column
-                for (uint32_t ci = 0; ci < a.n_costs; ci++) a.out[(size_t)ci * ld + j] = 0;
-                a.out[(size_t)a.n_costs * ld + j] = u;
-                if (u) atomicAdd(&counts[a.n_costs], (uint32_t)__popcll(u));
-                goto row_done;
-            }
+            // a row that satisfies no condition at all cannot be on any path: it only contributes to the "rest" column
+            if (a.all_conditional && !(any & u)) run = false;
         }
-        for (uint32_t i = 0; i < a.colprog_len; i++) {
-            const ColOp op = colprog[a.colprog_off + i];
-            unsigned long long x = SLOT(op.a), r;
-            if (op.op == 3)
-                r = x;
-            else {
-                unsigned long long y = SLOT(op.b);
-                r = op.op == 0 ? (x & y) : (op.op == 1 ? (x | y) : (x & ~y));
+        if (run) {
+            for (uint32_t i = 0; i < a.colprog_len; i++) {
+                const ColOp op = colprog[a.colprog_off + i];
+                unsigned long long x = SLOT(op.a), r;
+                if (op.op == 3)
+                    r = x;
+                else {
+                    unsigned long long y = SLOT(op.b);
+                    r = op.op == 0 ? (x & y) : (op.op == 1 ? (x | y) : (x & ~y));
+                }
+                SLOT(op.dst) = r;
             }
-            SLOT(op.dst) = r;
-        }
-        if (!SMEM && a.all_conditional) {
-            unsigned long long any = 0;
+            if (!SMEM && a.all_conditional) {
+                unsigned long long any = 0;
 #pragma unroll 4
-            for (uint32_t c = 0; c < n_cols; c++) any |= C[(size_t)c * ld + j];
-            if (!(any & u)) {
-                for (uint32_t ci = 0; ci < a.n_costs; ci++) a.out[(size_t)ci * ld + j] = 0;
-                a.out[(size_t)a.n_costs * ld + j] = u;
-                if (u) atomicAdd(&counts[a.n_costs], (uint32_t)__popcll(u));
-                goto row_done;
+                for (uint32_t c = 0; c < n_cols; c++) any |= C[(size_t)c * ld + j];
+                if (!(any & u)) run = false;
             }
         }
-        {
-        SLOT(n_cols + n_pairs - 1) = u;  // END has the single pair (cost 0), the last one
-        {
-            const uint32_t *prog = progpool + a.prog_off;
+        if (run) {
+            SLOT(n_cols + n_pairs - 1) = u;  // END has the single pair (cost 0), the last one
             const uint32_t plen = a.prog_len;  // multiple of 4 (padded with no-ops)
             uint32_t dst = n_cols + n_pairs - 2;
             unsigned long long acc = 0;
             for (uint32_t i = 0; i < plen; i += 4) {
                 const uint4 o4 = __ldg(reinterpret_cast<const uint4 *>(prog + i));
                 const uint32_t op[4] = {o4.x, o4.y, o4.z, o4.w};
-                unsigned long long cc[4], sv[4];
+                unsigned long long cc[4];
 #pragma unroll
                 for (int x = 0; x < 4; x++) cc[x] = SLOT(op[x] >> 16);  // a condition slot, or the constant ZERO / ONES slot
                 // sources written inside this group of four are re-read after the store (in-order per thread): read them one by one
 #pragma unroll
                 for (int x = 0; x < 4; x++) {
-                    sv[x] = SLOT(op[x] & 0x7fffu);
-                    acc |= sv[x] & cc[x];
+                    acc |= SLOT(op[x] & 0x7fffu) & cc[x];
                     if (op[x] & 0x8000u) {
                         SLOT(dst) = acc;
                         acc = 0;
@@ -747,118 +837,178 @@ __global__ void __launch_bounds__(128, SMEM ? 5 : 8) eval_dp_kernel(const TileDe
                 }
             }
         }
-        // buckets: cheapest cost first
-        const DpState root = st[0];
-        const uint16_t *cost_vals = costpool + a.cost_off;
+        // buckets, cheapest cost first; the counters are aggregated per warp before they touch shared memory
         unsigned long long taken = 0;
-        for (uint32_t ci = 0; ci < a.n_costs; ci++) {
-            uint32_t r = cost_vals[ci];
+        for (uint32_t ci = 0; ci < n_costs; ci++) {
+            const uint32_t r = cost_vals[ci];
             unsigned long long b = 0;
-            if (r >= root.rmin && r < (uint32_t)root.rmin + root.rcount) b = SLOT(n_cols + root.pair_off + r - root.rmin) & ~taken;
-            a.out[(size_t)ci * ld + j] = b;
-            if (b) {
-                taken |= b;
-                atomicAdd(&counts[ci], (uint32_t)__popcll(b));
-                if (a.want_paths) {
-                    // walk: every document follows the first edge (in order) it satisfies and can still finish from
-                    struct Frame {
-                        unsigned long long mask;
-                        uint16_t state, e, r;
-                    } stack[MAX_WALK];
-                    uint16_t pedges[MAX_WALK];
-                    int d = 0;
-                    stack[0].mask = b;
-                    stack[0].state = 0;
-                    stack[0].e = 0;
-                    stack[0].r = (uint16_t)r;
-                    while (d >= 0) {
-                        Frame &f = stack[d];
-                        const DpState fs = st[f.state];
-                        if (f.mask == 0 || f.e >= fs.n_edges) {
-                            d--;
-                            continue;
-                        }
-                        uint32_t eidx = fs.edge_begin + f.e;
-                        const DpEdge ee = ed[eidx];
-                        f.e++;
-                        if (ee.cost > f.r) continue;
-                        uint32_t rr = f.r - ee.cost;
-                        const DpState ds = st[ee.dst];
-                        if (rr < ds.rmin || rr >= (uint32_t)ds.rmin + ds.rcount) continue;
-                        unsigned long long take = f.mask & SLOT(n_cols + ds.pair_off + rr - ds.rmin);
-                        if (take && ee.col != 0xffff) take &= SLOT(ee.col);
-                        if (!take) continue;
-                        f.mask &= ~take;
-                        pedges[d] = (uint16_t)eidx;
-                        if (ee.dst == END) {
-                            // a complete path: report it once per activation
-                            unsigned long long h = mix64(0x9e3779b97f4a7c15ull * (ci + 1));
-                            for (int k = 0; k <= d; k++) h = mix64(h + 0xd6e8feb86659fd93ull * (unsigned long long)(pedges[k] + 1));
-                            h |= 1ull;
-                            // every row of this CTA belongs to the same activation: report a path to the global table only once per CTA
-                            bool known = false;
-                            {
-                                uint32_t sl = (uint32_t)(h >> 20) & 63u;
-                                for (int probe = 0; probe < 8; probe++) {
-                                    unsigned long long prev = atomicCAS(&s_seen[sl], 0ull, h);
-                                    if (prev == h) {
-                                        known = true;
-                                        break;
-                                    }
-                                    if (prev == 0ull) break;  // we claimed it: go on to the global table
-                                    sl = (sl + 1) & 63u;
-                                }
-                            }
-                            if (known) continue;
-                            uint32_t slot = (uint32_t)(h % a.tab_size);
-                            int fresh = -1;  // 1 new, 0 known, -1 table full
-                            for (uint32_t probe = 0; probe < a.tab_size; probe++) {
-                                unsigned long long prev = atomicCAS(&a.tab[slot], 0ull, h);
-                                if (prev == 0ull) {
-                                    fresh = 1;
-                                    break;
-                                }
-                                if (prev == h) {
-                                    fresh = 0;
-                                    break;
-                                }
-                                slot = slot + 1 == a.tab_size ? 0 : slot + 1;
-                            }
-                            if (fresh < 0) atomicOr(&results[a.res_off + 1 + a.n_costs + 1], 1u);  // dedup table saturated: the host reruns the step
-                            if (fresh > 0) {
-                                uint32_t at = atomicAdd(path_count, 1u);
-                                if (at < path_cap) {
-                                    PathOut po;
-                                    po.act = tile.act;
-                                    po.cost_idx = (uint16_t)ci;
-                                    po.len = (uint16_t)(d + 1);
-                                    for (int k = 0; k < (int)MAX_WALK; k++) po.edges[k] = k <= d ? pedges[k] : 0;
-                                    pathbuf[at] = po;
-                                }
-                            }
-                            continue;
-                        }
-                        if (d + 1 >= (int)MAX_WALK) continue;  // host guarantees path length <= MAX_WALK
-                        d++;
-                        stack[d].mask = take;
-                        stack[d].state = ee.dst;
-                        stack[d].e = 0;
-                        stack[d].r = (uint16_t)rr;
+            if (run && r >= a.root_rmin && r < a.root_rmin + a.root_rcount) b = SLOT(n_cols + r - a.root_rmin) & ~taken;  // START's pairs come first
+            if (active) out[(size_t)ci * ld + j] = b;
+            taken |= b;
+            const uint32_t pc = __reduce_add_sync(0xffffffffu, (uint32_t)__popcll(b));
+            if (lane == 0 && pc) atomicAdd(&counts[ci], pc);
+        }
+        const unsigned long long rest = u & ~taken;
+        if (active) out[(size_t)n_costs * ld + j] = rest;
+        {
+            const uint32_t pc = __reduce_add_sync(0xffffffffu, (uint32_t)__popcll(rest));
+            if (lane == 0 && pc) atomicAdd(&counts[n_costs], pc);
+        }
+#undef SLOT
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i <= n_costs; i += blockDim.x)
+        if (counts[i]) atomicAdd(&results[a.res_off + 1 + i], counts[i]);
+    if (threadIdx.x < 2) {  // non-empty buckets of this tile, 64 per word (walk_kernel skips whole tiles with it)
+        unsigned long long m = 0;
+        for (uint32_t i = 0; i < 64; i++) {
+            const uint32_t ci = threadIdx.x * 64 + i;
+            if (ci < n_costs && counts[ci]) m |= 1ull << i;
+        }
+        tile_summary[2 * (size_t)blockIdx.x + threadIdx.x] = m;
+    }
+}
+
+// Pass 2 over the same tiles (same grid, same shared-memory class): which paths produced the buckets the query can still need.
+// bucket_sort only descends into the cheapest buckets that together hold `need` documents (the hits it still has to return
+// plus the offset it still has to skip; every document of a bucket it enters is eventually returned or skipped), so only rows
+// holding documents of those buckets are re-evaluated: DP as in eval_dp_kernel, then every document *walks* the graph taking, at
+// each state, the first edge (in order) whose condition it satisfies and from which it can still finish with its remaining
+// budget.  Distinct walked paths are de-duplicated (per CTA in shared memory, then per activation in a global hash table) and
+// reported.  The path a document takes is a function of its condition bits alone, and a large bucket holds few distinct bit
+// patterns when the rule has few conditions: with at most 64 condition columns, a row with at most WALK_SPARSE needed documents
+// first hashes each document's pattern (its *signature*) into the same tables and is skipped when every signature is already
+// known — somebody else walks (or walked) a document with the same pattern.
+template <bool SMEM>
+__global__ void __launch_bounds__(128, 8) walk_kernel(const TileDesc *__restrict__ tiles, const ActDesc *__restrict__ acts,
+                                                      uint32_t *__restrict__ results, const ColOp *__restrict__ colprog,
+                                                      const DpState *__restrict__ states, const DpEdge *__restrict__ edges,
+                                                      const uint16_t *__restrict__ costpool, const uint32_t *__restrict__ progpool,
+                                                      const unsigned long long *__restrict__ tile_summary, PathOut *__restrict__ pathbuf,
+                                                      uint32_t *__restrict__ path_count, uint32_t path_cap) {
+    extern __shared__ unsigned long long s_slot[];  // SMEM: [n_cols + n_pairs + 2][128]
+    const TileDesc tile = tiles[blockIdx.x];
+    if (!acts[tile.act].want_paths) return;
+    __shared__ ActDesc a;
+    __shared__ unsigned long long s_seen[64];   // path reports already made by this CTA (hashes)
+    __shared__ unsigned long long s_sig[128];   // document signatures this CTA already met
+    __shared__ uint32_t s_m;
+    load_act(&a, &acts[tile.act]);
+    if (threadIdx.x < 64) s_seen[threadIdx.x] = 0;
+    s_sig[threadIdx.x] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // last needed bucket: the first one at which the cumulative count reaches `need`
+        const uint32_t *cnt = results + a.res_off + 1;
+        unsigned long long cum = 0;
+        uint32_t m = 0;
+        for (; m < a.n_costs; m++) {
+            cum += cnt[m];
+            if (cum >= a.need) break;
+        }
+        if (m >= a.n_costs) m = a.n_costs ? a.n_costs - 1 : 0;
+        s_m = m;
+        if (tile.row_begin == 0) results[a.res_off + 1 + a.n_costs + 2] = m;  // the host checks it before it descends
+    }
+    __syncthreads();
+    const uint32_t m = s_m;
+    {
+        const unsigned long long s0 = tile_summary[2 * (size_t)blockIdx.x], s1 = tile_summary[2 * (size_t)blockIdx.x + 1];
+        const unsigned long long k0 = m >= 63 ? ~0ull : ((2ull << m) - 1), k1 = m < 64 ? 0ull : (m >= 127 ? ~0ull : ((2ull << (m - 64)) - 1));
+        if (((s0 & k0) | (s1 & k1)) == 0) return;
+    }
+    const uint32_t rows = results[a.res_off];
+    const uint32_t n_cols = a.n_cols, n_pairs = a.n_pairs;
+    const uint32_t ZERO_SLOT = n_cols + n_pairs, ONES_SLOT = n_cols + n_pairs + 1;
+    const size_t ld = a.ld;
+    unsigned long long *const C = a.C;
+    unsigned long long *const Sg = a.S;
+    const uint32_t *const prog = progpool + a.prog_off;
+    const uint16_t *const cost_vals = costpool + a.cost_off;
+    if (SMEM) {
+        s_slot[(size_t)ZERO_SLOT * 128 + threadIdx.x] = 0ull;
+        s_slot[(size_t)ONES_SLOT * 128 + threadIdx.x] = ~0ull;
+    }
+    for (uint32_t rr_ = 0; rr_ < tile.rows_per_thread; rr_++) {
+        const uint32_t j = tile.row_begin + rr_ * 128 + threadIdx.x;
+        if (j >= rows) break;
+        unsigned long long needed = 0;
+        for (uint32_t ci = 0; ci <= m; ci++) needed |= a.out[(size_t)ci * ld + j];
+        if (!needed) continue;
+        unsigned long long g_const[2] = {0ull, ~0ull};
+#define SLOT(k) (*(SMEM ? &s_slot[(size_t)(k) * 128 + threadIdx.x] : ((k) < n_cols ? &C[(size_t)(k) * ld + j] : ((k) < ZERO_SLOT ? &Sg[(size_t)((k) - n_cols) * ld + j] : &g_const[(k) - ZERO_SLOT]))))
+        if (SMEM) {
+            uint32_t c = 0;
+            for (; c + 8 <= n_cols; c += 8) {
+                unsigned long long v[8];
+#pragma unroll
+                for (int x = 0; x < 8; x++) v[x] = C[(size_t)(c + x) * ld + j];
+#pragma unroll
+                for (int x = 0; x < 8; x++) s_slot[(size_t)(c + x) * 128 + threadIdx.x] = v[x];
+            }
+            for (; c < n_cols; c++) s_slot[(size_t)c * 128 + threadIdx.x] = C[(size_t)c * ld + j];
+        }
+        if (n_cols <= 64 && __popcll(needed) <= WALK_SPARSE) {
+            // signatures of the needed documents (raw condition columns; the global variant sees them after the column program,
+            // which is just as much a function of the document's bits)
+            bool any_new = false;
+            unsigned long long left = needed;
+            while (left) {
+                const uint32_t bit = (uint32_t)__ffsll((long long)left) - 1;
+                left &= left - 1;
+                unsigned long long w = 0;
+                for (uint32_t c = 0; c < n_cols; c++) w |= ((SLOT(c) >> bit) & 1ull) << c;
+                const unsigned long long h = mix64(w ^ ((unsigned long long)n_cols << 56) ^ 0x51ed270b1ull) | 3ull;  // bit 1 set: a signature
+                bool known = false;
+                uint32_t sl = (uint32_t)(h >> 20) & 127u;
+                for (int probe = 0; probe < 8; probe++) {
+                    unsigned long long prev = atomicCAS(&s_sig[sl], 0ull, h);
+                    if (prev == h) {
+                        known = true;
+                        break;
+                    }
+                    if (prev == 0ull) break;
+                    sl = (sl + 1) & 127u;
+                }
+                if (known) continue;
+                if (tab_insert(a, h) != 0) any_new = true;  // new for the activation, or the table is full (then walk: the walk reports the overflow)
+            }
+            if (!any_new) continue;
+        }
+        if (SMEM) {  // (the global variant already holds the column program's results in C and the DP table in S)
+            for (uint32_t i = 0; i < a.colprog_len; i++) {
+                const ColOp op = colprog[a.colprog_off + i];
+                unsigned long long x = SLOT(op.a), r;
+                if (op.op == 3)
+                    r = x;
+                else {
+                    unsigned long long y = SLOT(op.b);
+                    r = op.op == 0 ? (x & y) : (op.op == 1 ? (x | y) : (x & ~y));
+                }
+                SLOT(op.dst) = r;
+            }
+            SLOT(n_cols + n_pairs - 1) = a.ub[j];
+            const uint32_t plen = a.prog_len;
+            uint32_t dst = n_cols + n_pairs - 2;
+            unsigned long long acc = 0;
+            for (uint32_t i = 0; i < plen; i += 4) {
+                const uint4 o4 = __ldg(reinterpret_cast<const uint4 *>(prog + i));
+                const uint32_t op[4] = {o4.x, o4.y, o4.z, o4.w};
+#pragma unroll
+                for (int x = 0; x < 4; x++) {
+                    acc |= SLOT(op[x] & 0x7fffu) & SLOT(op[x] >> 16);
+                    if (op[x] & 0x8000u) {
+                        SLOT(dst) = acc;
+                        acc = 0;
+                        dst--;
                     }
                 }
             }
         }
-        unsigned long long rest = u & ~taken;
-        a.out[(size_t)a.n_costs * ld + j] = rest;
-        if (rest) atomicAdd(&counts[a.n_costs], (uint32_t)__popcll(rest));
-        }
-    row_done:;
+        walk_row(a, tile.act, m, states + a.state_off, edges + a.edge_off, cost_vals, j, [&](uint32_t k) { return SLOT(k); }, s_seen, results, pathbuf,
+                 path_count, path_cap);
 #undef SLOT
     }
-    }
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i <= a.n_costs; i += blockDim.x)
-        if (counts[i]) atomicAdd(&results[a.res_off + 1 + i], counts[i]);
 }
 
 // one warp per emission: ascending docids of OR(out[col_lo..col_hi)), skipping `skip`, taking `take`.
@@ -1156,17 +1306,16 @@ cudaError_t launch_pair_probe(cudaStream_t s, const PairSet *sets, uint32_t n_se
                                                              results, queue, qcount, qcap);
     return cudaGetLastError();
 }
-cudaError_t launch_scatter(cudaStream_t s, uint32_t n_ctas, const Job *queue, const uint32_t *qcount, uint32_t qcap, const ActDesc *acts,
+cudaError_t launch_scatter(cudaStream_t s, uint32_t n_ctas, const Job *queue, uint32_t *qcount, uint32_t qcap, const ActDesc *acts,
                            const uint32_t *results, const DListRef *lists, const uint32_t *pool) {
     scatter_kernel<<<n_ctas, 256, 0, s>>>(queue, qcount, qcap, acts, results, lists, pool);
     return cudaGetLastError();
 }
 cudaError_t launch_eval(cudaStream_t s, int cls, const TileDesc *tiles, uint32_t n_tiles, const ActDesc *acts, uint32_t *results,
-                        const ColOp *colprog, const DpState *states, const DpEdge *edges, const uint16_t *costpool, const uint32_t *progpool,
-                        PathOut *pathbuf, uint32_t *path_count, uint32_t path_cap) {
+                        const ColOp *colprog, const uint16_t *costpool, const uint32_t *progpool, unsigned long long *tile_summary) {
     if (!n_tiles) return cudaSuccess;
     if (cls >= (int)EVAL_CLASSES) {
-        eval_dp_kernel<false><<<n_tiles, 128, 0, s>>>(tiles, acts, results, colprog, states, edges, costpool, progpool, pathbuf, path_count, path_cap);
+        eval_dp_kernel<false><<<n_tiles, 128, 0, s>>>(tiles, acts, results, colprog, costpool, progpool, tile_summary);
         return cudaGetLastError();
     }
     static bool attr_done = false;
@@ -1174,8 +1323,25 @@ cudaError_t launch_eval(cudaStream_t s, int cls, const TileDesc *tiles, uint32_t
         CK(cudaFuncSetAttribute(eval_dp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EVAL_CLASS_SLOTS[EVAL_CLASSES - 1] * 1024)));
         attr_done = true;
     }
-    eval_dp_kernel<true><<<n_tiles, 128, (size_t)EVAL_CLASS_SLOTS[cls] * 1024, s>>>(tiles, acts, results, colprog, states, edges, costpool, progpool,
-                                                                                pathbuf, path_count, path_cap);
+    eval_dp_kernel<true><<<n_tiles, 128, (size_t)EVAL_CLASS_SLOTS[cls] * 1024, s>>>(tiles, acts, results, colprog, costpool, progpool, tile_summary);
+    return cudaGetLastError();
+}
+cudaError_t launch_walk(cudaStream_t s, int cls, const TileDesc *tiles, uint32_t n_tiles, const ActDesc *acts, uint32_t *results,
+                        const ColOp *colprog, const DpState *states, const DpEdge *edges, const uint16_t *costpool, const uint32_t *progpool,
+                        const unsigned long long *tile_summary, PathOut *pathbuf, uint32_t *path_count, uint32_t path_cap) {
+    if (!n_tiles) return cudaSuccess;
+    if (cls >= (int)EVAL_CLASSES) {
+        walk_kernel<false><<<n_tiles, 128, 0, s>>>(tiles, acts, results, colprog, states, edges, costpool, progpool, tile_summary, pathbuf, path_count,
+                                                   path_cap);
+        return cudaGetLastError();
+    }
+    static bool attr_done = false;
+    if (!attr_done) {
+        CK(cudaFuncSetAttribute(walk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EVAL_CLASS_SLOTS[EVAL_CLASSES - 1] * 1024)));
+        attr_done = true;
+    }
+    walk_kernel<true><<<n_tiles, 128, (size_t)EVAL_CLASS_SLOTS[cls] * 1024, s>>>(tiles, acts, results, colprog, states, edges, costpool, progpool,
+                                                                             tile_summary, pathbuf, path_count, path_cap);
     return cudaGetLastError();
 }
 cudaError_t launch_emit(cudaStream_t s, const EmitDesc *emits, uint32_t n_emits) {

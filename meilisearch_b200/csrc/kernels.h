@@ -14,12 +14,17 @@ cudaError_t launch_compact(cudaStream_t s, const CompactTile *tiles, uint32_t n_
 cudaError_t launch_pair_probe(cudaStream_t s, const PairSet *sets, uint32_t n_sets, uint32_t n_probes, const uint32_t *wordpool,
                               const unsigned long long *pair_keys, uint64_t n_pairs, uint32_t pair_list_base, const DListRef *lists,
                               const ActDesc *acts, const uint32_t *results, Job *queue, uint32_t *qcount, uint32_t qcap);
-cudaError_t launch_scatter(cudaStream_t s, uint32_t n_ctas, const Job *queue, const uint32_t *qcount, uint32_t qcap, const ActDesc *acts,
+// qcount: [0] number of jobs (host + pair_probe), [2] work cursor (must be 0 at launch)
+cudaError_t launch_scatter(cudaStream_t s, uint32_t n_ctas, const Job *queue, uint32_t *qcount, uint32_t qcap, const ActDesc *acts,
                            const uint32_t *results, const DListRef *lists, const uint32_t *pool);
-// cls: eval_class() of the tiles' activations (EVAL_CLASSES = DP table in global scratch)
-cudaError_t launch_eval(cudaStream_t s, int cls, const TileDesc *tiles, uint32_t n_tiles, const ActDesc *acts, uint32_t *results, const ColOp *colprog,
-                        const DpState *states, const DpEdge *edges, const uint16_t *costpool, const uint32_t *progpool, PathOut *pathbuf,
-                        uint32_t *path_count, uint32_t path_cap);
+// evaluation of the activations' tiles, pass 1 (DP, buckets, counts); cls: eval_class() of the tiles' activations (EVAL_CLASSES =
+// slots in global scratch); tile_summary: 2 u64 per tile (its non-empty buckets), indexed like `tiles`
+cudaError_t launch_eval(cudaStream_t s, int cls, const TileDesc *tiles, uint32_t n_tiles, const ActDesc *acts, uint32_t *results,
+                        const ColOp *colprog, const uint16_t *costpool, const uint32_t *progpool, unsigned long long *tile_summary);
+// pass 2 over the same tiles: surviving paths of the buckets a query can still need (ActDesc::need)
+cudaError_t launch_walk(cudaStream_t s, int cls, const TileDesc *tiles, uint32_t n_tiles, const ActDesc *acts, uint32_t *results,
+                        const ColOp *colprog, const DpState *states, const DpEdge *edges, const uint16_t *costpool, const uint32_t *progpool,
+                        const unsigned long long *tile_summary, PathOut *pathbuf, uint32_t *path_count, uint32_t path_cap);
 cudaError_t launch_emit(cudaStream_t s, const EmitDesc *emits, uint32_t n_emits);
 cudaError_t launch_vec_dist(cudaStream_t s, int n_ctas, int qt, const void *mat_fp16, const float *inv_norm, const uint32_t *docids,
                             uint64_t n_rows, uint32_t d, const float *queries, const float *q_inv_norm, const unsigned long long *cand,
