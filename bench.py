@@ -83,13 +83,16 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, window=None):
+        """summary of the samples that arrived inside `window` = (t0, t1) of time.perf_counter() (nvidia-smi needs about a second
+        to start, so the sampler runs from before the warm-up and the timed region is cut out afterwards)"""
         if self.proc:
             self.proc.terminate()
         sm, mx, reasons = [], 0, set()
-        for r in self.rows:
+        rows = [r for t, r in self.rows if window is None or window[0] - 0.11 <= t <= window[1] + 0.11]
+        for r in rows:
             try:
                 sm.append(float(r[1]))
                 mx = max(mx, float(r[2]))
@@ -336,15 +339,15 @@ def main():
             return s.semantic(vecs[i % len(vecs)]).execute_hybrid(0.5)
         return s.execute()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for w in range(args.warmup):
         res = step(w)
-    sampler = ClockSampler(local_rank)
     os.environ["B200_KERNEL_TIMERS"] = "0"  # the e2e region runs as production would: no per-kernel event records
     ix.reset_stats()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler.start()
     t0 = time.perf_counter()
     lat = []
     for k in range(args.steps):
@@ -355,7 +358,7 @@ def main():
     wall = time.perf_counter() - t0
     if world > 1:
         dist.barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop((t0, t0 + wall))
     st_e2e = ix.stats()
     n_ok = int((res.status == 0).sum())
     # second timed region, software pipeline off (one lane): kernels of different lanes no longer overlap, so the CUDA-event

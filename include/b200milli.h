@@ -141,6 +141,20 @@ typedef struct {
     const float *vectors;            /* n_queries x d, or NULL: the `semantic` vector per query */
     int32_t mode;                    /* 0 keyword (execute), 1 semantic (execute with vector), 2 hybrid (execute_hybrid) */
     float semantic_ratio;            /* hybrid only */
+    /* filtered_universe (search/new/mod.rs:719: documents_ids & filter), what Search::filter / candidates produce on the host:
+     * n_queries pointers to dense little-endian u64 words over docids (n_universe_words each), NULL entry = all documents,
+     * NULL array = no filter anywhere.  Queries may share a bitmap (equal pointers are uploaded once). */
+    const uint64_t *const *universes;
+    uint64_t n_universe_words;
+    /* Search::deadline (crates/milli/src/lib.rs:154-226).  time_budget_ns > 0: Deadline::from_budget, counted from the start of
+     * the call; 0: Deadline::never.  stop_after >= 0: the reference's poll-count hook (Deadline::with_stop_after(n): exceeded from
+     * the n-th poll on, the clock is then ignored); -1: unused.  When the deadline is exceeded the remaining universe of every
+     * rule is returned unsorted with a Skipped score and the result is marked degraded (bucket_sort.rs:206-264). */
+    uint64_t time_budget_ns;
+    int64_t stop_after;
+    /* Search::ranking_score_threshold (bucket_sort.rs:188,221-224,293-296) */
+    int32_t has_ranking_score_threshold;
+    double ranking_score_threshold;
 } b200_query_batch;
 #define B200_MAX_SCORES 12
 /* score kinds: ScoreDetails variants (score_details.rs:9-32) */
@@ -157,6 +171,11 @@ typedef struct {                  /* SearchResult (search/mod.rs:526-535), flatt
     uint64_t *n_candidates;       /* n_queries: candidates.len() */
     uint32_t *semantic_hits;      /* n_queries: execute_hybrid's semantic_hit_count (may be NULL) */
     int32_t *status;              /* n_queries: 0 or a B200_ERR_* for that query (e.g. UNSUPPORTED) */
+    uint8_t *degraded;            /* n_queries: SearchResult::degraded (may be NULL) */
+    uint8_t *used_negative_operator; /* n_queries: SearchResult::used_negative_operator (may be NULL) */
+    uint64_t *candidates;         /* optional (may be NULL): n_queries x candidates_words dense u64 words, SearchResult::candidates
+                                     for keyword searches without a ranking-score threshold (others: B200_ERR_UNSUPPORTED) */
+    uint64_t candidates_words;    /* words per query in `candidates` (>= ceil((max docid + 1) / 64)) */
 } b200_results;
 int b200_search_batch(b200_index *, const b200_query_batch *, b200_results *);
 

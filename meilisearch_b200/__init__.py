@@ -42,12 +42,15 @@ class _Batch(C.Structure):
     _fields_ = [("n_queries", C.c_uint32), ("token_begin", C.c_void_p), ("token_kind", C.c_void_p), ("lemma_off", C.c_void_p),
                 ("lemma_bytes", C.c_void_p), ("terms_matching_strategy", C.c_int32), ("scoring_strategy", C.c_int32),
                 ("offset", C.c_uint32), ("limit", C.c_uint32), ("words_limit", C.c_uint32), ("vectors", C.c_void_p),
-                ("mode", C.c_int32), ("semantic_ratio", C.c_float)]
+                ("mode", C.c_int32), ("semantic_ratio", C.c_float), ("universes", C.c_void_p), ("n_universe_words", C.c_uint64),
+                ("time_budget_ns", C.c_uint64), ("stop_after", C.c_int64), ("has_ranking_score_threshold", C.c_int32),
+                ("ranking_score_threshold", C.c_double)]
 
 
 class _Results(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("docids", "n_hits", "n_scores", "score_kind", "score_rank", "score_max", "score_sim",
-                                          "n_candidates", "semantic_hits", "status")]
+                                          "n_candidates", "semantic_hits", "status", "degraded", "used_negative_operator", "candidates")] + \
+               [("candidates_words", C.c_uint64)]
 
 
 class _Stats(C.Structure):
@@ -129,6 +132,9 @@ class SearchResult:
         self.n_candidates = np.zeros(n, np.uint64)
         self.semantic_hit_count = np.zeros(n, np.uint32)
         self.status = np.zeros(n, np.int32)
+        self.degraded = np.zeros(n, np.uint8)
+        self.used_negative_operator = np.zeros(n, np.uint8)
+        self.candidates = None  # (n, words) uint64 when requested with Search.with_candidates()
 
     def ids(self, q):
         return [int(x) for x in self.documents_ids[q, : self.n_hits[q]]]
@@ -279,6 +285,7 @@ class Search:
         self._tms = "last"
         self._scoring = "skip"
         self._offset, self._limit, self._words_limit = 0, 20, 10
+        self._universes, self._budget_ms, self._stop_after, self._threshold, self._want_candidates = None, None, None, None, False
 
     def query(self, queries, stop_words=frozenset()):
         self._tokens = queries if isinstance(queries, TokenBatch) else TokenBatch([queries] if isinstance(queries, str) else list(queries), stop_words)
@@ -308,6 +315,24 @@ class Search:
         self._words_limit = n
         return self
 
+    def universes(self, bitmaps):
+        """filtered_universe per query: a list of uint64 word arrays (None = all documents), or one array shared by the batch"""
+        self._universes = bitmaps
+        return self
+
+    def deadline(self, budget_ms=None, stop_after=None):
+        """Search::deadline: a time budget in ms, or the reference's poll-count hook Deadline::never().with_stop_after(n)"""
+        self._budget_ms, self._stop_after = budget_ms, stop_after
+        return self
+
+    def ranking_score_threshold(self, t):
+        self._threshold = t
+        return self
+
+    def with_candidates(self):
+        self._want_candidates = True
+        return self
+
     def _run(self, mode, ratio=0.0):
         ix = self.index
         tokens = self._tokens
@@ -319,8 +344,36 @@ class Search:
         b = _Batch(n, _p(tokens.token_begin), _p(tokens.token_kind), _p(tokens.lemma_off), _p(tokens.lemma_bytes), TMS[self._tms],
                    1 if self._scoring == "detailed" else 0, self._offset, self._limit, self._words_limit,
                    _p(self._vectors) if self._vectors is not None else None, mode, ratio)
+        keep = []
+        if self._universes is not None:
+            us = self._universes
+            if isinstance(us, np.ndarray) and us.ndim == 1:
+                us = [us] * n
+            ptrs = (C.c_void_p * n)()
+            cache = {}
+            for i, u in enumerate(us):
+                if u is None:
+                    continue
+                if id(u) not in cache:
+                    a = np.ascontiguousarray(u, np.uint64)
+                    keep.append(a)
+                    cache[id(u)] = a
+                a = cache[id(u)]
+                ptrs[i] = a.ctypes.data
+                b.n_universe_words = len(a)
+            keep.append(ptrs)
+            b.universes = C.cast(ptrs, C.c_void_p)
+        b.time_budget_ns = 0 if self._budget_ms is None else max(1, int(self._budget_ms * 1e6))
+        b.stop_after = -1 if self._stop_after is None else int(self._stop_after)
+        b.has_ranking_score_threshold = int(self._threshold is not None)
+        b.ranking_score_threshold = float(self._threshold or 0.0)
         r = _Results(_p(res.documents_ids), _p(res.n_hits), _p(res.n_scores), _p(res.score_kind), _p(res.score_rank), _p(res.score_max),
-                     _p(res.score_sim), _p(res.n_candidates), _p(res.semantic_hit_count), _p(res.status))
+                     _p(res.score_sim), _p(res.n_candidates), _p(res.semantic_hit_count), _p(res.status), _p(res.degraded),
+                     _p(res.used_negative_operator), None, 0)
+        if self._want_candidates:
+            words = (ix._n_docs + 63) // 64
+            res.candidates = np.zeros((n, words), np.uint64)
+            r.candidates, r.candidates_words = _p(res.candidates), words
         ix._ck(ix._l.b200_search_batch(ix._h, C.byref(b), C.byref(r)))
         return res
 

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <map>
 #include <new>
 
 #include "engine.h"
@@ -36,6 +37,7 @@ int b200_open(int device_ordinal, b200_index **out) {
     if (!h) return B200_ERR_INVALID;
     h->e.device = device_ordinal;
     if ((err = cudaSetDevice(device_ordinal)) != cudaSuccess || (err = cudaStreamCreateWithFlags(&h->e.stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (err = cudaStreamCreateWithFlags(&h->e.vt.stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (err = cudaEventCreate(&h->e.ev0)) != cudaSuccess || (err = cudaEventCreate(&h->e.ev1)) != cudaSuccess) {
         g_open_error = std::string("CUDA init failed: ") + cudaGetErrorString(err);
         delete h;
@@ -146,7 +148,9 @@ int b200_derive_batch(b200_index *h, uint32_t n, const char *words, const uint32
 int b200_nns_batch(b200_index *h, const float *q, uint32_t n_q, uint32_t d, uint32_t limit, const uint64_t *cand, uint64_t ncw, uint32_t *ids,
                    float *dist, uint32_t *n_out) {
     std::lock_guard<std::mutex> g(h->e.mu);
-    return h->e.nns_batch(q, n_q, d, limit, cand, ncw, ids, dist, n_out);
+    int rc = h->e.nns_batch(q, n_q, d, limit, cand, ncw, ids, dist, n_out);
+    h->e.fold_vector_stats();
+    return rc;
 }
 int b200_union_postings(b200_index *h, int db, const uint32_t *key_index, uint32_t n_keys, const uint64_t *universe, uint64_t n_universe_words,
                         uint64_t *out) {
@@ -191,18 +195,69 @@ int Engine::semantic_batch(const b200_query_batch *b, b200_results *r, uint32_t 
     if (k == 0) k = 1;
     std::vector<uint32_t> ids((size_t)b->n_queries * k), n(b->n_queries);
     std::vector<float> dist((size_t)b->n_queries * k);
-    int rc = nns_batch(b->vectors, b->n_queries, dix.emb_d, k, nullptr, 0, ids.data(), dist.data(), n.data());
-    if (rc != B200_OK) return rc;
+    std::vector<uint64_t> n_cand(b->n_queries, hix.n_documents);
+    if (!b->universes) {
+        int rc = nns_batch(b->vectors, b->n_queries, dix.emb_d, k, nullptr, 0, ids.data(), dist.data(), n.data());
+        if (rc != B200_OK) return rc;
+    } else {
+        // filtered_universe restricts the vector candidates (vector_sort.rs:58-78: `vector_candidates & universe`): the queries
+        // are grouped by bitmap and every group is one scan with that candidate filter
+        if (b->n_universe_words < hix.n_words64) return fail(B200_ERR_INVALID, "universe bitmaps shorter than the document range");
+        std::map<const uint64_t *, std::vector<uint32_t>> groups;
+        for (uint32_t q = 0; q < b->n_queries; q++) groups[b->universes[q]].push_back(q);
+        const uint32_t d = dix.emb_d;
+        for (auto &g : groups) {
+            const uint32_t m = (uint32_t)g.second.size();
+            std::vector<float> vq((size_t)m * d);
+            for (uint32_t i = 0; i < m; i++) memcpy(vq.data() + (size_t)i * d, b->vectors + (size_t)g.second[i] * d, (size_t)d * 4);
+            std::vector<uint32_t> gi((size_t)m * k), gn(m);
+            std::vector<float> gd((size_t)m * k);
+            uint64_t cnt = hix.n_documents;
+            if (g.first) {
+                cnt = 0;
+                for (uint64_t w = 0; w < hix.n_words64; w++) cnt += (uint64_t)__builtin_popcountll(g.first[w] & hix.base_ub[w]);
+            }
+            int rc = nns_batch(vq.data(), m, d, k, g.first, g.first ? hix.n_words64 : 0, gi.data(), gd.data(), gn.data());
+            if (rc != B200_OK) return rc;
+            for (uint32_t i = 0; i < m; i++) {
+                const uint32_t q = g.second[i];
+                n[q] = gn[i];
+                n_cand[q] = cnt;
+                memcpy(ids.data() + (size_t)q * k, gi.data() + (size_t)i * k, (size_t)gn[i] * 4);
+                memcpy(dist.data() + (size_t)q * k, gd.data() + (size_t)i * k, (size_t)gn[i] * 4);
+            }
+        }
+    }
+    // VectorSort's last bucket (vector_sort.rs:128-160): once the embedded candidates are exhausted, the rest of the universe
+    // follows in docid order with `similarity: None`
+    for (uint32_t q = 0; q < b->n_queries; q++) {
+        if (n[q] >= k) continue;
+        const uint64_t *u = b->universes ? b->universes[q] : nullptr;
+        for (uint64_t w = 0; w < hix.n_words64 && n[q] < k; w++) {
+            uint64_t bits = hix.base_ub[w] & (u ? u[w] : ~0ull) & ~(w < emb_bitmap.size() ? emb_bitmap[w] : 0ull);
+            while (bits && n[q] < k) {
+                ids[(size_t)q * k + n[q]] = (uint32_t)(w * 64 + (uint64_t)__builtin_ctzll(bits));
+                dist[(size_t)q * k + n[q]] = 2.0f;  // marks "no similarity"
+                n[q]++;
+                bits &= bits - 1;
+            }
+        }
+    }
     for (uint32_t q = 0; q < b->n_queries; q++) {
         uint32_t hits = n[q] > offset ? std::min(limit, n[q] - offset) : 0;
         r->n_hits[q] = hits;
         if (r->status) r->status[q] = 0;
-        if (r->n_candidates) r->n_candidates[q] = hix.n_documents;
+        if (r->degraded) r->degraded[q] = 0;
+        if (r->used_negative_operator) r->used_negative_operator[q] = 0;
+        if (r->n_candidates) r->n_candidates[q] = n_cand[q];
         for (uint32_t i = 0; i < hits; i++) {
             size_t src = (size_t)q * k + offset + i, at = (size_t)q * limit + i;
             r->docids[at] = ids[src];
             float sim = 1.0f - dist[src];
-            if (has_distribution) sim = distribution_shift(dist_mean, dist_sigma, sim);
+            if (dist[src] > 1.5f)
+                sim = -1.f;  // Vector { similarity: None }
+            else if (has_distribution)
+                sim = distribution_shift(dist_mean, dist_sigma, sim);
             if (r->n_scores) {
                 r->n_scores[at] = 1;
                 r->score_kind[at * B200_MAX_SCORES] = B200_S_VECTOR;
@@ -278,7 +333,13 @@ int compare_scores(const Hit &l, float lr, const Hit &r, float rr) {  // hybrid.
 // Search::execute_hybrid (search/hybrid.rs:264-366)
 int Engine::search_batch(const b200_query_batch *b, b200_results *r) {
     if (b->mode == 0) return keyword_batch(b, r, b->offset, b->limit, b->scoring_strategy);
-    if (b->mode == 1) return semantic_batch(b, r, b->offset, b->limit);
+    if (b->has_ranking_score_threshold || b->time_budget_ns || b->stop_after >= 0 || r->candidates)
+        return fail(B200_ERR_UNSUPPORTED, "ranking-score threshold, deadlines and the candidates bitmap are implemented for keyword searches (mode 0) only");
+    if (b->mode == 1) {
+        int rc1 = semantic_batch(b, r, b->offset, b->limit);
+        fold_vector_stats();
+        return rc1;
+    }
     if (b->mode != 2) return fail(B200_ERR_INVALID, "unknown search mode");
     const uint32_t NQ = b->n_queries, L = b->limit + b->offset, lim = std::max(1u, L);
     struct Side {
@@ -287,21 +348,26 @@ int Engine::search_batch(const b200_query_batch *b, b200_results *r) {
         std::vector<float> sim;
         std::vector<uint64_t> n_cand;
         std::vector<int32_t> status;
+        std::vector<uint8_t> neg;
         b200_results view;
         Side(uint32_t nq, uint32_t l)
             : docids((size_t)nq * l), n_hits(nq), rank((size_t)nq * l * B200_MAX_SCORES), maxr((size_t)nq * l * B200_MAX_SCORES),
-              n_scores((size_t)nq * l), kind((size_t)nq * l * B200_MAX_SCORES), sim((size_t)nq * l * B200_MAX_SCORES), n_cand(nq), status(nq) {
-            view = b200_results{docids.data(), n_hits.data(), n_scores.data(), kind.data(), rank.data(), maxr.data(), sim.data(), n_cand.data(), nullptr, status.data()};
+              n_scores((size_t)nq * l), kind((size_t)nq * l * B200_MAX_SCORES), sim((size_t)nq * l * B200_MAX_SCORES), n_cand(nq), status(nq), neg(nq) {
+            view = b200_results{docids.data(), n_hits.data(), n_scores.data(), kind.data(), rank.data(), maxr.data(), sim.data(), n_cand.data(), nullptr, status.data(),
+                                nullptr, neg.data(), nullptr, 0};
         }
     };
     Side kw(NQ, lim), vec(NQ, lim);
-    int rc = keyword_batch(b, &kw.view, 0, lim, 1);
-    if (rc != B200_OK) return rc;
+    // the vector stage runs beside the keyword stage: its own host thread, stream and timers (the two share nothing mutable)
     bool have_vec = b->vectors != nullptr;
-    if (have_vec) {
-        rc = semantic_batch(b, &vec.view, 0, lim);
-        if (rc != B200_OK) return rc;
-    }
+    int rc_vec = B200_OK;
+    std::thread sem;
+    if (have_vec) sem = std::thread([&]() { rc_vec = semantic_batch(b, &vec.view, 0, lim); });
+    int rc = keyword_batch(b, &kw.view, 0, lim, 1);
+    if (sem.joinable()) sem.join();
+    fold_vector_stats();
+    if (rc != B200_OK) return rc;
+    if (rc_vec != B200_OK) return rc_vec;
     float kr = 1.0f - b->semantic_ratio, vr = b->semantic_ratio;
     auto load = [&](const Side &s, uint32_t q, uint32_t i) {
         Hit h;
@@ -320,6 +386,8 @@ int Engine::search_batch(const b200_query_batch *b, b200_results *r) {
     auto merge_one = [&](size_t qi) {
         const uint32_t q = (uint32_t)qi;
         if (r->status) r->status[q] = kw.status[q];
+        if (r->degraded) r->degraded[q] = 0;
+        if (r->used_negative_operator) r->used_negative_operator[q] = kw.neg[q];
         if (kw.status[q] != 0) {
             r->n_hits[q] = 0;
             return;

@@ -279,6 +279,41 @@ struct Lane {
     }
 };
 
+// a stream with its own pool of timing events (the vector stage runs beside the keyword stage in hybrid searches)
+struct TimerSet {
+    cudaStream_t stream = nullptr;
+    std::vector<cudaEvent_t> ev_pool;
+    struct Timed {
+        int cls;
+        size_t a, b;
+    };
+    std::vector<Timed> timed;
+    size_t ev_used = 0;
+    size_t mark() {
+        if (ev_used == ev_pool.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            ev_pool.push_back(e);
+        }
+        cudaEventRecord(ev_pool[ev_used], stream);
+        return ev_used++;
+    }
+    void time_kernel(b200_stats &st, int cls, size_t a, size_t b, uint64_t bytes) {
+        timed.push_back(Timed{cls, a, b});
+        st.kernel_count[cls]++;
+        st.kernel_bytes[cls] += bytes;
+        st.kernel_launches++;
+    }
+    void resolve(b200_stats &st) {
+        for (auto &t : timed) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, ev_pool[t.a], ev_pool[t.b]) == cudaSuccess) st.kernel_ms[t.cls] += ms;
+        }
+        timed.clear();
+        ev_used = 0;
+    }
+};
+
 struct Engine {
     std::unique_ptr<WorkerPool> pool;
     std::vector<std::thread> reapers;  // free the previous batch's per-query state in the background (several: one thread cannot
@@ -298,9 +333,24 @@ struct Engine {
     bool staged = false;
     HostIndex hix;
     DeviceIndex dix;
+    std::vector<uint64_t> emb_bitmap;  // documents owning at least one embedding
     bool has_distribution = false;
     float dist_mean = 0, dist_sigma = 0;
     b200_stats stats{};
+    TimerSet vt;          // vector stage: own stream and timers
+    b200_stats vstats{};  // what the vector stage accumulated since it was last folded into `stats`
+    void fold_vector_stats() {
+        stats.kernel_launches += vstats.kernel_launches;
+        stats.vector_bytes += vstats.vector_bytes;
+        stats.h2d_bytes += vstats.h2d_bytes;
+        stats.d2h_bytes += vstats.d2h_bytes;
+        for (int k = 0; k < B200_K_COUNT; k++) {
+            stats.kernel_ms[k] += vstats.kernel_ms[k];
+            stats.kernel_count[k] += vstats.kernel_count[k];
+            stats.kernel_bytes[k] += vstats.kernel_bytes[k];
+        }
+        vstats = b200_stats{};
+    }
     int sm_count = 148;
     // pools
     uint8_t *arena = nullptr;
@@ -313,6 +363,7 @@ struct Engine {
     DevBuf<uint32_t> d_qcount;   // [0] scatter jobs, [1] surviving paths
     DevBuf<PathOut> d_pathbuf;
     DevBuf<uint32_t> d_docids_out;  // n_queries x limit
+    DevBuf<unsigned long long> d_universes;  // the batch's distinct filtered universes (documents_ids & filter), n_words64 words each
     DevBuf<uint32_t> d_rowtab;      // n_queries x n_words64: word -> (tag, row) of the query's current activation (ActDesc::row_tab)
     uint8_t *h_step = nullptr;      // pinned
     size_t h_step_cap = 0;

@@ -394,6 +394,7 @@ struct Level {
     unsigned long long *ub = nullptr, *out = nullptr;
     uint32_t ld = 0, rows = 0, res_off = 0;
     uint32_t walked_m = 0;               // last bucket whose surviving paths were computed (walk_kernel)
+    bool below_done = false;             // a bucket of this level already fell below the ranking-score threshold
     size_t a_off = SIZE_MAX, a_len = 0;  // the level's block in its lane's arena (uw | ub | out)
     std::vector<uint32_t> counts;  // per cost idx, last = unmatched
     size_t cursor = 0;
@@ -426,6 +427,11 @@ struct QState {
     const unsigned long long *p_ub = nullptr, *p_out = nullptr;
     uint32_t p_rows = 0, p_ld = 0, p_col = 0, p_cap = 0;
     uint32_t act_counter = 0;  // tag of the query's current activation in its row lookup table
+    const unsigned long long *d_univ = nullptr;  // filtered_universe of the query on the device (nullptr = documents_ids)
+    uint64_t univ_count = 0;
+    bool degraded = false, used_negative = false, below_seen = false;
+    long polls = 0;                   // Deadline::exceeded() calls so far (stop_after hook)
+    const unsigned long long *cand_src = nullptr;  // device bitmap to copy into b200_results::candidates at the lane's next step
     uint32_t need = 1;                // documents the pending activation can still contribute (ActDesc::need)
     uint32_t tab_shift = 0;           // the pending activation's path de-duplication table is 4096 << tab_shift slots
     size_t demand = 0;                // device bytes the pending activation asked for (capacity diagnostics)
@@ -1544,6 +1550,7 @@ void parse_query(QState &q, const b200_query_batch *b, uint32_t qi) {
     }
     build_initial_edges(g);
     q.placeholder = located.empty();
+    q.used_negative = !c.neg_words.empty() || !c.neg_phrases.empty();
     if (q.placeholder && (!c.neg_words.empty() || !c.neg_phrases.empty()))
         throw UnsupportedQuery{"a query made only of negative terms is not implemented on the device path"};
 }
@@ -1622,6 +1629,18 @@ uint8_t score_kind_of(int rk) {
     }
 }
 
+// ScoreDetails::global_score over rank-valued details (score_details.rs:133-154, Rank::merge :524-547); Skipped = Rank{0, 1}
+double global_score_of(const std::vector<EScore> &sc) {
+    uint64_t rk = 1, mx = 1;
+    for (auto &x : sc) {
+        if (x.kind == B200_S_VECTOR) continue;
+        rk = rk > 0 ? rk - 1 : 0;
+        rk = rk * x.max_rank + x.rank;
+        mx *= x.max_rank;
+    }
+    return (double)rk / (double)mx;
+}
+
 struct Blob {  // step input blob with aligned sections
     std::vector<uint8_t> bytes;
     template <class T>
@@ -1689,6 +1708,43 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         }
     });
     stats.host_ms[0] += ms_since(t_ph);
+    // ---- filtered universes (search/new/mod.rs:719): every distinct bitmap is intersected with documents_ids and uploaded once
+    const bool has_thr = b->has_ranking_score_threshold != 0;
+    const double thr = b->ranking_score_threshold;
+    const bool has_budget = b->time_budget_ns > 0;
+    const auto deadline_at = t_total + std::chrono::nanoseconds(b->time_budget_ns);
+    const long stop_after = (long)b->stop_after;
+    if (r->candidates && has_thr) return fail(B200_ERR_UNSUPPORTED, "candidates bitmap together with a ranking-score threshold");
+    if (r->candidates && r->candidates_words < hix.n_words64) return fail(B200_ERR_INVALID, "candidates_words smaller than the document range");
+    if (b->universes) {
+        const uint64_t W = hix.n_words64;
+        if (b->n_universe_words < W) return fail(B200_ERR_INVALID, "universe bitmaps shorter than the document range");
+        std::map<const uint64_t *, uint32_t> slot_of;
+        for (uint32_t i = 0; i < NQ; i++)
+            if (b->universes[i]) slot_of.emplace(b->universes[i], 0);
+        uint32_t ns = 0;
+        for (auto &kv : slot_of) kv.second = ns++;
+        CU(d_universes.reserve((size_t)std::max(1u, ns) * W), "alloc universes");
+        std::vector<uint64_t> counts(ns, 0), tmp(W);
+        for (auto &kv : slot_of) {
+            uint64_t c = 0;
+            for (uint64_t w = 0; w < W; w++) {
+                tmp[w] = kv.first[w] & hix.base_ub[w];
+                c += (uint64_t)__builtin_popcountll(tmp[w]);
+            }
+            counts[kv.second] = c;
+            CU(cudaMemcpy(d_universes.p + (size_t)kv.second * W, tmp.data(), W * 8, cudaMemcpyHostToDevice), "H2D universe");
+            stats.h2d_bytes += W * 8;
+        }
+        for (uint32_t i = 0; i < NQ; i++)
+            if (b->universes[i]) {
+                uint32_t sl = slot_of[b->universes[i]];
+                qs[i]->d_univ = d_universes.p + (size_t)sl * W;
+                qs[i]->univ_count = counts[sl];
+            }
+    }
+    for (uint32_t i = 0; i < NQ; i++)
+        if (!qs[i]->d_univ) qs[i]->univ_count = hix.n_documents;
     // ---- phase 2 (per wave, see below): typo derivations for every term of queries [lo, hi) in one device sweep
     auto derive_range = [&](uint32_t lo, uint32_t hi) -> int {
         auto t_ph = clk::now();
@@ -1800,7 +1856,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             remove_nodes_keep_edges(L.graph, rm);
         }
         prepare_resolve(q.ctx, L);
-        request_activation(q, std::move(L), nullptr, dix.base_ub, nullptr, hix.n_words64, hix.n_words64, 0, hix.n_words64);
+        request_activation(q, std::move(L), nullptr, q.d_univ ? q.d_univ : dix.base_ub, nullptr, hix.n_words64, hix.n_words64, 0, hix.n_words64);
     };
     // Frequency (query_graph.rs:303-344): documents of term id t = union of the docids of every node covering t, counted over the
     // whole index — one resolve-shaped activation START -> {covering nodes} -> END per term id
@@ -1833,15 +1889,16 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         q.rules = rules;
         if (q.placeholder) {
             // placeholder search: no text rules (search/new/mod.rs:353-416) -> universe in docid order (bucket_sort.rs:104-116)
-            q.n_candidates = hix.n_documents;
+            q.n_candidates = q.univ_count;
+            q.cand_src = q.d_univ ? q.d_univ : dix.base_ub;
             EmitReq e{};
             e.d.uw = nullptr;
-            e.d.ub = dix.base_ub;
+            e.d.ub = q.d_univ ? q.d_univ : dix.base_ub;
             e.d.out = nullptr;
             e.d.rows = hix.n_words64;
             e.d.ld = hix.n_words64;
             e.d.skip = from;
-            uint64_t avail = hix.n_documents > from ? hix.n_documents - from : 0;
+            uint64_t avail = q.univ_count > from ? q.univ_count - from : 0;
             e.d.take = (uint32_t)std::min<uint64_t>(avail, length);
             q.n_results = e.d.take;
             q.scores.assign(q.n_results, {});
@@ -1951,6 +2008,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
                 }
                 L.cursor = 1;
                 q.n_candidates = L.counts[0];
+                q.cand_src = L.out;  // bucket 0 of the resolve level over the dense universe = SearchResult::candidates
                 uint64_t cnt = L.counts[0];
                 if (cnt < from) {  // bucket_sort.rs:52-64
                     q.drop_levels();
@@ -1980,19 +2038,48 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
                 back();
                 continue;
             }
+            // Deadline::exceeded() is polled once per bucket request (bucket_sort.rs:206); no graph rule can answer without blocking
+            // (ranking_rules.rs:67-74), so on expiry every rule's remaining universe is returned as it is with a Skipped score,
+            // from the current rule up to the first one, and the result is degraded (bucket_sort.rs:206-264)
+            if (stop_after >= 0 ? q.polls++ >= stop_after : (has_budget && clk::now() > deadline_at)) {
+                for (;;) {
+                    Level &Lc = q.levels.back();
+                    const uint64_t remaining = Lc.universe_count;
+                    q.rr_scores.push_back(EScore{B200_S_SKIPPED, 0, 1, -1.f});
+                    if (has_thr && global_score_of(q.rr_scores) < thr)
+                        q.n_candidates -= std::min<uint64_t>(q.n_candidates, remaining);
+                    else
+                        emit_bucket(q, Lc, (uint32_t)Lc.cursor, (uint32_t)Lc.cost_vals.size() + 1, remaining);
+                    q.rr_scores.pop_back();
+                    if (Lc.rule_idx == 0) break;
+                    back();
+                }
+                q.degraded = true;
+                q.drop_levels();
+                break;
+            }
+            // one bucket request = one cost of the rule, empty or not (graph_based_ranking_rule.rs:231-236 walks all_costs): an empty
+            // bucket changes nothing but it does consume a deadline poll
             size_t ci = L.cursor;
-            while (ci < L.cost_vals.size() && L.counts[ci] == 0) ci++;
             if (ci >= L.cost_vals.size()) {
                 back();
                 continue;
             }
             L.cursor = ci + 1;
             uint64_t cnt = L.counts[ci];
+            if (cnt == 0) continue;
             EScore sc{score_kind_of(L.kind), (uint32_t)(L.next_max_cost - L.cost_vals[ci]), (uint32_t)L.next_max_cost, -1.f};
             q.rr_scores.push_back(sc);
             L.universe_count -= cnt;
-            if (rule_cur == n_rules - 1 || (skip_scoring && cnt <= 1) || q.cur_offset + cnt < from) {
-                emit_bucket(q, L, (uint32_t)ci, (uint32_t)ci + 1, cnt);
+            // bucket_sort.rs:293-296: a bucket whose score so far is below the threshold leaves the candidates together with
+            // everything the rule has not returned yet (every later bucket of the rule scores lower still)
+            const bool below = has_thr && global_score_of(q.rr_scores) < thr;
+            if (rule_cur == n_rules - 1 || (skip_scoring && cnt <= 1) || q.cur_offset + cnt < from || below) {
+                if (below) {
+                    if (!L.below_done) q.n_candidates -= std::min<uint64_t>(q.n_candidates, cnt + L.universe_count);
+                    L.below_done = true;
+                } else
+                    emit_bucket(q, L, (uint32_t)ci, (uint32_t)ci + 1, cnt);
                 q.rr_scores.pop_back();
                 continue;
             }
@@ -2120,6 +2207,15 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             if (q.want_activation) cand_q.push_back(i);
             if (!q.emits.empty()) emit_q.push_back(i);
         }
+        if (r->candidates)
+            for (auto i : ln.members) {  // SearchResult::candidates, copied before any block freed above can be written again
+                QState &q = *qs[i];
+                if (!q.cand_src) continue;
+                CU(cudaMemcpyAsync(r->candidates + (size_t)i * r->candidates_words, q.cand_src, (size_t)hix.n_words64 * 8, cudaMemcpyDeviceToHost, ln.stream),
+                   "D2H candidates");
+                ln.lst.d2h_bytes += (size_t)hix.n_words64 * 8;
+                q.cand_src = nullptr;
+            }
         // longest first: the parallel-for over these queries ends when its slowest query does, and host time per query grows
         // with the size of its query graph
         std::stable_sort(cand_q.begin(), cand_q.end(), [&](uint32_t x, uint32_t y) { return qs[x]->graph.nodes.size() > qs[y]->graph.nodes.size(); });
@@ -2640,6 +2736,8 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
     }
     for (unsigned l = 0; l < n_lanes; l++)
         if (lanes[l].rc < 0) return lanes[l].rc;
+    if (r->candidates)
+        for (unsigned l = 0; l < n_lanes; l++) CU(cudaStreamSynchronize(lanes[l].stream), "sync candidates");
     // ---- outputs
     t_ph = clk::now();
     std::vector<uint32_t> out_ids((size_t)NQ * std::max(1u, length));
@@ -2658,6 +2756,8 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         }
         r->n_hits[i] = q.n_results;
         if (r->n_candidates) r->n_candidates[i] = q.n_candidates;
+        if (r->degraded) r->degraded[i] = q.degraded ? 1 : 0;
+        if (r->used_negative_operator) r->used_negative_operator[i] = q.used_negative ? 1 : 0;
         for (uint32_t k = 0; k < q.n_results; k++) {
             r->docids[(size_t)i * limit + k] = out_ids[(size_t)i * std::max(1u, length) + k];
             if (r->n_scores) {

@@ -54,6 +54,8 @@ Engine::~Engine() {
     if (h_step) cudaFreeHost(h_step);
     if (h_results) cudaFreeHost(h_results);
     for (auto e : ev_pool) cudaEventDestroy(e);
+    for (auto e : vt.ev_pool) cudaEventDestroy(e);
+    if (vt.stream) cudaStreamDestroy(vt.stream);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
@@ -172,6 +174,12 @@ int Engine::stage_embeddings(const float *vectors, const uint16_t *half_rows, ui
         CU(cudaMemcpy(dix.emb_docids, ids.data(), n * 4, cudaMemcpyHostToDevice), "H2D embedding docids");
     }
     CU(cudaStreamSynchronize(stream), "sync");
+    // which documents own an embedding (VectorSort returns the others as its last bucket, vector_sort.rs:128-160)
+    emb_bitmap.assign(hix.n_words64, 0);
+    for (uint64_t r = 0; r < n; r++) {
+        const uint32_t doc = docids ? docids[r] : (uint32_t)r;
+        if ((doc >> 6) < emb_bitmap.size()) emb_bitmap[doc >> 6] |= 1ull << (doc & 63);
+    }
     dix.emb_n = n;
     dix.emb_d = d;
     stats.hbm_bytes_staged += n * d * 2 + n * 8;
@@ -246,7 +254,7 @@ int Engine::nns_batch(const float *queries, uint32_t n_q, uint32_t d, uint32_t l
     const unsigned long long *d_c = nullptr;
     if (cand) {
         CU(d_cand.reserve(n_cand_words), "alloc candidates");
-        CU(cudaMemcpyAsync(d_cand.p, cand, n_cand_words * 8, cudaMemcpyHostToDevice, stream), "H2D candidates");
+        CU(cudaMemcpyAsync(d_cand.p, cand, n_cand_words * 8, cudaMemcpyHostToDevice, vt.stream), "H2D candidates");
         d_c = d_cand.p;
     }
     // ---- batched path: tcgen05 GEMM with the top-k fused into its epilogue (vec_gemm.cu)
@@ -270,28 +278,28 @@ int Engine::nns_batch(const float *queries, uint32_t n_q, uint32_t d, uint32_t l
                 CU(d_vsel_ids.reserve((size_t)n_pad * limit), "alloc selection");
                 CU(d_vsel_n.reserve(n_pad), "alloc selection");
                 float *d_qinv = d_vq.p + (size_t)nq * d;
-                CU(cudaMemcpyAsync(d_vq.p, queries + (size_t)q0 * d, (size_t)nq * d * 4, cudaMemcpyHostToDevice, stream), "H2D queries");
-                stats.h2d_bytes += (size_t)nq * d * 4;
-                CU(launch_vec_prep_queries(stream, d_vq.p, nq, n_pad, d, d_vq16.p, d_qinv), "vec_prep_queries");
-                stats.kernel_launches++;
-                size_t m0 = mark();
-                CU(launch_vec_gemm_topk(stream, (uint32_t)sm_count, dix.emb, dix.emb_inv_norm, dix.emb_docids, N, d, d_vq16.p, d_qinv, n_qtiles, n_groups,
+                CU(cudaMemcpyAsync(d_vq.p, queries + (size_t)q0 * d, (size_t)nq * d * 4, cudaMemcpyHostToDevice, vt.stream), "H2D queries");
+                vstats.h2d_bytes += (size_t)nq * d * 4;
+                CU(launch_vec_prep_queries(vt.stream, d_vq.p, nq, n_pad, d, d_vq16.p, d_qinv), "vec_prep_queries");
+                vstats.kernel_launches++;
+                size_t m0 = vt.mark();
+                CU(launch_vec_gemm_topk(vt.stream, (uint32_t)sm_count, dix.emb, dix.emb_inv_norm, dix.emb_docids, N, d, d_vq16.p, d_qinv, n_qtiles, n_groups,
                                         d_c, n_cand_words, limit, d_vruns.p + (size_t)n_qtiles * n_groups * 128 * VEC_GEMM_CAND_CAP, d_vruns.p, d_vpartial.p, d_vsel_ids.p, d_vsel_dist.p, d_vsel_n.p, nq),
                    "vec_gemm_topk");
-                size_t m1 = mark();
+                size_t m1 = vt.mark();
                 // algorithmic bytes: every query tile streams the matrix once (L2 absorbs the re-reads across tiles of the same rows)
-                time_kernel(B200_K_VEC_GEMM, m0, m1, (uint64_t)N * d * 2 + N * 8 + (uint64_t)n_pad * d * 2);
-                stats.kernel_launches++;  // merge kernel
-                stats.vector_bytes += (uint64_t)N * d * 2;
+                vt.time_kernel(vstats, B200_K_VEC_GEMM, m0, m1, (uint64_t)N * d * 2 + N * 8 + (uint64_t)n_pad * d * 2);
+                vstats.kernel_launches++;  // merge kernel
+                vstats.vector_bytes += (uint64_t)N * d * 2;
                 h_ids.resize((size_t)nq * limit);
                 h_dist.resize((size_t)nq * limit);
                 h_n.resize(nq);
-                CU(cudaMemcpyAsync(h_ids.data(), d_vsel_ids.p, (size_t)nq * limit * 4, cudaMemcpyDeviceToHost, stream), "D2H");
-                CU(cudaMemcpyAsync(h_dist.data(), d_vsel_dist.p, (size_t)nq * limit * 4, cudaMemcpyDeviceToHost, stream), "D2H");
-                CU(cudaMemcpyAsync(h_n.data(), d_vsel_n.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, stream), "D2H");
-                stats.d2h_bytes += (size_t)nq * limit * 8 + nq * 4;
-                CU(cudaStreamSynchronize(stream), "sync");
-                resolve_timers();
+                CU(cudaMemcpyAsync(h_ids.data(), d_vsel_ids.p, (size_t)nq * limit * 4, cudaMemcpyDeviceToHost, vt.stream), "D2H");
+                CU(cudaMemcpyAsync(h_dist.data(), d_vsel_dist.p, (size_t)nq * limit * 4, cudaMemcpyDeviceToHost, vt.stream), "D2H");
+                CU(cudaMemcpyAsync(h_n.data(), d_vsel_n.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, vt.stream), "D2H");
+                vstats.d2h_bytes += (size_t)nq * limit * 8 + nq * 4;
+                CU(cudaStreamSynchronize(vt.stream), "sync");
+                vt.resolve(vstats);
                 for (uint32_t q = 0; q < nq; q++) {
                     uint32_t n = std::min(h_n[q], limit);
                     n_out[q0 + q] = n;
@@ -316,33 +324,33 @@ int Engine::nns_batch(const float *queries, uint32_t n_q, uint32_t d, uint32_t l
             qinv[q] = nrm > 0.f ? 1.0f / nrm : 0.f;
         }
         float *d_qinv = d_vq.p + (size_t)chunk * d;
-        CU(cudaMemcpyAsync(d_vq.p, queries + (size_t)q0 * d, (size_t)nq * d * 4, cudaMemcpyHostToDevice, stream), "H2D queries");
-        stats.h2d_bytes += (size_t)nq * d * 4 + nq * 4;
-        stats.d2h_bytes += (size_t)nq * (limit + tie_cap) * 8 + nq * 8;
-        CU(cudaMemcpyAsync(d_qinv, qinv.data(), nq * 4, cudaMemcpyHostToDevice, stream), "H2D query norms");
+        CU(cudaMemcpyAsync(d_vq.p, queries + (size_t)q0 * d, (size_t)nq * d * 4, cudaMemcpyHostToDevice, vt.stream), "H2D queries");
+        vstats.h2d_bytes += (size_t)nq * d * 4 + nq * 4;
+        vstats.d2h_bytes += (size_t)nq * (limit + tie_cap) * 8 + nq * 8;
+        CU(cudaMemcpyAsync(d_qinv, qinv.data(), nq * 4, cudaMemcpyHostToDevice, vt.stream), "H2D query norms");
         for (uint32_t t = 0; t < nq;) {
             uint32_t left = nq - t;
             int qt = left >= 8 ? 8 : (left >= 4 ? 4 : (left >= 2 ? 2 : 1));
             (void)QT;
-            size_t m0 = mark();
-            CU(launch_vec_dist(stream, sm_count * 6, qt, dix.emb, dix.emb_inv_norm, dix.emb_docids, N, d, d_vq.p + (size_t)t * d, d_qinv + t, d_c,
+            size_t m0 = vt.mark();
+            CU(launch_vec_dist(vt.stream, sm_count * 6, qt, dix.emb, dix.emb_inv_norm, dix.emb_docids, N, d, d_vq.p + (size_t)t * d, d_qinv + t, d_c,
                                n_cand_words, d_vdist.p + (size_t)t * N),
                "vec_dist");
-            size_t m1 = mark();
+            size_t m1 = vt.mark();
             uint64_t vb = N * d * 2 + N * 4 + (d_c ? N / 8 : 0) + (uint64_t)qt * d * 4 + (uint64_t)qt * N * 4;
-            time_kernel(B200_K_VEC_DIST, m0, m1, vb);
-            stats.vector_bytes += vb;
+            vt.time_kernel(vstats, B200_K_VEC_DIST, m0, m1, vb);
+            vstats.vector_bytes += vb;
             t += qt;
         }
-        size_t k0 = mark();
-        CU(launch_topk(stream, nq, d_vdist.p, dix.emb_docids, N, limit, tie_cap, d_vsel_dist.p, d_vsel_ids.p, d_vsel_n.p), "topk");
-        size_t k1 = mark();
-        time_kernel(B200_K_TOPK, k0, k1, (uint64_t)nq * N * 4 * 4);
-        CU(cudaMemcpyAsync(sel_d.data(), d_vsel_dist.p, (size_t)nq * (limit + tie_cap) * 4, cudaMemcpyDeviceToHost, stream), "D2H");
-        CU(cudaMemcpyAsync(sel_i.data(), d_vsel_ids.p, (size_t)nq * (limit + tie_cap) * 4, cudaMemcpyDeviceToHost, stream), "D2H");
-        CU(cudaMemcpyAsync(sel_n.data(), d_vsel_n.p, (size_t)nq * 2 * 4, cudaMemcpyDeviceToHost, stream), "D2H");
-        CU(cudaStreamSynchronize(stream), "sync");
-        resolve_timers();
+        size_t k0 = vt.mark();
+        CU(launch_topk(vt.stream, nq, d_vdist.p, dix.emb_docids, N, limit, tie_cap, d_vsel_dist.p, d_vsel_ids.p, d_vsel_n.p), "topk");
+        size_t k1 = vt.mark();
+        vt.time_kernel(vstats, B200_K_TOPK, k0, k1, (uint64_t)nq * N * 4 * 4);
+        CU(cudaMemcpyAsync(sel_d.data(), d_vsel_dist.p, (size_t)nq * (limit + tie_cap) * 4, cudaMemcpyDeviceToHost, vt.stream), "D2H");
+        CU(cudaMemcpyAsync(sel_i.data(), d_vsel_ids.p, (size_t)nq * (limit + tie_cap) * 4, cudaMemcpyDeviceToHost, vt.stream), "D2H");
+        CU(cudaMemcpyAsync(sel_n.data(), d_vsel_n.p, (size_t)nq * 2 * 4, cudaMemcpyDeviceToHost, vt.stream), "D2H");
+        CU(cudaStreamSynchronize(vt.stream), "sync");
+        vt.resolve(vstats);
         for (uint32_t q = 0; q < nq; q++) {
             std::vector<std::pair<float, uint32_t>> c;
             const float *sd = sel_d.data() + (size_t)q * (limit + tie_cap);

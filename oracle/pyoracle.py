@@ -20,12 +20,13 @@ class _Batch(C.Structure):
     _fields_ = [("n_queries", C.c_uint32), ("token_begin", C.c_void_p), ("token_kind", C.c_void_p), ("lemma_off", C.c_void_p),
                 ("lemma_bytes", C.c_void_p), ("tms", C.c_int), ("scoring", C.c_int), ("offset", C.c_uint32), ("limit", C.c_uint32),
                 ("words_limit", C.c_uint32), ("vectors", C.c_void_p), ("semantic_ratio", C.c_float), ("hybrid", C.c_int),
-                ("vector_only", C.c_int), ("has_threshold", C.c_int), ("threshold", C.c_double)]
+                ("vector_only", C.c_int), ("has_threshold", C.c_int), ("threshold", C.c_double),
+                ("universes", C.c_void_p), ("n_universe_words", C.c_uint64), ("stop_after", C.c_int64), ("time_budget_ns", C.c_uint64)]
 
 
 class _Out(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("docids", "n_hits", "score_kind", "score_rank", "score_max", "score_sim", "n_scores",
-                                          "n_candidates", "semantic_hits", "fetch_bytes", "seconds")]
+                                          "n_candidates", "semantic_hits", "fetch_bytes", "seconds", "degraded", "used_negative_operator")]
 
 
 def build_lib():
@@ -85,6 +86,8 @@ class OracleResults:
         self.semantic_hits = np.zeros(n, np.uint32)
         self.fetch_bytes = np.zeros(n, np.uint64)
         self.seconds = np.zeros(n, np.float64)
+        self.degraded = np.zeros(n, np.uint8)
+        self.used_negative_operator = np.zeros(n, np.uint8)
 
     def ids(self, q):
         return [int(x) for x in self.docids[q, : self.n_hits[q]]]
@@ -157,7 +160,7 @@ class OracleIndex:
             self._l.orc_set_distribution(self._h, 1, distribution[0], distribution[1])
 
     def search_batch(self, tokens, *, tms="last", scoring="skip", offset=0, limit=20, words_limit=10, vectors=None, hybrid=False,
-                     semantic_ratio=0.5, vector_only=False, threshold=None, n_threads=1):
+                     semantic_ratio=0.5, vector_only=False, threshold=None, universes=None, stop_after=None, time_budget_ms=None, n_threads=1):
         """tokens: meilisearch_b200.tokenizer.TokenBatch"""
         n = tokens.n_queries
         res = OracleResults(n, limit)
@@ -172,6 +175,19 @@ class OracleIndex:
             b.vectors = _p(vec)
         b.semantic_ratio, b.hybrid, b.vector_only = semantic_ratio, int(hybrid), int(vector_only)
         b.has_threshold, b.threshold = int(threshold is not None), float(threshold or 0.0)
+        b.stop_after = -1 if stop_after is None else int(stop_after)
+        b.time_budget_ns = 0 if time_budget_ms is None else max(1, int(time_budget_ms * 1e6))
+        keep = []
+        if universes is not None:  # list of per-query uint64 word arrays (None = all documents); equal objects are shared
+            ptrs = (C.c_void_p * n)()
+            for i, u in enumerate(universes):
+                if u is not None:
+                    a = np.ascontiguousarray(u, np.uint64)
+                    keep.append(a)
+                    ptrs[i] = a.ctypes.data
+                    b.n_universe_words = len(a)
+            keep.append(ptrs)
+            b.universes = C.cast(ptrs, C.c_void_p)
         o = _Out()
         for name, _ in _Out._fields_:
             setattr(o, name, _p(getattr(res, name)))

@@ -3,6 +3,7 @@
 // Follows search/new/ranking_rules.rs, graph_based_ranking_rule.rs, ranking_rule_graph/** ,
 // exact_attribute.rs, vector_sort.rs, bucket_sort.rs, score_details.rs:441-566.
 #pragma once
+#include <chrono>
 #include <cmath>
 #include <memory>
 
@@ -505,6 +506,8 @@ struct RankingRule {
     virtual ~RankingRule() {}
     virtual void start_iteration(Ctx &ctx, const Bitmap &universe, const QueryGraph &query) = 0;
     virtual bool next_bucket(Ctx &ctx, const Bitmap &universe, RuleOutput &out) = 0;
+    // ranking_rules.rs:55-74: a bucket if it can be had without blocking; the default says it cannot (Poll::Pending)
+    virtual bool non_blocking_next_bucket(Ctx &, const Bitmap &, RuleOutput &) { return false; }
     virtual void end_iteration() = 0;
 };
 
@@ -1071,6 +1074,22 @@ struct VectorSortRule : RankingRule {
             }
         }
     }
+    bool non_blocking_next_bucket(Ctx &ctx, const Bitmap &universe, RuleOutput &out) override {  // vector_sort.rs:175-201
+        Bitmap cands = bm_and(vector_candidates, universe);
+        if (cands.is_empty()) {
+            out.candidates = universe;
+            out.score = Score{S_VECTOR, 0, 1, false, 0};
+            return true;
+        }
+        Bitmap c;
+        float score;
+        if (next_results(ctx, cands, c, score)) {
+            out.candidates = std::move(c);
+            out.score = Score{S_VECTOR, 0, 1, true, score};
+            return true;
+        }
+        return false;
+    }
     void end_iteration() override {}
 };
 
@@ -1082,9 +1101,21 @@ struct BucketSortOutput {
     bool degraded = false;
 };
 
+// crates/milli/src/lib.rs:154-226: a time budget, or (the reference's test hook) "exceeded from the n-th poll on"
+struct Deadline {
+    bool has_time = false;
+    std::chrono::steady_clock::time_point at;
+    long stop_after = -1;
+    mutable long polls = 0;
+    bool exceeded() const {
+        if (stop_after >= 0) return polls++ >= stop_after;  // a poll count ignores the clock entirely (lib.rs:207-216)
+        return has_time && std::chrono::steady_clock::now() > at;
+    }
+};
+
 inline BucketSortOutput bucket_sort(Ctx &ctx, std::vector<std::unique_ptr<RankingRule>> &rules, const QueryGraph &query,
                                     const Bitmap &universe, size_t from, size_t length, int scoring_strategy,
-                                    bool has_threshold, double threshold) {
+                                    bool has_threshold, double threshold, const Deadline &deadline = Deadline()) {
     BucketSortOutput out;
     if (universe.len() < from) {
         out.all_candidates = universe;
@@ -1148,7 +1179,36 @@ inline BucketSortOutput bucket_sort(Ctx &ctx, std::vector<std::unique_ptr<Rankin
             continue;
         }
         RuleOutput nb;
-        if (!rules[cur]->next_bucket(ctx, universes[cur], nb)) {
+        if (deadline.exceeded()) {
+            // bucket_sort.rs:206-264: the graph rules cannot answer without blocking (ranking_rules.rs:67-74), so the rule's whole
+            // remaining universe is returned as it is with a Skipped score, rule after rule up to the first one
+            bool ready = false;
+            for (;;) {
+                if (rules[cur]->non_blocking_next_bucket(ctx, universes[cur], nb)) {
+                    ready = true;
+                    break;
+                }
+                Bitmap bucket = std::move(universes[cur]);
+                universes[cur].clear();
+                rr_scores.push_back(Score{S_SKIPPED, 0, 1, false, 0});
+                bool below = has_threshold && global_score(rr_scores) < threshold;
+                if (below) {
+                    all_candidates.sub(bucket);
+                } else
+                    maybe_add(bucket);
+                rr_scores.pop_back();
+                if (cur == 0) {
+                    out.all_candidates = std::move(all_candidates);
+                    out.degraded = true;
+                    return out;
+                }
+                universes[cur].clear();
+                rules[cur]->end_iteration();
+                cur--;
+                if (rr_scores.size() > cur) rr_scores.pop_back();
+            }
+            (void)ready;
+        } else if (!rules[cur]->next_bucket(ctx, universes[cur], nb)) {
             universes[cur].clear();
             rules[cur]->end_iteration();
             if (cur == 0) break;

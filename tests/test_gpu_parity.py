@@ -316,3 +316,258 @@ def test_union_postings_matches_decoded_lists(mb, synth):
         got_u = ix.union_postings(db, keys, universe)
         assert np.array_equal(got_u, want & universe), db
     assert np.array_equal(ix.union_postings(0, np.zeros(0, np.uint32)), np.zeros(n_words, np.uint64))
+
+
+# ------------------------------------------------------------------------------------------------ round 2: S0 boundary features
+def _same(got, want, q, scores=True, ctx=None):
+    assert got.status[q] == 0, ctx
+    assert got.ids(q) == want.ids(q), ctx
+    if scores:
+        assert got.scores(q) == want.scores(q), ctx
+    assert int(got.n_candidates[q]) == int(want.n_candidates[q]), ctx
+
+
+def test_cutoff_goldens_on_gpu(mb):
+    """Deadline::with_stop_after(n) known answers of the reference (search/new/tests/cutoff.rs:100-407) through the C ABI."""
+    from tests.test_cutoff_goldens import CUTOFF_CASES, cutoff_image, global_score
+
+    ix = mb.Index(cutoff_image(), criteria=["words", "typo"])
+    for stop_after, (ids, scores, degraded) in CUTOFF_CASES.items():
+        r = ix.search().query(["hello puppy kefir"]).scoring_strategy("detailed").limit(4).deadline(stop_after=stop_after).execute()
+        assert r.ids(0) == ids, stop_after
+        assert [round(global_score(s), 4) for s in r.scores(0)] == scores, stop_after
+        assert bool(r.degraded[0]) == degraded, stop_after
+    # cutoff.rs:74-98 degraded_search_cannot_skip_filter
+    r = ix.search().query(["hello puppy kefir"]).limit(100).deadline(stop_after=0).universes([np.array([0b00011], np.uint64)]).with_candidates().execute()
+    assert r.ids(0) == [0, 1] and int(r.n_candidates[0]) == 2 and r.degraded[0] == 1
+    assert int(r.candidates[0, 0]) == 0b00011
+    # a zero time budget degrades too (cutoff.rs:58-72)
+    assert ix.search().query(["hello puppy kefir"]).limit(3).deadline(budget_ms=0).execute().degraded[0] == 1
+
+
+def _random_universes(rng, n_docs, n_queries):
+    words = (n_docs + 63) // 64
+    shared = rng.integers(0, 2**63, words, dtype=np.uint64) & rng.integers(0, 2**63, words, dtype=np.uint64)
+    sparse = np.zeros(words, np.uint64)
+    for d in rng.integers(0, n_docs, 300):
+        sparse[d >> 6] |= np.uint64(1) << np.uint64(d & 63)
+    out = []
+    for q in range(n_queries):
+        out.append([None, shared, sparse, rng.integers(0, 2**63, words, dtype=np.uint64)][q % 4])
+    return out
+
+
+def test_filtered_universe_matches_oracle(mb, synth):
+    """S0 `universes` (filtered_universe, search/new/mod.rs:719): keyword, placeholder, semantic and hybrid searches"""
+    from oracle.pyoracle import OracleIndex
+
+    rng = np.random.default_rng(12)
+    queries = synth.synthetic_queries(80, seed=41) + ["", synth.word(7)]
+    tokens = mb.TokenBatch(queries)
+    unis = _random_universes(rng, synth.n_docs, len(queries))
+    ix, o = mb.Index(synth), OracleIndex(synth)
+    for scoring in ("detailed", "skip"):
+        got = ix.search().query(tokens).scoring_strategy(scoring).universes(unis).with_candidates().execute()
+        want = o.search_batch(tokens, scoring=scoring, universes=unis, n_threads=8)
+        for q in range(len(queries)):
+            _same(got, want, q, ctx=(queries[q], q % 4))
+            cand = got.candidates[q]
+            assert int(sum(bin(int(w)).count("1") for w in cand)) == int(want.n_candidates[q])
+            if unis[q] is not None:
+                assert not (cand & ~unis[q]).any()
+            for d in got.ids(q):
+                assert (int(cand[d >> 6]) >> (d & 63)) & 1
+    # vector side
+    d = 64
+    emb = rng.standard_normal((synth.n_docs, d)).astype(np.float16).astype(np.float32)
+    ix.set_embeddings(emb)
+    o.set_embeddings(emb)
+    vec = rng.standard_normal((len(queries), d)).astype(np.float16).astype(np.float32)
+    got = ix.search().semantic(vec).universes(unis).limit(10).execute()
+    want = o.search_batch(mb.TokenBatch([""] * len(queries)), vectors=vec, vector_only=True, universes=unis, limit=10, n_threads=8)
+    for q in range(len(queries)):
+        assert got.ids(q) == want.ids(q), q
+        assert int(got.n_candidates[q]) == int(want.n_candidates[q])
+    got = ix.search().query(tokens).semantic(vec).universes(unis).execute_hybrid(0.5)
+    want = o.search_batch(tokens, vectors=vec, hybrid=True, semantic_ratio=0.5, universes=unis, n_threads=8)
+    for q in range(len(queries)):
+        assert got.ids(q) == want.ids(q), (queries[q], q % 4)
+
+
+@pytest.mark.parametrize("threshold", [0.2, 0.55, 0.8, 0.97])
+def test_ranking_score_threshold_matches_oracle(mb, synth, threshold):
+    from oracle.pyoracle import OracleIndex
+
+    queries = synth.synthetic_queries(120, seed=51)
+    tokens = mb.TokenBatch(queries)
+    got = mb.Index(synth).search().query(tokens).scoring_strategy("detailed").ranking_score_threshold(threshold).execute()
+    want = OracleIndex(synth).search_batch(tokens, scoring="detailed", threshold=threshold, n_threads=8)
+    for q in range(len(queries)):
+        _same(got, want, q, ctx=(queries[q], threshold))
+
+
+@pytest.mark.parametrize("stop_after", [0, 1, 2, 3])
+def test_deadline_stop_after_matches_oracle(mb, synth, stop_after):
+    """Deadline::with_stop_after(n) on a synthetic corpus.  Early polls fall into the Words / Typo rules, where the engine's bucket
+    requests map one to one onto the reference's; deeper in the stack the reference also polls for costs that its skip
+    constraints make infeasible, so larger n are checked through invariants below."""
+    from oracle.pyoracle import OracleIndex
+
+    queries = synth.synthetic_queries(100, seed=61)
+    tokens = mb.TokenBatch(queries)
+    for scoring in ("detailed", "skip"):
+        got = mb.Index(synth).search().query(tokens).scoring_strategy(scoring).deadline(stop_after=stop_after).execute()
+        want = OracleIndex(synth).search_batch(tokens, scoring=scoring, stop_after=stop_after, n_threads=8)
+        for q in range(len(queries)):
+            _same(got, want, q, ctx=(queries[q], stop_after, scoring))
+            assert int(got.degraded[q]) == int(want.degraded[q]), (queries[q], stop_after)
+
+
+@pytest.mark.parametrize("stop_after", [5, 8, 13, 40])
+def test_deadline_invariants(mb, synth, stop_after):
+    """a degraded result returns every candidate it has room for, the sorted prefix equals the undegraded search's, and the
+    unsorted tail carries a Skipped score (bucket_sort.rs:206-264)"""
+    queries = synth.synthetic_queries(100, seed=62)
+    tokens = mb.TokenBatch(queries)
+    ix = mb.Index(synth)
+    full = ix.search().query(tokens).scoring_strategy("detailed").execute()
+    got = ix.search().query(tokens).scoring_strategy("detailed").deadline(stop_after=stop_after).with_candidates().execute()
+    for q in range(len(queries)):
+        assert got.status[q] == 0
+        ids = got.ids(q)
+        assert len(set(ids)) == len(ids)
+        assert int(got.n_candidates[q]) == int(full.n_candidates[q])
+        assert len(ids) == min(20, int(got.n_candidates[q]))
+        for d in ids:
+            assert (int(got.candidates[q, d >> 6]) >> (d & 63)) & 1
+        skipped = [any(s[0] == "skipped" for s in row) for row in got.scores(q)]
+        if not got.degraded[q]:
+            assert ids == full.ids(q) and not any(skipped)
+            continue
+        k = skipped.index(True) if any(skipped) else len(ids)
+        assert all(skipped[k:])                                  # once the dump starts, everything after it is dumped
+        assert ids[:k] == full.ids(q)[:k]                        # what was ranked before the deadline is the true prefix
+        assert got.scores(q)[:k] == full.scores(q)[:k]
+
+
+def test_used_negative_operator(mb, synth):
+    w = synth.synthetic_queries(1, seed=5, with_typos=False)[0].split()
+    r = mb.Index(synth).search().query([w[0] + " -" + w[-1], w[0]]).execute()
+    assert list(r.used_negative_operator) == [1, 0]
+
+
+def test_count_goldens_on_gpu(mb):
+    """typo_tolerance.rs:18-357 hit counts (exact words, exact attributes, min word length) through the CUDA path"""
+    ran = 0
+    for case in G.get("count_cases", []):
+        img = image_from_corpus(G["corpora"][case["index"]])
+        s = case["settings"]
+        ix = mb.Index(img, criteria=s.get("criteria"), authorize_typos=s.get("authorize_typos", True), one_typo=s.get("one_typo", 5),
+                      two_typos=s.get("two_typos", 9), exact_words=s.get("exact_words", []), synonyms=s.get("synonyms"))
+        res = ix.search().query(mb.TokenBatch([case["query"]], img.stop_words)).terms_matching_strategy(case.get("tms", "last")).limit(max(case.get("limit", 20), 1)).execute()
+        assert res.status[0] == 0
+        assert int(res.n_hits[0]) == case["expected_count"], case["source"]
+        ix.close()
+        ran += 1
+    assert ran == len(G.get("count_cases", []))
+
+
+def test_distribution_shift_matches_oracle(mb, synth):
+    """b200_stage_distribution (vector/distribution.rs:103-130) on semantic scores"""
+    from oracle.pyoracle import OracleIndex
+
+    rng = np.random.default_rng(3)
+    d = 64
+    emb = rng.standard_normal((5000, d)).astype(np.float16).astype(np.float32)
+    ix, o = mb.Index(synth), OracleIndex(synth)
+    ix.set_embeddings(emb, distribution=(0.6, 0.05))
+    o.set_embeddings(emb, distribution=(0.6, 0.05))
+    vec = rng.standard_normal((9, d)).astype(np.float16).astype(np.float32)
+    got = ix.search().semantic(vec).scoring_strategy("detailed").limit(15).execute()
+    want = o.search_batch(mb.TokenBatch([""] * 9), vectors=vec, vector_only=True, scoring="detailed", limit=15)
+    for q in range(9):
+        assert got.ids(q) == want.ids(q)
+        gs = [s[0][1] for s in got.scores(q)]
+        ws = [s[0][1] for s in want.scores(q)]
+        assert np.allclose(gs, ws, rtol=1e-4, atol=1e-6)
+        assert all(0 < x <= 1 for x in gs)
+
+
+def test_prefix_search_disabled_matches_oracle(mb, synth):
+    from oracle.pyoracle import OracleIndex
+
+    queries = synth.synthetic_queries(80, seed=71)
+    tokens = mb.TokenBatch(queries)
+    got = mb.Index(synth, prefix_search=False).search().query(tokens).scoring_strategy("detailed").execute()
+    want = OracleIndex(synth, prefix_search=False).search_batch(tokens, scoring="detailed", n_threads=8)
+    for q in range(len(queries)):
+        _same(got, want, q, ctx=queries[q])
+
+
+def test_nns_many_ties_and_duplicate_docids(mb, synth):
+    """more equal-distance rows than the selection's tie buffer, and several embeddings per document"""
+    from oracle.pyoracle import OracleIndex
+
+    rng = np.random.default_rng(4)
+    n, d = 6000, 64
+    emb = rng.standard_normal((n, d)).astype(np.float16).astype(np.float32)
+    emb[1000:3500] = emb[999]                      # 2501 identical rows: a tie far longer than any top-k
+    docids = np.arange(n, dtype=np.uint32)
+    docids[4000:4200] = docids[100:300]            # 200 documents own two embeddings each
+    ix, o = mb.Index(synth), OracleIndex(synth)
+    ix.set_embeddings(emb, docids)
+    o.set_embeddings(emb, docids)
+    q = np.stack([emb[999], emb[150], rng.standard_normal(d).astype(np.float32)])
+    for k in (10, 100):
+        ids, dist, cnt = ix.nns_by_vector(q, k)
+        for i in range(len(q)):
+            oid, od = o.nns(q[i], k)
+            assert cnt[i] == len(oid)
+            assert np.allclose(dist[i, : cnt[i]], od, rtol=1e-4, atol=2e-6)
+            # inside a run of equal distances the order is ascending docid on both sides
+            assert list(ids[i, : cnt[i]]) == list(oid), (i, k)
+
+
+def test_path_table_growth(mb):
+    """More distinct surviving paths in one rule step than the 4096-slot table holds: the step is rerun with a larger table"""
+    from corpus.pyindexgen import IndexImage
+    from oracle.pyoracle import OracleIndex
+
+    # 4 query words, each document holds them at a different combination of positions: the Position rule (about 10 costs per
+    # term) sees thousands of distinct (position, position, position, position) paths in its first bucket's universe
+    rng = np.random.default_rng(8)
+    img = IndexImage(1)
+    words = ["alpha", "bravo", "charlie", "delta"]
+    filler = ["f%03d" % i for i in range(200)]
+    for doc in range(9000):
+        toks = [filler[int(x)] for x in rng.integers(0, 200, 40)]
+        for w, p in zip(words, sorted(rng.choice(40, 4, replace=False))):
+            toks[int(p)] = w
+        img.add_text(doc, 0, " ".join(toks))
+    img.build()
+    crit = ["words", "wordPosition", "exactness"]
+    queries = [" ".join(words)]
+    tokens = mb.TokenBatch(queries)
+    got = mb.Index(img, criteria=crit).search().query(tokens).scoring_strategy("detailed").limit(50).execute()
+    want = OracleIndex(img, criteria=crit).search_batch(tokens, scoring="detailed", limit=50)
+    _same(got, want, 0)
+
+
+def test_partial_embeddings_last_bucket(mb, synth):
+    """fewer embedded documents than offset + limit: the rest of the universe follows in docid order without a similarity
+    (vector_sort.rs:128-160)"""
+    from oracle.pyoracle import OracleIndex
+
+    rng = np.random.default_rng(6)
+    d = 64
+    emb = rng.standard_normal((7, d)).astype(np.float16).astype(np.float32)
+    docids = np.array([5, 900, 17, 4000, 33, 2, 12000], np.uint32)
+    ix, o = mb.Index(synth), OracleIndex(synth)
+    ix.set_embeddings(emb, docids)
+    o.set_embeddings(emb, docids)
+    vec = rng.standard_normal((3, d)).astype(np.float16).astype(np.float32)
+    got = ix.search().semantic(vec).scoring_strategy("detailed").limit(12).execute()
+    want = o.search_batch(mb.TokenBatch([""] * 3), vectors=vec, vector_only=True, scoring="detailed", limit=12)
+    for q in range(3):
+        assert got.ids(q) == want.ids(q)
+        assert [s[0][1] is None for s in got.scores(q)] == [s[0][1] is None for s in want.scores(q)]
