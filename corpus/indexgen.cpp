@@ -165,15 +165,15 @@ void ig_set_stop_words(ig_builder *b, const char *words) {
 }
 
 static bool is_word_byte(unsigned char c) {
-    return (c >= 'a' && c <= 'z') || (c >= '0' && c <= '9') || c >= 0x80;
+    return (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || (c >= '0' && c <= '9') || c >= 0x80;
 }
 
 void ig_add_text(ig_builder *b, uint32_t docid, uint32_t fid, const char *text) {
     // Lowercase ASCII tokenizer standing in for charabia on plain Latin text.
     // Position rules: tokenize_document.rs:128-150 (first word +0, then +1, +8 after a hard separator).
+    // stop words are matched on the token as written (the reference's stop-word set is case sensitive:
+    // search/new/tests/stop_words.rs:1-10,25-29), everything else on the lowercased token
     std::string s(text);
-    for (auto &c : s)
-        if (c >= 'A' && c <= 'Z') c = (char)(c - 'A' + 'a');
     size_t i = 0, n = s.size();
     uint32_t pos = 0;
     bool first = true;
@@ -196,6 +196,9 @@ void ig_add_text(ig_builder *b, uint32_t docid, uint32_t fid, const char *text) 
         size_t j = i;
         while (j < n && is_word_byte((unsigned char)s[j])) j++;
         std::string w = s.substr(i, j - i);
+        const bool is_stop = b->stop_words.count(w) != 0;
+        for (auto &c : w)
+            if (c >= 'A' && c <= 'Z') c = (char)(c - 'A' + 'a');
         i = j;
         if (first) {
             first = false;
@@ -205,7 +208,7 @@ void ig_add_text(ig_builder *b, uint32_t docid, uint32_t fid, const char *text) 
         hard = false;
         if (pos >= 65536) break;
         if (w.size() > 250) continue;
-        if (b->stop_words.count(w)) continue;
+        if (is_stop) continue;
         b->toks.push_back({b->intern_word(w), docid, (uint16_t)fid, (uint16_t)pos});
     }
 }

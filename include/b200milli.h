@@ -112,6 +112,13 @@ int b200_derive_batch(b200_index *, uint32_t n_words, const char *words, const u
 int b200_union_postings(b200_index *, int db, const uint32_t *key_index, uint32_t n_keys, const uint64_t *universe, uint64_t n_universe_words,
                         uint64_t *out);
 
+/* Replaces ProximityGraph::resolve_condition for one edge (crates/milli/src/search/new/ranking_rule_graph/proximity/compute_docids.rs:15-108,
+ * the non-prefix lookups :172-211): out = universe AND the union, over every l in `left` and r in `right` (dictionary ranks, i.e.
+ * positions in the staged dictionary), of word_pair_proximity_docids[(fwd_prox, l, r)] and word_pair_proximity_docids[(bwd_prox, r, l)];
+ * a proximity of 0 disables that direction.  universe / out as in b200_union_postings. */
+int b200_proximity_pairs(b200_index *, const uint32_t *left, uint32_t n_left, const uint32_t *right, uint32_t n_right, uint32_t fwd_prox,
+                         uint32_t bwd_prox, const uint64_t *universe, uint64_t n_universe_words, uint64_t *out);
+
 /* ---- S4: vector store ------------------------------------------------------------------ */
 /* Replaces VectorStore::nns_by_vector (crates/milli/src/vector/store.rs:638-675) for a batch of queries:
  * exact scan, ascending distance (1 - cos)/2, ties by ascending docid.
@@ -178,6 +185,31 @@ typedef struct {                  /* SearchResult (search/mod.rs:526-535), flatt
     uint64_t candidates_words;    /* words per query in `candidates` (>= ceil((max docid + 1) / 64)) */
 } b200_results;
 int b200_search_batch(b200_index *, const b200_query_batch *, b200_results *);
+
+/* ---- S1: the RankingRule seam ---------------------------------------------------------- */
+/* Replaces `dyn RankingRule` as driven by bucket_sort (crates/milli/src/search/new/ranking_rules.rs:26-83, bucket_sort.rs:123,266,323)
+ * for the graph-based rules and ExactAttribute.  Query graphs are opaque library objects (a QueryGraph plus the terms it refers
+ * to): the first one comes from b200_graph_from_tokens (QueryGraph::from_query, query_graph.rs:96-187, with every term's
+ * derivations computed), the next ones from b200_rule_next (RankingRuleOutput::query: the graph rebuilt from the paths that
+ * produced the bucket, graph_based_ranking_rule.rs:340-353).  Every graph handed out must be released with b200_graph_free. */
+typedef struct b200_graph b200_graph;
+typedef struct b200_rule b200_rule;
+/* one_query: a b200_query_batch with n_queries == 1 (tokens, words_limit, terms_matching_strategy) */
+int b200_graph_from_tokens(b200_index *, const b200_query_batch *one_query, b200_graph **out);
+void b200_graph_free(b200_graph *);
+/* RankingRule::start_iteration(universe, query).  rule_kind: B200_S_WORDS, _TYPO, _PROXIMITY, _FID, _POSITION, _EXACT_ATTRIBUTE,
+ * _EXACT_WORDS (= Exactness); terms_matching_strategy matters for B200_S_WORDS only.  universe: dense u64 words, NULL = all
+ * documents.  All buckets of the rule are evaluated here, in one device step. */
+int b200_rule_start(b200_index *, int rule_kind, int terms_matching_strategy, const b200_graph *query, const uint64_t *universe,
+                    uint64_t n_universe_words, b200_rule **out);
+/* RankingRule::next_bucket(universe): returns 0 and the next bucket in ascending cost order (empty ones included, like the
+ * reference, graph_based_ranking_rule.rs:231-236), or 1 when the rule is exhausted (None).  out_bitmap (n_words words) =
+ * RankingRuleOutput::candidates = bucket AND universe (NULL = the start universe); rank / max_rank = the bucket's score
+ * (score_details.rs Rank); out_query = RankingRuleOutput::query (NULL for an empty bucket; caller frees). */
+int b200_rule_next(b200_rule *, const uint64_t *universe, uint64_t *out_bitmap, uint64_t n_words, uint32_t *rank, uint32_t *max_rank,
+                   b200_graph **out_query);
+/* RankingRule::end_iteration */
+void b200_rule_end(b200_rule *);
 
 /* ---- introspection for measurement ----------------------------------------------------- */
 /* kernel classes for the per-kernel accounting below */

@@ -101,6 +101,12 @@ def load_library():
         l.b200_union_postings.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
         l.b200_nns_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
         l.b200_search_batch.argtypes = [C.c_void_p, C.POINTER(_Batch), C.POINTER(_Results)]
+        l.b200_proximity_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
+        l.b200_graph_from_tokens.argtypes = [C.c_void_p, C.POINTER(_Batch), C.POINTER(C.c_void_p)]
+        l.b200_graph_free.argtypes = [C.c_void_p]
+        l.b200_rule_start.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+        l.b200_rule_next.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_void_p)]
+        l.b200_rule_end.argtypes = [C.c_void_p]
         l.b200_get_stats.argtypes = [C.c_void_p, C.POINTER(_Stats)]
         l.b200_reset_stats.argtypes = [C.c_void_p]
         _lib = l
@@ -109,7 +115,8 @@ def load_library():
 
 SYMBOLS = ["b200_open", "b200_close", "b200_last_error", "b200_open_error", "b200_stage_dictionary", "b200_stage_db",
            "b200_stage_documents_ids", "b200_stage_settings", "b200_stage_synonyms", "b200_stage_finish", "b200_stage_embeddings", "b200_stage_embeddings_f16", "b200_stage_distribution",
-           "b200_derive_batch", "b200_union_postings", "b200_nns_batch", "b200_search_batch", "b200_get_stats", "b200_reset_stats"]
+           "b200_derive_batch", "b200_union_postings", "b200_proximity_pairs", "b200_nns_batch", "b200_search_batch", "b200_graph_from_tokens",
+           "b200_graph_free", "b200_rule_start", "b200_rule_next", "b200_rule_end", "b200_get_stats", "b200_reset_stats"]
 
 
 def _p(a):
@@ -236,6 +243,26 @@ class Index:
         self._ck(self._l.b200_union_postings(self._h, int(db), _p(keys), len(keys), _p(uni), 0 if uni is None else len(uni), _p(out)))
         return out
 
+    def proximity_pairs(self, left, right, fwd_prox, bwd_prox, universe=None):
+        """S2 for proximity conditions: universe AND the union of word_pair_proximity_docids[(fwd, l, r)] and [(bwd, r, l)]"""
+        lw, rw = np.ascontiguousarray(left, np.uint32), np.ascontiguousarray(right, np.uint32)
+        n_words = (self._n_docs + 63) // 64
+        out = np.zeros(n_words, np.uint64)
+        uni = None if universe is None else np.ascontiguousarray(universe, np.uint64)
+        self._ck(self._l.b200_proximity_pairs(self._h, _p(lw), len(lw), _p(rw), len(rw), int(fwd_prox), int(bwd_prox), _p(uni),
+                                              0 if uni is None else len(uni), _p(out)))
+        return out
+
+    def query_graph(self, query, stop_words=frozenset(), terms_matching_strategy="last", words_limit=10):
+        """S1: QueryGraph::from_query for one query, as an opaque QueryGraph handle"""
+        tokens = query if isinstance(query, TokenBatch) else TokenBatch([query], stop_words)
+        b = _Batch(1, _p(tokens.token_begin), _p(tokens.token_kind), _p(tokens.lemma_off), _p(tokens.lemma_bytes), TMS[terms_matching_strategy], 0, 0, 1,
+                   words_limit, None, 0, 0.0)
+        b.stop_after = -1
+        g = C.c_void_p()
+        self._ck(self._l.b200_graph_from_tokens(self._h, C.byref(b), C.byref(g)))
+        return QueryGraph(self, g)
+
     def nns_by_vector(self, queries, limit, candidates=None):
         q = np.ascontiguousarray(np.atleast_2d(queries), np.float32)
         n = q.shape[0]
@@ -267,6 +294,45 @@ class Index:
         if getattr(self, "_h", None):
             self._l.b200_close(self._h)
             self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class QueryGraph:
+    """S1: an opaque query graph of the library (QueryGraph + its terms).  `rule()` is RankingRule::start_iteration .. next_bucket ..
+    end_iteration for one ranking rule (ranking_rules.rs:26-83)."""
+
+    def __init__(self, index, handle):
+        self.index, self._g = index, handle
+
+    def rule(self, kind, universe=None, terms_matching_strategy="last"):
+        """yields (candidates bitmap, rank, max_rank, child QueryGraph or None) per bucket in ascending cost order"""
+        ix = self.index
+        uni = None if universe is None else np.ascontiguousarray(universe, np.uint64)
+        r = C.c_void_p()
+        ix._ck(ix._l.b200_rule_start(ix._h, SCORE_KINDS.index(kind), TMS[terms_matching_strategy], self._g, _p(uni), 0 if uni is None else len(uni), C.byref(r)))
+        try:
+            n_words = (ix._n_docs + 63) // 64
+            while True:
+                out = np.zeros(n_words, np.uint64)
+                rank, mx, child = C.c_uint32(), C.c_uint32(), C.c_void_p()
+                rc = ix._l.b200_rule_next(r, None, _p(out), n_words, C.byref(rank), C.byref(mx), C.byref(child))
+                if rc == 1:
+                    return
+                if rc != 0:
+                    raise B200Error(rc, "b200_rule_next")
+                yield out, rank.value, mx.value, (QueryGraph(ix, child) if child.value else None)
+        finally:
+            ix._l.b200_rule_end(r)
+
+    def close(self):
+        if self._g is not None and self._g.value:
+            self.index._l.b200_graph_free(self._g)
+            self._g = None
 
     def __del__(self):
         try:

@@ -13,6 +13,15 @@ using namespace b200;
 struct b200_index {
     Engine e;
 };
+struct b200_rule {
+    Engine::RuleRun *run;
+    uint64_t n_words;
+};
+namespace b200 {
+int rule_next_impl(Engine::RuleRun *run, uint64_t n_words64, const uint64_t *universe, uint64_t *out_bitmap, uint64_t n_words, uint32_t *rank,
+                   uint32_t *max_rank, GraphObj **out_query);
+void rule_end_impl(Engine::RuleRun *run);
+}  // namespace b200
 
 static thread_local std::string g_open_error;
 
@@ -157,6 +166,45 @@ int b200_union_postings(b200_index *h, int db, const uint32_t *key_index, uint32
     std::lock_guard<std::mutex> g(h->e.mu);
     return h->e.union_postings(db, key_index, n_keys, universe, n_universe_words, out);
 }
+int b200_proximity_pairs(b200_index *h, const uint32_t *left, uint32_t n_left, const uint32_t *right, uint32_t n_right, uint32_t fwd_prox,
+                         uint32_t bwd_prox, const uint64_t *universe, uint64_t n_universe_words, uint64_t *out) {
+    std::lock_guard<std::mutex> g(h->e.mu);
+    return h->e.proximity_pairs(left, n_left, right, n_right, fwd_prox, bwd_prox, universe, n_universe_words, out);
+}
+int b200_graph_from_tokens(b200_index *h, const b200_query_batch *one_query, b200_graph **out) {
+    std::lock_guard<std::mutex> g(h->e.mu);
+    if (!h->e.staged) return h->e.fail(B200_ERR_STATE, "graph_from_tokens before b200_stage_finish");
+    GraphObj *go = nullptr;
+    int rc = h->e.graph_from_tokens(one_query, &go);
+    *out = reinterpret_cast<b200_graph *>(go);
+    return rc;
+}
+void b200_graph_free(b200_graph *g) { free_graph(reinterpret_cast<GraphObj *>(g)); }
+int b200_rule_start(b200_index *h, int rule_kind, int terms_matching_strategy, const b200_graph *query, const uint64_t *universe,
+                    uint64_t n_universe_words, b200_rule **out) {
+    std::lock_guard<std::mutex> g(h->e.mu);
+    *out = nullptr;
+    if (!h->e.staged) return h->e.fail(B200_ERR_STATE, "rule_start before b200_stage_finish");
+    Engine::RuleRun *run = nullptr;
+    int rc = h->e.rule_start(rule_kind, terms_matching_strategy, reinterpret_cast<const GraphObj *>(query), universe, n_universe_words, &run);
+    if (rc != B200_OK) return rc;
+    b200_rule *r = new b200_rule{run, h->e.hix.n_words64};
+    *out = r;
+    return B200_OK;
+}
+int b200_rule_next(b200_rule *r, const uint64_t *universe, uint64_t *out_bitmap, uint64_t n_words, uint32_t *rank, uint32_t *max_rank,
+                   b200_graph **out_query) {
+    if (!r) return B200_ERR_INVALID;
+    GraphObj *child = nullptr;
+    int rc = rule_next_impl(r->run, r->n_words, universe, out_bitmap, n_words, rank, max_rank, out_query ? &child : nullptr);
+    if (out_query) *out_query = reinterpret_cast<b200_graph *>(child);
+    return rc;
+}
+void b200_rule_end(b200_rule *r) {
+    if (!r) return;
+    rule_end_impl(r->run);
+    delete r;
+}
 int b200_search_batch(b200_index *h, const b200_query_batch *b, b200_results *r) {
     std::lock_guard<std::mutex> g(h->e.mu);
     if (!h->e.staged) return h->e.fail(B200_ERR_STATE, "search before b200_stage_finish");
@@ -197,7 +245,7 @@ int Engine::semantic_batch(const b200_query_batch *b, b200_results *r, uint32_t 
     std::vector<float> dist((size_t)b->n_queries * k);
     std::vector<uint64_t> n_cand(b->n_queries, hix.n_documents);
     if (!b->universes) {
-        int rc = nns_batch(b->vectors, b->n_queries, dix.emb_d, k, nullptr, 0, ids.data(), dist.data(), n.data());
+        int rc = nns_batch(b->vectors, b->n_queries, emb_d_user, k, nullptr, 0, ids.data(), dist.data(), n.data());
         if (rc != B200_OK) return rc;
     } else {
         // filtered_universe restricts the vector candidates (vector_sort.rs:58-78: `vector_candidates & universe`): the queries
@@ -205,7 +253,7 @@ int Engine::semantic_batch(const b200_query_batch *b, b200_results *r, uint32_t 
         if (b->n_universe_words < hix.n_words64) return fail(B200_ERR_INVALID, "universe bitmaps shorter than the document range");
         std::map<const uint64_t *, std::vector<uint32_t>> groups;
         for (uint32_t q = 0; q < b->n_queries; q++) groups[b->universes[q]].push_back(q);
-        const uint32_t d = dix.emb_d;
+        const uint32_t d = emb_d_user;
         for (auto &g : groups) {
             const uint32_t m = (uint32_t)g.second.size();
             std::vector<float> vq((size_t)m * d);

@@ -314,6 +314,10 @@ struct TimerSet {
     }
 };
 
+struct GraphObj;  // S1: opaque query graph (engine_search.cpp)
+struct S1Job;
+void free_graph(GraphObj *);
+
 struct Engine {
     std::unique_ptr<WorkerPool> pool;
     std::vector<std::thread> reapers;  // free the previous batch's per-query state in the background (several: one thread cannot
@@ -334,6 +338,7 @@ struct Engine {
     HostIndex hix;
     DeviceIndex dix;
     std::vector<uint64_t> emb_bitmap;  // documents owning at least one embedding
+    uint32_t emb_d_user = 0;           // the caller's embedding dimension (rows are zero-padded to a multiple of 8 on the device)
     bool has_distribution = false;
     float dist_mean = 0, dist_sigma = 0;
     b200_stats stats{};
@@ -410,7 +415,14 @@ struct Engine {
     int search_batch(const b200_query_batch *b, b200_results *r);
     int union_postings(int db, const uint32_t *key_index, uint32_t n_keys, const uint64_t *universe, uint64_t n_universe_words, uint64_t *out);
     DevBuf<uint8_t> d_s2;  // S2 scratch: universe | column | ActDesc | jobs | counters
-    int keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t offset, uint32_t limit, int scoring);
+    int keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t offset, uint32_t limit, int scoring, S1Job *s1 = nullptr);
+    // S1 (RankingRule seam): see include/b200milli.h
+    int graph_from_tokens(const b200_query_batch *one_query, GraphObj **out);
+    struct RuleRun;
+    int rule_start(int rule_kind, int tms, const GraphObj *query, const uint64_t *universe, uint64_t n_universe_words, RuleRun **out);
+    // S2 for proximity conditions
+    int proximity_pairs(const uint32_t *left, uint32_t n_left, const uint32_t *right, uint32_t n_right, uint32_t fwd_prox, uint32_t bwd_prox,
+                        const uint64_t *universe, uint64_t n_universe_words, uint64_t *out);
     int semantic_batch(const b200_query_batch *b, b200_results *r, uint32_t offset, uint32_t limit);
     ~Engine();
 };

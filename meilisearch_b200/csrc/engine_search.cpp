@@ -1652,6 +1652,33 @@ struct Blob {  // step input blob with aligned sections
     }
 };
 
+}  // namespace
+
+// S1: an opaque query graph (QueryGraph + the terms it refers to) and the job description keyword_batch runs for the seam
+struct GraphObj {
+    QCtx ctx;
+    EGraph graph;
+    explicit GraphObj(const HostIndex &ix) : ctx(ix) {}
+};
+struct S1Job {
+    enum { GRAPH_FROM_TOKENS, RULE } mode = GRAPH_FROM_TOKENS;
+    // GRAPH_FROM_TOKENS: out
+    GraphObj *graph_out = nullptr;
+    // RULE: in
+    const GraphObj *graph_in = nullptr;
+    int rule_kind = 0;  // RuleKind
+    // RULE: out, one entry per cost of the rule in ascending cost order (empty buckets included)
+    struct Bucket {
+        uint32_t rank, max_rank;
+        uint64_t count;
+        std::vector<uint64_t> bitmap;  // dense, n_words64 words
+        GraphObj *child = nullptr;     // the query graph of the paths that produced the bucket (nullptr: no path information)
+    };
+    std::vector<Bucket> buckets;
+};
+
+namespace {
+
 template <class F>
 void parallel_for(size_t n, unsigned nt, F f) {
     if (n == 0) return;
@@ -1676,7 +1703,7 @@ void parallel_for(size_t n, unsigned nt, F f) {
 }  // namespace
 
 // ================================================================================================ driver
-int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t offset, uint32_t limit, int scoring) {
+int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t offset, uint32_t limit, int scoring, S1Job *s1) {
     CU(cudaSetDevice(device), "cudaSetDevice");
     const uint32_t NQ = b->n_queries;
     if (!pool) {
@@ -1697,6 +1724,16 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
 
     // ---- phase 1: tokens -> terms -> query graph
     auto t_ph = clk::now();
+    if (s1 && s1->mode == S1Job::RULE) {
+        QState &q = *qs[0];
+        q.ctx.terms = s1->graph_in->ctx.terms;
+        q.ctx.phrases = s1->graph_in->ctx.phrases;
+        q.ctx.phrase_ids = s1->graph_in->ctx.phrase_ids;
+        q.ctx.neg_words = s1->graph_in->ctx.neg_words;
+        q.ctx.neg_phrases = s1->graph_in->ctx.neg_phrases;
+        q.ctx.freq_weight = s1->graph_in->ctx.freq_weight;
+        q.graph = s1->graph_in->graph;
+    } else
     pfor(NQ, [&](size_t i) {
         QState &q = *qs[i];
         try {
@@ -1887,6 +1924,17 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
     };
     auto start_query = [&](QState &q) {
         q.rules = rules;
+        if (s1 && s1->mode == S1Job::RULE) {
+            // S1: one ranking rule over the caller's universe and query graph (RankingRule::start_iteration)
+            Level C;
+            C.rule_idx = 0;
+            C.kind = s1->rule_kind;
+            C.graph = q.graph;
+            if (C.kind != RK_EXACT_ATTRIBUTE) prepare_graph_rule(q.ctx, C.kind, C.kind == RK_WORDS, tms, C);
+            request_activation(q, std::move(C), nullptr, q.d_univ ? q.d_univ : dix.base_ub, nullptr, hix.n_words64, hix.n_words64, 0, hix.n_words64);
+            q.need = 0xffffffffu;  // every bucket may be asked for: walk them all
+            return;
+        }
         if (q.placeholder) {
             // placeholder search: no text rules (search/new/mod.rs:353-416) -> universe in docid order (bucket_sort.rs:104-116)
             q.n_candidates = q.univ_count;
@@ -1965,6 +2013,50 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         q.cur_offset += count;
     };
     auto advance = [&](QState &q) {
+        if (s1 && s1->mode == S1Job::RULE) {
+            // S1: hand every bucket of the rule back (RankingRule::next_bucket serves them one by one): rank, documents, child graph
+            Level &L = q.levels.back();
+            const uint64_t W = hix.n_words64;
+            for (size_t ci = 0; ci < L.cost_vals.size(); ci++) {
+                S1Job::Bucket bk;
+                bk.rank = (uint32_t)(L.next_max_cost - L.cost_vals[ci]);
+                bk.max_rank = (uint32_t)L.next_max_cost;
+                bk.count = L.counts[ci];
+                bk.bitmap.assign(W, 0);
+                if (bk.count) {
+                    // the activation ran on the dense universe (row j = word j): bucket column ci is a dense bitmap
+                    cudaMemcpy(bk.bitmap.data(), L.out + (size_t)ci * L.ld, W * 8, cudaMemcpyDeviceToHost);
+                    GraphObj *child = new GraphObj(hix);
+                    child->ctx.terms = q.ctx.terms;
+                    child->ctx.phrases = q.ctx.phrases;
+                    child->ctx.phrase_ids = q.ctx.phrase_ids;
+                    child->ctx.neg_words = q.ctx.neg_words;
+                    child->ctx.neg_phrases = q.ctx.neg_phrases;
+                    child->ctx.freq_weight = q.ctx.freq_weight;
+                    if (L.kind == RK_EXACT_ATTRIBUTE)
+                        child->graph = L.graph;
+                    else {
+                        std::vector<const SurvPath *> sp;
+                        for (auto &p : L.surv)
+                            if (p.cost_idx == ci) sp.push_back(&p);
+                        std::sort(sp.begin(), sp.end(), [](const SurvPath *x, const SurvPath *y) { return x->edges < y->edges; });
+                        std::vector<std::vector<const ECond *>> good;
+                        for (auto *p : sp) {
+                            std::vector<const ECond *> pc;
+                            for (auto e : p->edges)
+                                if (L.sedges[e].cond >= 0) pc.push_back(&L.conds[L.sedges[e].cond]);
+                            good.push_back(std::move(pc));
+                        }
+                        child->graph = build_from_paths(good);
+                    }
+                    bk.child = child;
+                }
+                s1->buckets.push_back(std::move(bk));
+            }
+            q.drop_levels();
+            q.done = true;
+            return;
+        }
         const size_t n_rules = q.rules.size();
         for (;;) {
             if (q.n_results >= length) break;
@@ -2697,8 +2789,22 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         for (unsigned wv = 0; wv < n_waves && rc_prep == B200_OK; wv++) {
             const unsigned d0 = n_drivers * wv / n_waves, d1 = n_drivers * (wv + 1) / n_waves;
             const uint32_t lo = lane_lo(d0 * lanes_per_driver), hi = lane_lo(d1 * lanes_per_driver);
-            rc_prep = derive_range(lo, hi);
+            if (!(s1 && s1->mode == S1Job::RULE)) rc_prep = derive_range(lo, hi);
             if (rc_prep != B200_OK) break;
+            if (s1 && s1->mode == S1Job::GRAPH_FROM_TOKENS) {
+                // S1: QueryGraph::from_query with fully computed terms, as an opaque object
+                QState &q = *qs[0];
+                if (q.status != 0) return fail(q.status, q.error);
+                GraphObj *g = new GraphObj(hix);
+                g->ctx.terms = q.ctx.terms;
+                g->ctx.phrases = q.ctx.phrases;
+                g->ctx.phrase_ids = q.ctx.phrase_ids;
+                g->ctx.neg_words = q.ctx.neg_words;
+                g->ctx.neg_phrases = q.ctx.neg_phrases;
+                g->graph = q.graph;
+                s1->graph_out = g;
+                return B200_OK;
+            }
             start_range(lo, hi);
             cudaError_t ce = cudaStreamSynchronize(stream);  // row-table memset and derivations visible to the lanes
             if (ce != cudaSuccess) {
@@ -2812,4 +2918,97 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
     return B200_OK;
 }
 
+// ================================================================================================ S1: the RankingRule seam
+void free_graph(GraphObj *g) { delete g; }
+
+struct Engine::RuleRun {
+    std::vector<S1Job::Bucket> buckets;
+    size_t cursor = 0;
+    ~RuleRun() {
+        for (auto &b : buckets) delete b.child;
+    }
+};
+
+// QueryGraph::from_query (query_graph.rs:96-187) over located_query_terms_from_tokens (parse_query.rs:28-202), with every term's
+// derivations computed (compute_derivations.rs:21-37): what bucket_sort hands to the first ranking rule
+int Engine::graph_from_tokens(const b200_query_batch *one, GraphObj **out) {
+    *out = nullptr;
+    if (one->n_queries != 1) return fail(B200_ERR_INVALID, "graph_from_tokens takes exactly one query");
+    S1Job job;
+    job.mode = S1Job::GRAPH_FROM_TOKENS;
+    b200_results none{};
+    int rc = keyword_batch(one, &none, 0, 1, 0, &job);
+    if (rc != B200_OK) return rc;
+    *out = job.graph_out;
+    return B200_OK;
+}
+
+// RankingRule::start_iteration (ranking_rules.rs:35-45) for one of the graph-based rules or ExactAttribute: all buckets of the rule
+// over `universe` are evaluated at once (one device step) and served by rule_next
+int Engine::rule_start(int rule_kind, int tms, const GraphObj *query, const uint64_t *universe, uint64_t n_universe_words, RuleRun **out) {
+    *out = nullptr;
+    static const int kinds[7] = {RK_WORDS, RK_TYPO, RK_PROXIMITY, RK_FID, RK_POSITION, RK_EXACT_ATTRIBUTE, RK_EXACTNESS};
+    if (rule_kind < 0 || rule_kind > 6 || !query) return fail(B200_ERR_INVALID, "rule_start: unknown rule kind or null query graph");
+    S1Job job;
+    job.mode = S1Job::RULE;
+    job.graph_in = query;
+    job.rule_kind = kinds[rule_kind];
+    static const uint32_t zeros[2] = {0, 0};
+    static const uint8_t kind0[1] = {0};
+    b200_query_batch b{};
+    b.n_queries = 1;
+    b.token_begin = zeros;
+    b.token_kind = kind0;
+    b.lemma_off = zeros;
+    b.lemma_bytes = "";
+    b.terms_matching_strategy = tms;
+    b.limit = 1;
+    b.words_limit = 10;
+    b.stop_after = -1;
+    const uint64_t *up[1] = {universe};
+    if (universe) {
+        b.universes = up;
+        b.n_universe_words = n_universe_words;
+    }
+    uint32_t docids[1], n_hits[1];
+    int32_t status[1];
+    uint64_t n_cand[1];
+    b200_results r{};
+    r.docids = docids;
+    r.n_hits = n_hits;
+    r.status = status;
+    r.n_candidates = n_cand;
+    int rc = keyword_batch(&b, &r, 0, 1, 0, &job);
+    if (rc != B200_OK) {
+        for (auto &bk : job.buckets) delete bk.child;
+        return rc;
+    }
+    if (status[0] != 0) {
+        for (auto &bk : job.buckets) delete bk.child;
+        return fail(status[0], last_error);
+    }
+    RuleRun *run = new RuleRun();
+    run->buckets = std::move(job.buckets);
+    *out = run;
+    return B200_OK;
+}
+
+}  // namespace b200
+
+namespace b200 {
+int rule_next_impl(Engine::RuleRun *run, uint64_t n_words64, const uint64_t *universe, uint64_t *out_bitmap, uint64_t n_words, uint32_t *rank,
+                   uint32_t *max_rank, GraphObj **out_query) {
+    if (run->cursor >= run->buckets.size()) return 1;
+    S1Job::Bucket &b = run->buckets[run->cursor++];
+    if (rank) *rank = b.rank;
+    if (max_rank) *max_rank = b.max_rank;
+    if (out_bitmap)
+        for (uint64_t w = 0; w < n_words; w++) out_bitmap[w] = w < n_words64 ? (b.bitmap[w] & (universe ? universe[w] : ~0ull)) : 0ull;
+    if (out_query) {
+        *out_query = b.child;
+        b.child = nullptr;
+    }
+    return 0;
+}
+void rule_end_impl(Engine::RuleRun *run) { delete run; }
 }  // namespace b200

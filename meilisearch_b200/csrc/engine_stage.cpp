@@ -131,8 +131,20 @@ int Engine::stage_finish() {
 // device, chunk by chunk; `half_rows` non-null = the caller already holds IEEE binary16 rows.
 int Engine::stage_embeddings(const float *vectors, const uint16_t *half_rows, uint64_t n, uint32_t d, const uint32_t *docids) {
     CU(cudaSetDevice(device), "cudaSetDevice");
-    if (d == 0 || d % 8 != 0) return fail(B200_ERR_INVALID, "embedding dimension must be a positive multiple of 8");
+    if (d == 0) return fail(B200_ERR_INVALID, "embedding dimension must be positive");
     if (!vectors && !half_rows && n) return fail(B200_ERR_INVALID, "embeddings: null matrix");
+    if (d % 8 != 0) {
+        // the kernels read rows in 128-bit pieces: pad every row with zeros up to a multiple of 8 (cosine does not change)
+        const uint32_t dp = (d + 7) & ~7u;
+        std::vector<float> padded((size_t)n * dp, 0.f);
+        for (uint64_t r = 0; r < n; r++)
+            for (uint32_t i = 0; i < d; i++)
+                padded[r * dp + i] = vectors ? vectors[r * d + i] : __half2float(reinterpret_cast<const __half *>(half_rows)[r * d + i]);
+        int rc = stage_embeddings(padded.data(), nullptr, n, dp, docids);
+        if (rc == B200_OK) emb_d_user = d;
+        return rc;
+    }
+    emb_d_user = d;
     for (void *p : {(void *)dix.emb, (void *)dix.emb_inv_norm, (void *)dix.emb_docids})
         if (p) cudaFree(p);
     dix.emb = nullptr;
@@ -240,7 +252,12 @@ int Engine::nns_batch(const float *queries, uint32_t n_q, uint32_t d, uint32_t l
                       uint32_t *ids_out, float *dist_out, uint32_t *n_out) {
     CU(cudaSetDevice(device), "cudaSetDevice");
     if (!dix.emb) return fail(B200_ERR_STATE, "nns before b200_stage_embeddings");
-    if (d != dix.emb_d) return fail(B200_ERR_INVALID, "nns: query dimension differs from the staged embeddings");
+    if (d != emb_d_user && d != dix.emb_d) return fail(B200_ERR_INVALID, "nns: query dimension differs from the staged embeddings");
+    if (d != dix.emb_d) {  // rows were zero-padded at staging: pad the queries the same way
+        std::vector<float> padded((size_t)n_q * dix.emb_d, 0.f);
+        for (uint32_t q = 0; q < n_q; q++) memcpy(padded.data() + (size_t)q * dix.emb_d, queries + (size_t)q * d, (size_t)d * 4);
+        return nns_batch(padded.data(), n_q, dix.emb_d, limit, cand, n_cand_words, ids_out, dist_out, n_out);
+    }
     if (n_q == 0) return B200_OK;
     const uint64_t N = dix.emb_n;
     const uint32_t tie_cap = 1024;
@@ -429,6 +446,81 @@ int Engine::union_postings(int db, const uint32_t *key_index, uint32_t n_keys, c
     // scatter_kernel does not consult the universe for sparse lists (inside the engine the DP masks with it): apply it here
     for (uint64_t w = 0; w < W; w++) out[w] &= universe ? universe[w] : hix.base_ub[w];
     stats.h2d_bytes += (universe ? W * 8 : 0) + jobs.size() * sizeof(Job) + sizeof a;
+    stats.d2h_bytes += W * 8;
+    return B200_OK;
+}
+
+// S2 for proximity conditions: what ProximityGraph::resolve_condition (ranking_rule_graph/proximity/compute_docids.rs:15-108)
+// unions for one edge — every (l, r) of two word sets looked up forwards at proximity `fwd_prox` and backwards (r, l) at
+// `bwd_prox` (0 = no lookup in that direction) in word_pair_proximity_docids — restricted to a universe.  pair_probe_kernel
+// resolves the key probes against the staged key directory, scatter_kernel ORs the lists it found.
+int Engine::proximity_pairs(const uint32_t *left, uint32_t n_left, const uint32_t *right, uint32_t n_right, uint32_t fwd_prox, uint32_t bwd_prox,
+                            const uint64_t *universe, uint64_t n_universe_words, uint64_t *out) {
+    if (!staged) return fail(B200_ERR_STATE, "proximity_pairs before b200_stage_finish");
+    if (fwd_prox > 3 || bwd_prox > 3) return fail(B200_ERR_INVALID, "proximity_pairs: proximities are 0 (none) .. 3");
+    CU(cudaSetDevice(device), "cudaSetDevice");
+    const uint64_t W = hix.n_words64;
+    if (universe && n_universe_words < W) return fail(B200_ERR_INVALID, "proximity_pairs: universe bitmap shorter than the document range");
+    for (uint32_t i = 0; i < n_left; i++)
+        if (left[i] >= hix.n_words) return fail(B200_ERR_INVALID, "proximity_pairs: word id out of range");
+    for (uint32_t i = 0; i < n_right; i++)
+        if (right[i] >= hix.n_words) return fail(B200_ERR_INVALID, "proximity_pairs: word id out of range");
+    const uint64_t n_probes = (uint64_t)n_left * n_right;
+    if (n_probes == 0 || (fwd_prox == 0 && bwd_prox == 0)) {
+        memset(out, 0, W * 8);
+        return B200_OK;
+    }
+    if (n_probes > (1u << 26)) return fail(B200_ERR_CAPACITY, "proximity_pairs: more than 2^26 word pairs in one call");
+    const size_t qcap = std::max<size_t>((size_t)1 << 16, (size_t)n_probes * 4);
+    const size_t o_ub = 0, o_col = o_ub + W * 8, o_act = (o_col + W * 8 + 255) & ~(size_t)255, o_res = o_act + ((sizeof(ActDesc) + 255) & ~(size_t)255),
+                 o_set = o_res + 256, o_words = o_set + 256, o_queue = (o_words + ((size_t)n_left + n_right) * 4 + 255) & ~(size_t)255,
+                 total = o_queue + qcap * sizeof(Job);
+    CU(d_s2.reserve(total), "alloc S2 scratch");
+    uint8_t *base = d_s2.p;
+    if (universe)
+        CU(cudaMemcpyAsync(base + o_ub, universe, W * 8, cudaMemcpyHostToDevice, stream), "H2D universe");
+    else
+        CU(cudaMemcpyAsync(base + o_ub, dix.base_ub, W * 8, cudaMemcpyDeviceToDevice, stream), "universe");
+    CU(cudaMemsetAsync(base + o_col, 0, W * 8, stream), "zero column");
+    ActDesc a;
+    memset(&a, 0, sizeof a);
+    a.ub = reinterpret_cast<unsigned long long *>(base + o_ub);
+    a.C = reinterpret_cast<unsigned long long *>(base + o_col);
+    a.ld = (uint32_t)W;
+    a.n_cols = 1;
+    uint32_t counters[16] = {(uint32_t)W};  // results[0] = rows | qcount at +16: [0] jobs, [2] scatter cursor
+    PairSet ps{};
+    ps.left_off = 0;
+    ps.n_left = n_left;
+    ps.right_off = n_left;
+    ps.n_right = n_right;
+    ps.fwd_prox = (uint8_t)fwd_prox;
+    ps.bwd_prox = (uint8_t)bwd_prox;
+    CU(cudaMemcpyAsync(base + o_act, &a, sizeof a, cudaMemcpyHostToDevice, stream), "H2D activation");
+    CU(cudaMemcpyAsync(base + o_res, counters, sizeof counters, cudaMemcpyHostToDevice, stream), "H2D counters");
+    CU(cudaMemcpyAsync(base + o_set, &ps, sizeof ps, cudaMemcpyHostToDevice, stream), "H2D pair set");
+    CU(cudaMemcpyAsync(base + o_words, left, (size_t)n_left * 4, cudaMemcpyHostToDevice, stream), "H2D words");
+    CU(cudaMemcpyAsync(base + o_words + (size_t)n_left * 4, right, (size_t)n_right * 4, cudaMemcpyHostToDevice, stream), "H2D words");
+    uint32_t *d_res = reinterpret_cast<uint32_t *>(base + o_res), *d_qcount = d_res + 4;
+    size_t m0 = mark();
+    CU(launch_pair_probe(stream, reinterpret_cast<const PairSet *>(base + o_set), 1, (uint32_t)n_probes, reinterpret_cast<const uint32_t *>(base + o_words),
+                         dix.pair_keys, hix.pair_keys.size(), hix.pair_list_base, dix.lists, reinterpret_cast<const ActDesc *>(base + o_act), d_res,
+                         reinterpret_cast<Job *>(base + o_queue), d_qcount, (uint32_t)qcap),
+       "pair probe");
+    size_t m1 = mark();
+    time_kernel(B200_K_PAIR_PROBE, m0, m1, n_probes * 8 * 23);
+    CU(launch_scatter(stream, (uint32_t)sm_count * 5, reinterpret_cast<const Job *>(base + o_queue), d_qcount, (uint32_t)qcap,
+                      reinterpret_cast<const ActDesc *>(base + o_act), d_res, dix.lists, dix.pool),
+       "scatter");
+    time_kernel(B200_K_SCATTER, m1, mark(), 0);
+    uint32_t h_counts[8];
+    CU(cudaMemcpyAsync(h_counts, d_res, sizeof h_counts, cudaMemcpyDeviceToHost, stream), "D2H counters");
+    CU(cudaMemcpyAsync(out, base + o_col, W * 8, cudaMemcpyDeviceToHost, stream), "D2H column");
+    CU(cudaStreamSynchronize(stream), "sync");
+    resolve_timers();
+    if (h_counts[4] > qcap) return fail(B200_ERR_CAPACITY, "proximity_pairs: job queue overflow");
+    for (uint64_t w = 0; w < W; w++) out[w] &= universe ? universe[w] : hix.base_ub[w];
+    stats.h2d_bytes += (universe ? W * 8 : 0) + ((size_t)n_left + n_right) * 4 + sizeof a;
     stats.d2h_bytes += W * 8;
     return B200_OK;
 }

@@ -21,7 +21,7 @@ def _is_word_char(c: str) -> bool:
 
 def tokenize(query: str, stop_words=frozenset()):
     """-> list[(kind, lemma)]"""
-    s = query.lower()
+    s = query  # stop words are matched as written (the reference's set is case sensitive, stop_words.rs:1-10), lemmas are lowercased
     out = []
     i, n = 0, len(s)
     while i < n:
@@ -31,7 +31,7 @@ def tokenize(query: str, stop_words=frozenset()):
             while j < n and _is_word_char(s[j]):
                 j += 1
             w = s[i:j]
-            out.append((STOPWORD if w in stop_words else WORD, w))
+            out.append((STOPWORD if w in stop_words else WORD, w.lower()))
             i = j
         else:
             if c in ".," and i + 1 < n and s[i + 1] == " ":

@@ -259,6 +259,14 @@ def query_criteria_cases():
     tests = [("none", 62, "all", []), ("words", 63, "last", ["words"]), ("attribute", 64, "all", ["attribute"]), ("typo", 65, "all", ["typo"]),
              ("exactness", 66, "all", ["exactness"]), ("proximity", 67, "all", ["proximity"]),
              ("default_criteria_order", 97, "last", ["words", "typo", "proximity", "attribute", "exactness"])]
+    # criteria_mixup (query_criteria.rs:104-292) walks the 120 orders of {attribute, desc(asc_desc_rank), exactness, proximity, typo}
+    # after `words`, asserting `expected_order` for each.  The Desc criterion is a sort rule (out of this path's scope), so the 24
+    # orders of the four text criteria are transcribed instead, each under the test's strategy (Last) and under All, with the
+    # expected order computed exactly as the test does (tests/search/mod.rs:150-218, implemented below).
+    import itertools
+    for perm in itertools.permutations(["attribute", "exactness", "proximity", "typo"]):
+        for tms in ("last", "all"):
+            tests.append(("criteria_mixup " + ",".join(perm), 104, tms, ["words"] + list(perm)))
     out = []
     for name, line, tms, criteria in tests:
         groups = [list(range(len(docs)))]
@@ -300,6 +308,30 @@ def matching_strategy_cases():
         out.append({"source": f"crates/meilisearch/tests/search/matching_strategy.rs:{line}", "test": "matching_strategy", "index": index,
                     "settings": {}, "tms": sm.group(2), "scoring": "skip", "limit": 20, "offset": 0, "query": sm.group(1),
                     "expected_ids": [int(h["id"]) - 1 for h in hits]})
+    return out
+
+
+def phrase_search_count_cases():
+    """crates/milli/tests/search/phrase_search.rs:27-63: test_set.ndjson, stop words a/an/the/of, the phrase query
+    "the use of force" under TermsMatchingStrategy::All matches exactly one document, with no criteria and with
+    [proximity, attribute, exactness]."""
+    text = open("/root/reference/crates/milli/tests/assets/test_set.ndjson").read()
+    dec, i, docs = json.JSONDecoder(), 0, []
+    while True:
+        while i < len(text) and text[i].isspace():
+            i += 1
+        if i >= len(text):
+            break
+        o, i = dec.raw_decode(text, i)
+        docs.append(o)
+    index = {"searchable": ["title", "description"], "exact_attributes": [], "stop_words": ["a", "an", "the", "of"],
+             "docs": [{"id": k, "title": d["title"], "description": d["description"]} for k, d in enumerate(docs)]}
+    synonyms = {"hello": ["good morning"], "world": ["earth"], "america": ["the united states"]}
+    out = []
+    for line, criteria in ((54, []), (60, ["proximity", "attribute", "exactness"])):
+        out.append({"source": f"crates/milli/tests/search/phrase_search.rs:{line}", "test": "phrase_search_with_stop_words", "index": index,
+                    "settings": {"criteria": criteria, "synonyms": synonyms}, "tms": "all", "scoring": "skip", "limit": 10, "offset": 0,
+                    "query": '"the use of force"', "expected_count": 1})
     return out
 
 
@@ -351,8 +383,10 @@ def main():
                 apply_setting(sm, st)
             docs = parse_documents(body)
             unsupported = any(u in body for u in UNSUPPORTED) or docs is None or "searchable" not in st
-            if docs is not None and not all(ord(ch) < 128 for d in docs for v in d.values() if isinstance(v, str) for ch in v):
-                unsupported = True
+            if docs is not None:
+                # documents with non-ASCII text are outside the ASCII tokenizer stand-in: they are dropped (their docids stay
+                # reserved) and every case whose expected hits mention one of them is skipped below
+                docs = [d if all(ord(ch) < 128 for v in d.values() if isinstance(v, str) for ch in v) else None for d in docs]
             builders[m.group(1)] = (st, docs, unsupported)
         # tests
         for m in re.finditer(r"#\[test\]\s*fn (\w+)\(\)\s*\{", src):
@@ -416,7 +450,7 @@ def main():
                         lit = re.search(r'@"(\[[^"]*\])"', call)
                         if lit is None:
                             continue
-                        if not usable:
+                        if not usable or any(k >= len(docs) or docs[k] is None for k in json.loads(lit.group(1))):
                             skipped += 1
                             continue
                         cases.append(new_case(json.loads(lit.group(1))))
@@ -430,6 +464,9 @@ def main():
                             skipped += 1
                             continue
                         ids, scores = parse_snapshot_file(snap)
+                        if ids is not None and any(k >= len(docs) or docs[k] is None for k in ids):
+                            skipped += 1
+                            continue
                         rel = "crates/milli/src/search/new/tests/snapshots/" + os.path.basename(snap)
                         if vname == "document_ids_scores":
                             c = new_case(ids)
@@ -449,7 +486,7 @@ def main():
             keyed[k] = len(corpora)
             corpora.append(c["index"])
         c["index"] = keyed[k]
-    count_cases = typo_tolerance_count_cases()
+    count_cases = typo_tolerance_count_cases() + phrase_search_count_cases()
     for c in count_cases:
         k = json.dumps(c["index"], sort_keys=True)
         if k not in keyed:

@@ -16,6 +16,8 @@ def image_from_corpus(c):
     mask = sum(1 << fields.index(f) for f in c["exact_attributes"] if f in fields)
     img = IndexImage(len(fields), mask, c["stop_words"])
     for d, doc in enumerate(c["docs"]):
+        if doc is None:  # a document the extraction dropped (non-ASCII text); its docid stays unused
+            continue
         any_text = False
         for f, name in enumerate(fields):
             v = doc.get(name)

@@ -571,3 +571,104 @@ def test_partial_embeddings_last_bucket(mb, synth):
     for q in range(3):
         assert got.ids(q) == want.ids(q)
         assert [s[0][1] is None for s in got.scores(q)] == [s[0][1] is None for s in want.scores(q)]
+
+
+def test_hybrid_goldens_on_gpu(mb):
+    """hybrid.rs:195-430 `simple_search` (hit order, _rankingScore, semanticHitCount at semanticRatio 0.2 / 0.5 / 0.8) through the C ABI"""
+    from tests.test_hybrid_goldens import HYBRID_CASES, check, embeddings, hybrid_image
+
+    ix = mb.Index(hybrid_image(), weights=[0, 0, 0])
+    ix.set_embeddings(embeddings())
+    for ratio in HYBRID_CASES:
+        r = ix.search().query(["Captain"]).semantic(np.array([[1.0, 1.0]], np.float32)).scoring_strategy("detailed").execute_hybrid(ratio)
+        check(r.ids(0), r.scores(0), int(r.semantic_hit_count[0]), ratio)
+
+
+# ------------------------------------------------------------------------------------------------ round 2: S1 / S2 seams
+def _bits(words):
+    out = []
+    for w, v in enumerate(words):
+        v = int(v)
+        while v:
+            b = (v & -v).bit_length() - 1
+            out.append(w * 64 + b)
+            v &= v - 1
+    return out
+
+
+def test_rule_seam_matches_oracle_buckets(mb):
+    """S1 (b200_graph_from_tokens / b200_rule_start / _next / _end): the first two rules are driven bucket by bucket by the
+    caller, as bucket_sort does (bucket_sort.rs:123,266,323), and every bucket must hold exactly the documents the oracle scores
+    with that rule's rank (ScoringStrategy::Detailed with a limit covering every candidate)."""
+    from oracle.pyoracle import OracleIndex
+
+    img = synthetic_image(4000, 1500, seed=19)
+    ix, o = mb.Index(img), OracleIndex(img)
+    queries = img.synthetic_queries(25, seed=3)
+    for query in queries:
+        want = o.search_batch(mb.TokenBatch([query]), scoring="detailed", limit=4000)
+        by_doc = {d: s for d, s in zip(want.ids(0), want.scores(0))}
+        # the universe bucket_sort starts from: the documents of the maximally reduced query graph = the oracle's candidates
+        universe = np.zeros((img.n_docs + 63) // 64, np.uint64)
+        for d in by_doc:
+            universe[d >> 6] |= np.uint64(1) << np.uint64(d & 63)
+        assert len(by_doc) == int(want.n_candidates[0])
+        g = ix.query_graph(query)
+        seen = set()
+        for cand, rank, mx, child in g.rule("words", universe):
+            docs = _bits(cand)
+            for d in docs:
+                assert by_doc[d][0] == ("words", rank, mx), (query, d)
+            assert not (seen & set(docs))
+            seen |= set(docs)
+            if child is None:
+                assert not docs
+                continue
+            seen2 = set()
+            for cand2, rank2, mx2, child2 in child.rule("typo", cand):
+                docs2 = _bits(cand2)
+                for d in docs2:
+                    assert by_doc[d][1] == ("typo", rank2, mx2), (query, d)
+                seen2 |= set(docs2)
+                if child2 is not None:
+                    child2.close()
+            assert seen2 == set(docs), query
+            child.close()
+        assert seen == set(by_doc), query
+        g.close()
+
+
+def test_proximity_pairs_matches_decoded_lists(mb, synth):
+    """S2 (b200_proximity_pairs): forward + backward pair lookups of two word sets, against the CBO values decoded by the oracle's codec"""
+    from oracle.pyoracle import cbo_decode
+
+    ix = mb.Index(synth)
+    db = synth.dbs[4]
+    key_of = {db.key(i): i for i in range(int(db.n_keys))}
+    word_rank = {synth.word(i): i for i in range(synth.n_words)}
+    rng = np.random.default_rng(14)
+    n_words = (synth.n_docs + 63) // 64
+    # word sets drawn from real pair keys so that many probes hit
+    picks = rng.integers(0, int(db.n_keys), 60)
+    left, right = set(), set()
+    for i in picks:
+        k = db.key(int(i))
+        w1, w2 = k[1:].split(b"\0")
+        left.add(word_rank[w1.decode()])
+        right.add(word_rank[w2.decode()])
+    left, right = sorted(left), sorted(right)
+    universe = rng.integers(0, 2**63, n_words, dtype=np.uint64)
+    for fwd, bwd in ((1, 0), (2, 1), (3, 2), (0, 1)):
+        want = np.zeros(n_words, np.uint64)
+        for l in left:
+            for r in right:
+                for prox, a, b in ((fwd, l, r), (bwd, r, l)):
+                    if not prox:
+                        continue
+                    k = bytes([prox]) + synth.word(a).encode() + b"\0" + synth.word(b).encode()
+                    if k in key_of:
+                        ids = cbo_decode(db.val(key_of[k]))
+                        np.bitwise_or.at(want, ids >> 6, np.uint64(1) << (ids & 63).astype(np.uint64))
+        assert want.any() or fwd == 0
+        assert np.array_equal(ix.proximity_pairs(left, right, fwd, bwd), want), (fwd, bwd)
+        assert np.array_equal(ix.proximity_pairs(left, right, fwd, bwd, universe), want & universe), (fwd, bwd)
