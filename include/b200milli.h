@@ -127,6 +127,18 @@ int b200_proximity_pairs(b200_index *, const uint32_t *left, uint32_t n_left, co
 int b200_nns_batch(b200_index *, const float *queries, uint32_t n_q, uint32_t d, uint32_t limit, const uint64_t *cand_bitmap,
                    uint64_t n_cand_words, uint32_t *ids_out, float *dist_out, uint32_t *n_out);
 
+/* ---- corpus partitioned across GPUs (cfg 5) --------------------------------- */
+/* One process per GPU, each with the rows of its docid range staged (b200_stage_embeddings with global docids).  The library
+ * binds NCCL at run time (libnccl.so.2).  Rank 0 draws a unique id, the host application carries its 128 bytes to the other
+ * ranks, every rank calls b200_comm_init. */
+int b200_comm_unique_id(b200_index *, uint8_t *out128);
+int b200_comm_init(b200_index *, int rank, int world, const uint8_t *unique_id128);
+/* b200_nns_batch over the partitioned store: every rank passes the SAME queries (and candidate bitmap over global docids); each
+ * scans its shard, the per-shard top-`limit` lists are exchanged with one ncclAllGather on the library's vector stream and merged
+ * on the device by (distance, docid); every rank receives the global result. */
+int b200_nns_batch_sharded(b200_index *, const float *queries, uint32_t n_q, uint32_t d, uint32_t limit, const uint64_t *cand_bitmap,
+                           uint64_t n_cand_words, uint32_t *ids_out, float *dist_out, uint32_t *n_out);
+
 /* ---- S0: whole search ------------------------------------------------------------------ */
 /* Replaces milli::Search::execute / execute_hybrid (crates/milli/src/search/mod.rs:280-415,
  * search/hybrid.rs:264-366) for a batch of queries against one index, as called from

@@ -100,6 +100,9 @@ def load_library():
         l.b200_derive_batch.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_void_p] * 4
         l.b200_union_postings.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
         l.b200_nns_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+        l.b200_nns_batch_sharded.argtypes = l.b200_nns_batch.argtypes
+        l.b200_comm_unique_id.argtypes = [C.c_void_p, C.c_void_p]
+        l.b200_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         l.b200_search_batch.argtypes = [C.c_void_p, C.POINTER(_Batch), C.POINTER(_Results)]
         l.b200_proximity_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
         l.b200_graph_from_tokens.argtypes = [C.c_void_p, C.POINTER(_Batch), C.POINTER(C.c_void_p)]
@@ -115,7 +118,7 @@ def load_library():
 
 SYMBOLS = ["b200_open", "b200_close", "b200_last_error", "b200_open_error", "b200_stage_dictionary", "b200_stage_db",
            "b200_stage_documents_ids", "b200_stage_settings", "b200_stage_synonyms", "b200_stage_finish", "b200_stage_embeddings", "b200_stage_embeddings_f16", "b200_stage_distribution",
-           "b200_derive_batch", "b200_union_postings", "b200_proximity_pairs", "b200_nns_batch", "b200_search_batch", "b200_graph_from_tokens",
+           "b200_derive_batch", "b200_union_postings", "b200_proximity_pairs", "b200_nns_batch", "b200_nns_batch_sharded", "b200_comm_unique_id", "b200_comm_init", "b200_search_batch", "b200_graph_from_tokens",
            "b200_graph_free", "b200_rule_start", "b200_rule_next", "b200_rule_end", "b200_get_stats", "b200_reset_stats"]
 
 
@@ -271,6 +274,27 @@ class Index:
         cnt = np.zeros(n, np.uint32)
         cw = None if candidates is None else np.ascontiguousarray(candidates, np.uint64)
         self._ck(self._l.b200_nns_batch(self._h, _p(q), n, q.shape[1], limit, _p(cw), 0 if cw is None else len(cw), _p(ids), _p(dist), _p(cnt)))
+        return ids, dist, cnt
+
+    def comm_unique_id(self):
+        out = np.zeros(128, np.uint8)
+        self._ck(self._l.b200_comm_unique_id(self._h, _p(out)))
+        return out
+
+    def comm_init(self, rank, world, unique_id):
+        """join the NCCL communicator of a corpus partitioned across GPUs (unique_id: 128 bytes drawn by rank 0)"""
+        uid = np.ascontiguousarray(unique_id, np.uint8)
+        self._ck(self._l.b200_comm_init(self._h, int(rank), int(world), _p(uid)))
+
+    def nns_by_vector_sharded(self, queries, limit, candidates=None):
+        """every rank: the same queries; returns the merged global top-k (per-shard scan + ncclAllGather + device merge)"""
+        q = np.ascontiguousarray(np.atleast_2d(queries), np.float32)
+        n = q.shape[0]
+        ids = np.zeros((n, limit), np.uint32)
+        dist = np.zeros((n, limit), np.float32)
+        cnt = np.zeros(n, np.uint32)
+        cw = None if candidates is None else np.ascontiguousarray(candidates, np.uint64)
+        self._ck(self._l.b200_nns_batch_sharded(self._h, _p(q), n, q.shape[1], limit, _p(cw), 0 if cw is None else len(cw), _p(ids), _p(dist), _p(cnt)))
         return ids, dist, cnt
 
     def search(self):

@@ -161,6 +161,24 @@ int b200_nns_batch(b200_index *h, const float *q, uint32_t n_q, uint32_t d, uint
     h->e.fold_vector_stats();
     return rc;
 }
+int b200_comm_unique_id(b200_index *h, uint8_t *out128) {
+    std::lock_guard<std::mutex> g(h->e.mu);
+    int rc = h->e.comm_load();
+    if (rc != B200_OK) return rc;
+    int e = h->e.sc.get_unique_id(out128);
+    return e == 0 ? B200_OK : h->e.fail(B200_ERR_CUDA, "ncclGetUniqueId failed");
+}
+int b200_comm_init(b200_index *h, int rank, int world, const uint8_t *unique_id128) {
+    std::lock_guard<std::mutex> g(h->e.mu);
+    return h->e.comm_init(rank, world, unique_id128);
+}
+int b200_nns_batch_sharded(b200_index *h, const float *q, uint32_t n_q, uint32_t d, uint32_t limit, const uint64_t *cand, uint64_t ncw, uint32_t *ids,
+                           float *dist, uint32_t *n_out) {
+    std::lock_guard<std::mutex> g(h->e.mu);
+    int rc = h->e.nns_batch(q, n_q, d, limit, cand, ncw, ids, dist, n_out, true);
+    h->e.fold_vector_stats();
+    return rc;
+}
 int b200_union_postings(b200_index *h, int db, const uint32_t *key_index, uint32_t n_keys, const uint64_t *universe, uint64_t n_universe_words,
                         uint64_t *out) {
     std::lock_guard<std::mutex> g(h->e.mu);

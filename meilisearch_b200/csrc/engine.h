@@ -314,6 +314,24 @@ struct TimerSet {
     }
 };
 
+// NCCL, bound at run time (dlopen of libnccl.so.2: inside a torch process that is the copy torch already loaded): the library only
+// needs it when the corpus is partitioned across GPUs (one all-gather of the per-shard top-k)
+struct ShardComm {
+    void *lib = nullptr;
+    void *comm = nullptr;  // ncclComm_t
+    int rank = 0, world = 1;
+    int (*get_unique_id)(void *) = nullptr;
+    int (*comm_init_rank)(void **, int, struct NcclId, int) = nullptr;
+    int (*all_gather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+    int (*group_start)() = nullptr;
+    int (*group_end)() = nullptr;
+    int (*comm_destroy)(void *) = nullptr;
+    const char *(*get_error_string)(int) = nullptr;
+};
+struct NcclId {
+    char internal[128];
+};
+
 struct GraphObj;  // S1: opaque query graph (engine_search.cpp)
 struct S1Job;
 void free_graph(GraphObj *);
@@ -410,8 +428,15 @@ struct Engine {
     int stage_embeddings(const float *vectors, const uint16_t *half_rows, uint64_t n, uint32_t d, const uint32_t *docids);
     int derive_batch(uint32_t n, const char *words, const uint32_t *off, const uint8_t *max_typo, const uint8_t *is_prefix, uint32_t *one_out,
                      uint32_t *n_one, uint32_t *two_out, uint32_t *n_two);
+    // sharded: every rank passes the same queries and scans its own rows; the per-shard top-k lists are all-gathered (NCCL, on the
+    // vector stream) and merged on the device; every rank returns the merged result
     int nns_batch(const float *queries, uint32_t n_q, uint32_t d, uint32_t limit, const uint64_t *cand, uint64_t n_cand_words, uint32_t *ids_out,
-                  float *dist_out, uint32_t *n_out);
+                  float *dist_out, uint32_t *n_out, bool sharded = false);
+    ShardComm sc;
+    DevBuf<uint32_t> d_gather_ids, d_gather_n;
+    DevBuf<float> d_gather_dist;
+    int comm_load();
+    int comm_init(int rank, int world, const uint8_t *unique_id);
     int search_batch(const b200_query_batch *b, b200_results *r);
     int union_postings(int db, const uint32_t *key_index, uint32_t n_keys, const uint64_t *universe, uint64_t n_universe_words, uint64_t *out);
     DevBuf<uint8_t> d_s2;  // S2 scratch: universe | column | ActDesc | jobs | counters

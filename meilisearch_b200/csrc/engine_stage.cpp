@@ -1,5 +1,6 @@
 // Staging to HBM, term derivation (S3) and the vector store (S4).
 #include <cuda_fp16.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cmath>
@@ -54,6 +55,10 @@ Engine::~Engine() {
     if (h_step) cudaFreeHost(h_step);
     if (h_results) cudaFreeHost(h_results);
     for (auto e : ev_pool) cudaEventDestroy(e);
+    if (sc.comm && sc.comm_destroy) sc.comm_destroy(sc.comm);
+    d_gather_ids.release();
+    d_gather_dist.release();
+    d_gather_n.release();
     for (auto e : vt.ev_pool) cudaEventDestroy(e);
     if (vt.stream) cudaStreamDestroy(vt.stream);
     if (ev0) cudaEventDestroy(ev0);
@@ -248,15 +253,51 @@ int Engine::derive_batch(uint32_t n, const char *words, const uint32_t *off, con
     return B200_OK;
 }
 
+int Engine::comm_load() {
+    if (sc.lib) return B200_OK;
+    void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);  // the copy this process already has (torch's), if any
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW);
+    if (!lib) return fail(B200_ERR_STATE, std::string("cannot load libnccl.so.2: ") + dlerror());
+    sc.get_unique_id = reinterpret_cast<int (*)(void *)>(dlsym(lib, "ncclGetUniqueId"));
+    sc.comm_init_rank = reinterpret_cast<int (*)(void **, int, NcclId, int)>(dlsym(lib, "ncclCommInitRank"));
+    sc.all_gather = reinterpret_cast<int (*)(const void *, void *, size_t, int, void *, cudaStream_t)>(dlsym(lib, "ncclAllGather"));
+    sc.group_start = reinterpret_cast<int (*)()>(dlsym(lib, "ncclGroupStart"));
+    sc.group_end = reinterpret_cast<int (*)()>(dlsym(lib, "ncclGroupEnd"));
+    sc.comm_destroy = reinterpret_cast<int (*)(void *)>(dlsym(lib, "ncclCommDestroy"));
+    sc.get_error_string = reinterpret_cast<const char *(*)(int)>(dlsym(lib, "ncclGetErrorString"));
+    if (!sc.get_unique_id || !sc.comm_init_rank || !sc.all_gather || !sc.group_start || !sc.group_end || !sc.comm_destroy)
+        return fail(B200_ERR_STATE, "libnccl.so.2 lacks an expected symbol");
+    sc.lib = lib;
+    return B200_OK;
+}
+int Engine::comm_init(int rank, int world, const uint8_t *unique_id) {
+    int rc = comm_load();
+    if (rc != B200_OK) return rc;
+    if (world < 1 || rank < 0 || rank >= world) return fail(B200_ERR_INVALID, "comm_init: bad rank / world");
+    CU(cudaSetDevice(device), "cudaSetDevice");
+    if (sc.comm) {
+        sc.comm_destroy(sc.comm);
+        sc.comm = nullptr;
+    }
+    NcclId id;
+    memcpy(id.internal, unique_id, 128);
+    int e = sc.comm_init_rank(&sc.comm, world, id, rank);
+    if (e != 0) return fail(B200_ERR_CUDA, std::string("ncclCommInitRank: ") + (sc.get_error_string ? sc.get_error_string(e) : "error"));
+    sc.rank = rank;
+    sc.world = world;
+    return B200_OK;
+}
+
 int Engine::nns_batch(const float *queries, uint32_t n_q, uint32_t d, uint32_t limit, const uint64_t *cand, uint64_t n_cand_words,
-                      uint32_t *ids_out, float *dist_out, uint32_t *n_out) {
+                      uint32_t *ids_out, float *dist_out, uint32_t *n_out, bool sharded) {
+    if (sharded && (!sc.comm || sc.world < 1)) return fail(B200_ERR_STATE, "sharded nns before b200_comm_init");
     CU(cudaSetDevice(device), "cudaSetDevice");
     if (!dix.emb) return fail(B200_ERR_STATE, "nns before b200_stage_embeddings");
     if (d != emb_d_user && d != dix.emb_d) return fail(B200_ERR_INVALID, "nns: query dimension differs from the staged embeddings");
     if (d != dix.emb_d) {  // rows were zero-padded at staging: pad the queries the same way
         std::vector<float> padded((size_t)n_q * dix.emb_d, 0.f);
         for (uint32_t q = 0; q < n_q; q++) memcpy(padded.data() + (size_t)q * dix.emb_d, queries + (size_t)q * d, (size_t)d * 4);
-        return nns_batch(padded.data(), n_q, dix.emb_d, limit, cand, n_cand_words, ids_out, dist_out, n_out);
+        return nns_batch(padded.data(), n_q, dix.emb_d, limit, cand, n_cand_words, ids_out, dist_out, n_out, sharded);
     }
     if (n_q == 0) return B200_OK;
     const uint64_t N = dix.emb_n;
@@ -278,6 +319,10 @@ int Engine::nns_batch(const float *queries, uint32_t n_q, uint32_t d, uint32_t l
     {
         const char *force = getenv("B200_VEC_GEMM");
         bool want = force ? atoi(force) != 0 : n_q >= 16;
+        if (sharded) {
+            want = true;  // the exchange works on the device-resident top-k lists of the batched path
+            if (!vec_gemm_supported(d, limit)) return fail(B200_ERR_UNSUPPORTED, "sharded nns: dimension / limit outside the batched kernel's range");
+        }
         if (want && vec_gemm_supported(d, limit)) {
             const uint32_t tiles_per_pass = (uint32_t)sm_count;  // query tiles resident in one launch
             std::vector<uint32_t> h_ids, h_n;
@@ -303,6 +348,23 @@ int Engine::nns_batch(const float *queries, uint32_t n_q, uint32_t d, uint32_t l
                 CU(launch_vec_gemm_topk(vt.stream, (uint32_t)sm_count, dix.emb, dix.emb_inv_norm, dix.emb_docids, N, d, d_vq16.p, d_qinv, n_qtiles, n_groups,
                                         d_c, n_cand_words, limit, d_vruns.p + (size_t)n_qtiles * n_groups * 128 * VEC_GEMM_CAND_CAP, d_vruns.p, d_vpartial.p, d_vsel_ids.p, d_vsel_dist.p, d_vsel_n.p, nq),
                    "vec_gemm_topk");
+                if (sharded && sc.world > 1) {
+                    // one all-gather of the per-shard top-k (ids, distances, counts) on the vector stream, then the merge: the lists
+                    // never leave the device between the scan and the merged result
+                    const uint32_t Wd = (uint32_t)sc.world;
+                    CU(d_gather_ids.reserve((size_t)Wd * nq * limit), "alloc gather");
+                    CU(d_gather_dist.reserve((size_t)Wd * nq * limit), "alloc gather");
+                    CU(d_gather_n.reserve((size_t)Wd * nq), "alloc gather");
+                    int e = sc.group_start();
+                    if (!e) e = sc.all_gather(d_vsel_ids.p, d_gather_ids.p, (size_t)nq * limit * 4, 1 /* ncclUint8 */, sc.comm, vt.stream);
+                    if (!e) e = sc.all_gather(d_vsel_dist.p, d_gather_dist.p, (size_t)nq * limit * 4, 1, sc.comm, vt.stream);
+                    if (!e) e = sc.all_gather(d_vsel_n.p, d_gather_n.p, (size_t)nq * 4, 1, sc.comm, vt.stream);
+                    int e2 = sc.group_end();
+                    if (e || e2) return fail(B200_ERR_CUDA, std::string("ncclAllGather: ") + (sc.get_error_string ? sc.get_error_string(e ? e : e2) : "error"));
+                    CU(launch_shard_merge(vt.stream, d_gather_ids.p, d_gather_dist.p, d_gather_n.p, Wd, nq, limit, d_vsel_ids.p, d_vsel_dist.p, d_vsel_n.p),
+                       "shard merge");
+                    vstats.kernel_launches++;
+                }
                 size_t m1 = vt.mark();
                 // algorithmic bytes: every query tile streams the matrix once (L2 absorbs the re-reads across tiles of the same rows)
                 vt.time_kernel(vstats, B200_K_VEC_GEMM, m0, m1, (uint64_t)N * d * 2 + N * 8 + (uint64_t)n_pad * d * 2);

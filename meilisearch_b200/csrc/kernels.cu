@@ -1272,6 +1272,69 @@ cudaError_t launch_emb_norm_f16(cudaStream_t s, const void *rows_fp16, float *in
     return cudaGetLastError();
 }
 
+// ---- corpus-sharded vector stage: merge of the per-shard top-k lists after the all-gather
+// One CTA per query: the shards' runs (ascending (distance, docid), n valid entries each) become 64-bit keys
+// distance-bits << 32 | docid, are sorted by a bitonic network in shared memory, and the first `k` are written back.
+__global__ void __launch_bounds__(256) shard_merge_kernel(const uint32_t *__restrict__ g_ids, const float *__restrict__ g_dist,
+                                                          const uint32_t *__restrict__ g_n, uint32_t world, uint32_t n_q, uint32_t k,
+                                                          uint32_t cap /* power of two >= world * k */, uint32_t *__restrict__ out_ids,
+                                                          float *__restrict__ out_dist, uint32_t *__restrict__ out_n) {
+    extern __shared__ unsigned long long s_keys[];
+    const uint32_t q = blockIdx.x;
+    uint32_t total = 0;
+    for (uint32_t i = threadIdx.x; i < cap; i += blockDim.x) {
+        unsigned long long key = ~0ull;
+        if (i < world * k) {
+            const uint32_t sh = i / k, j = i % k;
+            const uint32_t n = min(g_n[(size_t)sh * n_q + q], k);
+            if (j < n) {
+                const size_t at = ((size_t)sh * n_q + q) * k + j;
+                key = ((unsigned long long)__float_as_uint(g_dist[at]) << 32) | g_ids[at];
+            }
+        }
+        s_keys[i] = key;
+    }
+    for (uint32_t sh = 0; sh < world; sh++) total += min(g_n[(size_t)sh * n_q + q], k);
+    __syncthreads();
+    for (uint32_t size = 2; size <= cap; size <<= 1)
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t i = threadIdx.x; i < cap; i += blockDim.x) {
+                const uint32_t j = i ^ stride;
+                if (j > i) {
+                    const bool up = (i & size) == 0;
+                    const unsigned long long a = s_keys[i], b = s_keys[j];
+                    if ((a > b) == up) {
+                        s_keys[i] = b;
+                        s_keys[j] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    const uint32_t n_out = min(total, k);
+    for (uint32_t i = threadIdx.x; i < n_out; i += blockDim.x) {
+        out_ids[(size_t)q * k + i] = (uint32_t)s_keys[i];
+        out_dist[(size_t)q * k + i] = __uint_as_float((uint32_t)(s_keys[i] >> 32));
+    }
+    if (threadIdx.x == 0) out_n[q] = n_out;
+}
+cudaError_t launch_shard_merge(cudaStream_t s, const uint32_t *g_ids, const float *g_dist, const uint32_t *g_n, uint32_t world, uint32_t n_q,
+                               uint32_t k, uint32_t *out_ids, float *out_dist, uint32_t *out_n) {
+    if (!n_q) return cudaSuccess;
+    uint32_t cap = 1;
+    while (cap < world * k) cap <<= 1;
+    const size_t smem = (size_t)cap * 8;
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(shard_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    shard_merge_kernel<<<n_q, 256, smem, s>>>(g_ids, g_dist, g_n, world, n_q, k, cap, out_ids, out_dist, out_n);
+    return cudaGetLastError();
+}
+
 // ======================================================================================== launch wrappers
 #define CK(x)                          \
     do {                               \

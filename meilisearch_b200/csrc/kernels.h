@@ -36,6 +36,10 @@ cudaError_t launch_topk(cudaStream_t s, uint32_t n_q, const float *dist, const u
 cudaError_t launch_emb_from_f32(cudaStream_t s, const float *in, void *out_fp16, float *inv_norm, uint64_t n, uint32_t d);
 cudaError_t launch_emb_norm_f16(cudaStream_t s, const void *rows_fp16, float *inv_norm, uint64_t n, uint32_t d);
 
+// corpus-sharded vector stage: merge `world` gathered per-shard top-k lists ([shard][query][k] + [shard][query] counts) per query
+cudaError_t launch_shard_merge(cudaStream_t s, const uint32_t *g_ids, const float *g_dist, const uint32_t *g_n, uint32_t world, uint32_t n_q,
+                               uint32_t k, uint32_t *out_ids, float *out_dist, uint32_t *out_n);
+
 // ---- vec_gemm.cu: batched vector stage on tcgen05 (queries x matrix^T with the top-k fused into the epilogue)
 #define VEC_GEMM_CAND_CAP 256
 #define VEC_GEMM_KMAX 128
