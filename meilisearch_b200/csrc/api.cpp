@@ -25,6 +25,21 @@ void rule_end_impl(Engine::RuleRun *run);
 
 static thread_local std::string g_open_error;
 
+// no exception crosses the C boundary: every entry point runs its body through this
+template <class F>
+static int guarded(b200_index *h, F body) {
+    if (!h) return B200_ERR_INVALID;
+    try {
+        return body();
+    } catch (const std::bad_alloc &) {
+        return h->e.fail(B200_ERR_CAPACITY, "out of host memory");
+    } catch (const std::exception &ex) {
+        return h->e.fail(B200_ERR_INVALID, ex.what());
+    } catch (...) {
+        return h->e.fail(B200_ERR_INVALID, "unexpected exception");
+    }
+}
+
 extern "C" {
 
 const char *b200_open_error(void) { return g_open_error.c_str(); }
@@ -61,31 +76,49 @@ void b200_close(b200_index *h) { delete h; }
 const char *b200_last_error(const b200_index *h) { return h ? h->e.last_error.c_str() : "null handle"; }
 
 int b200_stage_dictionary(b200_index *h, const uint8_t *bytes, const uint64_t *offsets, uint64_t n) {
-    std::lock_guard<std::mutex> g(h->e.mu);
-    h->e.raw_dict_off.assign(offsets, offsets + n + 1);
-    h->e.raw_dict_bytes.assign(bytes, bytes + offsets[n]);
-    return B200_OK;
+    return guarded(h, [&]() -> int {
+        std::lock_guard<std::mutex> g(h->e.mu);
+        if (h->e.staged) return h->e.fail(B200_ERR_STATE, "staging after b200_stage_finish: open a new handle");
+        if (!offsets || (!bytes && n && offsets[n])) return h->e.fail(B200_ERR_INVALID, "stage_dictionary: null argument");
+        for (uint64_t i = 0; i < n; i++)
+            if (offsets[i + 1] < offsets[i]) return h->e.fail(B200_ERR_INVALID, "stage_dictionary: offsets must not decrease");
+        h->e.raw_dict_off.assign(offsets, offsets + n + 1);
+        h->e.raw_dict_bytes.assign(bytes, bytes + offsets[n]);
+        return B200_OK;
+    });
 }
 int b200_stage_db(b200_index *h, int db, uint64_t n, const uint8_t *kb, const uint64_t *ko, const uint8_t *vb, const uint64_t *vo) {
-    std::lock_guard<std::mutex> g(h->e.mu);
-    if (db < 0 || db >= B200_DB_COUNT) return h->e.fail(B200_ERR_INVALID, "unknown database id");
-    RawDb &d = h->e.raw_dbs[db];
-    d.n = n;
-    d.koff.assign(ko, ko + n + 1);
-    d.voff.assign(vo, vo + n + 1);
-    d.keys.assign(kb, kb + ko[n]);
-    d.vals.assign(vb, vb + vo[n]);
-    return B200_OK;
+    return guarded(h, [&]() -> int {
+        std::lock_guard<std::mutex> g(h->e.mu);
+        if (h->e.staged) return h->e.fail(B200_ERR_STATE, "staging after b200_stage_finish: open a new handle");
+        if (db < 0 || db >= B200_DB_COUNT) return h->e.fail(B200_ERR_INVALID, "unknown database id");
+        if (!ko || !vo || (n && (!kb || !vb))) return h->e.fail(B200_ERR_INVALID, "stage_db: null argument");
+        for (uint64_t i = 0; i < n; i++)
+            if (ko[i + 1] < ko[i] || vo[i + 1] < vo[i]) return h->e.fail(B200_ERR_INVALID, "stage_db: offsets must not decrease");
+        RawDb &d = h->e.raw_dbs[db];
+        d.n = n;
+        d.koff.assign(ko, ko + n + 1);
+        d.voff.assign(vo, vo + n + 1);
+        d.keys.assign(kb, kb + ko[n]);
+        d.vals.assign(vb, vb + vo[n]);
+        return B200_OK;
+    });
 }
 int b200_stage_documents_ids(b200_index *h, const uint8_t *cbo, uint64_t len) {
-    std::lock_guard<std::mutex> g(h->e.mu);
-    h->e.raw_docids.assign(cbo, cbo + len);
-    return B200_OK;
+    return guarded(h, [&]() -> int {
+        std::lock_guard<std::mutex> g(h->e.mu);
+        if (h->e.staged) return h->e.fail(B200_ERR_STATE, "staging after b200_stage_finish: open a new handle");
+        if (!cbo && len) return h->e.fail(B200_ERR_INVALID, "stage_documents_ids: null argument");
+        h->e.raw_docids.assign(cbo, cbo + len);
+        return B200_OK;
+    });
 }
 int b200_stage_settings(b200_index *h, const b200_settings *s) {
+    if (!h || !s) return B200_ERR_INVALID;
     std::lock_guard<std::mutex> g(h->e.mu);
     Settings &t = h->e.hix.settings;
     if (s->n_fields == 0 || s->n_fields > 1024) return h->e.fail(B200_ERR_INVALID, "n_fields out of range");
+    if (!s->weights || (s->n_criteria && !s->criteria)) return h->e.fail(B200_ERR_INVALID, "stage_settings: null weights / criteria");
     t.n_fields = s->n_fields;
     t.weights.assign(s->weights, s->weights + s->n_fields);
     t.criteria.assign(s->criteria, s->criteria + s->n_criteria);
@@ -128,11 +161,14 @@ int b200_stage_synonyms(b200_index *h, uint32_t n, const char *const *from_words
     return B200_OK;
 }
 int b200_stage_finish(b200_index *h) {
-    std::lock_guard<std::mutex> g(h->e.mu);
-    Settings keep = h->e.hix.settings;
-    int rc = h->e.stage_finish();
-    h->e.hix.settings = keep;
-    return rc;
+    return guarded(h, [&]() -> int {
+        std::lock_guard<std::mutex> g(h->e.mu);
+        if (h->e.staged) return h->e.fail(B200_ERR_STATE, "b200_stage_finish was already called on this handle");
+        Settings keep = h->e.hix.settings;
+        int rc = h->e.stage_finish();
+        h->e.hix.settings = keep;
+        return rc;
+    });
 }
 int b200_stage_embeddings(b200_index *h, const float *v, uint64_t n, uint32_t d, const uint32_t *docids) {
     std::lock_guard<std::mutex> g(h->e.mu);
@@ -224,9 +260,18 @@ void b200_rule_end(b200_rule *r) {
     delete r;
 }
 int b200_search_batch(b200_index *h, const b200_query_batch *b, b200_results *r) {
-    std::lock_guard<std::mutex> g(h->e.mu);
-    if (!h->e.staged) return h->e.fail(B200_ERR_STATE, "search before b200_stage_finish");
-    return h->e.search_batch(b, r);
+    return guarded(h, [&]() -> int {
+        std::lock_guard<std::mutex> g(h->e.mu);
+        if (!h->e.staged) return h->e.fail(B200_ERR_STATE, "search before b200_stage_finish");
+        if (!b || !r || !r->docids || !r->n_hits) return h->e.fail(B200_ERR_INVALID, "search: null batch / results / docids / n_hits");
+        if (b->n_queries && (!b->token_begin || !b->lemma_off)) return h->e.fail(B200_ERR_INVALID, "search: null token arrays");
+        // every query starts with a definite status and no hits, whatever happens later
+        for (uint32_t i = 0; i < b->n_queries; i++) {
+            r->n_hits[i] = 0;
+            if (r->status) r->status[i] = 0;
+        }
+        return h->e.search_batch(b, r);
+    });
 }
 int b200_get_stats(b200_index *h, b200_stats *out) {
     std::lock_guard<std::mutex> g(h->e.mu);

@@ -2059,8 +2059,10 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         }
         const size_t n_rules = q.rules.size();
         for (;;) {
-            if (q.n_results >= length) break;
             if (q.levels.empty()) break;
+            // bucket_sort.rs:52-64,104-116: all_candidates is the universe even when no hit is asked for (limit 0)
+            if (q.levels.back().kind == RK_RESOLVE && q.levels.back().cursor == 0) q.n_candidates = q.levels.back().counts[0];
+            if (q.n_results >= length) break;
             size_t cur = q.levels.size() - 1;  // level index; rule index = cur - 1 (level 0 = resolve)
             Level &L = q.levels[cur];
             auto back = [&]() {

@@ -26,13 +26,17 @@ uint32_t cbo_decode_append(const uint8_t *p, size_t n, std::vector<uint32_t> &ou
     memcpy(&cookie, p, 4);
     memcpy(&nc, p + 4, 4);
     if (cookie != 12346) throw std::runtime_error("stage: roaring value with run containers / unknown cookie");
+    // every length comes from the value itself: check it against the bytes we were given before reading
+    if (nc == 0 || nc > 65536 || 8 + 8 * (size_t)nc > n) throw std::runtime_error("stage: malformed roaring value (container count)");
     const uint8_t *desc = p + 8;
     const uint8_t *data = p + 8 + 8 * (size_t)nc;
+    const uint8_t *const end = p + n;
     for (uint32_t c = 0; c < nc; c++) {
         uint16_t key, cm1;
         memcpy(&key, desc + 4 * c, 2);
         memcpy(&cm1, desc + 4 * c + 2, 2);
         uint32_t card = (uint32_t)cm1 + 1, hi = (uint32_t)key << 16;
+        if ((size_t)(end - data) < (card <= 4096 ? 2 * (size_t)card : (size_t)8192)) throw std::runtime_error("stage: malformed roaring value (truncated container)");
         if (card <= 4096) {
             for (uint32_t i = 0; i < card; i++) {
                 uint16_t lo;

@@ -672,3 +672,42 @@ def test_proximity_pairs_matches_decoded_lists(mb, synth):
         assert want.any() or fwd == 0
         assert np.array_equal(ix.proximity_pairs(left, right, fwd, bwd), want), (fwd, bwd)
         assert np.array_equal(ix.proximity_pairs(left, right, fwd, bwd, universe), want & universe), (fwd, bwd)
+
+
+def test_limit_zero_reports_candidates(mb, synth):
+    """limit 0 still reports SearchResult::candidates (estimatedTotalHits and facets rely on it, bucket_sort.rs:52-64,104-116)"""
+    from oracle.pyoracle import OracleIndex
+
+    queries = synth.synthetic_queries(30, seed=81)
+    tokens = mb.TokenBatch(queries)
+    full = OracleIndex(synth).search_batch(tokens, limit=20, n_threads=8)
+    got = mb.Index(synth).search().query(tokens).limit(0).execute()
+    for q in range(len(queries)):
+        assert got.status[q] == 0 and got.n_hits[q] == 0
+        assert int(got.n_candidates[q]) == int(full.n_candidates[q]), queries[q]
+
+
+def test_malformed_input_is_rejected(mb, synth):
+    """the ABI checks what it is given: a truncated roaring value and a repeated stage_finish are errors, not crashes"""
+    import copy
+
+    class Img:
+        pass
+    bad = Img()
+    for k in ("n_docs", "n_words", "n_fields", "dict_bytes", "dict_offsets", "documents_ids_cbo"):
+        setattr(bad, k, getattr(synth, k))
+    bad.dbs = list(synth.dbs)
+    db0 = copy.copy(synth.dbs[0])
+    lens = np.diff(np.asarray(db0.val_offsets))
+    big = int(np.argmax(lens))                       # a roaring-encoded value (> 7 docids)
+    assert lens[big] > 28
+    vb = np.array(db0.val_bytes, copy=True)
+    vb[int(db0.val_offsets[big]) + 4] = 0xFF          # container count 255+: the descriptors would run past the value
+    vb[int(db0.val_offsets[big]) + 5] = 0xFF
+    db0.val_bytes = vb
+    bad.dbs[0] = db0
+    with pytest.raises(mb.B200Error) as e:
+        mb.Index(bad)
+    assert e.value.code == -3
+    ix = mb.Index(synth)
+    assert ix._l.b200_stage_finish(ix._h) == -6        # B200_ERR_STATE
