@@ -244,8 +244,8 @@ typedef struct {
     uint64_t hbm_bytes_staged;
     uint64_t deferred;            /* ranking-rule activations that had to wait for a later device step (scratch / arena full) */
     uint64_t arena_peak_bytes;    /* high-water mark of the per-batch level storage (universes + bucket columns) */
-    uint64_t eval_class_launches[5]; /* eval_dp launches per DP-table class: <= 24 / 56 / 112 / 216 slots in shared memory, [4] = global matrices */
-    uint64_t eval_class_tiles[5];    /* 128-row tiles evaluated per class */
+    uint64_t eval_class_launches[9]; /* eval_dp launches per DP-table class: <= 16 / 24 / 40 / 56 / 80 / 112 / 160 / 216 slots in shared memory, [8] = global matrices */
+    uint64_t eval_class_tiles[9];    /* 128-row tiles evaluated per class */
 } b200_stats;
 int b200_get_stats(b200_index *, b200_stats *out);
 int b200_reset_stats(b200_index *);

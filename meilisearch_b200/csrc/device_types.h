@@ -120,8 +120,8 @@ struct TileDesc {
 // eval_dp_kernel keeps a row's condition words and DP table in thread-private shared-memory slots ([slot][128 rows] u64 = 1 KB per
 // slot and CTA); a step's tiles are binned by the slot count (n_cols + n_pairs) of their activation, one launch per class; wider
 // activations use the global-memory variant.
-constexpr uint32_t EVAL_CLASSES = 4;
-constexpr uint32_t EVAL_CLASS_SLOTS[EVAL_CLASSES] = {24, 56, 112, 216};
+constexpr uint32_t EVAL_CLASSES = 8;
+constexpr uint32_t EVAL_CLASS_SLOTS[EVAL_CLASSES] = {16, 24, 40, 56, 80, 112, 160, 216};
 inline uint32_t eval_class(uint32_t slots) {
     for (uint32_t c = 0; c < EVAL_CLASSES; c++)
         if (slots <= EVAL_CLASS_SLOTS[c]) return c;

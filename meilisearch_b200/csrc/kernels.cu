@@ -634,7 +634,7 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
 // Surviving paths (graph_based_ranking_rule.rs:340-353: the host rebuilds the next query graph from the paths that took at
 // least one document) are the business of walk_kernel, which runs after this kernel over the same tiles: this kernel leaves, per
 // tile, the set of its non-empty buckets (tile_summary), so that whole tiles are skipped there.
-constexpr int WALK_SPARSE = 8;
+constexpr int WALK_CLASSES = 8;  // distinct signatures tracked per row (more: every needed document of the row walks)
 __device__ __forceinline__ void load_act(ActDesc *dst, const ActDesc *src) {
     static_assert(sizeof(ActDesc) % 4 == 0, "ActDesc is copied word by word");
     const uint32_t *s = reinterpret_cast<const uint32_t *>(src);
@@ -654,12 +654,12 @@ __device__ __forceinline__ int tab_insert(const ActDesc &a, unsigned long long h
 }
 // The walk of one row: `slot(k)` reads the row's slot k (condition columns after the column program, then the DP table).
 template <class SlotFn>
-__device__ __forceinline__ void walk_row(const ActDesc &a, uint32_t act_i, uint32_t last_bucket, const DpState *st, const DpEdge *ed,
-                                         const uint16_t *cost_vals, size_t j, SlotFn slot, unsigned long long *s_seen /* 64 */, uint32_t *results, PathOut *pathbuf,
+__device__ __forceinline__ void walk_row(const ActDesc &a, uint32_t act_i, uint32_t last_bucket, unsigned long long only, const DpState *st,
+                                         const DpEdge *ed, const uint16_t *cost_vals, size_t j, SlotFn slot, unsigned long long *s_seen /* 64 */, uint32_t *results, PathOut *pathbuf,
                                          uint32_t *path_count, uint32_t path_cap) {
     const uint32_t END = a.n_states - 1, n_cols = a.n_cols;
     for (uint32_t ci = 0; ci <= last_bucket && ci < a.n_costs; ci++) {
-        const unsigned long long b = a.out[(size_t)ci * a.ld + j];
+        const unsigned long long b = a.out[(size_t)ci * a.ld + j] & only;
         if (!b) continue;
         struct Frame {
             unsigned long long mask;
@@ -876,9 +876,9 @@ __global__ void __launch_bounds__(128, 8) eval_dp_kernel(const TileDesc *__restr
 // each state, the first edge (in order) whose condition it satisfies and from which it can still finish with its remaining
 // budget.  Distinct walked paths are de-duplicated (per CTA in shared memory, then per activation in a global hash table) and
 // reported.  The path a document takes is a function of its condition bits alone, and a large bucket holds few distinct bit
-// patterns when the rule has few conditions: with at most 64 condition columns, a row with at most WALK_SPARSE needed documents
-// first hashes each document's pattern (its *signature*) into the same tables and is skipped when every signature is already
-// known — somebody else walks (or walked) a document with the same pattern.
+// patterns: with at most 64 condition columns, the needed documents of a row are first split into classes of identical bits
+// (their *signatures*), every class is looked up in the same tables, and only documents of classes nobody has met walk —
+// somebody else walks (or walked) a document with the same pattern.
 template <bool SMEM>
 __global__ void __launch_bounds__(128, 8) walk_kernel(const TileDesc *__restrict__ tiles, const ActDesc *__restrict__ acts,
                                                       uint32_t *__restrict__ results, const ColOp *__restrict__ colprog,
@@ -948,32 +948,56 @@ __global__ void __launch_bounds__(128, 8) walk_kernel(const TileDesc *__restrict
             }
             for (; c < n_cols; c++) s_slot[(size_t)c * 128 + threadIdx.x] = C[(size_t)c * ld + j];
         }
-        if (n_cols <= 64 && __popcll(needed) <= WALK_SPARSE) {
-            // signatures of the needed documents (raw condition columns; the global variant sees them after the column program,
-            // which is just as much a function of the document's bits)
-            bool any_new = false;
-            unsigned long long left = needed;
-            while (left) {
-                const uint32_t bit = (uint32_t)__ffsll((long long)left) - 1;
-                left &= left - 1;
-                unsigned long long w = 0;
-                for (uint32_t c = 0; c < n_cols; c++) w |= ((SLOT(c) >> bit) & 1ull) << c;
-                const unsigned long long h = mix64(w ^ ((unsigned long long)n_cols << 56) ^ 0x51ed270b1ull) | 3ull;  // bit 1 set: a signature
-                bool known = false;
-                uint32_t sl = (uint32_t)(h >> 20) & 127u;
-                for (int probe = 0; probe < 8; probe++) {
-                    unsigned long long prev = atomicCAS(&s_sig[sl], 0ull, h);
-                    if (prev == h) {
-                        known = true;
+        unsigned long long walk_mask = needed;  // the documents that have to walk
+        if (n_cols <= 64) {
+            // Partition refinement, bit-sliced: split the needed documents of the row into classes of identical condition bits
+            // (column after column, every class is cut in two by the column's word) — the classes are the row's distinct
+            // signatures.  A class somebody already met is dropped; only documents of new classes walk.
+            unsigned long long cm[WALK_CLASSES], cp[WALK_CLASSES];
+            int nc = 1;
+            bool overflow = false;
+            cm[0] = needed;
+            cp[0] = 0;
+            for (uint32_t c = 0; c < n_cols && !overflow; c++) {
+                const unsigned long long v = SLOT(c);
+                if (!(v & needed)) continue;
+                const int n0 = nc;
+                for (int k = 0; k < n0; k++) {
+                    const unsigned long long m1 = cm[k] & v;
+                    if (!m1) continue;
+                    if (m1 == cm[k])
+                        cp[k] |= 1ull << c;
+                    else if (nc == WALK_CLASSES) {
+                        overflow = true;
                         break;
+                    } else {
+                        cm[nc] = m1;
+                        cp[nc] = cp[k] | (1ull << c);
+                        cm[k] &= ~v;
+                        nc++;
                     }
-                    if (prev == 0ull) break;
-                    sl = (sl + 1) & 127u;
                 }
-                if (known) continue;
-                if (tab_insert(a, h) != 0) any_new = true;  // new for the activation, or the table is full (then walk: the walk reports the overflow)
             }
-            if (!any_new) continue;
+            if (!overflow) {
+                walk_mask = 0;
+                for (int k = 0; k < nc; k++) {
+                    const unsigned long long h = mix64(cp[k] ^ ((unsigned long long)n_cols << 56) ^ 0x51ed270b1ull) | 3ull;  // bit 1 set: a signature
+                    bool known = false;
+                    uint32_t sl = (uint32_t)(h >> 20) & 127u;
+                    for (int probe = 0; probe < 8; probe++) {
+                        unsigned long long prev = atomicCAS(&s_sig[sl], 0ull, h);
+                        if (prev == h) {
+                            known = true;
+                            break;
+                        }
+                        if (prev == 0ull) break;
+                        sl = (sl + 1) & 127u;
+                    }
+                    if (known) continue;
+                    if (tab_insert(a, h) != 0) walk_mask |= cm[k];  // new for the activation, or the table is full (then walk: the walk reports the overflow)
+                }
+                if (!walk_mask) continue;
+            }
         }
         if (SMEM) {  // (the global variant already holds the column program's results in C and the DP table in S)
             for (uint32_t i = 0; i < a.colprog_len; i++) {
@@ -1005,24 +1029,25 @@ __global__ void __launch_bounds__(128, 8) walk_kernel(const TileDesc *__restrict
                 }
             }
         }
-        walk_row(a, tile.act, m, states + a.state_off, edges + a.edge_off, cost_vals, j, [&](uint32_t k) { return SLOT(k); }, s_seen, results, pathbuf,
-                 path_count, path_cap);
+        walk_row(a, tile.act, m, walk_mask, states + a.state_off, edges + a.edge_off, cost_vals, j, [&](uint32_t k) { return SLOT(k); }, s_seen, results,
+                 pathbuf, path_count, path_cap);
 #undef SLOT
     }
 }
 
-// one warp per emission: ascending docids of OR(out[col_lo..col_hi)), skipping `skip`, taking `take`.
-// 256 rows per round — 8 consecutive rows per lane, loads issued together — because a sparse bucket of a large universe is a long
+// one CTA per emission: ascending docids of OR(out[col_lo..col_hi)), skipping `skip`, taking `take`.
+// 2048 rows per round — 8 consecutive rows per thread, loads issued together — because a sparse bucket of a large universe is a long
 // scan (a 20-document bucket of a 150 k-row universe) whose cost is the number of dependent global-memory round trips.
-constexpr int EMIT_ROWS_PER_LANE = 8;
-__global__ void __launch_bounds__(128) emit_kernel(const EmitDesc *__restrict__ emits, uint32_t n_emits) {
-    uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+constexpr int EMIT_ROWS_PER_LANE = 8, EMIT_THREADS = 256;
+__global__ void __launch_bounds__(EMIT_THREADS) emit_kernel(const EmitDesc *__restrict__ emits, uint32_t n_emits) {
+    const uint32_t e = blockIdx.x;
     if (e >= n_emits) return;
     const EmitDesc d = emits[e];
-    uint32_t lane = threadIdx.x & 31;
+    __shared__ uint32_t warp_tot[EMIT_THREADS / 32];
+    const uint32_t lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
     uint32_t seen = 0;  // documents of the bucket in the rows before this round
-    for (uint32_t j0 = 0; j0 < d.rows && seen < d.skip + d.take; j0 += 32 * EMIT_ROWS_PER_LANE) {
-        const uint32_t jb = j0 + lane * EMIT_ROWS_PER_LANE;
+    for (uint32_t j0 = 0; j0 < d.rows && seen < d.skip + d.take; j0 += EMIT_THREADS * EMIT_ROWS_PER_LANE) {
+        const uint32_t jb = j0 + threadIdx.x * EMIT_ROWS_PER_LANE;
         unsigned long long v[EMIT_ROWS_PER_LANE];
 #pragma unroll
         for (int i = 0; i < EMIT_ROWS_PER_LANE; i++) {
@@ -1044,8 +1069,16 @@ __global__ void __launch_bounds__(128) emit_kernel(const EmitDesc *__restrict__ 
             uint32_t t = __shfl_up_sync(0xffffffffu, pre, s);
             if (lane >= (uint32_t)s) pre += t;
         }
-        const uint32_t total = __shfl_sync(0xffffffffu, pre, 31);
-        uint32_t rk = seen + pre - pc;  // rank of this lane's first document within the bucket
+        if (lane == 31) warp_tot[wrp] = pre;
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < EMIT_THREADS / 32; w++) {
+            const uint32_t t = warp_tot[w];
+            before += (uint32_t)w < wrp ? t : 0u;
+            total += t;
+        }
+        uint32_t rk = seen + before + pre - pc;  // rank of this thread's first document within the bucket
         if (pc && rk < d.skip + d.take && rk + pc > d.skip) {
 #pragma unroll
             for (int i = 0; i < EMIT_ROWS_PER_LANE; i++) {
@@ -1064,6 +1097,7 @@ __global__ void __launch_bounds__(128) emit_kernel(const EmitDesc *__restrict__ 
             }
         }
         seen += total;
+        __syncthreads();
     }
 }
 
@@ -1409,7 +1443,7 @@ cudaError_t launch_walk(cudaStream_t s, int cls, const TileDesc *tiles, uint32_t
 }
 cudaError_t launch_emit(cudaStream_t s, const EmitDesc *emits, uint32_t n_emits) {
     if (!n_emits) return cudaSuccess;
-    emit_kernel<<<(n_emits * 32 + 127) / 128, 128, 0, s>>>(emits, n_emits);
+    emit_kernel<<<n_emits, EMIT_THREADS, 0, s>>>(emits, n_emits);
     return cudaGetLastError();
 }
 
