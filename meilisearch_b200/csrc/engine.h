@@ -205,6 +205,7 @@ struct Lane {
     DevBuf<uint8_t> d_step;
     DevBuf<uint32_t> d_results, d_qcount, d_segcount;
     DevBuf<Job> d_queue;
+    DevBuf<uint32_t> d_bigq;  // indices of the step's big scatter jobs (scatter_kernel -> scatter_big_kernel)
     DevBuf<PathOut> d_pathbuf;
     DevBuf<unsigned long long> d_tile_summary;  // 2 u64 per eval tile: its non-empty buckets (eval_dp_kernel -> walk_kernel)
     uint8_t *h_step = nullptr;
@@ -265,6 +266,7 @@ struct Lane {
         d_segcount.release();
         d_pathbuf.release();
         d_tile_summary.release();
+        d_bigq.release();
         if (h_step) cudaFreeHost(h_step);
         if (h_results) cudaFreeHost(h_results);
         for (auto e : ev_pool) cudaEventDestroy(e);

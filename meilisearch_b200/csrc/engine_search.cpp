@@ -2591,7 +2591,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         size_t qcap = std::max<size_t>((size_t)n_jobs + ((size_t)1 << 20), (size_t)4 << 20);
         CU(ln.d_queue.reserve(qcap), "job queue");
         qcap = ln.d_queue.cap;
-        CU(ln.d_qcount.reserve(4), "job counter");
+        CU(ln.d_qcount.reserve(8), "job counter");
         CU(ln.d_results.reserve(res_words + 4), "results");
         if (res_words + 4 > ln.h_results_cap) {
             if (ln.h_results) cudaFreeHost(ln.h_results);
@@ -2612,7 +2612,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             CU(cudaMemsetAsync(ln.d_results.p, 0, (size_t)(res_words + 4) * 4, st), "zero results");
             CU(cudaMemsetAsync(ln.scratch, 0, z_used, st), "zero condition matrix");
             CU(ln.d_pathbuf.reserve(PATH_CAP), "path buffer");
-            CU(cudaMemsetAsync(ln.d_qcount.p + 1, 0, 12, st), "zero path count, scatter cursor, walk count");
+            CU(cudaMemsetAsync(ln.d_qcount.p + 1, 0, 16, st), "zero path count and the scatter cursors");
             size_t t0 = ln.mark();
             CU(ln.d_segcount.reserve(n_ctiles + 1), "segment counts");
             CU(launch_compact(st, reinterpret_cast<const CompactTile *>(ln.d_step.p + o_ctiles), n_ctiles, multi_segment, dacts, ln.d_segcount.p,
@@ -2627,7 +2627,11 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
                "pair probe");
             size_t t2 = ln.mark();
             if (n_probes) ln.time_kernel(ln.lst, B200_K_PAIR_PROBE, t1, t2, (uint64_t)n_probes * 8 * 23);
-            CU(launch_scatter(st, (uint32_t)sm_count * 5, ln.d_queue.p, ln.d_qcount.p, (uint32_t)qcap, dacts, ln.d_results.p, dix.lists, dix.pool), "scatter");
+            CU(ln.d_bigq.reserve(qcap), "big-job queue");
+            CU(launch_scatter(st, (uint32_t)sm_count * 5, ln.d_queue.p, ln.d_qcount.p, (uint32_t)qcap, dacts, ln.d_results.p, dix.lists, dix.pool,
+                              ln.d_bigq.p),
+               "scatter");
+            ln.lst.kernel_launches++;
             size_t t3 = ln.mark();
             ln.time_kernel(ln.lst, B200_K_SCATTER, t2, t3, fill_bytes);
             // the classes are independent (different activations): class 0 stays on the lane's stream, the others run beside it on

@@ -471,7 +471,8 @@ int Engine::union_postings(int db, const uint32_t *key_index, uint32_t n_keys, c
         for (uint32_t k = 0; k < (units + JOB_CHUNK - 1) / JOB_CHUNK; k++) jobs.push_back(Job{0, 0, list, k});
     }
     const size_t o_ub = 0, o_col = o_ub + W * 8, o_act = (o_col + W * 8 + 255) & ~(size_t)255, o_res = o_act + ((sizeof(ActDesc) + 255) & ~(size_t)255),
-                 o_jobs = o_res + 256, total = o_jobs + std::max<size_t>(1, jobs.size()) * sizeof(Job);
+                 o_jobs = o_res + 256, o_bigq = (o_jobs + std::max<size_t>(1, jobs.size()) * sizeof(Job) + 255) & ~(size_t)255,
+                 total = o_bigq + std::max<size_t>(1, jobs.size()) * 4;
     CU(d_s2.reserve(total), "alloc S2 scratch");
     uint8_t *base = d_s2.p;
     if (universe)
@@ -487,7 +488,7 @@ int Engine::union_postings(int db, const uint32_t *key_index, uint32_t n_keys, c
     a.n_cols = 1;
     a.res_off = 0;
     uint32_t counters[4] = {(uint32_t)W, 0, 0, 0};      // results[0] = rows
-    uint32_t qcount[4] = {(uint32_t)jobs.size(), 0, 0, 0};
+    uint32_t qcount[8] = {(uint32_t)jobs.size(), 0, 0, 0, 0, 0, 0, 0};
     CU(cudaMemcpyAsync(base + o_act, &a, sizeof a, cudaMemcpyHostToDevice, stream), "H2D activation");
     CU(cudaMemcpyAsync(base + o_res, counters, sizeof counters, cudaMemcpyHostToDevice, stream), "H2D rows");
     CU(cudaMemcpyAsync(base + o_res + 64, qcount, sizeof qcount, cudaMemcpyHostToDevice, stream), "H2D job count");
@@ -496,7 +497,7 @@ int Engine::union_postings(int db, const uint32_t *key_index, uint32_t n_keys, c
         size_t m0 = mark();
         CU(launch_scatter(stream, (uint32_t)sm_count * 5, reinterpret_cast<const Job *>(base + o_jobs), reinterpret_cast<uint32_t *>(base + o_res + 64),
                           (uint32_t)jobs.size(), reinterpret_cast<const ActDesc *>(base + o_act), reinterpret_cast<const uint32_t *>(base + o_res),
-                          dix.lists, dix.pool),
+                          dix.lists, dix.pool, reinterpret_cast<uint32_t *>(base + o_bigq)),
            "scatter");
         uint64_t bytes = 0;
         for (auto &j : jobs) bytes += hix.lists[j.list].dense ? (uint64_t)JOB_CHUNK * 8 : (uint64_t)std::min<uint32_t>(JOB_CHUNK, hix.lists[j.list].card) * 4;
@@ -536,7 +537,7 @@ int Engine::proximity_pairs(const uint32_t *left, uint32_t n_left, const uint32_
     const size_t qcap = std::max<size_t>((size_t)1 << 16, (size_t)n_probes * 4);
     const size_t o_ub = 0, o_col = o_ub + W * 8, o_act = (o_col + W * 8 + 255) & ~(size_t)255, o_res = o_act + ((sizeof(ActDesc) + 255) & ~(size_t)255),
                  o_set = o_res + 256, o_words = o_set + 256, o_queue = (o_words + ((size_t)n_left + n_right) * 4 + 255) & ~(size_t)255,
-                 total = o_queue + qcap * sizeof(Job);
+                 o_bigq = o_queue + qcap * sizeof(Job), total = o_bigq + qcap * 4;
     CU(d_s2.reserve(total), "alloc S2 scratch");
     uint8_t *base = d_s2.p;
     if (universe)
@@ -572,7 +573,7 @@ int Engine::proximity_pairs(const uint32_t *left, uint32_t n_left, const uint32_
     size_t m1 = mark();
     time_kernel(B200_K_PAIR_PROBE, m0, m1, n_probes * 8 * 23);
     CU(launch_scatter(stream, (uint32_t)sm_count * 5, reinterpret_cast<const Job *>(base + o_queue), d_qcount, (uint32_t)qcap,
-                      reinterpret_cast<const ActDesc *>(base + o_act), d_res, dix.lists, dix.pool),
+                      reinterpret_cast<const ActDesc *>(base + o_act), d_res, dix.lists, dix.pool, reinterpret_cast<uint32_t *>(base + o_bigq)),
        "scatter");
     time_kernel(B200_K_SCATTER, m1, mark(), 0);
     uint32_t h_counts[8];

@@ -550,9 +550,14 @@ __device__ __forceinline__ void scatter_job_coop(const Job job, const ActDesc &a
     }
 }
 
+// Two launches per step.  scatter_kernel takes the jobs 32 at a time: tiny lists (the common case for word-pair lists) are handled
+// one per lane, the others are only *noted* in a second queue (bigq).  scatter_big_kernel then gives every noted job to a whole
+// warp.  Handling the big jobs inside the first kernel made a warp that drew 20 of them work through 20 x 2048 elements alone
+// while the rest of the GPU idled (measured: every launch took ~300 us whatever its size).
 __global__ void __launch_bounds__(256) scatter_kernel(const Job *__restrict__ queue, uint32_t *__restrict__ qcount, uint32_t qcap,
                                                       const ActDesc *__restrict__ acts, const uint32_t *__restrict__ results,
-                                                      const DListRef *__restrict__ lists, const uint32_t *__restrict__ pool) {
+                                                      const DListRef *__restrict__ lists, const uint32_t *__restrict__ pool,
+                                                      uint32_t *__restrict__ bigq) {
     const uint32_t n_jobs = min(qcount[0], qcap);
     const uint32_t lane = threadIdx.x & 31;
     // Persistent warps pull 32 jobs at a time from a shared cursor (qcount[2], zeroed by the host): the cost of a job ranges from
@@ -593,16 +598,48 @@ __global__ void __launch_bounds__(256) scatter_kernel(const Job *__restrict__ qu
                     if (j[x] >= 0) atomicOr(&col[j[x]], 1ull << (d[x] & 63));
             }
         }
-        unsigned big = __ballot_sync(0xffffffffu, live && !small);
-        while (big) {
-            int src = __ffs(big) - 1;
-            big &= big - 1;
+        const bool is_big = live && !small;
+        const unsigned big = __ballot_sync(0xffffffffu, is_big);
+        if (big) {  // note the big jobs for scatter_big_kernel: qcount[3] = number noted
+            uint32_t at = 0;
+            if (lane == 0) at = atomicAdd(&qcount[3], (uint32_t)__popc(big));
+            at = __shfl_sync(0xffffffffu, at, 0);
+            if (is_big) bigq[at + __popc(big & ((1u << lane) - 1))] = jb;
+        }
+    }
+}
+__global__ void __launch_bounds__(256) scatter_big_kernel(const Job *__restrict__ queue, uint32_t *__restrict__ qcount,
+                                                          const ActDesc *__restrict__ acts, const uint32_t *__restrict__ results,
+                                                          const DListRef *__restrict__ lists, const uint32_t *__restrict__ pool,
+                                                          const uint32_t *__restrict__ bigq) {
+    const uint32_t n_big = qcount[3];
+    const uint32_t lane = threadIdx.x & 31;
+    // up to eight jobs per draw: lanes 0..7 fetch the descriptors of their job side by side (five dependent loads each), then the warp
+    // works through the eight one after the other
+    // (fewer per draw when the step has few big jobs: then the length of the longest warp's chain is what the launch costs)
+    const uint32_t GRAB = min(8u, max(1u, n_big / (2u * ((gridDim.x * blockDim.x) >> 5))));
+    for (;;) {
+        uint32_t k0 = 0;
+        if (lane == 0) k0 = atomicAdd(&qcount[4], GRAB);
+        k0 = __shfl_sync(0xffffffffu, k0, 0);
+        if (k0 >= n_big) break;
+        Job job{0, 0, 0, 0};
+        uint32_t rows = 0;
+        const bool have = lane < GRAB && k0 + lane < n_big;
+        if (have) {
+            job = queue[bigq[k0 + lane]];
+            rows = results[acts[job.act].res_off];
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, have);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
             Job bj;
             bj.act = __shfl_sync(0xffffffffu, job.act, src);
             bj.col = __shfl_sync(0xffffffffu, job.col, src);
             bj.list = __shfl_sync(0xffffffffu, job.list, src);
             bj.chunk = __shfl_sync(0xffffffffu, job.chunk, src);
-            uint32_t brows = __shfl_sync(0xffffffffu, rows, src);
+            const uint32_t brows = __shfl_sync(0xffffffffu, rows, src);
             scatter_job_coop(bj, acts[bj.act], brows, lists[bj.list], pool, lane);
         }
     }
@@ -1404,8 +1441,9 @@ cudaError_t launch_pair_probe(cudaStream_t s, const PairSet *sets, uint32_t n_se
     return cudaGetLastError();
 }
 cudaError_t launch_scatter(cudaStream_t s, uint32_t n_ctas, const Job *queue, uint32_t *qcount, uint32_t qcap, const ActDesc *acts,
-                           const uint32_t *results, const DListRef *lists, const uint32_t *pool) {
-    scatter_kernel<<<n_ctas, 256, 0, s>>>(queue, qcount, qcap, acts, results, lists, pool);
+                           const uint32_t *results, const DListRef *lists, const uint32_t *pool, uint32_t *bigq) {
+    scatter_kernel<<<n_ctas, 256, 0, s>>>(queue, qcount, qcap, acts, results, lists, pool, bigq);
+    scatter_big_kernel<<<n_ctas, 256, 0, s>>>(queue, qcount, acts, results, lists, pool, bigq);
     return cudaGetLastError();
 }
 cudaError_t launch_eval(cudaStream_t s, int cls, const TileDesc *tiles, uint32_t n_tiles, const ActDesc *acts, uint32_t *results,

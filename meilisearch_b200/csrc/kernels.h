@@ -14,9 +14,10 @@ cudaError_t launch_compact(cudaStream_t s, const CompactTile *tiles, uint32_t n_
 cudaError_t launch_pair_probe(cudaStream_t s, const PairSet *sets, uint32_t n_sets, uint32_t n_probes, const uint32_t *wordpool,
                               const unsigned long long *pair_keys, uint64_t n_pairs, uint32_t pair_list_base, const DListRef *lists,
                               const ActDesc *acts, const uint32_t *results, Job *queue, uint32_t *qcount, uint32_t qcap);
-// qcount: [0] number of jobs (host + pair_probe), [2] work cursor (must be 0 at launch)
+// qcount: [0] number of jobs (host + pair_probe), [2] work cursor, [3] big jobs noted, [4] big-job cursor ([2..4] must be 0 at
+// launch); bigq: qcap u32 of scratch
 cudaError_t launch_scatter(cudaStream_t s, uint32_t n_ctas, const Job *queue, uint32_t *qcount, uint32_t qcap, const ActDesc *acts,
-                           const uint32_t *results, const DListRef *lists, const uint32_t *pool);
+                           const uint32_t *results, const DListRef *lists, const uint32_t *pool, uint32_t *bigq);
 // evaluation of the activations' tiles, pass 1 (DP, buckets, counts); cls: eval_class() of the tiles' activations (EVAL_CLASSES =
 // slots in global scratch); tile_summary: 2 u64 per tile (its non-empty buckets), indexed like `tiles`
 cudaError_t launch_eval(cudaStream_t s, int cls, const TileDesc *tiles, uint32_t n_tiles, const ActDesc *acts, uint32_t *results,
