@@ -472,10 +472,21 @@ int Engine::search_batch(const b200_query_batch *b, b200_results *r) {
     // the vector stage runs beside the keyword stage: its own host thread, stream and timers (the two share nothing mutable)
     bool have_vec = b->vectors != nullptr;
     int rc_vec = B200_OK;
+    // It starts once the keyword stage has derived the terms of its first wave: the term sweep is a short, SM-filling kernel that
+    // the persistent GEMM would otherwise slow down threefold, while the step loop that follows leaves most of the GPU idle.
+    // B200_HYBRID_SERIAL=1 runs the two stages one after the other (bench.py's device-time pass: kernel intervals must not overlap).
     std::thread sem;
-    if (have_vec) sem = std::thread([&]() { rc_vec = semantic_batch(b, &vec.view, 0, lim); });
+    const bool serial = getenv("B200_HYBRID_SERIAL") != nullptr;
+    kw_derived.store(0);
+    if (have_vec && !serial)
+        sem = std::thread([&]() {
+            while (kw_derived.load(std::memory_order_acquire) == 0) std::this_thread::yield();
+            rc_vec = semantic_batch(b, &vec.view, 0, lim);
+        });
     int rc = keyword_batch(b, &kw.view, 0, lim, 1);
+    kw_derived.store(1, std::memory_order_release);  // (also when the keyword stage returned early)
     if (sem.joinable()) sem.join();
+    if (have_vec && serial) rc_vec = semantic_batch(b, &vec.view, 0, lim);
     fold_vector_stats();
     if (rc != B200_OK) return rc;
     if (rc_vec != B200_OK) return rc_vec;

@@ -362,6 +362,7 @@ struct Engine {
     bool has_distribution = false;
     float dist_mean = 0, dist_sigma = 0;
     b200_stats stats{};
+    std::atomic<int> kw_derived{0};  // hybrid: the keyword stage has derived its first wave's terms (the vector stage starts then)
     TimerSet vt;          // vector stage: own stream and timers
     b200_stats vstats{};  // what the vector stage accumulated since it was last folded into `stats`
     void fold_vector_stats() {
@@ -435,6 +436,8 @@ struct Engine {
     int nns_batch(const float *queries, uint32_t n_q, uint32_t d, uint32_t limit, const uint64_t *cand, uint64_t n_cand_words, uint32_t *ids_out,
                   float *dist_out, uint32_t *n_out, bool sharded = false);
     ShardComm sc;
+    DevBuf<float> d_vpart_dist;  // sliced top-k selection: per-slice candidates
+    DevBuf<uint32_t> d_vpart_ids, d_vpart_n;
     DevBuf<uint32_t> d_gather_ids, d_gather_n;
     DevBuf<float> d_gather_dist;
     int comm_load();

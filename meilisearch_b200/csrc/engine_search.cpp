@@ -2813,6 +2813,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
                 return B200_OK;
             }
             start_range(lo, hi);
+            kw_derived.store(1, std::memory_order_release);
             cudaError_t ce = cudaStreamSynchronize(stream);  // row-table memset and derivations visible to the lanes
             if (ce != cudaSuccess) {
                 rc_prep = cuda_fail(ce, "sync");

@@ -324,14 +324,15 @@ int Engine::nns_batch(const float *queries, uint32_t n_q, uint32_t d, uint32_t l
             if (!vec_gemm_supported(d, limit)) return fail(B200_ERR_UNSUPPORTED, "sharded nns: dimension / limit outside the batched kernel's range");
         }
         if (want && vec_gemm_supported(d, limit)) {
-            const uint32_t tiles_per_pass = (uint32_t)sm_count;  // query tiles resident in one launch
+            const uint32_t vec_sms = getenv("B200_VEC_SMS") ? (uint32_t)std::max(8, std::min(sm_count, atoi(getenv("B200_VEC_SMS")))) : (uint32_t)sm_count;
+            const uint32_t tiles_per_pass = vec_sms;  // query tiles resident in one launch
             std::vector<uint32_t> h_ids, h_n;
             std::vector<float> h_dist;
             for (uint32_t q0 = 0; q0 < n_q; q0 += tiles_per_pass * 128) {
                 uint32_t nq = std::min<uint32_t>(n_q - q0, tiles_per_pass * 128);
                 uint32_t n_qtiles = (nq + 127) / 128, n_pad = n_qtiles * 128;
                 uint64_t n_row_tiles = (N + 63) / 64;
-                uint32_t n_groups = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sm_count / n_qtiles, n_row_tiles));
+                uint32_t n_groups = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)vec_sms / n_qtiles, n_row_tiles));
                 CU(d_vq.reserve((size_t)nq * d + n_pad), "alloc queries");
                 CU(d_vq16.reserve((size_t)n_pad * d), "alloc fp16 queries");
                 CU(d_vruns.reserve((size_t)n_qtiles * n_groups * 128 * VEC_GEMM_CAND_CAP + (size_t)n_pad * n_groups), "alloc candidate runs");
@@ -345,7 +346,7 @@ int Engine::nns_batch(const float *queries, uint32_t n_q, uint32_t d, uint32_t l
                 CU(launch_vec_prep_queries(vt.stream, d_vq.p, nq, n_pad, d, d_vq16.p, d_qinv), "vec_prep_queries");
                 vstats.kernel_launches++;
                 size_t m0 = vt.mark();
-                CU(launch_vec_gemm_topk(vt.stream, (uint32_t)sm_count, dix.emb, dix.emb_inv_norm, dix.emb_docids, N, d, d_vq16.p, d_qinv, n_qtiles, n_groups,
+                CU(launch_vec_gemm_topk(vt.stream, vec_sms, dix.emb, dix.emb_inv_norm, dix.emb_docids, N, d, d_vq16.p, d_qinv, n_qtiles, n_groups,
                                         d_c, n_cand_words, limit, d_vruns.p + (size_t)n_qtiles * n_groups * 128 * VEC_GEMM_CAND_CAP, d_vruns.p, d_vpartial.p, d_vsel_ids.p, d_vsel_dist.p, d_vsel_n.p, nq),
                    "vec_gemm_topk");
                 if (sharded && sc.world > 1) {
@@ -422,7 +423,16 @@ int Engine::nns_batch(const float *queries, uint32_t n_q, uint32_t d, uint32_t l
             t += qt;
         }
         size_t k0 = vt.mark();
-        CU(launch_topk(vt.stream, nq, d_vdist.p, dix.emb_docids, N, limit, tie_cap, d_vsel_dist.p, d_vsel_ids.p, d_vsel_n.p), "topk");
+        // long rows are selected in pieces side by side (one CTA per >= 16 k distances, about two waves of CTAs per query batch)
+        const uint32_t n_slices = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>(128, (uint64_t)sm_count * 4 / std::max(1u, nq)), N / 16384));
+        if (n_slices > 1) {
+            CU(d_vpart_dist.reserve((size_t)nq * n_slices * (limit + tie_cap)), "alloc partial selection");
+            CU(d_vpart_ids.reserve((size_t)nq * n_slices * (limit + tie_cap)), "alloc partial selection");
+            CU(d_vpart_n.reserve((size_t)nq * n_slices * 2), "alloc partial selection");
+        }
+        CU(launch_topk(vt.stream, nq, d_vdist.p, dix.emb_docids, N, limit, tie_cap, n_slices, d_vpart_dist.p, d_vpart_ids.p, d_vpart_n.p, d_vsel_dist.p,
+                       d_vsel_ids.p, d_vsel_n.p),
+           "topk");
         size_t k1 = vt.mark();
         vt.time_kernel(vstats, B200_K_TOPK, k0, k1, (uint64_t)nq * N * 4 * 4);
         CU(cudaMemcpyAsync(sel_d.data(), d_vsel_dist.p, (size_t)nq * (limit + tie_cap) * 4, cudaMemcpyDeviceToHost, vt.stream), "D2H");

@@ -1212,29 +1212,43 @@ __global__ void __launch_bounds__(256) vec_dist_kernel(const __half *__restrict_
     }
 }
 
-// exact top-k by two-level radix select on the (non-negative) float bit patterns; one CTA per query
-__global__ void __launch_bounds__(1024) topk_select_kernel(const float *__restrict__ dist, const uint32_t *__restrict__ docids,
-                                                           uint64_t n_rows, uint32_t k, uint32_t tie_cap, float *__restrict__ out_dist,
-                                                           uint32_t *__restrict__ out_ids, uint32_t *__restrict__ out_n /* per query */) {
-    __shared__ uint32_t hist[4096];
+// exact top-k by radix select (4 x 8 bits) on the (non-negative) float bit patterns.  One CTA per (query, slice): a query's
+// distance row is cut into n_slices pieces that are selected side by side (a single CTA walking 10^7 distances four times was 80 %
+// of a B = 1 query); the slices' outputs (k + tie_cap slots each, unused ones set to 3.0 = "no candidate") are then selected once
+// more by the same kernel with n_slices = 1 and per-query id arrays (ids_stride != 0).
+__global__ void __launch_bounds__(1024) topk_select_kernel(const float *__restrict__ dist, uint64_t dist_stride, const uint32_t *__restrict__ docids,
+                                                           uint64_t ids_stride, uint64_t n_rows_total, uint32_t n_slices, uint32_t k,
+                                                           uint32_t tie_cap, float *__restrict__ out_dist, uint32_t *__restrict__ out_ids,
+                                                           uint32_t *__restrict__ out_n /* 2 per (query, slice) */) {
+    __shared__ uint32_t hist[256];
     __shared__ uint32_t s_prefix, s_remaining, s_count_lt, s_count_eq;
-    const float *dq = dist + (uint64_t)blockIdx.x * n_rows;
+    const uint32_t qi = blockIdx.x / n_slices, sl = blockIdx.x % n_slices;
+    const uint64_t slice_len = (n_rows_total + n_slices - 1) / n_slices, r_begin = (uint64_t)sl * slice_len;
+    const uint64_t n_rows = r_begin < n_rows_total ? min(slice_len, n_rows_total - r_begin) : 0;
+    const float *dq = dist + (uint64_t)qi * dist_stride + r_begin;
+    docids += (uint64_t)qi * ids_stride + r_begin;
     float *od = out_dist + (uint64_t)blockIdx.x * (k + tie_cap);
     uint32_t *oi = out_ids + (uint64_t)blockIdx.x * (k + tie_cap);
     // number of selectable rows (distance <= 1.0)
     uint32_t prefix = 0, remaining = k;
-    // three passes of 12 + 12 + 8 bits, most significant first
-    const int shifts[3] = {20, 8, 0};
-    const int bits[3] = {12, 12, 8};
+    // four passes of 8 bits, most significant first (256 bins: the serial scan of the histogram by one thread stays short; with
+    // 4096 bins it was the longest part of a pass)
+    const int shifts[4] = {24, 16, 8, 0};
+    const int bits[4] = {8, 8, 8, 8};
     uint32_t mask_hi = 0;
-    for (int pass = 0; pass < 3; pass++) {
-        for (uint32_t i = threadIdx.x; i < 4096; i += blockDim.x) hist[i] = 0;
+    for (int pass = 0; pass < 4; pass++) {
+        for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
         __syncthreads();
         for (uint64_t r = threadIdx.x; r < n_rows; r += blockDim.x) {
             float v = dq[r];
             if (v > 1.5f) continue;
             uint32_t b = __float_as_uint(v);
-            if ((b & mask_hi) == prefix) atomicAdd(&hist[(b >> shifts[pass]) & ((1u << bits[pass]) - 1)], 1u);
+            if ((b & mask_hi) == prefix) {
+                // distances cluster (cosine of random directions: nearly all share their top byte): count per warp first
+                const uint32_t bin = (b >> shifts[pass]) & ((1u << bits[pass]) - 1);
+                const unsigned peers = __match_any_sync(__activemask(), bin);
+                if ((threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&hist[bin], (uint32_t)__popc(peers));
+            }
         }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -1291,9 +1305,12 @@ __global__ void __launch_bounds__(1024) topk_select_kernel(const float *__restri
         }
     }
     __syncthreads();
+    const uint32_t n_lt = min(s_count_lt, k), n_eq = min(s_count_eq, tie_cap);
+    for (uint32_t i = n_lt + threadIdx.x; i < k; i += blockDim.x) od[i] = 3.0f;           // unused slots: "no candidate"
+    for (uint32_t i = n_eq + threadIdx.x; i < tie_cap; i += blockDim.x) od[k + i] = 3.0f;
     if (threadIdx.x == 0) {
-        out_n[2 * blockIdx.x] = min(s_count_lt, k);
-        out_n[2 * blockIdx.x + 1] = min(s_count_eq, tie_cap);
+        out_n[2 * blockIdx.x] = n_lt;
+        out_n[2 * blockIdx.x + 1] = n_eq;
     }
 }
 
@@ -1506,9 +1523,16 @@ cudaError_t launch_vec_dist(cudaStream_t s, int n_ctas, int qt, const void *mat,
     return cudaGetLastError();
 }
 cudaError_t launch_topk(cudaStream_t s, uint32_t n_q, const float *dist, const uint32_t *docids, uint64_t n_rows, uint32_t k, uint32_t tie_cap,
-                        float *out_dist, uint32_t *out_ids, uint32_t *out_n) {
+                        uint32_t n_slices, float *part_dist, uint32_t *part_ids, uint32_t *part_n, float *out_dist, uint32_t *out_ids,
+                        uint32_t *out_n) {
     if (!n_q) return cudaSuccess;
-    topk_select_kernel<<<n_q, 1024, 0, s>>>(dist, docids, n_rows, k, tie_cap, out_dist, out_ids, out_n);
+    if (n_slices <= 1) {
+        topk_select_kernel<<<n_q, 1024, 0, s>>>(dist, n_rows, docids, 0, n_rows, 1, k, tie_cap, out_dist, out_ids, out_n);
+        return cudaGetLastError();
+    }
+    const uint64_t part_len = (uint64_t)n_slices * (k + tie_cap);
+    topk_select_kernel<<<n_q * n_slices, 1024, 0, s>>>(dist, n_rows, docids, 0, n_rows, n_slices, k, tie_cap, part_dist, part_ids, part_n);
+    topk_select_kernel<<<n_q, 1024, 0, s>>>(part_dist, part_len, part_ids, part_len, part_len, 1, k, tie_cap, out_dist, out_ids, out_n);
     return cudaGetLastError();
 }
 

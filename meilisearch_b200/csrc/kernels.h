@@ -30,8 +30,11 @@ cudaError_t launch_emit(cudaStream_t s, const EmitDesc *emits, uint32_t n_emits)
 cudaError_t launch_vec_dist(cudaStream_t s, int n_ctas, int qt, const void *mat_fp16, const float *inv_norm, const uint32_t *docids,
                             uint64_t n_rows, uint32_t d, const float *queries, const float *q_inv_norm, const unsigned long long *cand,
                             uint64_t n_cand_words, float *dist);
+// n_slices > 1: every query's distance row is selected in n_slices pieces side by side (part_*: n_q * n_slices * (k + tie_cap) slots
+// and 2 counters per piece), then the pieces' candidates once more
 cudaError_t launch_topk(cudaStream_t s, uint32_t n_q, const float *dist, const uint32_t *docids, uint64_t n_rows, uint32_t k, uint32_t tie_cap,
-                        float *out_dist, uint32_t *out_ids, uint32_t *out_n);
+                        uint32_t n_slices, float *part_dist, uint32_t *part_ids, uint32_t *part_n, float *out_dist, uint32_t *out_ids,
+                        uint32_t *out_n);
 
 // staging of the vector store: f32 rows -> fp16 rows + inverse norms; inverse norms of fp16 rows
 cudaError_t launch_emb_from_f32(cudaStream_t s, const float *in, void *out_fp16, float *inv_norm, uint64_t n, uint32_t d);

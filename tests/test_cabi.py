@@ -47,3 +47,12 @@ def test_tokenizer():
     assert tokenize("Hello, wor-ld. x") == [(WORD, "hello"), (SEP_HARD, ", "), (WORD, "wor"), (SEP_SOFT, "-"), (WORD, "ld"), (SEP_HARD, ". "), (WORD, "x")]
     tb = TokenBatch(["a b", ""])
     assert list(tb.token_begin) == [0, 3, 3]
+
+
+def test_integration_doc_declares_every_entry_point():
+    """INTEGRATION.md's `extern "C"` block is the binding a maintainer would add: it must name every function of the header"""
+    hdr = open(os.path.join(ROOT, "include", "b200milli.h")).read()
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    declared = set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", hdr))
+    bound = set(re.findall(r"pub fn (b200_[a-z0-9_]+)\(", doc))
+    assert declared - bound == set(), declared - bound
