@@ -397,6 +397,8 @@ def main():
 
     # ranks share the host: keep the per-rank worker pools inside the machine's cores
     os.environ.setdefault("B200_HOST_THREADS", str(max(8, min(32, (os.cpu_count() or 64) // max(1, world)))))
+    if world >= 4:
+        os.environ.setdefault("B200_POOL_SPIN_US", "30")  # idle workers of many ranks must not spin on each other's cores
     img, batches, emb, vecs = build_workload(args, rank, world)
     t = time.time()
     ix = mb.Index(img, device=local_rank)

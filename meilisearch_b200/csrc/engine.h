@@ -69,6 +69,8 @@ struct WorkerPool {
     std::atomic<size_t> next{0}, generation{0}, ready{0}, remaining{0}, entered{0}, left{0};
     size_t n = 0;
     std::atomic<bool> stop{false};
+    // how long an idle worker spins before it blocks (B200_POOL_SPIN_US; several ranks sharing one host want it short)
+    long spin_us = getenv("B200_POOL_SPIN_US") ? std::max(0, atoi(getenv("B200_POOL_SPIN_US"))) : 300;
     explicit WorkerPool(unsigned nt) {
         for (unsigned t = 0; t < nt; t++)
             threads.emplace_back([this]() {
@@ -83,7 +85,7 @@ struct WorkerPool {
                             got = true;
                             break;
                         }
-                        if ((spin & 63) == 63 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(300)) break;
+                        if ((spin & 63) == 63 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(spin_us)) break;
 #if defined(__x86_64__)
                         __builtin_ia32_pause();
 #endif

@@ -405,6 +405,31 @@ struct EmitReq {
     EmitDesc d;
 };
 
+// Tree mode (no deadline): every needed bucket of a level is expanded as soon as the level's counts are known — the result window of
+// each bucket follows from the counts of the buckets before it, so sibling subtrees are independent searches.  A Node is one rule
+// level of one query: its Level, where it stands in the result order and the scores its documents carry on entry.
+struct Node {
+    Level L;
+    Node *parent = nullptr;
+    uint32_t live_children = 0;   // child nodes whose subtree is not finished (they read this level's buckets)
+    bool self_done = false;       // this level's own bucket loop is done
+    uint64_t off0 = 0;            // documents of the query that come before this level's universe in result order
+    std::vector<EScore> scores;   // ranking-rule scores on entry (the path of buckets that led here)
+};
+
+// One requested activation: the level it evaluates, the device work description and where its parent universe is.
+struct Pending {
+    Level *L = nullptr;           // in QState::levels (sequential mode: stable until the activation completes) or in a Node
+    Node *node = nullptr;         // tree mode
+    StepOut o;
+    const uint32_t *p_uw = nullptr;
+    const unsigned long long *p_ub = nullptr, *p_out = nullptr;
+    uint32_t p_rows = 0, p_ld = 0, p_col = 0, p_cap = 0;
+    uint32_t need = 1;            // documents bucket_sort can still use from this activation (ActDesc::need)
+    uint32_t tab_shift = 0;       // path de-duplication table = 4096 << tab_shift slots
+    size_t demand = 0;            // device bytes asked for (capacity diagnostics)
+};
+
 struct QState {
     QCtx ctx;
     int status = 0;
@@ -418,23 +443,18 @@ struct QState {
     uint64_t cur_offset = 0;
     uint64_t n_candidates = 0;
     std::vector<std::vector<EScore>> scores;  // per hit
-    // pending device work for the next step
-    bool want_activation = false;
-    StepOut pend;
+    // device work requested for the next steps (sequential mode: at most one)
+    std::vector<std::unique_ptr<Pending>> pendings;
     std::vector<EmitReq> emits;
-    // parent of the pending activation
-    const uint32_t *p_uw = nullptr;
-    const unsigned long long *p_ub = nullptr, *p_out = nullptr;
-    uint32_t p_rows = 0, p_ld = 0, p_col = 0, p_cap = 0;
-    uint32_t act_counter = 0;  // tag of the query's current activation in its row lookup table
+    // tree mode
+    bool tree = false;
+    std::vector<std::unique_ptr<Node>> nodes;
+    uint32_t outstanding = 0;  // activations requested and not yet expanded
     const unsigned long long *d_univ = nullptr;  // filtered_universe of the query on the device (nullptr = documents_ids)
     uint64_t univ_count = 0;
     bool degraded = false, used_negative = false, below_seen = false;
     long polls = 0;                   // Deadline::exceeded() calls so far (stop_after hook)
     const unsigned long long *cand_src = nullptr;  // device bitmap to copy into b200_results::candidates at the lane's next step
-    uint32_t need = 1;                // documents the pending activation can still contribute (ActDesc::need)
-    uint32_t tab_shift = 0;           // the pending activation's path de-duplication table is 4096 << tab_shift slots
-    size_t demand = 0;                // device bytes the pending activation asked for (capacity diagnostics)
     std::vector<uint64_t> term_freq;  // Frequency: documents per term id, filled one device step per term before anything else
     uint32_t n_term_ids = 0;
     // arena blocks of levels bucket_sort has left; the lane's driver returns them to its allocator at the start of its next step
@@ -1861,25 +1881,55 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
 #define PROF(i) ProfScope prof_scope_##i(prof ? &prof_ns[i] : nullptr)
     // ---- phase 3: initial requests (universe resolution) or placeholder emission
     std::vector<int> rules = rule_list(hix.settings, tms);
-    auto request_activation = [&](QState &q, Level &&L, const uint32_t *p_uw, const unsigned long long *p_ub, const unsigned long long *p_out,
-                                  uint32_t p_rows, uint32_t p_ld, uint32_t p_col, uint32_t cap) {
+    // tree-parallel bucket sort unless the order of bucket requests is observable: a deadline polls once per request, and a bucket
+    // dropped by the ranking-score threshold moves every later hit forward
+    const bool use_tree = stop_after < 0 && !has_budget && !has_thr && !getenv("B200_NO_TREE");
+    auto make_pending = [&](QState &q, Level &L, const uint32_t *p_uw, const unsigned long long *p_ub, const unsigned long long *p_out, uint32_t p_rows,
+                            uint32_t p_ld, uint32_t p_col, uint32_t cap, uint64_t off0) -> Pending * {
         PROF(2);
-        q.pend = StepOut{};
-        if (L.kind == RK_EXACT_ATTRIBUTE) prepare_exact_attribute(q.ctx, L, q.pend);
-        emit_activation_work(q.ctx, L, q.pend);
+        std::unique_ptr<Pending> pd(new Pending());
+        if (L.kind == RK_EXACT_ATTRIBUTE) prepare_exact_attribute(q.ctx, L, pd->o);
+        emit_activation_work(q.ctx, L, pd->o);
+        // what bucket_sort can still use from this activation: the hits it has to return plus the offset it has to skip, counted from
+        // the first document of this level; the walk (pass 2) only looks at the cheapest buckets that together hold that many documents
+        const uint64_t window_end = (uint64_t)from + length;
+        pd->need = (uint32_t)std::min<uint64_t>(0xffffffffull, window_end > off0 ? window_end - off0 : 1);
+        if (pd->need == 0) pd->need = 1;
+        pd->p_uw = p_uw;
+        pd->p_ub = p_ub;
+        pd->p_out = p_out;
+        pd->p_rows = p_rows;
+        pd->p_ld = p_ld;
+        pd->p_col = p_col;
+        pd->p_cap = cap;
+        q.pendings.push_back(std::move(pd));
+        return q.pendings.back().get();
+    };
+    // sequential mode: the level goes on the query's stack
+    auto request_activation = [&](QState &q, Level &&L, const uint32_t *p_uw, const unsigned long long *p_ub, const unsigned long long *p_out,
+                                  uint32_t p_rows, uint32_t p_ld, uint32_t p_col, uint32_t cap) -> Pending * {
         q.levels.push_back(std::move(L));
-        q.want_activation = true;
-        // what bucket_sort can still use from this activation: the hits it has to return plus the offset it has to skip; the walk
-        // (pass 2) only looks at the cheapest buckets that together hold that many documents
-        q.need = (uint32_t)std::min<uint64_t>(0xffffffffull, (from > q.cur_offset ? from - q.cur_offset : 0) + (uint64_t)(length - std::min(length, q.n_results)));
-        if (q.need == 0) q.need = 1;
-        q.p_uw = p_uw;
-        q.p_ub = p_ub;
-        q.p_out = p_out;
-        q.p_rows = p_rows;
-        q.p_ld = p_ld;
-        q.p_col = p_col;
-        q.p_cap = cap;
+        // documents already returned or skipped: everything before this level in result order
+        Pending *pd = make_pending(q, q.levels.back(), p_uw, p_ub, p_out, p_rows, p_ld, p_col, cap, q.cur_offset);
+        pd->L = &q.levels.back();
+        return pd;
+    };
+    // tree mode: the level becomes a node under `parent`
+    auto request_node = [&](QState &q, Node *parent, Level &&L, const uint32_t *p_uw, const unsigned long long *p_ub, const unsigned long long *p_out,
+                            uint32_t p_rows, uint32_t p_ld, uint32_t p_col, uint32_t cap, uint64_t off0, std::vector<EScore> scores) -> Pending * {
+        std::unique_ptr<Node> nd(new Node());
+        nd->L = std::move(L);
+        nd->parent = parent;
+        nd->off0 = off0;
+        nd->scores = std::move(scores);
+        if (parent) parent->live_children++;
+        q.outstanding++;
+        Node *np = nd.get();
+        q.nodes.push_back(std::move(nd));
+        Pending *pd = make_pending(q, np->L, p_uw, p_ub, p_out, p_rows, p_ld, p_col, cap, off0);
+        pd->L = &np->L;
+        pd->node = np;
+        return pd;
     };
     // resolve_maximally_reduced_query_graph (search/new/mod.rs:273-301)
     auto start_resolve = [&](QState &q) {
@@ -1893,7 +1943,10 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             remove_nodes_keep_edges(L.graph, rm);
         }
         prepare_resolve(q.ctx, L);
-        request_activation(q, std::move(L), nullptr, q.d_univ ? q.d_univ : dix.base_ub, nullptr, hix.n_words64, hix.n_words64, 0, hix.n_words64);
+        if (q.tree)
+            request_node(q, nullptr, std::move(L), nullptr, q.d_univ ? q.d_univ : dix.base_ub, nullptr, hix.n_words64, hix.n_words64, 0, hix.n_words64, 0, {});
+        else
+            request_activation(q, std::move(L), nullptr, q.d_univ ? q.d_univ : dix.base_ub, nullptr, hix.n_words64, hix.n_words64, 0, hix.n_words64);
     };
     // Frequency (query_graph.rs:303-344): documents of term id t = union of the docids of every node covering t, counted over the
     // whole index — one resolve-shaped activation START -> {covering nodes} -> END per term id
@@ -1924,6 +1977,8 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
     };
     auto start_query = [&](QState &q) {
         q.rules = rules;
+        // tree mode unless a deadline is in force (its polls are defined on the sequential order of bucket requests) or S1 drives one rule
+        q.tree = use_tree && !s1;
         if (s1 && s1->mode == S1Job::RULE) {
             // S1: one ranking rule over the caller's universe and query graph (RankingRule::start_iteration)
             Level C;
@@ -1931,8 +1986,8 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             C.kind = s1->rule_kind;
             C.graph = q.graph;
             if (C.kind != RK_EXACT_ATTRIBUTE) prepare_graph_rule(q.ctx, C.kind, C.kind == RK_WORDS, tms, C);
-            request_activation(q, std::move(C), nullptr, q.d_univ ? q.d_univ : dix.base_ub, nullptr, hix.n_words64, hix.n_words64, 0, hix.n_words64);
-            q.need = 0xffffffffu;  // every bucket may be asked for: walk them all
+            Pending *pd = request_activation(q, std::move(C), nullptr, q.d_univ ? q.d_univ : dix.base_ub, nullptr, hix.n_words64, hix.n_words64, 0, hix.n_words64);
+            pd->need = 0xffffffffu;  // every bucket may be asked for: walk them all
             return;
         }
         if (q.placeholder) {
@@ -2219,6 +2274,144 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         q.done = true;
     };
 
+    // tree mode: the documents of bucket [col_lo, col_hi) stand at [off, off + cnt) in the query's result order; write the part inside
+    // the window [from, from + length) to its final place
+    auto emit_window = [&](QState &q, Level &L, uint32_t col_lo, uint32_t col_hi, uint64_t cnt, uint64_t off, const std::vector<EScore> &sc) {
+        const uint64_t win_end = (uint64_t)from + length;
+        const uint64_t skip = off < from ? from - off : 0;
+        if (skip >= cnt) return;
+        const uint64_t start = std::max<uint64_t>(off, from);
+        if (start >= win_end) return;
+        const uint64_t take = std::min<uint64_t>(cnt - skip, win_end - start);
+        EmitReq e{};
+        e.d.uw = L.uw;
+        e.d.ub = L.ub;
+        e.d.out = L.out;
+        e.d.rows = L.rows;
+        e.d.ld = L.ld;
+        e.d.col_lo = col_lo;
+        e.d.col_hi = col_hi;
+        e.d.skip = (uint32_t)skip;
+        e.d.take = (uint32_t)take;
+        e.d.dst = reinterpret_cast<uint32_t *>((uintptr_t)(start - from));
+        q.emits.push_back(e);
+        const size_t at = (size_t)(start - from);
+        if (q.scores.size() < at + take) q.scores.resize(at + take);
+        for (uint64_t k = 0; k < take; k++) q.scores[at + k] = sc;
+        q.n_results += (uint32_t)take;
+    };
+    auto release_node = [&](QState &q, Node *n) {
+        q.release_level(n->L);
+        Level &L = n->L;  // the host side of the level is not needed any more either
+        L.graph = EGraph();
+        std::vector<ECond>().swap(L.conds);
+        std::vector<SEdge>().swap(L.sedges);
+        std::vector<SurvPath>().swap(L.surv);
+    };
+    // tree mode: the activation of node N is complete — place or descend into every bucket of it that reaches the result window
+    // (the same decisions as advance(), bucket_sort.rs:193-330, taken for all buckets at once)
+    auto expand = [&](QState &q, Node *N) {
+        Level &L = N->L;
+        if (N->parent && --N->parent->live_children == 0 && N->parent->self_done) release_node(q, N->parent);  // nothing reads the parent's buckets any more
+        const size_t n_rules = q.rules.size();
+        const uint64_t win_end = (uint64_t)from + length;
+        uint64_t off = N->off0;
+        auto child_graph = [&](Level &C, size_t ci) {
+            if (L.kind == RK_EXACT_ATTRIBUTE) {
+                C.graph = L.graph;
+                return;
+            }
+            PROF(0);
+            std::vector<const SurvPath *> sp;
+            for (auto &p : L.surv)
+                if (p.cost_idx == ci) sp.push_back(&p);
+            std::sort(sp.begin(), sp.end(), [](const SurvPath *x, const SurvPath *y) { return x->edges < y->edges; });
+            std::vector<std::vector<const ECond *>> good;
+            for (auto *p : sp) {
+                std::vector<const ECond *> pc;
+                for (auto e : p->edges)
+                    if (L.sedges[e].cond >= 0) pc.push_back(&L.conds[L.sedges[e].cond]);
+                good.push_back(std::move(pc));
+            }
+            C.graph = build_from_paths(good);
+        };
+        if (L.kind == RK_RESOLVE) {
+            const uint64_t cnt = L.counts[0];
+            q.n_candidates = cnt;
+            q.cand_src = L.out;
+            if (length != 0 && cnt >= from) {  // bucket_sort.rs:52-64
+                if (n_rules == 0)
+                    emit_window(q, L, 0, 1, cnt, 0, {});
+                else {
+                    Level C;
+                    C.rule_idx = 0;
+                    C.kind = q.rules[0];
+                    C.graph = q.graph;
+                    if (C.kind != RK_EXACT_ATTRIBUTE) {
+                        PROF(1);
+                        prepare_graph_rule(q.ctx, C.kind, C.kind == RK_WORDS, tms, C);
+                    }
+                    if (n_rules == 1) C.want_paths = false;
+                    request_node(q, N, std::move(C), L.uw, L.ub, L.out, L.rows, L.ld, 0, (uint32_t)std::min<uint64_t>(cnt, L.rows), 0, {});
+                }
+            }
+        } else {
+            const size_t rule_cur = (size_t)L.rule_idx;
+            uint64_t remaining = L.universe_count;
+            std::vector<EScore> sc = N->scores;
+            for (size_t ci = 0; off < win_end; ci++) {
+                if (remaining == 0 || (skip_scoring && remaining == 1)) {
+                    if (remaining == 1) emit_window(q, L, (uint32_t)ci, (uint32_t)L.cost_vals.size() + 1, 1, off, N->scores);
+                    break;
+                }
+                if (ci >= L.cost_vals.size()) break;
+                const uint64_t cnt = L.counts[ci];
+                if (cnt == 0) continue;
+                remaining -= cnt;
+                sc.push_back(EScore{score_kind_of(L.kind), (uint32_t)(L.next_max_cost - L.cost_vals[ci]), (uint32_t)L.next_max_cost, -1.f});
+                if (rule_cur == n_rules - 1 || (skip_scoring && cnt <= 1) || off + cnt <= from)
+                    emit_window(q, L, (uint32_t)ci, (uint32_t)ci + 1, cnt, off, sc);
+                else {
+                    if (L.kind != RK_EXACT_ATTRIBUTE && ci > L.walked_m) {  // cannot happen: buckets 0..walked_m hold every document this level still needed
+                        q.status = B200_ERR_STATE;
+                        q.error = "internal: descent into a bucket whose surviving paths were not computed";
+                        return false;
+                    }
+                    Level C;
+                    C.rule_idx = (int)rule_cur + 1;
+                    C.kind = q.rules[rule_cur + 1];
+                    child_graph(C, ci);
+                    if (C.kind != RK_EXACT_ATTRIBUTE) {
+                        PROF(1);
+                        prepare_graph_rule(q.ctx, C.kind, false, tms, C);
+                    }
+                    if ((size_t)C.rule_idx + 1 == n_rules) C.want_paths = false;  // nothing descends from the last rule
+                    request_node(q, N, std::move(C), L.uw, L.ub, L.out, L.rows, L.ld, (uint32_t)ci, (uint32_t)std::min<uint64_t>(cnt, L.rows), off, sc);
+                }
+                sc.pop_back();
+                off += cnt;
+            }
+        }
+        N->self_done = true;
+        if (N->live_children == 0) release_node(q, N);
+        if (--q.outstanding == 0) {
+            q.scores.resize(q.n_results);
+            q.nodes.clear();
+            q.done = true;
+        }
+        return true;
+    };
+    // a query that cannot go on: give everything it holds back
+    auto abandon = [&](QState &q) {
+        q.pendings.clear();
+        q.emits.clear();
+        q.drop_levels();
+        for (auto &n : q.nodes) q.release_level(n->L);
+        q.nodes.clear();
+        q.outstanding = 0;
+        q.done = true;
+    };
+
     // ---- phase 4: step loop.  The batch is split over lanes; every lane has its own stream, device buffers, arena slice, host
     // driver thread and worker sub-pool, so the host phases of one lane overlap both the kernels and the host phases of the others.
     // Drivers are host threads; each alternates between its lanes (software pipeline: while one lane's kernels run, the driver packs
@@ -2272,12 +2465,17 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
     auto lane_lo = [&](unsigned l) { return (uint32_t)((uint64_t)NQ * l / n_lanes); };
     for (unsigned l = 0; l < n_lanes; l++)
         for (uint32_t i = lane_lo(l); i < lane_lo(l + 1); i++) lanes[l].members.push_back(i);
-    // per-query row lookup tables (scatter_kernel): zeroed once per batch, entries are tagged with the activation that wrote them
+    // row lookup tables (scatter_kernel): NQ slots of n_words64 entries, zeroed once per batch.  A lane owns the slots of its query
+    // range and lends each to at most one activation per step; entries carry the tag of the use that wrote them (12 bits, so a slot
+    // serves 4094 steps), which makes the leftovers of earlier uses read as misses.  Activations without a slot search their rows.
     const bool use_rowtab = hix.n_words64 <= (1u << 20) && !getenv("B200_NO_ROWTAB");
     if (use_rowtab) {
         CU(d_rowtab.reserve((size_t)NQ * hix.n_words64), "row lookup tables");
         CU(cudaMemsetAsync(d_rowtab.p, 0, (size_t)NQ * hix.n_words64 * 4, stream), "zero row lookup tables");
     }
+    std::vector<uint32_t> slot_tag(NQ, 0);
+    const uint32_t rowtab_min_rows = getenv("B200_ROWTAB_MIN") ? (uint32_t)atoi(getenv("B200_ROWTAB_MIN")) : 64;
+    std::vector<std::vector<std::unique_ptr<Pending>>> lane_acts(n_lanes);
     const size_t PATH_CAP = (size_t)1 << 20;
     struct WorkHist {
         std::mutex mu;
@@ -2293,12 +2491,20 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
     auto launch = [&](Lane &ln) -> int {
         auto t_pack = clk::now();
         ln.act_q.clear();
-        std::vector<uint32_t> emit_q, cand_q;
+        const unsigned li = (unsigned)(&ln - lanes);
+        std::vector<std::unique_ptr<Pending>> &acts = lane_acts[li];
+        acts.clear();
+        struct Cand {
+            uint32_t qi;
+            Pending *pd;
+        };
+        std::vector<uint32_t> emit_q;
+        std::vector<Cand> cand_q;
         for (auto i : ln.members) {
             QState &q = *qs[i];
             for (auto &f : q.freed) ln.alloc.give(f.first, f.second);  // levels left since the lane's previous step
             q.freed.clear();
-            if (q.want_activation) cand_q.push_back(i);
+            for (auto &pd : q.pendings) cand_q.push_back(Cand{i, pd.get()});
             if (!q.emits.empty()) emit_q.push_back(i);
         }
         if (r->candidates)
@@ -2312,12 +2518,12 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             }
         // longest first: the parallel-for over these queries ends when its slowest query does, and host time per query grows
         // with the size of its query graph
-        std::stable_sort(cand_q.begin(), cand_q.end(), [&](uint32_t x, uint32_t y) { return qs[x]->graph.nodes.size() > qs[y]->graph.nodes.size(); });
+        std::stable_sort(cand_q.begin(), cand_q.end(), [&](const Cand &x, const Cand &y) { return x.pd->L->graph.nodes.size() > y.pd->L->graph.nodes.size(); });
         if (cand_q.empty() && emit_q.empty()) return 0;
         // pass 1 (serial, light): sizes, offsets, device memory
         struct Plan {
             uint32_t jobs, sets, words, colprog, states, edges, costs, tiles, probes, res_off, ctiles, n_seg, prog;
-            uint32_t ld, cls, tab_size, rpt;
+            uint32_t ld, cls, tab_size, rpt, rt_slot, rt_tag;
             uint8_t *pb;
             size_t coff, toff, soff_from_end;
             bool identity;
@@ -2336,10 +2542,13 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         // than ~60 % full, so that the queries already descending can finish.  When nothing at all fits and the lane is idle, the
         // waiting query with the largest demand fails alone with B200_ERR_CAPACITY and the others go on.
         bool admit_all = false;
+        std::vector<size_t> sched;  // indices in cand_q of the activations that join this step
+        uint32_t next_slot = lane_lo(li);
+        const uint32_t slot_end = lane_lo(li + 1);
     plan_again:
         for (size_t ci = 0; ci < cand_q.size(); ci++) {
-            QState &q = *qs[cand_q[ci]];
-            StepOut &o = q.pend;
+            Pending &pd = *cand_q[ci].pd;
+            StepOut &o = pd.o;
             Plan pl{};
             pl.jobs = n_jobs;
             pl.sets = n_sets;
@@ -2351,11 +2560,11 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             pl.prog = n_prog;
             pl.probes = n_probes;
             pl.res_off = res_words;
-            uint32_t ld = std::max(1u, q.p_cap);
+            uint32_t ld = std::max(1u, pd.p_cap);
             pl.ld = ld;
-            pl.identity = !q.p_uw && !q.p_out;  // first activation of a query: the universe is the dense documents bitmap itself
+            pl.identity = !pd.p_uw && !pd.p_out;  // first activation of a query: the universe is the dense documents bitmap itself
             uint32_t n_cols = std::max(1u, o.n_cols);
-            uint32_t tab_size = o.want_paths ? 4096u << q.tab_shift : 1;
+            uint32_t tab_size = o.want_paths ? 4096u << pd.tab_shift : 1;
             pl.tab_size = tab_size;
             pl.cls = eval_class(n_cols + o.n_pairs + EVAL_EXTRA_SLOTS);
             pl.rpt = 1;  // rows per thread: > 1 only pays for grids far larger than the GPU (it lengthens the tail of small grids); measured
@@ -2368,16 +2577,22 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             pl.coff = (z_used + 255) & ~(size_t)255;
             pl.toff = (pl.coff + cbytes + 255) & ~(size_t)255;
             size_t s_need = (sbytes + 255) & ~(size_t)255;
-            q.demand = persist + cbytes + tbytes + s_need;
-            if (pl.toff + tbytes + s_need + s_used > ln.scratch_bytes) continue;                                   // next step
-            if (pl.identity && !admit_all && ln.alloc.used * 5 > ln.alloc.total * 3 && q.levels.size() <= 1) continue;  // admission
+            pd.demand = persist + cbytes + tbytes + s_need;
+            if (pl.toff + tbytes + s_need + s_used > ln.scratch_bytes) continue;                  // next step
+            if (pl.identity && !admit_all && ln.alloc.used * 5 > ln.alloc.total * 3) continue;  // admission
             size_t aoff = ln.alloc.take(persist);
             if (aoff == SIZE_MAX) continue;
             pl.pb = ln.arena + aoff;
-            {
-                Level &L = q.levels.back();
-                L.a_off = aoff;
-                L.a_len = persist;
+            pd.L->a_off = aoff;
+            pd.L->a_len = persist;
+            pl.rt_slot = UINT32_MAX;
+            if (use_rowtab && !pl.identity && ld >= rowtab_min_rows) {
+                while (next_slot < slot_end && slot_tag[next_slot] >= 4094) next_slot++;
+                if (next_slot < slot_end) {
+                    pl.rt_slot = next_slot;
+                    pl.rt_tag = ++slot_tag[next_slot];
+                    next_slot++;
+                }
             }
             n_jobs += (uint32_t)o.jobs.size();
             n_sets += (uint32_t)o.pairsets.size();
@@ -2393,23 +2608,24 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             n_tiles += my_tiles;
             for (auto &ps : o.pairsets) n_probes += ps.n_left * ps.n_right;
             res_words += 4 + o.n_costs;  // rows | n_costs + 1 bucket counts | path-table saturation flag | last walked bucket
-            pl.n_seg = pl.identity ? 1u : std::max(1u, (q.p_rows + COMPACT_SEG - 1) / COMPACT_SEG);
+            pl.n_seg = pl.identity ? 1u : std::max(1u, (pd.p_rows + COMPACT_SEG - 1) / COMPACT_SEG);
             pl.ctiles = n_ctiles;
             n_ctiles += pl.n_seg;
             multi_segment = multi_segment || pl.n_seg > 1;
             z_used = pl.toff + tbytes;
             s_used += s_need;
             pl.soff_from_end = s_used;
-            ln.act_q.push_back(cand_q[ci]);
+            ln.act_q.push_back(cand_q[ci].qi);
+            sched.push_back(ci);
             ln.lst.posting_bytes += o.posting_bytes;
             // algorithmic bytes of the evaluation: condition columns in, universe word in, bucket columns out (the DP table is on-chip)
             uint64_t mb = (uint64_t)ld * 8 * (n_cols + o.n_costs + 2);
             ln.lst.matrix_bytes += mb;
             eval_bytes += mb;
-            if (!pl.identity) compact_bytes += (uint64_t)q.p_rows * 8 + (uint64_t)ld * 12;
+            if (!pl.identity) compact_bytes += (uint64_t)pd.p_rows * 8 + (uint64_t)ld * 12;
             fill_bytes += o.posting_bytes;
             if (work_hist) {  // B200_WORK_HIST=1: where the step's work comes from (developer statistics, see tools/)
-                const int kind = q.levels.back().kind;
+                const int kind = pd.L->kind;
                 const int ub = ld >= 65536 ? 3 : (ld >= 4096 ? 2 : (ld >= 128 ? 1 : 0));
                 std::lock_guard<std::mutex> g(work_hist->mu);
                 for (auto &jb : o.jobs) {
@@ -2436,24 +2652,36 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
                 admit_all = true;
                 goto plan_again;
             }
-            uint32_t worst = cand_q[0];
-            for (auto i : cand_q)
-                if (qs[i]->demand > qs[worst]->demand) worst = i;
-            QState &q = *qs[worst];
+            size_t worst = 0;
+            for (size_t k = 1; k < cand_q.size(); k++)
+                if (cand_q[k].pd->demand > cand_q[worst].pd->demand) worst = k;
+            const uint32_t wq = cand_q[worst].qi;
+            QState &q = *qs[wq];
             q.status = B200_ERR_CAPACITY;
             q.error = "a single ranking-rule step of this query needs more device memory than the lane owns (B200_ARENA_MB / B200_SCRATCH_MB)";
-            q.want_activation = false;
-            q.drop_levels();
-            q.done = true;
+            cand_q.erase(std::remove_if(cand_q.begin(), cand_q.end(), [&](const Cand &c) { return c.qi == wq; }), cand_q.end());
+            abandon(q);
             for (auto &f : q.freed) ln.alloc.give(f.first, f.second);
             q.freed.clear();
-            cand_q.erase(std::find(cand_q.begin(), cand_q.end(), worst));
             ln.lst.deferred++;
             if (cand_q.empty()) return 0;
             admit_all = false;
             goto plan_again;
         }
         ln.lst.deferred += cand_q.size() - ln.act_q.size();
+        // the scheduled activations leave their queries' pending lists for the lane's step
+        for (auto ci : sched) {
+            QState &q = *qs[cand_q[ci].qi];
+            for (auto &up : q.pendings)
+                if (up.get() == cand_q[ci].pd) {
+                    acts.push_back(std::move(up));
+                    break;
+                }
+        }
+        for (auto ci : sched) {
+            auto &pv = qs[cand_q[ci].qi]->pendings;
+            pv.erase(std::remove(pv.begin(), pv.end(), nullptr), pv.end());
+        }
         uint32_t tile_base[EVAL_CLASSES + 2] = {};
         for (uint32_t c = 0; c <= EVAL_CLASSES; c++) tile_base[c + 1] = tile_base[c] + n_tiles_cls[c];
         for (auto &pl : plan) pl.tiles += tile_base[pl.cls];
@@ -2484,19 +2712,19 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         uint8_t *hb = ln.h_step;
         // pass 2 (parallel): write every activation's slice of the blob straight into pinned memory
         ln.pool->run(NA, [&](size_t a) {
-            QState &q = *qs[act_q[a]];
-            Level &L = q.levels.back();
-            StepOut &o = q.pend;
+            Pending &pd = *acts[a];
+            Level &L = *pd.L;
+            StepOut &o = pd.o;
             const Plan &pl = plan[a];
             ActDesc d;
             memset(&d, 0, sizeof d);
-            d.p_uw = q.p_uw;
-            d.p_ub = q.p_ub;
-            d.p_out = q.p_out;
-            d.p_rows = q.p_rows;
-            d.p_ld = q.p_ld;
-            d.p_col_lo = q.p_col;
-            d.p_col_hi = q.p_col + 1;
+            d.p_uw = pd.p_uw;
+            d.p_ub = pd.p_ub;
+            d.p_out = pd.p_out;
+            d.p_rows = pd.p_rows;
+            d.p_ld = pd.p_ld;
+            d.p_col_lo = pd.p_col;
+            d.p_col_hi = pd.p_col + 1;
             uint32_t ld = pl.ld;
             d.ld = ld;
             d.n_cols = std::max(1u, o.n_cols);
@@ -2510,7 +2738,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             d.C = reinterpret_cast<unsigned long long *>(ln.scratch + pl.coff);
             if (pl.identity) {
                 d.uw = nullptr;
-                d.ub = const_cast<unsigned long long *>(q.p_ub);
+                d.ub = const_cast<unsigned long long *>(pd.p_ub);
                 d.out = reinterpret_cast<unsigned long long *>(pl.pb);
             } else {
                 d.uw = reinterpret_cast<uint32_t *>(pl.pb);
@@ -2519,9 +2747,9 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             }
             d.row_tab = nullptr;
             d.row_tag = 0;
-            if (use_rowtab && !pl.identity && q.act_counter < 4094) {
-                d.row_tag = ++q.act_counter;
-                d.row_tab = d_rowtab.p + (size_t)act_q[a] * hix.n_words64;
+            if (pl.rt_slot != UINT32_MAX) {
+                d.row_tag = pl.rt_tag;
+                d.row_tab = d_rowtab.p + (size_t)pl.rt_slot * hix.n_words64;
             }
             L.uw = d.uw;
             L.ub = d.ub;
@@ -2535,7 +2763,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             d.prog_off = pl.prog;
             d.prog_len = (uint32_t)o.prog.size();
             d.n_pairs = o.n_pairs;
-            d.need = q.need;
+            d.need = pd.need;
             d.root_rmin = o.dp_states.empty() ? 0 : o.dp_states[0].rmin;
             d.root_rcount = o.dp_states.empty() ? 0 : o.dp_states[0].rcount;
             if (!o.prog.empty()) memcpy(hb + o_prog + (size_t)pl.prog * 4, o.prog.data(), o.prog.size() * 4);
@@ -2566,7 +2794,6 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             for (uint32_t r0 = 0, k = 0; r0 < ld; r0 += 128 * pl.rpt, k++) td[k] = TileDesc{(uint32_t)a, r0, pl.rpt, 0};
             CompactTile *ct = reinterpret_cast<CompactTile *>(hb + o_ctiles) + pl.ctiles;
             for (uint32_t sg = 0; sg < pl.n_seg; sg++) ct[sg] = CompactTile{(uint32_t)a, sg, pl.ctiles, pl.n_seg};
-            q.want_activation = false;
         });
         {
             EmitDesc *ed = reinterpret_cast<EmitDesc *>(hb + o_emits);
@@ -2690,6 +2917,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             ln.resolve_timers(ln.lst);
         }
         const std::vector<uint32_t> &act_q = ln.act_q;
+        std::vector<std::unique_ptr<Pending>> &acts = lane_acts[(unsigned)(&ln - lanes)];
         const uint32_t res_words = ln.res_words;
         if (!act_q.empty()) {
             if (ln.h_results[res_words] > ln.qcap) return lane_fail(ln, B200_ERR_CAPACITY, "scatter job queue overflow");
@@ -2701,9 +2929,9 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
                 CU(cudaStreamSynchronize(ln.stream), "sync paths");
                 ln.lst.d2h_bytes += (size_t)np * sizeof(PathOut);
             }
-            for (size_t a = 0; a < act_q.size(); a++) qs[act_q[a]]->levels.back().surv.clear();
+            for (auto &pd : acts) pd->L->surv.clear();
             for (auto &po : pouts) {
-                Level &L = qs[act_q[po.act]]->levels.back();
+                Level &L = *acts[po.act]->L;
                 SurvPath sp;
                 sp.cost_idx = po.cost_idx;
                 sp.edges.assign(po.edges, po.edges + std::min<uint32_t>(po.len, MAX_WALK));
@@ -2713,9 +2941,17 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         ln.lst.host_ms[4] += ms_since(t_wait);
         auto t_adv = clk::now();
         const bool dbg = getenv("B200_DEBUG") != nullptr;
-        ln.pool->run(act_q.size(), [&](size_t a) {
-            QState &q = *qs[act_q[a]];
-            Level &L = q.levels.back();
+        // the activations of one query are handled by one thread, in the order they were packed
+        std::vector<uint32_t> order(act_q.size());
+        for (size_t a = 0; a < order.size(); a++) order[a] = (uint32_t)a;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return act_q[x] < act_q[y]; });
+        std::vector<uint32_t> grp;  // start of every query's run in `order`
+        for (size_t k = 0; k < order.size(); k++)
+            if (k == 0 || act_q[order[k]] != act_q[order[k - 1]]) grp.push_back((uint32_t)k);
+        grp.push_back((uint32_t)order.size());
+        auto complete = [&](QState &q, uint32_t qi, std::unique_ptr<Pending> &up) {
+            Pending &pd = *up;
+            Level &L = *pd.L;
             const uint32_t *res = ln.h_results + L.res_off;
             L.rows = res[0];
             size_t nc = L.cost_vals.size();
@@ -2726,37 +2962,45 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             L.walked_m = res[1 + nc + 2];
             if (res[1 + nc + 1] != 0) {
                 // more distinct surviving paths than the de-duplication table holds: some were not reported.  Run the activation again
-                // with a table 16x larger (its work description q.pend is still in place); give up at 16 M slots.
+                // with a table 16x larger (its work description is still in place); give up at 16 M slots.
                 q.release_level(L);
-                if (q.tab_shift >= 12) {
+                if (pd.tab_shift >= 12) {
                     q.status = B200_ERR_CAPACITY;
                     q.error = "more distinct surviving paths in one ranking-rule step than the device path table holds";
-                    q.drop_levels();
-                    q.done = true;
+                    abandon(q);
                     return;
                 }
-                q.tab_shift += 4;
-                q.want_activation = true;
+                pd.tab_shift += 4;
+                q.pendings.push_back(std::move(up));
                 return;
             }
-            q.tab_shift = 0;
             if (dbg) {
-                std::string msg = "[b200 debug] q" + std::to_string(act_q[a]) + " level " + std::to_string(q.levels.size() - 1) + " kind " +
-                                  std::to_string(L.kind) + " rows " + std::to_string(L.rows) + "/" + std::to_string(L.ld) + " states " +
-                                  std::to_string(L.n_states) + " edges " + std::to_string(L.sedges.size()) + " conds " + std::to_string(L.conds.size()) +
-                                  " cols " + std::to_string(q.pend.n_cols) + " jobs " + std::to_string(q.pend.jobs.size()) + " costs:";
+                std::string msg = "[b200 debug] q" + std::to_string(qi) + " rule " + std::to_string(L.rule_idx) + " kind " + std::to_string(L.kind) +
+                                  " rows " + std::to_string(L.rows) + "/" + std::to_string(L.ld) + " states " + std::to_string(L.n_states) + " edges " +
+                                  std::to_string(L.sedges.size()) + " conds " + std::to_string(L.conds.size()) + " cols " + std::to_string(pd.o.n_cols) +
+                                  " jobs " + std::to_string(pd.o.jobs.size()) + " costs:";
                 for (size_t k = 0; k < L.cost_vals.size(); k++) msg += " " + std::to_string(L.cost_vals[k]) + "=" + std::to_string(L.counts[k]);
                 msg += " rest=" + std::to_string(L.counts.back()) + " surv " + std::to_string(L.surv.size());
                 fprintf(stderr, "%s\n", msg.c_str());
             }
             try {
                 PROF(3);
-                advance(q);
+                if (pd.node) {
+                    if (!expand(q, pd.node)) abandon(q);
+                } else
+                    advance(q);
             } catch (const TooComplex &t) {
                 q.status = B200_ERR_CAPACITY;
                 q.error = t.why;
-                q.done = true;
-                q.want_activation = false;
+                abandon(q);
+            }
+        };
+        ln.pool->run(grp.size() - 1, [&](size_t g) {
+            const uint32_t qi = act_q[order[grp[g]]];
+            QState &q = *qs[qi];
+            for (uint32_t k = grp[g]; k < grp[g + 1]; k++) {
+                if (q.done && q.status != 0) break;  // abandoned by an earlier activation of this step
+                complete(q, qi, acts[order[k]]);
             }
         });
         ln.lst.host_ms[5] += ms_since(t_adv);
