@@ -69,6 +69,7 @@ int b200_open(int device_ordinal, b200_index **out) {
     }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device_ordinal) == cudaSuccess) h->e.sm_count = prop.multiProcessorCount;
+    h->e.affinity.detect(device_ordinal);
     *out = h;
     return B200_OK;
 }

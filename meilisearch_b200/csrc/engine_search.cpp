@@ -411,7 +411,7 @@ struct EmitReq {
 struct Node {
     Level L;
     Node *parent = nullptr;
-    uint32_t live_children = 0;   // child nodes whose subtree is not finished (they read this level's buckets)
+    std::atomic<uint32_t> live_children{0};  // child nodes whose activation has not completed (it reads this level's buckets)
     bool self_done = false;       // this level's own bucket loop is done
     uint64_t off0 = 0;            // documents of the query that come before this level's universe in result order
     std::vector<EScore> scores;   // ranking-rule scores on entry (the path of buckets that led here)
@@ -428,6 +428,19 @@ struct Pending {
     uint32_t need = 1;            // documents bucket_sort can still use from this activation (ActDesc::need)
     uint32_t tab_shift = 0;       // path de-duplication table = 4096 << tab_shift slots
     size_t demand = 0;            // device bytes asked for (capacity diagnostics)
+};
+
+// What the completion of one activation adds to its query in tree mode.  Activations of the same query complete on different
+// threads; each fills its own ActOut and the query folds them in afterwards (one thread per query).
+struct ActOut {
+    std::vector<EmitReq> emits;
+    std::vector<std::unique_ptr<Node>> nodes;
+    std::vector<std::unique_ptr<Pending>> pendings;
+    std::vector<std::pair<size_t, size_t>> freed;
+    uint32_t n_results = 0;
+    int status = 0;
+    std::string error;
+    bool retry = false, expanded = false;
 };
 
 struct QState {
@@ -1725,6 +1738,7 @@ void parallel_for(size_t n, unsigned nt, F f) {
 // ================================================================================================ driver
 int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t offset, uint32_t limit, int scoring, S1Job *s1) {
     CU(cudaSetDevice(device), "cudaSetDevice");
+    AffinityScope on_gpu_socket(affinity);  // before any thread of this call is created
     const uint32_t NQ = b->n_queries;
     if (!pool) {
         unsigned hw = std::thread::hardware_concurrency();
@@ -1885,7 +1899,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
     // dropped by the ranking-score threshold moves every later hit forward
     const bool use_tree = stop_after < 0 && !has_budget && !has_thr && !getenv("B200_NO_TREE");
     auto make_pending = [&](QState &q, Level &L, const uint32_t *p_uw, const unsigned long long *p_ub, const unsigned long long *p_out, uint32_t p_rows,
-                            uint32_t p_ld, uint32_t p_col, uint32_t cap, uint64_t off0) -> Pending * {
+                            uint32_t p_ld, uint32_t p_col, uint32_t cap, uint64_t off0, std::vector<std::unique_ptr<Pending>> &dst) -> Pending * {
         PROF(2);
         std::unique_ptr<Pending> pd(new Pending());
         if (L.kind == RK_EXACT_ATTRIBUTE) prepare_exact_attribute(q.ctx, L, pd->o);
@@ -1902,31 +1916,36 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         pd->p_ld = p_ld;
         pd->p_col = p_col;
         pd->p_cap = cap;
-        q.pendings.push_back(std::move(pd));
-        return q.pendings.back().get();
+        dst.push_back(std::move(pd));
+        return dst.back().get();
     };
     // sequential mode: the level goes on the query's stack
     auto request_activation = [&](QState &q, Level &&L, const uint32_t *p_uw, const unsigned long long *p_ub, const unsigned long long *p_out,
                                   uint32_t p_rows, uint32_t p_ld, uint32_t p_col, uint32_t cap) -> Pending * {
         q.levels.push_back(std::move(L));
         // documents already returned or skipped: everything before this level in result order
-        Pending *pd = make_pending(q, q.levels.back(), p_uw, p_ub, p_out, p_rows, p_ld, p_col, cap, q.cur_offset);
+        Pending *pd = make_pending(q, q.levels.back(), p_uw, p_ub, p_out, p_rows, p_ld, p_col, cap, q.cur_offset, q.pendings);
         pd->L = &q.levels.back();
         return pd;
     };
     // tree mode: the level becomes a node under `parent`
     auto request_node = [&](QState &q, Node *parent, Level &&L, const uint32_t *p_uw, const unsigned long long *p_ub, const unsigned long long *p_out,
-                            uint32_t p_rows, uint32_t p_ld, uint32_t p_col, uint32_t cap, uint64_t off0, std::vector<EScore> scores) -> Pending * {
+                            uint32_t p_rows, uint32_t p_ld, uint32_t p_col, uint32_t cap, uint64_t off0, std::vector<EScore> scores,
+                            ActOut *out) -> Pending * {
         std::unique_ptr<Node> nd(new Node());
         nd->L = std::move(L);
         nd->parent = parent;
         nd->off0 = off0;
         nd->scores = std::move(scores);
         if (parent) parent->live_children++;
-        q.outstanding++;
         Node *np = nd.get();
-        q.nodes.push_back(std::move(nd));
-        Pending *pd = make_pending(q, np->L, p_uw, p_ub, p_out, p_rows, p_ld, p_col, cap, off0);
+        if (out)
+            out->nodes.push_back(std::move(nd));  // the query counts it when it folds `out` in
+        else {
+            q.outstanding++;
+            q.nodes.push_back(std::move(nd));
+        }
+        Pending *pd = make_pending(q, np->L, p_uw, p_ub, p_out, p_rows, p_ld, p_col, cap, off0, out ? out->pendings : q.pendings);
         pd->L = &np->L;
         pd->node = np;
         return pd;
@@ -1944,7 +1963,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         }
         prepare_resolve(q.ctx, L);
         if (q.tree)
-            request_node(q, nullptr, std::move(L), nullptr, q.d_univ ? q.d_univ : dix.base_ub, nullptr, hix.n_words64, hix.n_words64, 0, hix.n_words64, 0, {});
+            request_node(q, nullptr, std::move(L), nullptr, q.d_univ ? q.d_univ : dix.base_ub, nullptr, hix.n_words64, hix.n_words64, 0, hix.n_words64, 0, {}, nullptr);
         else
             request_activation(q, std::move(L), nullptr, q.d_univ ? q.d_univ : dix.base_ub, nullptr, hix.n_words64, hix.n_words64, 0, hix.n_words64);
     };
@@ -2276,7 +2295,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
 
     // tree mode: the documents of bucket [col_lo, col_hi) stand at [off, off + cnt) in the query's result order; write the part inside
     // the window [from, from + length) to its final place
-    auto emit_window = [&](QState &q, Level &L, uint32_t col_lo, uint32_t col_hi, uint64_t cnt, uint64_t off, const std::vector<EScore> &sc) {
+    auto emit_window = [&](QState &q, Level &L, uint32_t col_lo, uint32_t col_hi, uint64_t cnt, uint64_t off, const std::vector<EScore> &sc, ActOut &out) {
         const uint64_t win_end = (uint64_t)from + length;
         const uint64_t skip = off < from ? from - off : 0;
         if (skip >= cnt) return;
@@ -2294,15 +2313,16 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         e.d.skip = (uint32_t)skip;
         e.d.take = (uint32_t)take;
         e.d.dst = reinterpret_cast<uint32_t *>((uintptr_t)(start - from));
-        q.emits.push_back(e);
-        const size_t at = (size_t)(start - from);
-        if (q.scores.size() < at + take) q.scores.resize(at + take);
+        out.emits.push_back(e);
+        const size_t at = (size_t)(start - from);  // q.scores was sized when the universe was resolved; windows of different buckets are disjoint
         for (uint64_t k = 0; k < take; k++) q.scores[at + k] = sc;
-        q.n_results += (uint32_t)take;
+        out.n_results += (uint32_t)take;
     };
-    auto release_node = [&](QState &q, Node *n) {
-        q.release_level(n->L);
-        Level &L = n->L;  // the host side of the level is not needed any more either
+    auto release_node = [&](Node *n, ActOut &out) {
+        Level &L = n->L;
+        if (L.a_off != SIZE_MAX) out.freed.emplace_back(L.a_off, L.a_len);
+        L.a_off = SIZE_MAX;
+        // the host side of the level is not needed any more either
         L.graph = EGraph();
         std::vector<ECond>().swap(L.conds);
         std::vector<SEdge>().swap(L.sedges);
@@ -2310,9 +2330,10 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
     };
     // tree mode: the activation of node N is complete — place or descend into every bucket of it that reaches the result window
     // (the same decisions as advance(), bucket_sort.rs:193-330, taken for all buckets at once)
-    auto expand = [&](QState &q, Node *N) {
+    auto expand = [&](QState &q, Node *N, ActOut &out) {
         Level &L = N->L;
-        if (N->parent && --N->parent->live_children == 0 && N->parent->self_done) release_node(q, N->parent);  // nothing reads the parent's buckets any more
+        // the parent was expanded in an earlier step (self_done); the last of its children to complete gives its buckets back
+        if (N->parent && N->parent->live_children.fetch_sub(1) == 1) release_node(N->parent, out);
         const size_t n_rules = q.rules.size();
         const uint64_t win_end = (uint64_t)from + length;
         uint64_t off = N->off0;
@@ -2340,8 +2361,9 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             q.n_candidates = cnt;
             q.cand_src = L.out;
             if (length != 0 && cnt >= from) {  // bucket_sort.rs:52-64
+                q.scores.resize((size_t)std::min<uint64_t>(length, cnt - from));
                 if (n_rules == 0)
-                    emit_window(q, L, 0, 1, cnt, 0, {});
+                    emit_window(q, L, 0, 1, cnt, 0, {}, out);
                 else {
                     Level C;
                     C.rule_idx = 0;
@@ -2352,7 +2374,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
                         prepare_graph_rule(q.ctx, C.kind, C.kind == RK_WORDS, tms, C);
                     }
                     if (n_rules == 1) C.want_paths = false;
-                    request_node(q, N, std::move(C), L.uw, L.ub, L.out, L.rows, L.ld, 0, (uint32_t)std::min<uint64_t>(cnt, L.rows), 0, {});
+                    request_node(q, N, std::move(C), L.uw, L.ub, L.out, L.rows, L.ld, 0, (uint32_t)std::min<uint64_t>(cnt, L.rows), 0, {}, &out);
                 }
             }
         } else {
@@ -2361,7 +2383,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             std::vector<EScore> sc = N->scores;
             for (size_t ci = 0; off < win_end; ci++) {
                 if (remaining == 0 || (skip_scoring && remaining == 1)) {
-                    if (remaining == 1) emit_window(q, L, (uint32_t)ci, (uint32_t)L.cost_vals.size() + 1, 1, off, N->scores);
+                    if (remaining == 1) emit_window(q, L, (uint32_t)ci, (uint32_t)L.cost_vals.size() + 1, 1, off, N->scores, out);
                     break;
                 }
                 if (ci >= L.cost_vals.size()) break;
@@ -2370,12 +2392,12 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
                 remaining -= cnt;
                 sc.push_back(EScore{score_kind_of(L.kind), (uint32_t)(L.next_max_cost - L.cost_vals[ci]), (uint32_t)L.next_max_cost, -1.f});
                 if (rule_cur == n_rules - 1 || (skip_scoring && cnt <= 1) || off + cnt <= from)
-                    emit_window(q, L, (uint32_t)ci, (uint32_t)ci + 1, cnt, off, sc);
+                    emit_window(q, L, (uint32_t)ci, (uint32_t)ci + 1, cnt, off, sc, out);
                 else {
                     if (L.kind != RK_EXACT_ATTRIBUTE && ci > L.walked_m) {  // cannot happen: buckets 0..walked_m hold every document this level still needed
-                        q.status = B200_ERR_STATE;
-                        q.error = "internal: descent into a bucket whose surviving paths were not computed";
-                        return false;
+                        out.status = B200_ERR_STATE;
+                        out.error = "internal: descent into a bucket whose surviving paths were not computed";
+                        return;
                     }
                     Level C;
                     C.rule_idx = (int)rule_cur + 1;
@@ -2386,20 +2408,15 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
                         prepare_graph_rule(q.ctx, C.kind, false, tms, C);
                     }
                     if ((size_t)C.rule_idx + 1 == n_rules) C.want_paths = false;  // nothing descends from the last rule
-                    request_node(q, N, std::move(C), L.uw, L.ub, L.out, L.rows, L.ld, (uint32_t)ci, (uint32_t)std::min<uint64_t>(cnt, L.rows), off, sc);
+                    request_node(q, N, std::move(C), L.uw, L.ub, L.out, L.rows, L.ld, (uint32_t)ci, (uint32_t)std::min<uint64_t>(cnt, L.rows), off, sc, &out);
                 }
                 sc.pop_back();
                 off += cnt;
             }
         }
         N->self_done = true;
-        if (N->live_children == 0) release_node(q, N);
-        if (--q.outstanding == 0) {
-            q.scores.resize(q.n_results);
-            q.nodes.clear();
-            q.done = true;
-        }
-        return true;
+        if (N->live_children.load() == 0) release_node(N, out);  // no child: nothing will read these buckets after the emissions queued above
+        out.expanded = true;
     };
     // a query that cannot go on: give everything it holds back
     auto abandon = [&](QState &q) {
@@ -2941,16 +2958,13 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         ln.lst.host_ms[4] += ms_since(t_wait);
         auto t_adv = clk::now();
         const bool dbg = getenv("B200_DEBUG") != nullptr;
-        // the activations of one query are handled by one thread, in the order they were packed
-        std::vector<uint32_t> order(act_q.size());
-        for (size_t a = 0; a < order.size(); a++) order[a] = (uint32_t)a;
-        std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return act_q[x] < act_q[y]; });
-        std::vector<uint32_t> grp;  // start of every query's run in `order`
-        for (size_t k = 0; k < order.size(); k++)
-            if (k == 0 || act_q[order[k]] != act_q[order[k - 1]]) grp.push_back((uint32_t)k);
-        grp.push_back((uint32_t)order.size());
-        auto complete = [&](QState &q, uint32_t qi, std::unique_ptr<Pending> &up) {
-            Pending &pd = *up;
+        std::vector<ActOut> outs(acts.size());
+        // 1. every activation on its own (activations of one query run on different threads: they only touch their own node, their
+        //    ActOut and disjoint entries of the query's score table); sequential-mode queries have one activation and own their state
+        ln.pool->run(acts.size(), [&](size_t a) {
+            QState &q = *qs[act_q[a]];
+            Pending &pd = *acts[a];
+            ActOut &out = outs[a];
             Level &L = *pd.L;
             const uint32_t *res = ln.h_results + L.res_off;
             L.rows = res[0];
@@ -2963,19 +2977,19 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             if (res[1 + nc + 1] != 0) {
                 // more distinct surviving paths than the de-duplication table holds: some were not reported.  Run the activation again
                 // with a table 16x larger (its work description is still in place); give up at 16 M slots.
-                q.release_level(L);
+                if (L.a_off != SIZE_MAX) out.freed.emplace_back(L.a_off, L.a_len);
+                L.a_off = SIZE_MAX;
                 if (pd.tab_shift >= 12) {
-                    q.status = B200_ERR_CAPACITY;
-                    q.error = "more distinct surviving paths in one ranking-rule step than the device path table holds";
-                    abandon(q);
+                    out.status = B200_ERR_CAPACITY;
+                    out.error = "more distinct surviving paths in one ranking-rule step than the device path table holds";
                     return;
                 }
                 pd.tab_shift += 4;
-                q.pendings.push_back(std::move(up));
+                out.retry = true;
                 return;
             }
             if (dbg) {
-                std::string msg = "[b200 debug] q" + std::to_string(qi) + " rule " + std::to_string(L.rule_idx) + " kind " + std::to_string(L.kind) +
+                std::string msg = "[b200 debug] q" + std::to_string(act_q[a]) + " rule " + std::to_string(L.rule_idx) + " kind " + std::to_string(L.kind) +
                                   " rows " + std::to_string(L.rows) + "/" + std::to_string(L.ld) + " states " + std::to_string(L.n_states) + " edges " +
                                   std::to_string(L.sedges.size()) + " conds " + std::to_string(L.conds.size()) + " cols " + std::to_string(pd.o.n_cols) +
                                   " jobs " + std::to_string(pd.o.jobs.size()) + " costs:";
@@ -2985,22 +2999,46 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             }
             try {
                 PROF(3);
-                if (pd.node) {
-                    if (!expand(q, pd.node)) abandon(q);
-                } else
+                if (pd.node)
+                    expand(q, pd.node, out);
+                else
                     advance(q);
             } catch (const TooComplex &t) {
-                q.status = B200_ERR_CAPACITY;
-                q.error = t.why;
-                abandon(q);
+                out.status = B200_ERR_CAPACITY;
+                out.error = t.why;
             }
-        };
+        });
+        // 2. fold the outcomes into the queries, one thread per query
+        std::vector<uint32_t> order(act_q.size());
+        for (size_t a = 0; a < order.size(); a++) order[a] = (uint32_t)a;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return act_q[x] < act_q[y]; });
+        std::vector<uint32_t> grp;  // start of every query's run in `order`
+        for (size_t k = 0; k < order.size(); k++)
+            if (k == 0 || act_q[order[k]] != act_q[order[k - 1]]) grp.push_back((uint32_t)k);
+        grp.push_back((uint32_t)order.size());
         ln.pool->run(grp.size() - 1, [&](size_t g) {
-            const uint32_t qi = act_q[order[grp[g]]];
-            QState &q = *qs[qi];
+            QState &q = *qs[act_q[order[grp[g]]]];
             for (uint32_t k = grp[g]; k < grp[g + 1]; k++) {
-                if (q.done && q.status != 0) break;  // abandoned by an earlier activation of this step
-                complete(q, qi, acts[order[k]]);
+                ActOut &out = outs[order[k]];
+                for (auto &f : out.freed) q.freed.push_back(f);
+                if (out.status != 0 && q.status == 0) {
+                    q.status = out.status;
+                    q.error = out.error;
+                }
+                if (out.retry) q.pendings.push_back(std::move(acts[order[k]]));
+                for (auto &e : out.emits) q.emits.push_back(e);
+                for (auto &p : out.pendings) q.pendings.push_back(std::move(p));
+                q.outstanding += (uint32_t)out.nodes.size();
+                for (auto &n : out.nodes) q.nodes.push_back(std::move(n));
+                q.n_results += out.n_results;
+                if (out.expanded) q.outstanding--;
+            }
+            if (q.status != 0)
+                abandon(q);
+            else if (q.tree && q.outstanding == 0 && q.pendings.empty() && !q.done) {
+                q.scores.resize(q.n_results);
+                q.nodes.clear();
+                q.done = true;
             }
         });
         ln.lst.host_ms[5] += ms_since(t_adv);

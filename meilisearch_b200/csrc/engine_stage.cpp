@@ -3,7 +3,10 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <cctype>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -11,6 +14,55 @@
 #include "kernels.h"
 
 namespace b200 {
+
+void HostAffinity::detect(int device) {
+    valid = false;
+    if (const char *env = getenv("B200_PIN"))
+        if (atoi(env) == 0) return;
+    char bus[32] = {};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) return;
+    for (char *c = bus; *c; c++) *c = (char)tolower((unsigned char)*c);
+    int node = -1;
+    {
+        std::string path = std::string("/sys/bus/pci/devices/") + bus + "/numa_node";
+        FILE *f = fopen(path.c_str(), "r");
+        if (!f) return;
+        if (fscanf(f, "%d", &node) != 1) node = -1;
+        fclose(f);
+    }
+    if (node < 0) return;
+    char list[4096] = {};
+    {
+        std::string path = "/sys/devices/system/node/node" + std::to_string(node) + "/cpulist";
+        FILE *f = fopen(path.c_str(), "r");
+        if (!f) return;
+        if (!fgets(list, sizeof list, f)) list[0] = 0;
+        fclose(f);
+    }
+    cpu_set_t allowed, want;
+    if (sched_getaffinity(0, sizeof allowed, &allowed) != 0) return;
+    CPU_ZERO(&want);
+    int n = 0, n_allowed = CPU_COUNT(&allowed);
+    for (const char *c = list; *c;) {  // "0-31,64-95"
+        if (*c < '0' || *c > '9') {
+            c++;
+            continue;
+        }
+        char *end;
+        long a = strtol(c, &end, 10), b2 = a;
+        if (*end == '-') b2 = strtol(end + 1, &end, 10);
+        for (long k = a; k <= b2 && k < CPU_SETSIZE; k++)
+            if (CPU_ISSET((int)k, &allowed)) {
+                CPU_SET((int)k, &want);
+                n++;
+            }
+        c = end;
+    }
+    if (n < 4 || n == n_allowed) return;  // nothing to narrow, or too little left to work with
+    cpus = want;
+    valid = true;
+}
+
 
 #define CU(call, what)                         \
     do {                                       \
