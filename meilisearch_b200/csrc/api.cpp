@@ -473,19 +473,21 @@ int Engine::search_batch(const b200_query_batch *b, b200_results *r) {
     // the vector stage runs beside the keyword stage: its own host thread, stream and timers (the two share nothing mutable)
     bool have_vec = b->vectors != nullptr;
     int rc_vec = B200_OK;
-    // It starts once the keyword stage has derived the terms of its first wave: the term sweep is a short, SM-filling kernel that
-    // the persistent GEMM would otherwise slow down threefold, while the step loop that follows leaves most of the GPU idle.
+    // It starts once the keyword stage has derived its terms (kw_derived counts the derivation waves done; B200_VEC_START picks the
+    // wave, 0 = at once): the term sweep is a short, SM-filling kernel that the persistent GEMM would otherwise hold up for its whole
+    // run time, while the step loop that follows leaves part of the GPU idle.
     // B200_HYBRID_SERIAL=1 runs the two stages one after the other (bench.py's device-time pass: kernel intervals must not overlap).
     std::thread sem;
     const bool serial = getenv("B200_HYBRID_SERIAL") != nullptr;
+    const int vec_start = getenv("B200_VEC_START") ? atoi(getenv("B200_VEC_START")) : VEC_START_DEFAULT;
     kw_derived.store(0);
     if (have_vec && !serial)
         sem = std::thread([&]() {
-            while (kw_derived.load(std::memory_order_acquire) == 0) std::this_thread::yield();
+            while (kw_derived.load(std::memory_order_acquire) < vec_start) std::this_thread::yield();
             rc_vec = semantic_batch(b, &vec.view, 0, lim);
         });
     int rc = keyword_batch(b, &kw.view, 0, lim, 1);
-    kw_derived.store(1, std::memory_order_release);  // (also when the keyword stage returned early)
+    kw_derived.store(KW_DERIVED_ALL, std::memory_order_release);  // (also when the keyword stage returned early)
     if (sem.joinable()) sem.join();
     if (have_vec && serial) rc_vec = semantic_batch(b, &vec.view, 0, lim);
     fold_vector_stats();

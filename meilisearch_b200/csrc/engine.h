@@ -390,7 +390,10 @@ struct Engine {
     bool has_distribution = false;
     float dist_mean = 0, dist_sigma = 0;
     b200_stats stats{};
-    std::atomic<int> kw_derived{0};  // hybrid: the keyword stage has derived its first wave's terms (the vector stage starts then)
+    // hybrid: derivation waves the keyword stage has finished (KW_DERIVED_ALL after the last one); the vector stage waits for
+    // VEC_START_DEFAULT of them
+    static constexpr int KW_DERIVED_ALL = 1 << 20, VEC_START_DEFAULT = 1;
+    std::atomic<int> kw_derived{0};
     TimerSet vt;          // vector stage: own stream and timers
     b200_stats vstats{};  // what the vector stage accumulated since it was last folded into `stats`
     void fold_vector_stats() {

@@ -3095,7 +3095,7 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
                 return B200_OK;
             }
             start_range(lo, hi);
-            kw_derived.store(1, std::memory_order_release);
+            kw_derived.store(wv + 1 == n_waves ? KW_DERIVED_ALL : (int)wv + 1, std::memory_order_release);
             cudaError_t ce = cudaStreamSynchronize(stream);  // row-table memset and derivations visible to the lanes
             if (ce != cudaSuccess) {
                 rc_prep = cuda_fail(ce, "sync");

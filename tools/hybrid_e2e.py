@@ -25,11 +25,15 @@ def run(label, reps=6):
     print(f"{label}: {ms:.1f} ms/batch = {1024e3 / ms:.0f} q/s", flush=True)
 
 
-run("overlapped, all SMs")
-for sms in os.environ.get("SMS", "128,112,96,72").split(","):
-    os.environ["B200_VEC_SMS"] = sms
-    run(f"overlapped, GEMM on {sms} SMs")
-del os.environ["B200_VEC_SMS"]
+for start in os.environ.get("STARTS", "0,1,2").split(","):
+    os.environ["B200_VEC_START"] = start
+    os.environ.pop("B200_VEC_SMS", None)
+    run(f"vector stage after derivation wave {start}, all SMs")
+    for sms in os.environ.get("SMS", "96").split(","):
+        os.environ["B200_VEC_SMS"] = sms
+        run(f"vector stage after derivation wave {start}, GEMM on {sms} SMs")
+os.environ.pop("B200_VEC_SMS", None)
+os.environ.pop("B200_VEC_START", None)
 os.environ["B200_HYBRID_SERIAL"] = "1"
 run("serial")
 del os.environ["B200_HYBRID_SERIAL"]
