@@ -486,6 +486,9 @@ def main():
                 "algorithmic_bytes_per_launch": d["bytes"] / d["count"]}
 
     roofline = roof(dom)
+    # a "launch" of the keyword kinds is the group of kernels of that kind in one device step, timed by one pair of CUDA events on the
+    # lane's stream (eval_paths = eval_dp_kernel of every shared-memory class + walk_kernel); `traffic` is ncu's DRAM bytes per such group
+    roofline["launch_unit"] = "one device step's kernels of this kind (eval_paths: eval_dp_kernel x classes + walk_kernel)"
     roofline["kernel_time_share"] = {k: round(v["ms"] / tot_ms, 4) for k, v in kern.items()}
     roofline["all_kernels"] = {k: {"frac": round(roof(k)["frac"], 4), "unit": roof(k)["unit"], "achieved": round(roof(k)["achieved"], 1),
                                    "ms_per_step": round(kern[k]["ms"] / args.steps, 3)} for k in kern}
