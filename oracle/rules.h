@@ -1011,7 +1011,9 @@ inline void batch_nns(const Index &ix, const float *queries, uint32_t nq, size_t
         for (auto &x : all) out.push_back({x.second, x.first});
     }
 }
-inline float distribution_shift(float mean, float sigma, float score) {  // vector/distribution.rs:103-130
+// vector/distribution.rs:103-130.  Rust never contracts a*b+c into a fused multiply-add; this file is built with -march=x86-64-v3, so
+// contraction is switched off here (pinned by hybrid.rs:549-568: 0.19161224365234375, one f32 rounding away from the fused result).
+__attribute__((optimize("fp-contract=off"))) inline float distribution_shift(float mean, float sigma, float score) {
     float factor = 0.4f / sigma;
     float offset = 0.5f - (factor * mean);
     float s = factor * score + offset;

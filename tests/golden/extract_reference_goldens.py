@@ -311,6 +311,86 @@ def matching_strategy_cases():
     return out
 
 
+def http_search_cases():
+    """crates/meilisearch/tests/search/mod.rs: known answers of the HTTP search tests that exercise only this path, transcribed by hand
+    (source line beside every row).  Fixtures: crates/meilisearch/tests/common/mod.rs:223-256 `DOCUMENTS` and :276-300
+    `SCORE_DOCUMENTS`; default settings (searchableAttributes ["*"]: every field searchable with the same weight — `weights` all 0;
+    serde_json maps iterate in key order, `_vectors` is not indexed as text).  The title "Gläss" is stored as "Glass": the reference's
+    tokenizer folds the diacritic (the test at mod.rs:86 searches "glass"), the tokenizer mirror here is ASCII-only.
+    `expected_ranking_scores` = `_rankingScore`, `expected_candidates` = `estimatedTotalHits`, `expected_rule_scores` = the `score`
+    of every `_rankingScoreDetails` entry in rule order (exactness = ExactAttribute's rank / max when no word-level detail applies)."""
+    src = "crates/meilisearch/tests/search/mod.rs"
+    docs = [("287947", "Shazam!", "green blue"), ("299537", "Captain Marvel", "yellow blue"), ("522681", "Escape Room", "yellow red"),
+            ("166428", "How to Train Your Dragon: The Hidden World", "green red"), ("450465", "Glass", "blue red")]
+
+    def documents(stop_words=()):
+        return {"searchable": ["color", "id", "title"], "exact_attributes": [], "stop_words": list(stop_words),
+                "docs": [{"color": c, "id": i, "title": t} for i, t, c in docs]}
+
+    score_docs = {"searchable": ["id", "title"], "exact_attributes": [], "stop_words": [],
+                  "docs": [{"id": i, "title": t} for i, t in (("A", "Batman the dark knight returns: Part 1"), ("B", "Batman the dark knight returns: Part 2"),
+                                                               ("C", "Batman Returns"), ("D", "Batman"), ("E", "Badman"))]}
+    w3, w2 = {"weights": [0, 0, 0]}, {"weights": [0, 0]}
+    stop7 = ("the", "The", "a", "an", "to", "in", "of")
+    rows = [
+        # line, test, index, settings, query, expected ids, extras
+        (70, "simple_placeholder_search", documents(), w3, "", [0, 1, 2, 3, 4], {}),
+        (89, "simple_search", documents(), w3, "glass", [4], {}),
+        (141, "search_with_stop_word", documents(stop7), w3, "to the", [], {}),
+        (149, "search_with_stop_word", documents(stop7), w3, "to the ", [0, 1, 2, 3, 4], {}),
+        (237, "phrase_search_with_stop_word", documents(("the", "of")), w3, 'how "to" train "the', [3], {}),
+        (248, "negative_phrase_search", documents(), w3, '-"train your dragon"', [0, 1, 2, 4], {}),
+        (264, "negative_word_search", documents(), w3, "-escape", [0, 1, 3, 4], {}),
+        (277, "negative_word_search", documents(), w3, "-escape escape", [], {}),
+        (289, "non_negative_search", documents(), w3, "- escape", [2], {}),
+        (298, "non_negative_search", documents(), w3, '- "train your dragon"', [3], {}),
+        (322, "negative_special_cases_search", documents(), dict(w3, synonyms={"escape": ["glass"]}), "-escape escape", [4], {}),
+        (781, "test_score_details", documents(), w3, "train dragon", [3],
+         {"expected_rule_scores": [[1.0, 1.0, 0.75, 1.0, 0.8095238095238095, 0.3333333333333333]]}),
+        (924, "test_score", score_docs, w2, "Badman the dark knight returns 1", [0, 1, 4, 2, 3],
+         {"expected_ranking_scores": [0.9746605609456898, 0.8055252965383685, 0.16666666666666666, 0.07702020202020202, 0.07702020202020202]}),
+        (973, "test_score_threshold", score_docs, w2, "Badman dark returns 1", [0, 1, 4, 2, 3],
+         {"threshold": 0.0, "expected_candidates": 5,
+          "expected_ranking_scores": [0.93430081300813, 0.6685627880184332, 0.25, 0.11553030303030302, 0.11553030303030302]}),
+        (1016, "test_score_threshold", score_docs, w2, "Badman dark returns 1", [0, 1, 4],
+         {"threshold": 0.2, "expected_candidates": 3, "expected_ranking_scores": [0.93430081300813, 0.6685627880184332, 0.25]}),
+        (1049, "test_score_threshold", score_docs, w2, "Badman dark returns 1", [0, 1],
+         {"threshold": 0.5, "expected_candidates": 2, "expected_ranking_scores": [0.93430081300813, 0.6685627880184332]}),
+        (1077, "test_score_threshold", score_docs, w2, "Badman dark returns 1", [0],
+         {"threshold": 0.8, "expected_candidates": 1, "expected_ranking_scores": [0.93430081300813]}),
+        (1100, "test_score_threshold", score_docs, w2, "Badman dark returns 1", [], {"threshold": 1.0, "expected_candidates": 0}),
+    ]
+    out = []
+    for line, test, index, st, q, ids, extra in rows:
+        c = {"source": f"{src}:{line}", "test": test, "index": index, "settings": dict(st), "tms": "last", "scoring": "detailed", "limit": 20,
+             "offset": 0, "query": q, "expected_ids": ids}
+        c.update(extra)
+        out.append(c)
+    # crates/meilisearch/tests/search/multi/mod.rs: multi-search / federated search over the same fixtures.  Federation itself is outside
+    # this path, but every merged hit carries the ranking score it got from the query at `queriesPosition` (federation weight 1.0):
+    # `expected_doc_scores` = [docid, weightedRankingScore] pairs a single query must reproduce (expected_ids null: the merged list
+    # does not show the query's other hits).
+    msrc = "crates/meilisearch/tests/search/multi/mod.rs"
+    mrows = [
+        (164, "simple_search_single_index", documents(), w3, "glass", [4], []),
+        (165, "simple_search_single_index", documents(), w3, "captain", [1], []),
+        (329, "federation_two_search_single_index", documents(), w3, "glass", None, [[4, 1.0]]),
+        (330, "federation_two_search_single_index", documents(), w3, "captain", None, [[1, 0.9848484848484848]]),
+        (628, "federation_multiple_search_multiple_indexes", documents(), w3, "Escape", None, [[2, 0.9848484848484848]]),
+        (631, "federation_multiple_search_multiple_indexes", documents(), w3, "the bat", None, [[3, 0.4166666666666667]]),
+        (258, "federation_multiple_search_single_index", score_docs, w2, "badman returns", None, [[4, 0.5]]),
+        (259, "federation_multiple_search_single_index", score_docs, w2, "batman", None, [[3, 1.0], [0, 0.9848484848484848], [1, 0.9848484848484848]]),
+        (260, "federation_multiple_search_single_index", score_docs, w2, "batman returns", None, [[2, 1.0]]),
+    ]
+    for line, test, index, st, q, ids, doc_scores in mrows:
+        c = {"source": f"{msrc}:{line}", "test": test, "index": index, "settings": dict(st), "tms": "last", "scoring": "detailed", "limit": 20,
+             "offset": 0, "query": q, "expected_ids": ids}
+        if doc_scores:
+            c["expected_doc_scores"] = doc_scores
+        out.append(c)
+    return out
+
+
 def phrase_search_count_cases():
     """crates/milli/tests/search/phrase_search.rs:27-63: test_set.ndjson, stop words a/an/the/of, the phrase query
     "the use of force" under TermsMatchingStrategy::All matches exactly one document, with no criteria and with
@@ -478,6 +558,7 @@ def main():
                             last_case["scores_source"] = rel
     cases.extend(query_criteria_cases())
     cases.extend(matching_strategy_cases())
+    cases.extend(http_search_cases())
     # de-duplicate identical corpora into a table to keep the fixture small
     corpora, keyed = [], {}
     for c in cases:

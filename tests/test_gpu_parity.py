@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 from tests.helpers import image_from_corpus, load_goldens, synthetic_image
+from tests.test_oracle_goldens import check_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -164,13 +165,14 @@ def test_reference_goldens_on_gpu(mb):
             images[ci] = image_from_corpus(G["corpora"][ci])
         img = images[ci]
         ix = mb.Index(img, criteria=s.get("criteria"), authorize_typos=s.get("authorize_typos", True), one_typo=s.get("one_typo", 5),
-                      two_typos=s.get("two_typos", 9), exact_words=s.get("exact_words", []), synonyms=s.get("synonyms"))
-        res = (ix.search().query(mb.TokenBatch([case["query"]], img.stop_words)).terms_matching_strategy(case["tms"])
-               .scoring_strategy(case["scoring"]).limit(max(case["limit"], 1)).offset(case["offset"]).execute())
+                      two_typos=s.get("two_typos", 9), exact_words=s.get("exact_words", []), synonyms=s.get("synonyms"), weights=s.get("weights"))
+        search = (ix.search().query(mb.TokenBatch([case["query"]], img.stop_words)).terms_matching_strategy(case["tms"])
+                  .scoring_strategy(case["scoring"]).limit(max(case["limit"], 1)).offset(case["offset"]))
+        if case.get("threshold") is not None:
+            search = search.ranking_score_threshold(case["threshold"])
+        res = search.execute()
         assert res.status[0] == 0
-        assert res.ids(0) == case["expected_ids"], case["source"]
-        if "expected_scores" in case and case["scoring"] == "detailed":
-            assert [[list(x) for x in row] for row in res.scores(0)] == case["expected_scores"], case["scores_source"]
+        check_golden(case, res.ids(0), res.scores(0), int(res.n_candidates[0]))
         ix.close()
         ran += 1
     assert ran == len(G["cases"])
@@ -582,6 +584,31 @@ def test_hybrid_goldens_on_gpu(mb):
     for ratio in HYBRID_CASES:
         r = ix.search().query(["Captain"]).semantic(np.array([[1.0, 1.0]], np.float32)).scoring_strategy("detailed").execute_hybrid(ratio)
         check(r.ids(0), r.scores(0), int(r.semantic_hit_count[0]), ratio)
+
+
+def test_hybrid_more_goldens_on_gpu(mb):
+    """the other known answers of hybrid.rs (limit_offset, distribution_shift, highlighter, single_document, query_combination:
+    tests/test_hybrid_goldens.py MORE_CASES) through the C ABI, routed as the HTTP layer routes them"""
+    from tests.test_hybrid_goldens import MORE_CASES, check_more, embeddings, more_image, route
+
+    for case in MORE_CASES:
+        _, q, vector, ratio, offset, limit, distribution, n_docs, _, _, _ = case
+        ix = mb.Index(more_image(n_docs), weights=[0, 0, 0])
+        ix.set_embeddings(embeddings()[:n_docs], distribution=distribution)
+        kind = route(q, vector, ratio)
+        vec = None if vector is None else np.array([vector], np.float32)
+        s = ix.search().scoring_strategy("detailed").offset(offset).limit(limit)
+        if kind == "keyword":
+            r = s.query([q or ""]).execute()
+            sem = None
+        elif kind == "semantic":
+            r = s.semantic(vec).execute()
+            sem = len(r.ids(0))
+        else:
+            r = s.query([q]).semantic(vec).execute_hybrid(ratio)
+            sem = int(r.semantic_hit_count[0])
+        check_more(case, r.ids(0), r.scores(0), sem)
+        ix.close()
 
 
 # ------------------------------------------------------------------------------------------------ round 2: S1 / S2 seams

@@ -18,19 +18,39 @@ def _image(ci):
     return _images[ci]
 
 
+def check_golden(case, ids, scores, n_candidates):
+    """what a golden case pins: hit order; ScoreDetails tuples; `_rankingScore`; per-rule scores; `estimatedTotalHits`"""
+    from tests.test_cutoff_goldens import global_score
+
+    if case["expected_ids"] is not None:
+        assert ids == case["expected_ids"], case["source"]
+    for doc, want in case.get("expected_doc_scores", []):
+        assert doc in ids, case["source"]
+        assert abs(global_score(scores[ids.index(doc)]) - want) < 1e-14, case["source"]
+    if "expected_scores" in case and case["scoring"] == "detailed":
+        assert [[list(x) for x in row] for row in scores] == case["expected_scores"], case["scores_source"]
+    if "expected_ranking_scores" in case:  # rationals of small integers: the f64 value is the reference's to the last digits it prints
+        assert np.allclose([global_score(s) for s in scores], case["expected_ranking_scores"], rtol=0, atol=1e-14), case["source"]
+    if "expected_rule_scores" in case:
+        for row, want in zip(scores, case["expected_rule_scores"]):
+            got = [rk / mx for _, rk, mx in row]
+            # the reference reports ExactAttribute + ExactWords as one `exactness` entry (score_details.rs): its score is
+            # ExactAttribute's unless the match type is exact
+            assert np.allclose(got[:len(want)], want, rtol=0, atol=1e-14), case["source"]
+    if "expected_candidates" in case:
+        assert n_candidates == case["expected_candidates"], case["source"]
+
+
 @pytest.mark.parametrize("case", G["cases"], ids=[c["source"].split("/")[-1] + ":" + c["query"][:24] for c in G["cases"]])
 def test_reference_golden(case):
     img = _image(case["index"])
     s = case["settings"]
     ix = OracleIndex(img, criteria=s.get("criteria"), authorize_typos=s.get("authorize_typos", True),
-                     one_typo=s.get("one_typo", 5), two_typos=s.get("two_typos", 9))
+                     one_typo=s.get("one_typo", 5), two_typos=s.get("two_typos", 9), weights=s.get("weights"))
     ix.update_settings(exact_words=s.get("exact_words", []), synonyms=s.get("synonyms", {}))
     r = ix.search_batch(TokenBatch([case["query"]], img.stop_words), tms=case["tms"], scoring=case["scoring"],
-                        limit=max(case["limit"], 1), offset=case["offset"])
-    assert r.ids(0) == case["expected_ids"], case["source"]
-    if "expected_scores" in case and case["scoring"] == "detailed":
-        got = [[list(x) for x in row] for row in r.scores(0)]
-        assert got == case["expected_scores"], case["scores_source"]
+                        limit=max(case["limit"], 1), offset=case["offset"], threshold=case.get("threshold"))
+    check_golden(case, r.ids(0), r.scores(0), int(r.n_candidates[0]))
 
 
 @pytest.mark.parametrize("case", G.get("count_cases", []), ids=[c["source"].split("/")[-1] + ":" + c["query"] for c in G.get("count_cases", [])])
