@@ -20,7 +20,7 @@ extern "C" {
 #define B200_ERR_NO_DEVICE (-1)   /* no CUDA device / driver (the product never falls back to the CPU) */
 #define B200_ERR_CUDA (-2)        /* a CUDA call failed; see b200_last_error */
 #define B200_ERR_INVALID (-3)     /* bad argument */
-#define B200_ERR_UNSUPPORTED (-4) /* query feature outside the implemented scope (sort, filters, only-negative queries, ...) */
+#define B200_ERR_UNSUPPORTED (-4) /* query feature outside the implemented scope (sort, filters, more than 12 terms, ...) */
 #define B200_ERR_CAPACITY (-5)    /* a device work queue / arena overflowed */
 #define B200_ERR_STATE (-6)       /* call order (e.g. search before b200_stage_finish) */
 

@@ -387,6 +387,7 @@ struct Level {
     std::vector<std::pair<uint16_t, uint16_t>> state_cost_range;  // (rmin, rcount) per state
     std::vector<uint32_t> cost_vals;
     bool want_paths = false;
+    bool neg_only = false;  // RK_RESOLVE of a query made only of negative terms: the one condition is the ignored documents, the answer the rest
     std::vector<SurvPath> surv;
     uint64_t next_max_cost = 1;
     // device buffers (arena)
@@ -447,7 +448,7 @@ struct QState {
     QCtx ctx;
     int status = 0;
     std::string error;
-    bool done = false, placeholder = false;
+    bool done = false, placeholder = false, neg_only = false;
     EGraph graph;
     std::vector<int> rules;  // RuleKind per rule
     std::vector<Level> levels;
@@ -1335,7 +1336,16 @@ EGraph build_from_paths(const std::vector<std::vector<const ECond *>> &paths) {
 
 // conditions -> columns, scatter jobs, column program; state graph -> device form
 void emit_activation_work(const QCtx &c, Level &L, StepOut &o) {
-    if (L.kind != RK_EXACT_ATTRIBUTE) {
+    if (L.kind == RK_RESOLVE && L.neg_only) {
+        // the single condition of the level = documents of the negative words and phrases (search/new/mod.rs:719-731); the level's
+        // "unmatched" column (universe minus every bucket) is then the universe the placeholder search returns
+        ActBuilder b(c, o);
+        uint16_t ign = b.new_col();
+        L.conds[0].col = ign;
+        for (auto w : c.neg_words) b.add_word_docids(ign, WordRef{w, false});
+        for (auto ph : c.neg_phrases) b.op(1, ign, ign, b.phrase_col(ph));
+        o.n_cols = b.next_col;
+    } else if (L.kind != RK_EXACT_ATTRIBUTE) {
         ActBuilder b(c, o);
         for (auto &cd : L.conds) cd.col = b.new_col();
         for (auto &cd : L.conds) build_cond(b, cd);
@@ -1582,10 +1592,11 @@ void parse_query(QState &q, const b200_query_batch *b, uint32_t qi) {
         if (i >= 2) make_ngram(i - 2, i);
     }
     build_initial_edges(g);
-    q.placeholder = located.empty();
     q.used_negative = !c.neg_words.empty() || !c.neg_phrases.empty();
-    if (q.placeholder && (!c.neg_words.empty() || !c.neg_phrases.empty()))
-        throw UnsupportedQuery{"a query made only of negative terms is not implemented on the device path"};
+    // no positive term: a placeholder search (search/new/mod.rs:733-737) — over the universe minus the negative terms' documents
+    // when there are any (:719-731), which needs one device step
+    q.neg_only = located.empty() && q.used_negative;
+    q.placeholder = located.empty() && !q.used_negative;
 }
 
 // get_ranking_rules_for_query_graph_search (search/new/mod.rs:510-649)
@@ -2009,6 +2020,24 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
             pd->need = 0xffffffffu;  // every bucket may be asked for: walk them all
             return;
         }
+        if (q.neg_only) {
+            q.tree = false;
+            Level L;
+            L.kind = RK_RESOLVE;
+            L.neg_only = true;
+            ECond x;
+            x.rule = RK_RESOLVE;
+            L.conds.push_back(x);
+            struct AEdge {
+                uint32_t src, dst, cost;
+                int32_t cond;
+            };
+            std::vector<AEdge> ae{{0, 1, 0, 0}};  // START -[ignored documents]-> END
+            finish_state_graph(L, ae, 0, 1, false);
+            L.next_max_cost = 1;
+            request_activation(q, std::move(L), nullptr, q.d_univ ? q.d_univ : dix.base_ub, nullptr, hix.n_words64, hix.n_words64, 0, hix.n_words64);
+            return;
+        }
         if (q.placeholder) {
             // placeholder search: no text rules (search/new/mod.rs:353-416) -> universe in docid order (bucket_sort.rs:104-116)
             q.n_candidates = q.univ_count;
@@ -2135,7 +2164,8 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
         for (;;) {
             if (q.levels.empty()) break;
             // bucket_sort.rs:52-64,104-116: all_candidates is the universe even when no hit is asked for (limit 0)
-            if (q.levels.back().kind == RK_RESOLVE && q.levels.back().cursor == 0) q.n_candidates = q.levels.back().counts[0];
+            if (q.levels.back().kind == RK_RESOLVE && q.levels.back().cursor == 0)
+                q.n_candidates = q.levels.back().neg_only ? q.levels.back().counts.back() : q.levels.back().counts[0];
             if (q.n_results >= length) break;
             size_t cur = q.levels.size() - 1;  // level index; rule index = cur - 1 (level 0 = resolve)
             Level &L = q.levels[cur];
@@ -2175,6 +2205,17 @@ int Engine::keyword_batch(const b200_query_batch *b, b200_results *r, uint32_t o
                     break;
                 }
                 L.cursor = 1;
+                if (L.neg_only) {
+                    // placeholder search over universe - ignored documents = the level's unmatched column (the one after its
+                    // single bucket), in docid order (bucket_sort.rs:104-116)
+                    const uint64_t rest = L.counts.back();
+                    const uint32_t rest_col = (uint32_t)L.cost_vals.size();
+                    q.n_candidates = rest;
+                    q.cand_src = L.out + (size_t)rest_col * L.ld;
+                    if (rest >= from) emit_bucket(q, L, rest_col, rest_col + 1, rest);
+                    q.drop_levels();
+                    break;
+                }
                 q.n_candidates = L.counts[0];
                 q.cand_src = L.out;  // bucket 0 of the resolve level over the dense universe = SearchResult::candidates
                 uint64_t cnt = L.counts[0];

@@ -265,13 +265,34 @@ def test_phrases_negatives_match_oracle(mb, synth):
         assert got.scores(q) == want.scores(q), queries[q]
 
 
+def test_only_negative_terms_is_a_placeholder_search_over_the_rest(mb, synth):
+    """search/new/mod.rs:719-737: no positive term -> placeholder search over universe minus the negative words' / phrases' documents"""
+    from oracle.pyoracle import OracleIndex
+
+    qs = synth.synthetic_queries(6, seed=31, with_typos=False)
+    w = [q.split() for q in qs]
+    queries = ["-" + w[0][0], "-" + w[1][0] + " -" + w[2][0], '-"' + " ".join(w[3][:2]) + '"', "- " + w[4][0], "-" + w[5][0] + " -zzzzqqqqxxxx"]
+    tokens = mb.TokenBatch(queries)
+    ix, o = mb.Index(synth), OracleIndex(synth)
+    for offset, limit in ((0, 20), (7, 5)):
+        got = ix.search().query(tokens).scoring_strategy("detailed").offset(offset).limit(limit).with_candidates().execute()
+        want = o.search_batch(tokens, scoring="detailed", offset=offset, limit=limit, n_threads=4)
+        for q in range(len(queries)):
+            assert got.status[q] == 0
+            assert got.ids(q) == want.ids(q), queries[q]
+            assert got.scores(q) == want.scores(q), queries[q]
+            assert int(got.n_candidates[q]) == int(want.n_candidates[q]), queries[q]
+            assert bool(got.used_negative_operator[q]) == bool(want.used_negative_operator[q])
+            assert int(np.bitwise_count(got.candidates[q]).sum()) == int(want.n_candidates[q])
+
+
 def test_unsupported_is_reported_not_faked(mb, synth):
     ix = mb.Index(synth)
     w = synth.synthetic_queries(1, seed=5, with_typos=False)[0].split()[0]
     long_query = " ".join(synth.synthetic_queries(8, seed=6, with_typos=False))
     assert len(long_query.split()) > 12
     res = ix.search().query(["-" + w, "plain", long_query]).words_limit(20).execute()
-    assert res.status[0] == -4 and res.n_hits[0] == 0
+    assert res.status[0] == 0
     assert res.status[1] == 0
     assert res.status[2] == -4 and res.n_hits[2] == 0
     # with the default words_limit (10) the same long query is in scope
