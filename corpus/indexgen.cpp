@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <thread>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -142,6 +143,30 @@ struct ig_builder {
     }
 };
 
+// Thread count of the generators.  Launchers such as torchrun export OMP_NUM_THREADS=1 to every rank; a one-off 10 M-document build or
+// a 15 GB embedding fill would then run on one core.  B200_GEN_THREADS wins; an OMP_NUM_THREADS other than 1 is respected; otherwise
+// the host's threads are shared out over the ranks of this node (LOCAL_WORLD_SIZE).  The previous setting is restored on return.
+struct GenThreads {
+    int before;
+    GenThreads() : before(omp_get_max_threads()) {
+        int n = 0;
+        if (const char *e = getenv("B200_GEN_THREADS")) n = atoi(e);
+        if (n <= 0) {
+            const char *o = getenv("OMP_NUM_THREADS");
+            if (o && atoi(o) > 1)
+                n = atoi(o);
+            else {
+                int hw = (int)std::thread::hardware_concurrency();
+                const char *lw = getenv("LOCAL_WORLD_SIZE");
+                int ranks = lw ? std::max(1, atoi(lw)) : 1;
+                n = std::max(1, hw / ranks);
+            }
+        }
+        omp_set_num_threads(n);
+    }
+    ~GenThreads() { omp_set_num_threads(before); }
+};
+
 extern "C" {
 
 ig_builder *ig_new(uint32_t n_fields, uint32_t exact_mask) {
@@ -238,6 +263,7 @@ static std::string mutate(const std::string &w, Rng &r) {
 
 void ig_add_synthetic(ig_builder *b, uint32_t n_docs, uint32_t vocab, double zipf_s, uint32_t len_lo,
                       uint32_t len_hi, uint64_t seed) {
+    GenThreads gen_threads;
     Rng r(seed);
     // vocabulary: rank -> interned id
     std::vector<uint32_t> vid(vocab);
@@ -408,6 +434,7 @@ static void emit_db(Db &db, std::vector<std::pair<uint64_t, uint32_t>> &tuples, 
 }  // extern "C++"
 
 void ig_build(ig_builder *b) {
+    GenThreads gen_threads;
     // 1. sorted dictionary, remap word ids to ranks
     size_t nw = b->words.size();
     std::vector<uint32_t> order(nw);
@@ -667,6 +694,7 @@ void ig_query_source(const ig_builder *b, uint8_t **word_bytes, uint64_t **word_
 // cfg 4 embeddings: rows i.i.d. N(0,1) then L2-normalised, stored fp16.  Row r has its own generator (seed, r), so
 // any row range can be produced by any number of threads; `out` holds n x d IEEE binary16 values for rows [first_row, first_row+n).
 void ig_fill_embeddings_f16(uint16_t *out, uint64_t first_row, uint64_t n, uint32_t d, uint64_t seed) {
+    GenThreads gen_threads;
 #pragma omp parallel
     {
         std::vector<float> v(d + 1);
